@@ -1,0 +1,111 @@
+"""CPU twin of the alias sampler (oracle/): Vose tables are exact, and the rejection sampler's
+empirical transition frequencies match the reference's exact second-order probabilities
+(RS:27-44 weights normalised) -- parity level P2's distribution half, on the CPU."""
+import importlib
+
+import numpy as np
+import pytest
+
+from conftest import KARATE
+
+synth = importlib.import_module("stellar-random-walk_b200.synth")
+
+
+def _weighted_karate(oracle):
+    rng = np.random.RandomState(5)
+    rows = [ln.split() for ln in open(KARATE).read().split("\n") if ln]
+    txt = "".join("%s %s %.3f\n" % (a, b, 0.25 + rng.randint(0, 16) / 4.0) for a, b in rows)
+    return oracle.Graph().load_text(txt, weighted=True)
+
+
+def test_vose_tables_reconstruct_weights(oracle):
+    g = _weighted_karate(oracle)
+    a = oracle.AliasGraph(g)
+    assert a.has_alias
+    v = a.view()
+    for r in range(a.nv):
+        lo, hi = v["offsets"][r], v["offsets"][r + 1]
+        n = hi - lo
+        w = v["w"][lo:hi].astype(np.float64)
+        thr = v["thr"][lo:hi].astype(np.float64)
+        thr[v["thr"][lo:hi] == 0xFFFFFFFF] = 2.0 ** 32
+        mass = thr / 2.0 ** 32
+        got = mass.copy()
+        np.add.at(got, v["alias"][lo:hi].astype(np.int64), 1.0 - mass)
+        np.testing.assert_allclose(got / n, w / w.sum(), rtol=0, atol=1e-6)
+        assert (np.diff(v["col"][lo:hi]) >= 0).all()
+
+
+def test_unweighted_graph_has_no_alias_arrays(oracle):
+    a = oracle.AliasGraph(oracle.Graph().load_file(KARATE))
+    assert not a.has_alias and "thr" not in a.view()
+
+
+def test_thresholds(oracle):
+    assert oracle.alias_thresholds(1.0, 1.0) == (2 ** 32, 2 ** 32, 2 ** 32)
+    assert oracle.alias_thresholds(0.5, 2.0) == (2 ** 32, 2 ** 31, 2 ** 30)
+    assert oracle.alias_thresholds(0.25, 4.0) == (2 ** 32, 2 ** 30, 2 ** 28)
+    assert oracle.alias_thresholds(2.0, 0.5) == (2 ** 30, 2 ** 31, 2 ** 32)
+
+
+def _exact_transition(oracle, g, prev, curr, p, q):
+    bw = oracle.second_order_weights(p, q, prev, g.neighbors(prev), g.neighbors(curr))
+    probs = {}
+    tot = sum(float(w) for _, w in bw)
+    for d, w in bw:
+        probs[d] = probs.get(d, 0.0) + float(w) / tot
+    return probs
+
+
+@pytest.mark.parametrize("weighted,p,q", [(False, 0.5, 2.0), (True, 0.25, 4.0), (True, 2.0, 0.5), (False, 1.0, 1.0)])
+def test_alias_walk_distribution(oracle, weighted, p, q):
+    g = _weighted_karate(oracle) if weighted else oracle.Graph().load_file(KARATE)
+    a = oracle.AliasGraph(g)
+    ids, offs, st = a.walk(walk_length=40, num_walks=300, p=p, q=q, seed=11)
+    paths = ids.reshape(-1, 42)
+    assert st.steps == paths.shape[0] * 41
+    # transition counts per (prev, curr) context
+    ctx = {}
+    for k in range(2, 42):
+        for a_, b_, c_ in zip(paths[:, k - 2], paths[:, k - 1], paths[:, k]):
+            ctx.setdefault((int(a_), int(b_)), {}).setdefault(int(c_), 0)
+            ctx[(int(a_), int(b_))][int(c_)] += 1
+    chi2, dof = 0.0, 0
+    for (pv, cu), cnt in ctx.items():
+        n = sum(cnt.values())
+        if n < 400:
+            continue
+        probs = _exact_transition(oracle, g, pv, cu, p, q)
+        assert set(cnt) <= set(probs)
+        for d, pr in probs.items():
+            e = n * pr
+            if e >= 5:
+                chi2 += (cnt.get(d, 0) - e) ** 2 / e
+                dof += 1
+        dof -= 1
+    assert dof > 50
+    # chi2 ~ N(dof, 2 dof): 5 sigma
+    assert abs(chi2 - dof) < 5.0 * (2.0 * dof) ** 0.5, (chi2, dof)
+
+
+def test_alias_walk_is_counter_based(oracle):
+    """Same (seed, walker, step) -> same path regardless of threads / subset."""
+    g = oracle.Graph().load_file(KARATE)
+    a = oracle.AliasGraph(g)
+    i1, o1, _ = a.walk(walk_length=20, num_walks=3, p=0.5, q=2.0, seed=3, threads=1)
+    i2, o2, _ = a.walk(walk_length=20, num_walks=3, p=0.5, q=2.0, seed=3, threads=4)
+    assert (i1 == i2).all() and (o1 == o2).all()
+    i3, o3, _ = a.walk(walk_length=20, num_walks=3, p=0.5, q=2.0, seed=3, sample_mod=5)
+    full = oracle.paths_as_lists(i1, o1)
+    assert oracle.paths_as_lists(i3, o3) == full[::5]
+
+
+def test_rmat_generator_shape():
+    s, d = synth.rmat_edges(8, 4, seed=42)
+    assert len(s) == 4 << 8 and s.min() >= 0 and s.max() < 256 and d.max() < 256
+    s2, d2 = synth.rmat_edges(8, 4, seed=42, first=100, count=50)
+    assert (s2 == s[100:150]).all() and (d2 == d[100:150]).all()
+    # skew: quadrant a dominates -> low ids are hubs
+    assert (s < 128).mean() > 0.7
+    w = synth.edge_weights(1000)
+    assert w.dtype == np.float32 and w.min() >= 1.0 and w.max() < 2.0
