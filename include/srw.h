@@ -1,0 +1,194 @@
+/*
+ * srw.h -- C ABI of libsrw, the B200-native node2vec second-order random-walk engine.
+ *
+ * Drop-in boundary for the hot path of data61/stellar-random-walk (reference @ 0b2da95).  The
+ * reference has no FFI; its seam is the Scala trait `RandomWalk` as driven by `Main.doRandomWalk`.
+ * Every entry point below names the reference interface it replaces.  Paths are relative to
+ * /root/reference/randomwalk/src/main/scala/au/csiro/data61/randomwalk/ :
+ *   Main = Main.scala, CP = common/CommandParser.scala, Params = common/Params.scala,
+ *   RW = algorithm/RandomWalk.scala, URW = algorithm/UniformRandomWalk.scala,
+ *   VRW = algorithm/VCutRandomWalk.scala, GM = algorithm/GraphMap.scala,
+ *   RS = algorithm/RandomSample.scala.
+ *
+ * Conventions: plain pointers and sizes only; every function returns srw_status (0 = OK) unless
+ * stated otherwise; the message for the calling thread's last failure is srw_last_error();
+ * handles are opaque and freed by the caller.  Calls are blocking.  The library has NO CPU
+ * walk path: graph and walk calls fail with SRW_ERR_NO_DEVICE when no CUDA device is present.
+ * Pointers named h_* are host memory, d_* are device memory of the current CUDA device.
+ */
+#ifndef SRW_H
+#define SRW_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum srw_status {
+  SRW_OK = 0,
+  SRW_ERR_ARG = 1,        /* bad argument */
+  SRW_ERR_USAGE = 2,      /* CP:32-109 parse failure: caller prints srw_usage(), exits 1 (Main:25) */
+  SRW_ERR_PARSE = 3,      /* edge-list line the reference would throw on (URW:34) */
+  SRW_ERR_IO = 4,
+  SRW_ERR_CUDA = 5,
+  SRW_ERR_NO_DEVICE = 6,
+  SRW_ERR_UNSUPPORTED = 7
+} srw_status;
+
+/* CP:7-10 TaskName */
+enum { SRW_TASK_NODE2VEC = 0, SRW_TASK_RANDOMWALK = 1, SRW_TASK_EMBEDDING = 2 };
+/* sampler: ALIAS = Vose proposal + p/q rejection (throughput path); EXACT = RS:12-62 literal
+ * float32/float64 inverse-CDF (bit-parity path) */
+enum { SRW_SAMPLER_ALIAS = 0, SRW_SAMPLER_EXACT = 1 };
+/* where a draw comes from: Philox4x32-10 keyed by (seed; walker, step, trial), or the constant
+ * generator the reference's tests inject (`nextFloat = () => rValue`, RS:5, T-URW:183-185) */
+enum { SRW_U_PHILOX = 0, SRW_U_CONST = 1 };
+
+#define SRW_PATH_MAX 1024
+
+/* Params.scala:7-23, field for field, followed by this build's additive options. */
+typedef struct srw_params {
+  int32_t w2v_iter;        /* w2vIter = 10        (accepted, unused: word2vec is out of scope) */
+  double w2v_lr;           /* w2vLr = 0.025 */
+  int32_t w2v_partitions;  /* w2vPartitions = 1 */
+  int32_t w2v_dim;         /* w2vDim = 128 */
+  int32_t w2v_window;      /* w2vWindow = 10 */
+  int32_t walk_length;     /* walkLength = 80 */
+  int32_t num_walks;       /* numWalks = 10 */
+  double p;                /* p = 1.0 */
+  double q;                /* q = 1.0 */
+  int32_t weighted;        /* weighted = true */
+  int32_t directed;        /* directed = false */
+  char input[SRW_PATH_MAX];   /* input = null  -> "" */
+  char output[SRW_PATH_MAX];  /* output = null -> "" */
+  int32_t rdd_partitions;  /* rddPartitions = 200 */
+  int32_t single_output;   /* singleOutput = true */
+  int32_t partitioned;     /* partitioned = false */
+  int32_t cmd;             /* cmd = node2vec */
+  /* ---- additive ---- */
+  uint64_t seed;           /* --seed (default 1): the reference has no seed at all */
+  int32_t sampler;         /* --sampler alias|exact (default alias) */
+  int32_t u_mode;          /* SRW_U_PHILOX; SRW_U_CONST for the reference's constant-u tests */
+  float u_const;
+  int32_t num_gpus;        /* --gpus (default 1) */
+} srw_params;
+
+typedef struct srw_edges srw_edges;   /* parsed edge list (host) */
+typedef struct srw_graph srw_graph;   /* GraphMap replacement: CSR (+sorted copy, +Vose slots) in HBM */
+typedef struct srw_paths srw_paths;   /* result of a walk: RDD[Array[Int]] replacement */
+typedef struct srw_graphmap srw_graphmap; /* incremental builder with GraphMap.addVertex semantics */
+
+const char *srw_last_error(void);
+const char *srw_version(void);
+int srw_device_count(void);           /* number of CUDA devices visible (0 = none), never fails */
+
+/* ---- Params / CommandParser ---- */
+srw_status srw_params_default(srw_params *out);                        /* Params:7-23 */
+/* CP:32-109 (scopt): --name value pairs, --input/--output/--cmd required, scopt booleans
+ * (true/false/yes/no/1/0), unknown option or bad value => SRW_ERR_USAGE. */
+srw_status srw_params_parse_argv(int argc, const char *const *argv, srw_params *out);
+const char *srw_usage(void);                                           /* CP:33-105 usage text */
+
+/* ---- A1: edge-list text -> arrays (URW:23-34 rules; VRW:19-34 when partitioned) ---- */
+srw_status srw_edges_parse_file(const char *path, int weighted, int partitioned, srw_edges **out);
+srw_status srw_edges_parse_buffer(const char *buf, size_t len, int weighted, int partitioned, srw_edges **out);
+/* any out pointer may be NULL; *h_pid is NULL unless parsed with partitioned != 0 */
+srw_status srw_edges_view(const srw_edges *e, int64_t *n, const int32_t **h_src, const int32_t **h_dst,
+                          const float **h_w, const int32_t **h_pid);
+void srw_edges_free(srw_edges *e);
+
+/* ---- A1+A2: adjacency build (URW:35-43 + GM:41-64 semantics) on the device ---- */
+#define SRW_BUILD_EXACT 1u   /* keep the file-appearance-order rows (needed by SRW_SAMPLER_EXACT) */
+#define SRW_BUILD_ALIAS 2u   /* build neighbour-sorted rows + Vose slots (needed by SRW_SAMPLER_ALIAS) */
+#define SRW_BUILD_ALL 3u
+srw_status srw_graph_from_edges(int64_t n, const int32_t *h_src, const int32_t *h_dst, const float *h_w /*NULL=1.0f*/,
+                                const int32_t *h_pid /*NULL*/, int directed, unsigned flags, srw_graph **out);
+srw_status srw_graph_from_device_edges(int64_t n, const int32_t *d_src, const int32_t *d_dst, const float *d_w,
+                                       const int32_t *d_pid, int directed, unsigned flags, srw_graph **out);
+/* loadGraph(): URW:17-88 / VRW:13-98 chosen by params->partitioned (Main:54-57) */
+srw_status srw_graph_load(const srw_params *params, unsigned flags, srw_graph **out);
+/* RW:23-24 nVertices / nEdges (= adjacency entries) */
+srw_status srw_graph_stats(const srw_graph *g, int64_t *n_vertices, int64_t *n_edges);
+/* GM:109-120 getNeighbors: *n = -1 unknown vid (reference: null), 0 dead end, else degree.
+ * Copies up to cap entries (file-appearance order) into h_dst / h_w (either may be NULL). */
+srw_status srw_graph_neighbors(const srw_graph *g, int32_t vid, int32_t *h_dst, float *h_w, int64_t cap, int64_t *n);
+/* GM:66-68 getPartition: *found = 0 when the vid was never a neighbour in a partitioned load */
+srw_status srw_graph_partition(const srw_graph *g, int32_t vid, int32_t *pid, int *found);
+/* ascending vertex ids (this build's emission order) */
+srw_status srw_graph_vertex_ids(const srw_graph *g, int32_t *h_out, int64_t cap);
+/* device layout for inspection/tests: row offsets [nv+1], sorted neighbour ranks [nnz], and when
+ * has_alias the Vose slots {thr, own, alias_vertex, alias_index} [nnz]; any pointer may be NULL */
+srw_status srw_graph_layout(const srw_graph *g, int64_t *h_offsets, int32_t *h_col_sorted, uint32_t *h_slots4,
+                            int *has_alias);
+int64_t srw_graph_device_bytes(const srw_graph *g);
+void srw_graph_free(srw_graph *g);
+
+/* GraphMap.addVertex x3 / reset (GM:23-56, 83-85, 99-107) as an incremental host builder */
+srw_status srw_graphmap_new(srw_graphmap **out);
+srw_status srw_graphmap_add_vertex(srw_graphmap *m, int32_t vid, int64_t n, const int32_t *h_dst,
+                                   const int32_t *h_pid /*NULL*/, const float *h_w /*NULL=1.0f*/);
+srw_status srw_graphmap_reset(srw_graphmap *m);
+srw_status srw_graphmap_counts(const srw_graphmap *m, int64_t *n_vertices, int64_t *n_edges); /* GM:87-93 */
+srw_status srw_graphmap_finalize(const srw_graphmap *m, unsigned flags, srw_graph **out);
+void srw_graphmap_free(srw_graphmap *m);
+
+/* ---- A5-A7 on the device, for known-answer tests (one sampler call through the same device
+ * functions the exact walk kernel uses) ---- */
+srw_status srw_sample(int64_t n, const int32_t *h_dst, const float *h_w, float u, int32_t *dst_out, float *w_out); /* RS:12-25 */
+srw_status srw_second_order_weights(float p, float q, int32_t prev, int64_t np, const int32_t *h_pdst, int64_t nc,
+                                    const int32_t *h_cdst, const float *h_cw, float *h_out);          /* RS:27-44 */
+srw_status srw_second_order_sample(float p, float q, int32_t prev, int64_t np, const int32_t *h_pdst, int64_t nc,
+                                   const int32_t *h_cdst, const float *h_cw, float u, int32_t *dst_out,
+                                   float *w_out);                                                     /* RS:55-62 */
+srw_status srw_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);          /* device KAT */
+
+/* ---- A8-A10: randomWalk(initPaths) (RW:75-176): all numWalks rounds; one walker per vertex per
+ * round; uses walk_length, num_walks, p, q, seed, sampler, u_mode, u_const, num_gpus ---- */
+srw_status srw_walk(const srw_graph *g, const srw_params *params, srw_paths **out);
+/* Device-resident variant: walkers [walker_first, walker_first + n_walkers) with walker id =
+ * round * nVertices + vertex rank.  d_paths is [n_walkers][walk_length+2] int32 (vertex ids,
+ * row-major), d_lens [n_walkers].  Nothing leaves the device.  stream: a cudaStream_t or NULL. */
+srw_status srw_walk_device(const srw_graph *g, const srw_params *params, uint64_t walker_first, int64_t n_walkers,
+                           int32_t *d_paths, int32_t *d_lens, void *stream);
+/* timing / counters of the calling thread's most recent srw_walk* call */
+typedef struct srw_walk_info {
+  double kernel_ms;        /* CUDA-event time of the walk kernel(s) alone */
+  int64_t kernel_launches; /* number of kernels launched (walk + finalize) */
+  int64_t steps;           /* sampled transitions = sum(len - 1) */
+  int64_t proposals;       /* alias proposals on second-order steps (0 unless stats were requested) */
+  int64_t member_tests;
+  int64_t probes_log2;     /* sum over membership tests of ceil(log2(deg(prev)+1)) */
+} srw_walk_info;
+srw_status srw_last_walk_info(srw_walk_info *out);
+/* make the next srw_walk_device of this thread also count proposals/member tests (slower kernel) */
+srw_status srw_walk_collect_stats(int enable);
+
+/* ragged view, host memory owned by the handle: ids[offsets[i] .. offsets[i+1]) is path i, in
+ * (round, ascending vertex id) order */
+srw_status srw_paths_view(srw_paths *paths, int64_t *n_paths, const int32_t **h_ids, const int64_t **h_offsets);
+srw_status srw_paths_counts(const srw_paths *paths, int64_t *n_paths, int64_t *n_steps);
+/* RW:234-241 save(): <output>/path/part-NNNNN, ids joined by '\t', one path per line; 1 file when
+ * single_output else rdd_partitions files (Main:64-69), plus an empty _SUCCESS marker */
+srw_status srw_save(srw_paths *paths, const srw_params *params);
+/* the same text into a caller buffer; *needed = bytes required */
+srw_status srw_paths_format(srw_paths *paths, char *h_buf, int64_t cap, int64_t *needed);
+void srw_paths_free(srw_paths *paths);
+
+/* Main.main / runJob for --cmd randomwalk (Main:18-27, 109-127): parse, load, walk, save.
+ * Prints the reference's "edges:/vertices:" lines (URW:69-72).  Returns the process exit code. */
+int srw_main(int argc, const char *const *argv);
+
+/* ---- synthetic inputs for the benchmark; device-resident, not on the walk path ---- */
+srw_status srw_synth_rmat_device(int scale, int edge_factor, uint64_t seed, int64_t first, int64_t count,
+                                 int32_t *d_src, int32_t *d_dst);
+srw_status srw_synth_weights_device(uint64_t seed, int64_t first, int64_t count, float *d_w);
+/* random 32-byte-sector gather micro-benchmark over a table of table_bytes: returns achieved
+ * sectors/s and the GB/s of sector traffic (the "random-gather roofline" of the north star) */
+srw_status srw_gather_ceiling(int64_t table_bytes, int64_t gathers, double *sectors_per_s, double *gb_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

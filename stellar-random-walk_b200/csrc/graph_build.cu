@@ -1,0 +1,400 @@
+// graph_build.cu -- K1/K2/K3: edge list -> CSR in HBM (+ neighbour-sorted copy, + Vose alias slots).
+//
+// Replaces the reference's Spark adjacency build (URW:35-43 `reduceByKey(_ ++ _)`, VRW:35-49) and
+// GraphMap.addVertex (GM:23-64): per-vertex neighbour arrays in FILE-APPEARANCE order (for one input
+// line the src-side entry precedes the dst-side entry), duplicates and self-loops kept, every id seen
+// in the file is a vertex (|V| = distinct ids, RW:23; a vertex without out-neighbours has an empty row,
+// GM:50-52).  Vertices are ranked by ascending id; ranks index every device array.
+//
+// Layout produced (all in HBM, sized for 64-bit row offsets -- RMAT-26 has 2^31 adjacency entries,
+// beyond the reference's Int offsetCounter, GM:18):
+//   d_off[nv+1] int64, d_col_app/d_w_app [nnz] (appearance order, exact sampler),
+//   d_col[nnz] (ascending per row: membership search + unweighted proposals),
+//   d_slot[nnz] 16-byte Vose slots (weighted graphs only).
+//
+// Sorting/scanning uses CUB device primitives (a CUDA toolkit library, like cuBLAS for GEMMs); the
+// build runs once per graph and is timed separately from the walk.
+#include <cub/cub.cuh>
+
+#include "philox.cuh"
+#include "srw_internal.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+inline unsigned grid_for(int64_t n, int threads = kThreads) {
+  int64_t b = (n + threads - 1) / threads;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+struct DevBuf {  // RAII scratch
+  void *p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  template <class T> T *as() { return (T *)p; }
+  cudaError_t alloc(size_t bytes) { if (p) { cudaFree(p); p = nullptr; } return cudaMalloc(&p, bytes ? bytes : 16); }
+  void *release() { void *q = p; p = nullptr; return q; }
+};
+
+__device__ __forceinline__ int32_t rank_of(const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ wordrank,
+                                           int32_t id_min, int32_t id) {
+  const uint32_t rel = (uint32_t)id - (uint32_t)id_min;
+  const uint32_t w = rel >> 5, b = rel & 31u;
+  return (int32_t)(wordrank[w] + __popc(bitmap[w] & ((1u << b) - 1u)));
+}
+
+__global__ void k_mark(int64_t n, const int32_t *__restrict__ ids, int32_t id_min, uint32_t *bitmap) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t rel = (uint32_t)ids[i] - (uint32_t)id_min;
+    const uint32_t bit = 1u << (rel & 31u);
+    if (!(bitmap[rel >> 5] & bit)) atomicOr(&bitmap[rel >> 5], bit);
+  }
+}
+__global__ void k_popc(uint64_t words, const uint32_t *__restrict__ bitmap, uint32_t *cnt) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < words; i += (uint64_t)gridDim.x * blockDim.x)
+    cnt[i] = __popc(bitmap[i]);
+}
+__global__ void k_vids(uint64_t words, const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ wordrank,
+                       int32_t id_min, int32_t *vids) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < words; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t bits = bitmap[i];
+    uint32_t r = wordrank[i];
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      vids[r++] = (int32_t)((uint32_t)id_min + (uint32_t)(i * 32 + b));
+    }
+  }
+}
+// adjacency entries in appearance order: undirected entry 2e = (src -> dst), 2e+1 = (dst -> src)
+// (URW:38); directed entry e = (src -> dst) (URW:36).  Also counts degrees.
+__global__ void k_entries(int64_t n, const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int directed,
+                          const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ wordrank, int32_t id_min,
+                          uint32_t *ent_row, uint32_t *ent_col, uint32_t *deg) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t rs = rank_of(bitmap, wordrank, id_min, src[e]);
+    const uint32_t rd = rank_of(bitmap, wordrank, id_min, dst[e]);
+    if (directed) {
+      ent_row[e] = rs; ent_col[e] = rd;
+      atomicAdd(&deg[rs], 1u);
+    } else {
+      ent_row[2 * e] = rs; ent_col[2 * e] = rd;
+      ent_row[2 * e + 1] = rd; ent_col[2 * e + 1] = rs;
+      atomicAdd(&deg[rs], 1u);
+      atomicAdd(&deg[rd], 1u);
+    }
+  }
+}
+__global__ void k_iota(int64_t n, uint32_t *a) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a[i] = (uint32_t)i;
+}
+__global__ void k_gather_u32(int64_t n, const uint32_t *__restrict__ idx, const uint32_t *__restrict__ table, uint32_t *out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = table[idx[i]];
+}
+// entry index -> input edge weight (shift = 1 when each edge made two entries)
+__global__ void k_gather_w(int64_t n, const uint32_t *__restrict__ idx, const float *__restrict__ w, int shift, float *out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = w ? w[idx[i] >> shift] : 1.0f;
+}
+__global__ void k_any_non_unit(int64_t n, const float *__restrict__ w, int *flag) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (w[i] != 1.0f) *flag = 1;
+}
+// GM:31 vertexPartitionMap.put(dst, pId): the partition id of the last input line (file order) in
+// which the vertex is a neighbour.  (The reference's winner depends on hash-partition order: unpinned.)
+__global__ void k_vpid_last(int64_t n, const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int directed,
+                            const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ wordrank, int32_t id_min,
+                            unsigned long long *last_line) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    atomicMax(&last_line[rank_of(bitmap, wordrank, id_min, dst[e])], (unsigned long long)(e + 1));
+    if (!directed) atomicMax(&last_line[rank_of(bitmap, wordrank, id_min, src[e])], (unsigned long long)(e + 1));
+  }
+}
+__global__ void k_vpid_fill(int64_t nv, const unsigned long long *__restrict__ last_line, const int32_t *__restrict__ pid,
+                            int32_t *vpid) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nv; v += (int64_t)gridDim.x * blockDim.x)
+    vpid[v] = last_line[v] ? pid[last_line[v] - 1] : -1;
+}
+
+// K3: Vose alias table by the in-order sweep (two cursors, no work lists), one row per thread.
+// Arithmetic is IEEE double with explicit rounding intrinsics so that oracle/srw_oracle.c
+// (alias_row) reproduces every bit.
+__device__ __forceinline__ double scaled_w(const float *__restrict__ w, int64_t k, double dn, double W) {
+  return __ddiv_rn(__dmul_rn((double)w[k], dn), W);
+}
+__global__ void k_alias_rows(int64_t nv, const int64_t *__restrict__ off, const int32_t *__restrict__ col,
+                             const float *__restrict__ w_all, AliasSlot *slot_all) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nv; v += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t o = off[v], n = off[v + 1] - o;
+    if (n <= 0) continue;
+    const float *w = w_all + o;
+    const int32_t *c = col + o;
+    AliasSlot *slot = slot_all + o;
+    double W = 0.0;
+    for (int64_t k = 0; k < n; ++k) {
+      W = __dadd_rn(W, (double)w[k]);
+      AliasSlot s; s.thr = 0xFFFFFFFFu; s.own = c[k]; s.alias_vertex = c[k]; s.alias_index = (uint32_t)k;
+      slot[k] = s;
+    }
+    const double dn = (double)n;
+    int64_t i = 0, j = 0;
+    while (i < n && !(scaled_w(w, i, dn, W) < 1.0)) i++;
+    while (j < n && (scaled_w(w, j, dn, W) < 1.0)) j++;
+    if (j >= n) continue;
+    double r = scaled_w(w, j, dn, W);
+    while (j < n) {
+      if (!(r < 1.0)) {
+        if (i >= n) break;
+        const double si = scaled_w(w, i, dn, W);
+        slot[i].thr = (uint32_t)__dmul_rn(si, 4294967296.0);
+        slot[i].alias_vertex = c[j];
+        slot[i].alias_index = (uint32_t)j;
+        r = __dadd_rn(__dadd_rn(r, si), -1.0);
+        i++;
+        while (i < n && !(scaled_w(w, i, dn, W) < 1.0)) i++;
+      } else {
+        int64_t j2 = j + 1;
+        while (j2 < n && (scaled_w(w, j2, dn, W) < 1.0)) j2++;
+        if (j2 >= n) break;
+        slot[j].thr = (uint32_t)__dmul_rn(r, 4294967296.0);
+        slot[j].alias_vertex = c[j2];
+        slot[j].alias_index = (uint32_t)j2;
+        r = __dadd_rn(__dadd_rn(r, scaled_w(w, j2, dn, W)), -1.0);
+        j = j2;
+      }
+    }
+  }
+}
+
+struct CastU32ToI64 {
+  __host__ __device__ int64_t operator()(uint32_t x) const { return (int64_t)x; }
+};
+
+int bits_for(int64_t nv) {
+  int b = 1;
+  while (((int64_t)1 << b) < nv) b++;
+  return b;
+}
+
+srw_status sort_pairs(uint32_t *&k_in, uint32_t *&k_out, uint32_t *&v_in, uint32_t *&v_out, int64_t n, int end_bit) {
+  cub::DoubleBuffer<uint32_t> dk(k_in, k_out), dv(v_in, v_out);
+  size_t tmp_bytes = 0;
+  SRW_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, n, 0, end_bit));
+  DevBuf tmp;
+  SRW_CUDA(tmp.alloc(tmp_bytes));
+  SRW_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, dk, dv, n, 0, end_bit));
+  SRW_CUDA(cudaDeviceSynchronize());
+  k_in = dk.Current(); k_out = dk.Alternate();
+  v_in = dv.Current(); v_out = dv.Alternate();
+  return SRW_OK;
+}
+
+template <class T>
+srw_status reduce_minmax(const T *d, int64_t n, T *mn, T *mx) {
+  DevBuf out, tmp;
+  SRW_CUDA(out.alloc(2 * sizeof(T)));
+  size_t b1 = 0, b2 = 0;
+  SRW_CUDA(cub::DeviceReduce::Min(nullptr, b1, d, out.as<T>(), n));
+  SRW_CUDA(cub::DeviceReduce::Max(nullptr, b2, d, out.as<T>() + 1, n));
+  SRW_CUDA(tmp.alloc(b1 > b2 ? b1 : b2));
+  SRW_CUDA(cub::DeviceReduce::Min(tmp.p, b1, d, out.as<T>(), n));
+  SRW_CUDA(cub::DeviceReduce::Max(tmp.p, b2, d, out.as<T>() + 1, n));
+  T h[2];
+  SRW_CUDA(cudaMemcpy(h, out.p, 2 * sizeof(T), cudaMemcpyDeviceToHost));
+  *mn = h[0]; *mx = h[1];
+  return SRW_OK;
+}
+
+}  // namespace
+
+void srw_alias_thresholds(double p, double q, uint64_t *t_ret, uint64_t *t_common, uint64_t *t_far) {
+  // accept a proposal x with probability f(x)/M, f = 1/p (x == prev), 1 (x in N(prev)), 1/q (else):
+  // the RS:33-41 bias rule; p and q narrowed to float32 first as in RW:112-113.
+  const double inv_p = 1.0 / (double)(float)p, inv_q = 1.0 / (double)(float)q;
+  double M = inv_p > 1.0 ? inv_p : 1.0;
+  if (inv_q > M) M = inv_q;
+  auto thr = [M](double f) -> uint64_t { return f >= M ? 4294967296ULL : (uint64_t)((f / M) * 4294967296.0); };
+  *t_ret = thr(inv_p);
+  *t_common = thr(1.0);
+  *t_far = thr(inv_q);
+}
+
+static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_dst, const float *d_w, const int32_t *d_pid,
+                             int directed, unsigned flags, int64_t n_extra, const int32_t *d_extra, srw_graph *g) {
+  g->directed = directed != 0;
+  g->flags = flags;
+  SRW_CUDA(cudaGetDevice(&g->device));
+  if (n + n_extra <= 0) {  // empty graph
+    SRW_CUDA(cudaMalloc(&g->d_off, sizeof(int64_t)));
+    SRW_CUDA(cudaMemset(g->d_off, 0, sizeof(int64_t)));
+    return SRW_OK;
+  }
+  const int64_t nnz = directed ? n : 2 * n;
+  if (nnz >= ((int64_t)1 << 32)) { srw_set_error("more than 2^32-1 adjacency entries are not supported"); return SRW_ERR_UNSUPPORTED; }
+
+  // ---- id range and presence bitmap ----
+  int32_t mn = INT32_MAX, mx = INT32_MIN, a, b;
+  if (n > 0) {
+    SRW_TRY(reduce_minmax(d_src, n, &a, &b)); mn = a < mn ? a : mn; mx = b > mx ? b : mx;
+    SRW_TRY(reduce_minmax(d_dst, n, &a, &b)); mn = a < mn ? a : mn; mx = b > mx ? b : mx;
+  }
+  if (n_extra > 0) { SRW_TRY(reduce_minmax(d_extra, n_extra, &a, &b)); mn = a < mn ? a : mn; mx = b > mx ? b : mx; }
+  g->id_min = mn;
+  const uint64_t range = (uint64_t)((int64_t)mx - (int64_t)mn) + 1;
+  const uint64_t words = (range + 31) / 32;
+  g->id_words = words;
+  SRW_CUDA(cudaMalloc(&g->d_bitmap, words * 4));
+  SRW_CUDA(cudaMalloc(&g->d_wordrank, (words + 1) * 4));
+  SRW_CUDA(cudaMemset(g->d_bitmap, 0, words * 4));
+  const unsigned gmax = 148 * 16;
+  auto grid = [&](int64_t m) { unsigned x = grid_for(m); return x > gmax ? gmax : x; };
+  if (n > 0) {
+    k_mark<<<grid(n), kThreads>>>(n, d_src, mn, g->d_bitmap);
+    k_mark<<<grid(n), kThreads>>>(n, d_dst, mn, g->d_bitmap);
+  }
+  if (n_extra > 0) k_mark<<<grid(n_extra), kThreads>>>(n_extra, d_extra, mn, g->d_bitmap);
+  {
+    DevBuf cnt, tmp;
+    SRW_CUDA(cnt.alloc((words + 1) * 4));
+    SRW_CUDA(cudaMemset(cnt.p, 0, (words + 1) * 4));
+    k_popc<<<grid((int64_t)words), kThreads>>>(words, g->d_bitmap, cnt.as<uint32_t>());
+    size_t tb = 0;
+    SRW_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.as<uint32_t>(), g->d_wordrank, (int64_t)(words + 1)));
+    SRW_CUDA(tmp.alloc(tb));
+    SRW_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt.as<uint32_t>(), g->d_wordrank, (int64_t)(words + 1)));
+    uint32_t nv32 = 0;
+    SRW_CUDA(cudaMemcpy(&nv32, g->d_wordrank + words, 4, cudaMemcpyDeviceToHost));
+    g->nv = nv32;
+  }
+  const int64_t nv = g->nv;
+  g->nnz = nnz;
+  SRW_CUDA(cudaMalloc(&g->d_vids, (size_t)nv * 4));
+  k_vids<<<grid((int64_t)words), kThreads>>>(words, g->d_bitmap, g->d_wordrank, mn, g->d_vids);
+
+  // ---- adjacency entries + degrees -> row offsets ----
+  DevBuf ent_row, ent_col, deg;
+  SRW_CUDA(ent_row.alloc((size_t)nnz * 4));
+  SRW_CUDA(ent_col.alloc((size_t)nnz * 4));
+  SRW_CUDA(deg.alloc((size_t)(nv + 1) * 4));
+  SRW_CUDA(cudaMemset(deg.p, 0, (size_t)(nv + 1) * 4));
+  if (n > 0)
+    k_entries<<<grid(n), kThreads>>>(n, d_src, d_dst, directed, g->d_bitmap, g->d_wordrank, mn, ent_row.as<uint32_t>(),
+                                     ent_col.as<uint32_t>(), deg.as<uint32_t>());
+  SRW_CUDA(cudaMalloc(&g->d_off, (size_t)(nv + 1) * 8));
+  {
+    cub::TransformInputIterator<int64_t, CastU32ToI64, uint32_t *> it(deg.as<uint32_t>(), CastU32ToI64());
+    size_t tb = 0;
+    DevBuf tmp;
+    SRW_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, it, g->d_off, nv + 1));
+    SRW_CUDA(tmp.alloc(tb));
+    SRW_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, it, g->d_off, nv + 1));
+  }
+  SRW_CUDA(cudaDeviceSynchronize());
+  deg.alloc(0);
+
+  if (d_pid) {  // GM:21,31
+    DevBuf last;
+    SRW_CUDA(last.alloc((size_t)nv * 8));
+    SRW_CUDA(cudaMemset(last.p, 0, (size_t)nv * 8));
+    k_vpid_last<<<grid(n), kThreads>>>(n, d_src, d_dst, directed, g->d_bitmap, g->d_wordrank, mn, last.as<unsigned long long>());
+    SRW_CUDA(cudaMalloc(&g->d_vpid, (size_t)nv * 4));
+    k_vpid_fill<<<grid(nv), kThreads>>>(nv, last.as<unsigned long long>(), d_pid, g->d_vpid);
+    SRW_CUDA(cudaDeviceSynchronize());
+    g->has_pid = true;
+  }
+  if (nnz == 0) return SRW_OK;
+
+  const int rbits = bits_for(nv);
+  const int wshift = directed ? 0 : 1;
+  DevBuf kb0, kb1, vb0, vb1;
+  SRW_CUDA(kb0.alloc((size_t)nnz * 4)); SRW_CUDA(kb1.alloc((size_t)nnz * 4));
+  SRW_CUDA(vb0.alloc((size_t)nnz * 4)); SRW_CUDA(vb1.alloc((size_t)nnz * 4));
+  uint32_t *k_in = kb0.as<uint32_t>(), *k_out = kb1.as<uint32_t>(), *v_in = vb0.as<uint32_t>(), *v_out = vb1.as<uint32_t>();
+
+  // ---- K1: appearance-order rows = stable sort of the entries by row ----
+  if (flags & SRW_BUILD_EXACT) {
+    SRW_CUDA(cudaMemcpy(k_in, ent_row.p, (size_t)nnz * 4, cudaMemcpyDeviceToDevice));
+    k_iota<<<grid(nnz), kThreads>>>(nnz, v_in);
+    SRW_TRY(sort_pairs(k_in, k_out, v_in, v_out, nnz, rbits));
+    SRW_CUDA(cudaMalloc(&g->d_col_app, (size_t)nnz * 4));
+    SRW_CUDA(cudaMalloc(&g->d_w_app, (size_t)nnz * 4));
+    k_gather_u32<<<grid(nnz), kThreads>>>(nnz, v_in, ent_col.as<uint32_t>(), (uint32_t *)g->d_col_app);
+    k_gather_w<<<grid(nnz), kThreads>>>(nnz, v_in, d_w, wshift, g->d_w_app);
+    SRW_CUDA(cudaDeviceSynchronize());
+  }
+
+  // ---- K2: neighbour-sorted rows = stable sort by column, then stable sort by row ----
+  SRW_CUDA(cudaMemcpy(k_in, ent_col.p, (size_t)nnz * 4, cudaMemcpyDeviceToDevice));
+  k_iota<<<grid(nnz), kThreads>>>(nnz, v_in);
+  SRW_TRY(sort_pairs(k_in, k_out, v_in, v_out, nnz, rbits));
+  k_gather_u32<<<grid(nnz), kThreads>>>(nnz, v_in, ent_row.as<uint32_t>(), k_in);
+  SRW_TRY(sort_pairs(k_in, k_out, v_in, v_out, nnz, rbits));
+  SRW_CUDA(cudaMalloc(&g->d_col, (size_t)nnz * 4));
+  k_gather_u32<<<grid(nnz), kThreads>>>(nnz, v_in, ent_col.as<uint32_t>(), (uint32_t *)g->d_col);
+  SRW_CUDA(cudaDeviceSynchronize());
+  ent_row.alloc(0); ent_col.alloc(0);
+
+  // ---- K3: Vose slots over the sorted rows (weighted graphs only) ----
+  if ((flags & SRW_BUILD_ALIAS) && d_w) {
+    DevBuf flag;
+    SRW_CUDA(flag.alloc(4));
+    SRW_CUDA(cudaMemset(flag.p, 0, 4));
+    k_any_non_unit<<<grid(n), kThreads>>>(n, d_w, flag.as<int>());
+    int h = 0;
+    SRW_CUDA(cudaMemcpy(&h, flag.p, 4, cudaMemcpyDeviceToHost));
+    if (h) {
+      DevBuf ws;
+      SRW_CUDA(ws.alloc((size_t)nnz * 4));
+      k_gather_w<<<grid(nnz), kThreads>>>(nnz, v_in, d_w, wshift, ws.as<float>());
+      SRW_CUDA(cudaMalloc(&g->d_slot, (size_t)nnz * sizeof(AliasSlot)));
+      k_alias_rows<<<grid_for(nv, 64), 64>>>(nv, g->d_off, g->d_col, ws.as<float>(), g->d_slot);
+      SRW_CUDA(cudaDeviceSynchronize());
+      g->has_alias = true;
+    }
+  }
+  SRW_CUDA(cudaGetLastError());
+  g->device_bytes = (int64_t)(words * 8 + (size_t)nv * 12 + (size_t)nnz * 4) + (g->d_col_app ? nnz * 8 : 0) +
+                    (g->d_slot ? nnz * 16 : 0) + (g->d_vpid ? nv * 4 : 0);
+  return SRW_OK;
+}
+
+srw_status srw_build_graph_device(int64_t n, const int32_t *d_src, const int32_t *d_dst, const float *d_w,
+                                  const int32_t *d_pid, int directed, unsigned flags, srw_graph **out) {
+  SRW_TRY(srw_require_device());
+  if (n < 0 || !out || (n > 0 && (!d_src || !d_dst))) { srw_set_error("srw_graph_from_device_edges: bad argument"); return SRW_ERR_ARG; }
+  srw_graph *g = new srw_graph();
+  srw_status s = build_impl(n, d_src, d_dst, d_w, d_pid, directed, flags ? flags : SRW_BUILD_ALL, 0, nullptr, g);
+  if (s != SRW_OK) { srw_graph_free(g); return s; }
+  *out = g;
+  return SRW_OK;
+}
+
+srw_status srw_build_graph_rows(int64_t n_rows, const int32_t *h_vids, const int64_t *h_row_off, const int64_t *h_row_len,
+                                const int32_t *h_dst, const int32_t *h_pid, const float *h_w, unsigned flags,
+                                srw_graph **out) {
+  SRW_TRY(srw_require_device());
+  // rows -> directed edge list in row order; added vertices without neighbours become extra ids
+  std::vector<int32_t> src, dst, pid;
+  std::vector<float> w;
+  for (int64_t r = 0; r < n_rows; ++r)
+    for (int64_t k = 0; k < h_row_len[r]; ++k) {
+      src.push_back(h_vids[r]);
+      dst.push_back(h_dst[h_row_off[r] + k]);
+      w.push_back(h_w ? h_w[h_row_off[r] + k] : 1.0f);
+      if (h_pid) pid.push_back(h_pid[h_row_off[r] + k]);
+    }
+  const int64_t n = (int64_t)src.size();
+  DevBuf ds, dd, dw, dp, dx;
+  SRW_CUDA(ds.alloc(n * 4)); SRW_CUDA(dd.alloc(n * 4)); SRW_CUDA(dw.alloc(n * 4)); SRW_CUDA(dx.alloc(n_rows * 4));
+  SRW_CUDA(cudaMemcpy(ds.p, src.data(), n * 4, cudaMemcpyHostToDevice));
+  SRW_CUDA(cudaMemcpy(dd.p, dst.data(), n * 4, cudaMemcpyHostToDevice));
+  SRW_CUDA(cudaMemcpy(dw.p, w.data(), n * 4, cudaMemcpyHostToDevice));
+  SRW_CUDA(cudaMemcpy(dx.p, h_vids, n_rows * 4, cudaMemcpyHostToDevice));
+  if (h_pid) { SRW_CUDA(dp.alloc(n * 4)); SRW_CUDA(cudaMemcpy(dp.p, pid.data(), n * 4, cudaMemcpyHostToDevice)); }
+  srw_graph *g = new srw_graph();
+  srw_status s = build_impl(n, ds.as<int32_t>(), dd.as<int32_t>(), dw.as<float>(), h_pid ? dp.as<int32_t>() : nullptr, 1,
+                            flags ? flags : SRW_BUILD_ALL, n_rows, dx.as<int32_t>(), g);
+  if (s != SRW_OK) { srw_graph_free(g); return s; }
+  *out = g;
+  return SRW_OK;
+}

@@ -1,0 +1,351 @@
+// srw_abi.cu -- extern "C" entry points that touch the device: graph handles, the walk driver
+// (RW:31-33 execute / RW:75-176 randomWalk), Main (Main:18-27,109-127), synthetic inputs.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <vector>
+
+#include "philox.cuh"
+#include "srw_internal.h"
+
+srw_status srw_require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    srw_set_error("no CUDA device available (%s): libsrw has no CPU walk path", e == cudaSuccess ? "0 devices" : cudaGetErrorString(e));
+    cudaGetLastError();
+    return SRW_ERR_NO_DEVICE;
+  }
+  return SRW_OK;
+}
+
+extern "C" int srw_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// graph handles
+// ------------------------------------------------------------------------------------------
+namespace {
+template <class T>
+struct Dev {
+  T *p = nullptr;
+  ~Dev() { if (p) cudaFree(p); }
+  cudaError_t put(const T *h, int64_t n) {
+    cudaError_t e = cudaMalloc(&p, (size_t)(n > 0 ? n : 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return n > 0 ? cudaMemcpy(p, h, (size_t)n * sizeof(T), cudaMemcpyHostToDevice) : cudaSuccess;
+  }
+};
+srw_status host_vids(const srw_graph *g) {
+  if ((int64_t)g->h_vids.size() != g->nv) {
+    g->h_vids.resize((size_t)g->nv);
+    if (g->nv) SRW_CUDA(cudaMemcpy(g->h_vids.data(), g->d_vids, (size_t)g->nv * 4, cudaMemcpyDeviceToHost));
+  }
+  return SRW_OK;
+}
+// rank of vid, or -1
+int64_t host_rank(const srw_graph *g, int32_t vid) {
+  auto it = std::lower_bound(g->h_vids.begin(), g->h_vids.end(), vid);
+  if (it == g->h_vids.end() || *it != vid) return -1;
+  return (int64_t)(it - g->h_vids.begin());
+}
+}  // namespace
+
+extern "C" srw_status srw_graph_from_device_edges(int64_t n, const int32_t *d_src, const int32_t *d_dst, const float *d_w,
+                                                  const int32_t *d_pid, int directed, unsigned flags, srw_graph **out) {
+  return srw_build_graph_device(n, d_src, d_dst, d_w, d_pid, directed, flags, out);
+}
+
+extern "C" srw_status srw_graph_from_edges(int64_t n, const int32_t *h_src, const int32_t *h_dst, const float *h_w,
+                                           const int32_t *h_pid, int directed, unsigned flags, srw_graph **out) {
+  SRW_TRY(srw_require_device());
+  if (n < 0 || !out || (n > 0 && (!h_src || !h_dst))) { srw_set_error("srw_graph_from_edges: bad argument"); return SRW_ERR_ARG; }
+  Dev<int32_t> s, d, pid;
+  Dev<float> w;
+  SRW_CUDA(s.put(h_src, n));
+  SRW_CUDA(d.put(h_dst, n));
+  if (h_w) SRW_CUDA(w.put(h_w, n));
+  if (h_pid) SRW_CUDA(pid.put(h_pid, n));
+  return srw_build_graph_device(n, s.p, d.p, h_w ? w.p : nullptr, h_pid ? pid.p : nullptr, directed, flags, out);
+}
+
+extern "C" srw_status srw_graph_load(const srw_params *params, unsigned flags, srw_graph **out) {
+  if (!params || !out) return SRW_ERR_ARG;
+  srw_edges *e = nullptr;
+  SRW_TRY(srw_edges_parse_file(params->input, params->weighted, params->partitioned, &e));   // URW:23-34 | VRW:19-34
+  srw_status s = srw_graph_from_edges((int64_t)e->src.size(), e->src.data(), e->dst.data(), e->w.data(),
+                                      e->has_pid ? e->pid.data() : nullptr, params->directed, flags, out);
+  srw_edges_free(e);
+  return s;
+}
+
+extern "C" srw_status srw_graph_stats(const srw_graph *g, int64_t *nv, int64_t *ne) {
+  if (!g) return SRW_ERR_ARG;
+  if (nv) *nv = g->nv;
+  if (ne) *ne = g->nnz;
+  return SRW_OK;
+}
+
+extern "C" srw_status srw_graph_neighbors(const srw_graph *g, int32_t vid, int32_t *h_dst, float *h_w, int64_t cap, int64_t *n) {
+  if (!g || !n) return SRW_ERR_ARG;
+  SRW_TRY(host_vids(g));
+  const int64_t r = host_rank(g, vid);
+  if (r < 0) { *n = -1; return SRW_OK; }                       // GM:118 case None => null
+  int64_t ext[2];
+  SRW_CUDA(cudaMemcpy(ext, g->d_off + r, 16, cudaMemcpyDeviceToHost));
+  const int64_t deg = ext[1] - ext[0];
+  *n = deg;
+  const int64_t m = std::min(deg, cap);
+  if (m <= 0) return SRW_OK;
+  const int32_t *col = g->d_col_app ? g->d_col_app : g->d_col;  // appearance order when it was kept
+  if (h_dst) {
+    std::vector<int32_t> ranks((size_t)m);
+    SRW_CUDA(cudaMemcpy(ranks.data(), col + ext[0], (size_t)m * 4, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < m; ++i) h_dst[i] = g->h_vids[(size_t)ranks[i]];
+  }
+  if (h_w) {
+    if (g->d_w_app) SRW_CUDA(cudaMemcpy(h_w, g->d_w_app + ext[0], (size_t)m * 4, cudaMemcpyDeviceToHost));
+    else for (int64_t i = 0; i < m; ++i) h_w[i] = 1.0f;
+  }
+  return SRW_OK;
+}
+
+extern "C" srw_status srw_graph_partition(const srw_graph *g, int32_t vid, int32_t *pid, int *found) {
+  if (!g || !found) return SRW_ERR_ARG;
+  *found = 0;
+  if (!g->d_vpid) return SRW_OK;
+  SRW_TRY(host_vids(g));
+  const int64_t r = host_rank(g, vid);
+  if (r < 0) return SRW_OK;
+  int32_t v = -1;
+  SRW_CUDA(cudaMemcpy(&v, g->d_vpid + r, 4, cudaMemcpyDeviceToHost));
+  if (v >= 0) { *found = 1; if (pid) *pid = v; }
+  return SRW_OK;
+}
+
+extern "C" srw_status srw_graph_vertex_ids(const srw_graph *g, int32_t *h_out, int64_t cap) {
+  if (!g || (cap > 0 && !h_out)) return SRW_ERR_ARG;
+  const int64_t m = std::min(cap, g->nv);
+  if (m > 0) SRW_CUDA(cudaMemcpy(h_out, g->d_vids, (size_t)m * 4, cudaMemcpyDeviceToHost));
+  return SRW_OK;
+}
+
+extern "C" srw_status srw_graph_layout(const srw_graph *g, int64_t *h_off, int32_t *h_col, uint32_t *h_slots4, int *has_alias) {
+  if (!g) return SRW_ERR_ARG;
+  if (has_alias) *has_alias = g->has_alias ? 1 : 0;
+  if (h_off) SRW_CUDA(cudaMemcpy(h_off, g->d_off, (size_t)(g->nv + 1) * 8, cudaMemcpyDeviceToHost));
+  if (h_col && g->nnz) SRW_CUDA(cudaMemcpy(h_col, g->d_col, (size_t)g->nnz * 4, cudaMemcpyDeviceToHost));
+  if (h_slots4 && g->has_alias) SRW_CUDA(cudaMemcpy(h_slots4, g->d_slot, (size_t)g->nnz * 16, cudaMemcpyDeviceToHost));
+  return SRW_OK;
+}
+
+extern "C" int64_t srw_graph_device_bytes(const srw_graph *g) { return g ? g->device_bytes : 0; }
+
+extern "C" void srw_graph_free(srw_graph *g) {
+  if (!g) return;
+  cudaFree(g->d_bitmap); cudaFree(g->d_wordrank); cudaFree(g->d_vids); cudaFree(g->d_off);
+  cudaFree(g->d_col_app); cudaFree(g->d_w_app); cudaFree(g->d_col); cudaFree(g->d_slot); cudaFree(g->d_vpid);
+  delete g;
+}
+
+// ------------------------------------------------------------------------------------------
+// walk driver
+// ------------------------------------------------------------------------------------------
+extern "C" srw_status srw_walk_device(const srw_graph *g, const srw_params *params, uint64_t walker_first, int64_t n_walkers,
+                                      int32_t *d_paths, int32_t *d_lens, void *stream) {
+  SRW_TRY(srw_require_device());
+  if (!g || !params || (n_walkers > 0 && (!d_paths || !d_lens))) { srw_set_error("srw_walk_device: bad argument"); return SRW_ERR_ARG; }
+  WalkLaunch l{walker_first, n_walkers, d_paths, d_lens, (cudaStream_t)stream};
+  return srw_walk_launch(g, params, l);
+}
+
+// RW:75-176: numWalks rounds, one walker per vertex per round.  Rounds are independent under the
+// counter-based RNG; they run in device-sized batches and are compacted into a ragged host array.
+extern "C" srw_status srw_walk(const srw_graph *g, const srw_params *params, srw_paths **out) {
+  SRW_TRY(srw_require_device());
+  if (!g || !params || !out) { srw_set_error("srw_walk: bad argument"); return SRW_ERR_ARG; }
+  if (params->num_walks < 0) { srw_set_error("numWalks must be >= 0"); return SRW_ERR_ARG; }
+  if (params->num_gpus > 1) { srw_set_error("srw_walk is single-GPU; the sharded walk is driven per rank (see shard API)"); return SRW_ERR_UNSUPPORTED; }
+  SRW_CUDA(cudaSetDevice(g->device));
+  const int32_t stride = params->walk_length + 2;
+  const int64_t total = (int64_t)params->num_walks * g->nv;
+  srw_paths *P = new srw_paths();
+  P->stride = stride;
+  P->offsets.push_back(0);
+  size_t free_b = 0, total_b = 0;
+  SRW_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  int64_t batch = (int64_t)(free_b / 2) / ((int64_t)stride * 4 + 4);
+  if (batch > total) batch = total;
+  if (batch < 1) batch = 1;
+  Dev<int32_t> d_paths, d_lens;
+  SRW_CUDA(cudaMalloc(&d_paths.p, (size_t)batch * stride * 4));
+  SRW_CUDA(cudaMalloc(&d_lens.p, (size_t)batch * 4));
+  std::vector<int32_t> h_paths((size_t)batch * stride), h_lens((size_t)batch);
+  double kernel_ms = 0;
+  int64_t launches = 0, steps = 0, props = 0, mem = 0, logs = 0;
+  for (int64_t first = 0; first < total; first += batch) {
+    const int64_t n = std::min(batch, total - first);
+    WalkLaunch l{(uint64_t)first, n, d_paths.p, d_lens.p, nullptr};
+    srw_status s = srw_walk_launch(g, params, l);
+    if (s != SRW_OK) { delete P; return s; }
+    srw_walk_info wi;
+    srw_last_walk_info(&wi);
+    kernel_ms += wi.kernel_ms; launches += wi.kernel_launches; steps += wi.steps;
+    props += wi.proposals; mem += wi.member_tests; logs += wi.probes_log2;
+    SRW_CUDA(cudaMemcpy(h_paths.data(), d_paths.p, (size_t)n * stride * 4, cudaMemcpyDeviceToHost));
+    SRW_CUDA(cudaMemcpy(h_lens.data(), d_lens.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < n; ++i) {
+      P->ids.insert(P->ids.end(), h_paths.begin() + i * stride, h_paths.begin() + i * stride + h_lens[i]);
+      P->offsets.push_back((int64_t)P->ids.size());
+    }
+  }
+  P->n_paths = total;
+  P->n_steps = steps;
+  // expose the totals of the whole call
+  srw_set_walk_info(kernel_ms, launches, steps, props, mem, logs);
+  *out = P;
+  return SRW_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Main.main / runJob for --cmd randomwalk (Main:18-27, 53-62, 109-127)
+// ------------------------------------------------------------------------------------------
+extern "C" int srw_main(int argc, const char *const *argv) {
+  srw_params prm;
+  if (srw_params_parse_argv(argc, argv, &prm) != SRW_OK) {      // CP:107 -> None => sys.exit(1) (Main:25)
+    fprintf(stderr, "%s\n%s", srw_last_error(), srw_usage());
+    return 1;
+  }
+  if (prm.cmd != SRW_TASK_RANDOMWALK) {
+    // Main:113-124: node2vec / embedding need MLlib Word2Vec, which is outside this engine's scope
+    fprintf(stderr, "Error: --cmd %s is not supported by this engine (only randomwalk)\n", prm.cmd == SRW_TASK_NODE2VEC ? "node2vec" : "embedding");
+    return 1;
+  }
+  const unsigned flags = prm.sampler == SRW_SAMPLER_EXACT ? SRW_BUILD_EXACT : SRW_BUILD_ALIAS;
+  srw_graph *g = nullptr;
+  auto t0 = std::chrono::steady_clock::now();
+  if (srw_graph_load(&prm, flags, &g) != SRW_OK) { fprintf(stderr, "Exception: %s\n", srw_last_error()); return 2; }
+  int64_t nv = 0, ne = 0;
+  srw_graph_stats(g, &nv, &ne);
+  printf("edges: %lld\nvertices: %lld\n", (long long)ne, (long long)nv);   // URW:71-72
+  auto t1 = std::chrono::steady_clock::now();
+  srw_paths *paths = nullptr;
+  if (srw_walk(g, &prm, &paths) != SRW_OK) { fprintf(stderr, "Exception: %s\n", srw_last_error()); srw_graph_free(g); return 2; }
+  auto t2 = std::chrono::steady_clock::now();
+  printf("Unfinished Walkers: 0\n");                                        // RW:154 (last super-step)
+  int rc = 0;
+  if (srw_save(paths, &prm) != SRW_OK) { fprintf(stderr, "Exception: %s\n", srw_last_error()); rc = 2; }   // Main:59-60
+  auto t3 = std::chrono::steady_clock::now();
+  srw_walk_info wi;
+  srw_last_walk_info(&wi);
+  auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  fprintf(stderr, "[srw] load+build %.1f ms, walk %.1f ms (kernels %.2f ms, %lld steps), save %.1f ms\n", ms(t0, t1), ms(t1, t2),
+          wi.kernel_ms, (long long)wi.steps, ms(t2, t3));
+  srw_paths_free(paths);
+  srw_graph_free(g);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// synthetic inputs + gather ceiling (benchmark utilities)
+// ------------------------------------------------------------------------------------------
+namespace {
+constexpr uint32_t kRmatTag = 0x524D4154u, kWeightTag = 0x57454947u;
+__global__ void k_rmat(int scale, uint32_t seed, int64_t first, int64_t count, uint32_t A, uint32_t AB, uint32_t ABC,
+                       int32_t *src, int32_t *dst) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t e = (uint64_t)(first + i);
+    uint32_t s = 0, d = 0;
+    for (int blk = 0; blk * 4 < scale; ++blk) {
+      const Philox4 r = philox4x32_10((uint32_t)e, (uint32_t)(e >> 32), (uint32_t)blk, kRmatTag, seed, 0u);
+      const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (blk * 4 + k >= scale) break;
+        const uint32_t x = w[k];
+        s = (s << 1) | (x >= AB ? 1u : 0u);
+        d = (d << 1) | (((x >= A && x < AB) || x >= ABC) ? 1u : 0u);
+      }
+    }
+    src[i] = (int32_t)s;
+    dst[i] = (int32_t)d;
+  }
+}
+__global__ void k_weights(uint32_t seed, int64_t first, int64_t count, float *w) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t e = (uint64_t)(first + i);
+    const Philox4 r = philox4x32_10((uint32_t)e, (uint32_t)(e >> 32), 0u, kWeightTag, seed, 0u);
+    w[i] = __fadd_rn(1.0f, __fdiv_rn((float)(r.x % 1000u), 1000.0f));
+  }
+}
+// every thread chases `per_thread` independent random 32-byte sectors (4 in flight)
+__global__ void k_gather(const uint4 *__restrict__ table, uint64_t n_sectors2, int per_thread, uint32_t *sink) {
+  const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  uint32_t acc = 0;
+  for (int k = 0; k < per_thread; k += 4) {
+    const Philox4 r = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)k, 0x47415448u, 7u, 0u);
+    const uint64_t i0 = __umul64hi(((uint64_t)r.x << 32) | r.y, n_sectors2);
+    const uint64_t i1 = __umul64hi(((uint64_t)r.y << 32) | r.z, n_sectors2);
+    const uint64_t i2 = __umul64hi(((uint64_t)r.z << 32) | r.w, n_sectors2);
+    const uint64_t i3 = __umul64hi(((uint64_t)r.w << 32) | r.x, n_sectors2);
+    const uint4 a = __ldg(table + 2 * i0), b = __ldg(table + 2 * i1), c = __ldg(table + 2 * i2), d = __ldg(table + 2 * i3);
+    acc += a.x ^ b.y ^ c.z ^ d.w;
+  }
+  if (acc == 0x12345678u) *sink = acc;
+}
+}  // namespace
+
+extern "C" srw_status srw_synth_rmat_device(int scale, int edge_factor, uint64_t seed, int64_t first, int64_t count,
+                                            int32_t *d_src, int32_t *d_dst) {
+  SRW_TRY(srw_require_device());
+  if (scale < 1 || scale > 30 || edge_factor < 1 || count < 0 || (count > 0 && (!d_src || !d_dst))) return SRW_ERR_ARG;
+  if (count == 0) return SRW_OK;
+  const uint32_t A = (uint32_t)(0.57 * 4294967296.0), AB = (uint32_t)((0.57 + 0.19) * 4294967296.0),
+                 ABC = (uint32_t)((0.57 + 0.19 + 0.19) * 4294967296.0);
+  k_rmat<<<148 * 8, 256>>>(scale, (uint32_t)seed, first, count, A, AB, ABC, d_src, d_dst);
+  SRW_CUDA(cudaDeviceSynchronize());
+  return SRW_OK;
+}
+extern "C" srw_status srw_synth_weights_device(uint64_t seed, int64_t first, int64_t count, float *d_w) {
+  SRW_TRY(srw_require_device());
+  if (count < 0 || (count > 0 && !d_w)) return SRW_ERR_ARG;
+  if (count == 0) return SRW_OK;
+  k_weights<<<148 * 8, 256>>>((uint32_t)seed, first, count, d_w);
+  SRW_CUDA(cudaDeviceSynchronize());
+  return SRW_OK;
+}
+extern "C" srw_status srw_gather_ceiling(int64_t table_bytes, int64_t gathers, double *sectors_per_s, double *gb_per_s) {
+  SRW_TRY(srw_require_device());
+  if (table_bytes < 64 || gathers < 1) return SRW_ERR_ARG;
+  Dev<uint4> table; Dev<uint32_t> sink;
+  SRW_CUDA(cudaMalloc(&table.p, (size_t)table_bytes));
+  SRW_CUDA(cudaMemset(table.p, 1, (size_t)table_bytes));
+  SRW_CUDA(cudaMalloc(&sink.p, 4));
+  const int per_thread = 64;
+  const int64_t threads = (gathers + per_thread - 1) / per_thread;
+  const unsigned grid = (unsigned)((threads + 255) / 256);
+  cudaEvent_t a, b;
+  SRW_CUDA(cudaEventCreate(&a)); SRW_CUDA(cudaEventCreate(&b));
+  k_gather<<<grid, 256>>>(table.p, (uint64_t)table_bytes / 32, per_thread, sink.p);   // warm-up
+  float best = 1e30f;
+  for (int it = 0; it < 3; ++it) {
+    SRW_CUDA(cudaEventRecord(a));
+    k_gather<<<grid, 256>>>(table.p, (uint64_t)table_bytes / 32, per_thread, sink.p);
+    SRW_CUDA(cudaEventRecord(b));
+    SRW_CUDA(cudaEventSynchronize(b));
+    float ms = 0;
+    SRW_CUDA(cudaEventElapsedTime(&ms, a, b));
+    if (ms < best) best = ms;
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  const double n = (double)grid * 256.0 * per_thread;
+  if (sectors_per_s) *sectors_per_s = n / (best * 1e-3);
+  if (gb_per_s) *gb_per_s = n * 32.0 / (best * 1e-3) / 1e9;
+  return SRW_OK;
+}

@@ -1,0 +1,99 @@
+// Internal structures of libsrw (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <unordered_set>
+#include <vector>
+
+#include "../../include/srw.h"
+
+void srw_set_error(const char *fmt, ...);
+
+#define SRW_CUDA(call)                                                                          \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess) {                                                                    \
+      srw_set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+      return SRW_ERR_CUDA;                                                                      \
+    }                                                                                           \
+  } while (0)
+#define SRW_TRY(call)                 \
+  do {                                \
+    srw_status s_ = (call);           \
+    if (s_ != SRW_OK) return s_;      \
+  } while (0)
+
+srw_status srw_require_device();
+
+struct srw_edges {
+  std::vector<int32_t> src, dst, pid;
+  std::vector<float> w;
+  bool has_pid = false;
+};
+
+// Vose slot, one 16-byte gather per proposal: own and alias target vertex are both inline.
+struct __align__(16) AliasSlot {
+  uint32_t thr;           // take `own` iff r < thr
+  int32_t own;            // neighbour rank stored at this slot
+  int32_t alias_vertex;   // neighbour rank of the alias slot
+  uint32_t alias_index;   // row-relative index of the alias slot
+};
+
+struct srw_graph {
+  int device = 0;
+  int64_t nv = 0, nnz = 0;
+  bool directed = false, has_alias = false, has_pid = false;
+  unsigned flags = 0;
+  // id <-> rank
+  int32_t id_min = 0;
+  uint64_t id_words = 0;
+  uint32_t *d_bitmap = nullptr, *d_wordrank = nullptr;
+  int32_t *d_vids = nullptr;      // [nv] ascending original ids
+  int64_t *d_off = nullptr;       // [nv+1]
+  int32_t *d_col_app = nullptr;   // [nnz] neighbour ranks, file-appearance order   (SRW_BUILD_EXACT)
+  float *d_w_app = nullptr;       // [nnz]
+  int32_t *d_col = nullptr;       // [nnz] neighbour ranks, ascending per row (membership + unweighted proposals)
+  AliasSlot *d_slot = nullptr;    // [nnz] iff has_alias                              (SRW_BUILD_ALIAS)
+  int32_t *d_vpid = nullptr;      // [nv] GM:21 vertexPartitionMap (-1 = absent)
+  int64_t device_bytes = 0;
+  mutable std::vector<int32_t> h_vids;  // lazy host copies for the query entry points
+  mutable std::vector<int64_t> h_off;
+};
+
+struct srw_paths {
+  int64_t n_paths = 0, n_steps = 0;
+  int32_t stride = 0;
+  std::vector<int32_t> ids;       // ragged
+  std::vector<int64_t> offsets;
+};
+
+struct srw_graphmap {
+  std::vector<int32_t> vids;            // insertion order
+  std::unordered_set<int32_t> seen;
+  std::vector<int64_t> row_off;         // per inserted vertex
+  std::vector<int64_t> row_len;
+  std::vector<int32_t> dst, pid;
+  std::vector<float> w;
+  bool any_pid = false;
+};
+
+// walk.cu
+struct WalkLaunch {
+  uint64_t walker_first;
+  int64_t n_walkers;
+  int32_t *d_paths, *d_lens;
+  cudaStream_t stream;
+};
+srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLaunch &l);
+void srw_set_walk_info(double kernel_ms, int64_t launches, int64_t steps, int64_t proposals, int64_t member_tests, int64_t probes_log2);
+
+// graph_build.cu
+srw_status srw_build_graph_device(int64_t n, const int32_t *d_src, const int32_t *d_dst, const float *d_w,
+                                  const int32_t *d_pid, int directed, unsigned flags, srw_graph **out);
+// adjacency rows given explicitly (GraphMap builder): entries already grouped by row in row order
+srw_status srw_build_graph_rows(int64_t n_rows, const int32_t *h_vids, const int64_t *h_row_off, const int64_t *h_row_len,
+                                const int32_t *h_dst, const int32_t *h_pid, const float *h_w, unsigned flags,
+                                srw_graph **out);
+void srw_alias_thresholds(double p, double q, uint64_t *t_ret, uint64_t *t_common, uint64_t *t_far);

@@ -1,0 +1,377 @@
+// walk.cu -- K4/K5/K6: first step + second-order walk steps on the device.
+//
+// Replaces RandomWalk.initFirstStep (RW:51-66), the per-walker hot loop of RandomWalk.randomWalk
+// (RW:95-139) and RandomSample (RS:5-63).  Two samplers:
+//
+//  * EXACT  (walk_exact_kernel): RS:12-62 literally -- float32 bias weights (w/p, w/q, RS:34-38),
+//    float64 left-to-right sum and inverse-CDF scan with `acc >= u` and the edges.head fallback
+//    (RS:14-24) over the file-appearance-order row.  The O(d_c*d_p) `exists` scan (RS:38) is replaced
+//    by a binary search in the sorted row of prev (same truth value).  Bit-identical to the oracle.
+//  * ALIAS  (walk_alias_kernel): one alias-table proposal per trial from the static weights, accepted
+//    with probability f(x)/M where f is the RS:33-41 bias factor; distribution-equal to EXACT,
+//    bit-identical to the CPU twin in oracle/ (oracle_alias_walk).
+//
+// One walker per thread; a draw is Philox4x32-10 keyed by (seed; walker, step, trial).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "philox.cuh"
+#include "srw_internal.h"
+
+namespace {
+
+struct WalkArgs {
+  const int64_t *__restrict__ off;
+  const int32_t *__restrict__ col;        // sorted rows
+  const AliasSlot *__restrict__ slot;     // Vose slots (weighted) or nullptr
+  const int32_t *__restrict__ col_app;    // appearance-order rows (exact sampler)
+  const float *__restrict__ w_app;
+  const int32_t *__restrict__ vids;
+  int64_t nv;
+  uint64_t walker_first;
+  int64_t n_walkers;
+  int32_t stride;                         // walk_length + 2 (RW:103)
+  uint32_t seed_lo, seed_hi;
+  uint64_t t_ret, t_common, t_far;        // alias acceptance thresholds
+  float p, q;                             // exact sampler (RW:112-113 .toFloat)
+  int32_t u_mode;
+  float u_const;
+  int32_t *paths;
+  int32_t *lens;
+  unsigned long long *stats;              // [steps, proposals, member_tests, probes_log2]
+};
+
+// x in sorted row [lo, lo+n)?
+__device__ __forceinline__ bool row_contains(const int32_t *__restrict__ col, int64_t lo, int64_t n, int32_t x) {
+  int64_t a = 0, b = n;
+  while (a < b) {
+    const int64_t m = (a + b) >> 1;
+    if (__ldg(col + lo + m) < x) a = m + 1; else b = m;
+  }
+  return a < n && __ldg(col + lo + a) == x;
+}
+
+__device__ __forceinline__ int ceil_log2_p1(int64_t d) { return d <= 0 ? 0 : 64 - __clzll(d); }
+
+// alias proposal from row [off, off+deg): slot index from 64 random bits, Vose coin from r.y
+template <bool HAS_ALIAS>
+__device__ __forceinline__ int32_t propose(const WalkArgs &a, int64_t off, int64_t deg, const Philox4 &r) {
+  const uint64_t R = ((uint64_t)r.x << 32) | (uint64_t)r.w;
+  const int64_t k = (int64_t)__umul64hi(R, (uint64_t)deg);
+  if (HAS_ALIAS) {
+    const int4 raw = __ldg(reinterpret_cast<const int4 *>(a.slot + off + k));
+    return (r.y < (uint32_t)raw.x) ? raw.y : raw.z;
+  } else {
+    return __ldg(a.col + off + k);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K6: alias sampler
+// ------------------------------------------------------------------------------------------
+template <bool HAS_ALIAS, bool STATS>
+__global__ void __launch_bounds__(256) walk_alias_kernel(WalkArgs a) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= a.n_walkers) return;
+  const uint64_t walker = a.walker_first + (uint64_t)i;
+  int32_t curr = (int32_t)(walker % (uint64_t)a.nv);
+  int32_t *path = a.paths + i * a.stride;
+  path[0] = curr;
+  int32_t len = 1;
+  int64_t off = __ldg(a.off + curr), deg = __ldg(a.off + curr + 1) - off;
+  unsigned long long n_prop = 0, n_mem = 0, n_log = 0;
+  if (deg > 0) {
+    // RW:51-66 first step: first-order draw, the proposal is the sample
+    Philox4 r = walker_rng(a.seed_lo, a.seed_hi, walker, 0u, 0u);
+    int32_t prev = curr;
+    int64_t poff = off, pdeg = deg;
+    curr = propose<HAS_ALIAS>(a, off, deg, r);
+    path[len++] = curr;
+    const uint64_t t_lo = a.t_common < a.t_far ? a.t_common : a.t_far;
+    const uint64_t t_hi = a.t_common < a.t_far ? a.t_far : a.t_common;
+    while (len != a.stride) {                                  // RW:103
+      off = __ldg(a.off + curr);
+      deg = __ldg(a.off + curr + 1) - off;
+      if (deg <= 0) break;                                     // RW:115-119 dead end
+      int32_t x;
+      if (deg == 1) {
+        x = __ldg(a.col + off);                                // single choice: any trial count accepts it
+        if (STATS) n_prop++;
+      } else {
+        for (uint32_t trial = 0;; ++trial) {
+          r = walker_rng(a.seed_lo, a.seed_hi, walker, (uint32_t)(len - 1), trial);
+          x = propose<HAS_ALIAS>(a, off, deg, r);
+          if (STATS) n_prop++;
+          const uint64_t y = r.z;
+          uint64_t t;
+          if (x == prev) t = a.t_ret;                          // RS:36  w/p
+          else if (y < t_lo) break;                            // below both bounds: accept without a test
+          else if (y >= t_hi) continue;                        // above both bounds: reject without a test
+          else {
+            if (STATS) { n_mem++; n_log += ceil_log2_p1(pdeg); }
+            t = row_contains(a.col, poff, pdeg, x) ? a.t_common : a.t_far;   // RS:38 w  |  RS:34 w/q
+          }
+          if (y < t) break;
+        }
+      }
+      prev = curr; poff = off; pdeg = deg;
+      curr = x;
+      path[len++] = x;                                         // RW:114
+    }
+  }
+  a.lens[i] = len;
+  if (STATS) {
+    atomicAdd(a.stats + 1, n_prop);
+    atomicAdd(a.stats + 2, n_mem);
+    atomicAdd(a.stats + 3, n_log);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: exact sampler (also used by the KAT entry points)
+// ------------------------------------------------------------------------------------------
+// RS:12-25 over weights produced by `wf(i)`: two passes, float64 accumulation, left to right.
+template <class WF>
+__device__ __forceinline__ int64_t cdf_pick(int64_t n, float u, WF wf) {
+  double sum = 0.0;
+  for (int64_t i = 0; i < n; ++i) sum = __dadd_rn(sum, (double)wf(i));     // RS:14
+  double acc = 0.0;
+  for (int64_t i = 0; i < n; ++i) {
+    acc = __dadd_rn(acc, __ddiv_rn((double)wf(i), sum));                   // RS:19
+    if (acc >= (double)u) return i;                                        // RS:20
+  }
+  return 0;                                                                // RS:24 edges.head
+}
+
+// RS:33-41 for one neighbour
+__device__ __forceinline__ float biased_weight(float p, float q, int32_t prev, int32_t dst, float w, bool in_prev_row) {
+  float un = __fdiv_rn(w, q);
+  if (dst == prev) un = __fdiv_rn(w, p);
+  else if (in_prev_row) un = w;
+  return un;
+}
+
+__device__ __forceinline__ float draw_u(const WalkArgs &a, uint64_t walker, uint32_t step) {
+  if (a.u_mode == SRW_U_CONST) return a.u_const;
+  return u01_from_bits(walker_rng(a.seed_lo, a.seed_hi, walker, step, 0u).x);
+}
+
+__global__ void __launch_bounds__(128) walk_exact_kernel(WalkArgs a) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= a.n_walkers) return;
+  const uint64_t walker = a.walker_first + (uint64_t)i;
+  int32_t curr = (int32_t)(walker % (uint64_t)a.nv);
+  int32_t *path = a.paths + i * a.stride;
+  path[0] = curr;
+  int32_t len = 1;
+  int64_t off = a.off[curr], deg = a.off[curr + 1] - off;
+  if (deg > 0) {
+    const float *w0 = a.w_app + off;
+    int64_t k = cdf_pick(deg, draw_u(a, walker, 0u), [&](int64_t j) { return w0[j]; });   // RW:57
+    int32_t prev = curr;
+    int64_t poff = off, pdeg = deg;
+    curr = a.col_app[off + k];
+    path[len++] = curr;
+    while (len != a.stride) {
+      off = a.off[curr];
+      deg = a.off[curr + 1] - off;
+      if (deg <= 0) break;
+      const int32_t *cd = a.col_app + off;
+      const float *cw = a.w_app + off;
+      const float u = draw_u(a, walker, (uint32_t)(len - 1));
+      k = cdf_pick(deg, u, [&](int64_t j) {
+        const int32_t d = cd[j];
+        const bool need = (d != prev) && (a.p != 1.0f || a.q != 1.0f);
+        return biased_weight(a.p, a.q, prev, d, cw[j], need ? row_contains(a.col, poff, pdeg, d) : false);
+      });
+      prev = curr; poff = off; pdeg = deg;
+      curr = cd[k];
+      path[len++] = curr;
+    }
+  }
+  a.lens[i] = len;
+}
+
+// ranks -> original vertex ids, and the step count
+__global__ void finalize_paths_kernel(int64_t n_walkers, int32_t stride, const int32_t *__restrict__ vids,
+                                      const int32_t *__restrict__ lens, int32_t *paths, unsigned long long *stats) {
+  unsigned long long steps = 0;
+  const int64_t total = n_walkers * stride;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t wk = t / stride;
+    const int32_t k = (int32_t)(t - wk * stride);
+    const int32_t len = lens[wk];
+    if (k < len) paths[t] = __ldg(vids + paths[t]);
+    else paths[t] = -1;
+    if (k == 0) steps += (unsigned long long)(len - 1);
+  }
+  // warp-reduce then one atomic per warp
+  for (int o = 16; o > 0; o >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, o);
+  if ((threadIdx.x & 31) == 0 && steps) atomicAdd(stats, steps);
+}
+
+// ---- KAT kernels: one thread, same device functions as the exact walk ----
+__global__ void kat_sample_kernel(int64_t n, const float *w, float u, int64_t *out) {
+  *out = cdf_pick(n, u, [&](int64_t j) { return w[j]; });
+}
+__global__ void kat_second_order_kernel(float p, float q, int32_t prev, int64_t np, const int32_t *pd_sorted, int64_t nc,
+                                        const int32_t *cd, const float *cw, float u, float *w_out, int64_t *k_out) {
+  for (int64_t j = 0; j < nc; ++j)
+    w_out[j] = biased_weight(p, q, prev, cd[j], cw[j], row_contains(pd_sorted, 0, np, cd[j]));
+  if (k_out) *k_out = cdf_pick(nc, u, [&](int64_t j) { return w_out[j]; });
+}
+__global__ void kat_philox_kernel(const uint32_t *ctr, const uint32_t *key, uint32_t *out) {
+  Philox4 r = philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+  out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+thread_local srw_walk_info t_info = {};
+thread_local int t_collect_stats = 0;
+
+struct EventPair {
+  cudaEvent_t a = nullptr, b = nullptr;
+  ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+};
+
+}  // namespace
+
+srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLaunch &l) {
+  if (p->walk_length < 0 || l.n_walkers < 0) { srw_set_error("walkLength and the walker count must be >= 0"); return SRW_ERR_ARG; }
+  if (!(p->p > 0.0) || !(p->q > 0.0)) { srw_set_error("p and q must be > 0"); return SRW_ERR_ARG; }
+  t_info = srw_walk_info{};
+  if (l.n_walkers == 0 || g->nv == 0) return SRW_OK;
+  const bool exact = p->sampler == SRW_SAMPLER_EXACT;
+  if (exact && g->nnz > 0 && !g->d_col_app) { srw_set_error("graph was built without SRW_BUILD_EXACT"); return SRW_ERR_ARG; }
+  if (!exact && p->u_mode == SRW_U_CONST) { srw_set_error("the constant-u generator is defined for --sampler exact only"); return SRW_ERR_ARG; }
+  SRW_CUDA(cudaSetDevice(g->device));
+  WalkArgs a{};
+  a.off = g->d_off; a.col = g->d_col; a.slot = g->d_slot; a.col_app = g->d_col_app; a.w_app = g->d_w_app; a.vids = g->d_vids;
+  a.nv = g->nv; a.walker_first = l.walker_first; a.n_walkers = l.n_walkers; a.stride = p->walk_length + 2;
+  a.seed_lo = (uint32_t)p->seed; a.seed_hi = (uint32_t)(p->seed >> 32);
+  srw_alias_thresholds(p->p, p->q, &a.t_ret, &a.t_common, &a.t_far);
+  a.p = (float)p->p; a.q = (float)p->q; a.u_mode = p->u_mode; a.u_const = p->u_const;
+  a.paths = l.d_paths; a.lens = l.d_lens;
+  unsigned long long *d_stats = nullptr;
+  SRW_CUDA(cudaMalloc(&d_stats, 4 * sizeof(unsigned long long)));
+  SRW_CUDA(cudaMemsetAsync(d_stats, 0, 4 * sizeof(unsigned long long), l.stream));
+  a.stats = d_stats;
+  EventPair ev;
+  SRW_CUDA(cudaEventCreate(&ev.a));
+  SRW_CUDA(cudaEventCreate(&ev.b));
+  SRW_CUDA(cudaEventRecord(ev.a, l.stream));
+  if (exact) {
+    walk_exact_kernel<<<(unsigned)((l.n_walkers + 127) / 128), 128, 0, l.stream>>>(a);
+  } else {
+    const unsigned grid = (unsigned)((l.n_walkers + 255) / 256);
+    const bool st = t_collect_stats != 0;
+    if (g->has_alias) { if (st) walk_alias_kernel<true, true><<<grid, 256, 0, l.stream>>>(a); else walk_alias_kernel<true, false><<<grid, 256, 0, l.stream>>>(a); }
+    else              { if (st) walk_alias_kernel<false, true><<<grid, 256, 0, l.stream>>>(a); else walk_alias_kernel<false, false><<<grid, 256, 0, l.stream>>>(a); }
+  }
+  SRW_CUDA(cudaEventRecord(ev.b, l.stream));
+  {
+    const int64_t total = l.n_walkers * (int64_t)a.stride;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    finalize_paths_kernel<<<(unsigned)blocks, 256, 0, l.stream>>>(l.n_walkers, a.stride, g->d_vids, l.d_lens, l.d_paths, d_stats);
+  }
+  unsigned long long h_stats[4];
+  SRW_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, l.stream));
+  SRW_CUDA(cudaStreamSynchronize(l.stream));
+  SRW_CUDA(cudaGetLastError());
+  float ms = 0.f;
+  SRW_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));
+  cudaFree(d_stats);
+  t_info.kernel_ms = ms;
+  t_info.kernel_launches = 2;
+  t_info.steps = (int64_t)h_stats[0];
+  t_info.proposals = (int64_t)h_stats[1];
+  t_info.member_tests = (int64_t)h_stats[2];
+  t_info.probes_log2 = (int64_t)h_stats[3];
+  return SRW_OK;
+}
+
+void srw_set_walk_info(double kernel_ms, int64_t launches, int64_t steps, int64_t proposals, int64_t member_tests, int64_t probes_log2) {
+  t_info.kernel_ms = kernel_ms; t_info.kernel_launches = launches; t_info.steps = steps;
+  t_info.proposals = proposals; t_info.member_tests = member_tests; t_info.probes_log2 = probes_log2;
+}
+
+extern "C" srw_status srw_last_walk_info(srw_walk_info *out) {
+  if (!out) return SRW_ERR_ARG;
+  *out = t_info;
+  return SRW_OK;
+}
+extern "C" srw_status srw_walk_collect_stats(int enable) {
+  t_collect_stats = enable;
+  return SRW_OK;
+}
+
+// ---- KAT entry points (RS:12-62 on the device) ----
+namespace {
+template <class T>
+struct DevArr {
+  T *p = nullptr;
+  ~DevArr() { if (p) cudaFree(p); }
+  cudaError_t upload(const T *h, int64_t n) {
+    cudaError_t e = cudaMalloc(&p, (size_t)(n > 0 ? n : 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return (n > 0 && h) ? cudaMemcpy(p, h, (size_t)n * sizeof(T), cudaMemcpyHostToDevice) : cudaSuccess;
+  }
+};
+}  // namespace
+
+extern "C" srw_status srw_sample(int64_t n, const int32_t *h_dst, const float *h_w, float u, int32_t *dst_out, float *w_out) {
+  SRW_TRY(srw_require_device());
+  if (n <= 0 || !h_dst || !h_w) { srw_set_error("srw_sample: empty edge array (reference: edges.head on empty throws)"); return SRW_ERR_ARG; }
+  DevArr<float> w; DevArr<int64_t> k;
+  SRW_CUDA(w.upload(h_w, n));
+  SRW_CUDA(k.upload(nullptr, 1));
+  kat_sample_kernel<<<1, 1>>>(n, w.p, u, k.p);
+  int64_t hk = 0;
+  SRW_CUDA(cudaMemcpy(&hk, k.p, 8, cudaMemcpyDeviceToHost));
+  if (dst_out) *dst_out = h_dst[hk];
+  if (w_out) *w_out = h_w[hk];
+  return SRW_OK;
+}
+
+static srw_status second_order(float p, float q, int32_t prev, int64_t np, const int32_t *h_pdst, int64_t nc,
+                               const int32_t *h_cdst, const float *h_cw, float u, float *h_out, int64_t *k_out) {
+  SRW_TRY(srw_require_device());
+  if (nc <= 0 || !h_cdst || !h_cw) { srw_set_error("second-order sample: empty currNeighbors"); return SRW_ERR_ARG; }
+  std::vector<int32_t> ps(h_pdst, h_pdst + (np > 0 ? np : 0));
+  std::sort(ps.begin(), ps.end());
+  DevArr<int32_t> pd, cd; DevArr<float> cw, wo; DevArr<int64_t> k;
+  SRW_CUDA(pd.upload(ps.data(), np));
+  SRW_CUDA(cd.upload(h_cdst, nc));
+  SRW_CUDA(cw.upload(h_cw, nc));
+  SRW_CUDA(wo.upload(nullptr, nc));
+  SRW_CUDA(k.upload(nullptr, 1));
+  kat_second_order_kernel<<<1, 1>>>(p, q, prev, np, pd.p, nc, cd.p, cw.p, u, wo.p, k_out ? k.p : nullptr);
+  SRW_CUDA(cudaMemcpy(h_out, wo.p, (size_t)nc * 4, cudaMemcpyDeviceToHost));
+  if (k_out) SRW_CUDA(cudaMemcpy(k_out, k.p, 8, cudaMemcpyDeviceToHost));
+  return SRW_OK;
+}
+
+extern "C" srw_status srw_second_order_weights(float p, float q, int32_t prev, int64_t np, const int32_t *h_pdst, int64_t nc,
+                                               const int32_t *h_cdst, const float *h_cw, float *h_out) {
+  if (!h_out) return SRW_ERR_ARG;
+  return second_order(p, q, prev, np, h_pdst, nc, h_cdst, h_cw, 0.f, h_out, nullptr);
+}
+extern "C" srw_status srw_second_order_sample(float p, float q, int32_t prev, int64_t np, const int32_t *h_pdst, int64_t nc,
+                                              const int32_t *h_cdst, const float *h_cw, float u, int32_t *dst_out, float *w_out) {
+  std::vector<float> w((size_t)(nc > 0 ? nc : 1));
+  int64_t k = 0;
+  SRW_TRY(second_order(p, q, prev, np, h_pdst, nc, h_cdst, h_cw, u, w.data(), &k));
+  if (dst_out) *dst_out = h_cdst[k];
+  if (w_out) *w_out = w[k];     // the BIASED weight (T-RS:76)
+  return SRW_OK;
+}
+extern "C" srw_status srw_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  SRW_TRY(srw_require_device());
+  DevArr<uint32_t> c, k, o;
+  SRW_CUDA(c.upload(ctr, 4)); SRW_CUDA(k.upload(key, 2)); SRW_CUDA(o.upload(nullptr, 4));
+  kat_philox_kernel<<<1, 1>>>(c.p, k.p, o.p);
+  SRW_CUDA(cudaMemcpy(out, o.p, 16, cudaMemcpyDeviceToHost));
+  return SRW_OK;
+}

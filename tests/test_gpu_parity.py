@@ -1,0 +1,269 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle.
+
+P0  reference KATs on the device functions (T-RS, T-GM, karate counts, constant-u walks)
+P1  exact sampler  == oracle, bit for bit (Philox u), several (p, q, weighted, directed, seed)
+P2  alias sampler  == CPU twin, bit for bit; graph layout (sorted rows, Vose slots) == twin's
+"""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import KARATE, TESTGRAPH
+
+pytestmark = pytest.mark.gpu
+srw = importlib.import_module("stellar-random-walk_b200")
+synth = importlib.import_module("stellar-random-walk_b200.synth")
+
+
+# ---- P0: RandomSampleTest.scala on the device ------------------------------------------------
+def test_kat_random_sample():
+    edges = [(1, 1.0), (2, 1.0), (3, 1.0)]
+    for u, e in ((0.1, edges[0]), (0.4, edges[1]), (0.7, edges[2])):
+        assert srw.RandomSample(lambda: u).sample(edges) == e
+
+
+def test_kat_second_order():
+    w1 = 1.0
+    e12, e21, e23, e24, e14, e15 = (2, w1), (1, w1), (3, w1), (4, w1), (4, w1), (5, w1)
+    prev, prev_n, curr_n = 1, [e12, e14, e15], [e21, e23, e24]
+    rs = srw.RandomSample()
+    assert rs.computeSecondOrderWeights(1.0, 1.0, prev, prev_n, curr_n) == curr_n
+    for u, e in ((0.1, e21), (0.4, e23), (0.7, e24)):
+        assert srw.RandomSample(lambda: u).secondOrderSample(1.0, 1.0, prev, prev_n, curr_n) == e
+    assert rs.computeSecondOrderWeights(2.0, 2.0, prev, [e12, e15], curr_n) == [(1, 0.5), (3, 0.5), (4, 0.5)]
+    expect = [(1, 0.5), (3, 0.5), (4, 1.0)]
+    assert rs.computeSecondOrderWeights(2.0, 2.0, prev, prev_n, curr_n) == expect
+    for u, e in ((0.24, expect[0]), (0.26, expect[1]), (0.51, expect[2]), (0.99, expect[2])):
+        assert srw.RandomSample(lambda: u).secondOrderSample(2.0, 2.0, prev, prev_n, curr_n) == e
+
+
+def test_kat_philox_device(oracle):
+    import ctypes as C
+    for ctr, key in (([0] * 4, [0] * 2), ([0xffffffff] * 4, [0xffffffff] * 2),
+                     ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0])):
+        c, k, o = (C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), (C.c_uint32 * 4)()
+        srw.check(srw.lib().srw_philox4x32_10(c, k, o))
+        assert list(o) == oracle.philox(ctr, key).tolist()
+
+
+# ---- P0: GraphMapTest.scala ------------------------------------------------------------------
+def test_kat_graphmap():
+    e1, e2, e3, e4 = [(2, 1.0)], [(3, 1.0)], [(3, 1.0)], [(1, 1.0)]
+    gm = srw.GraphMap()
+    gm.addVertex(1, e1)
+    gm.addVertex(2)
+    assert gm.getNumEdges == 1 and gm.getNumVertices == 2
+    assert gm.getNeighbors(1) == e1
+    gm.reset()
+    gm.addVertex(1, e1 + e2)
+    gm.addVertex(2)
+    gm.addVertex(3)
+    assert gm.getNeighbors(1) == e1 + e2
+    gm.reset()
+    gm.addVertex(2, e3 + e4)
+    gm.addVertex(1, e1 + e2)
+    gm.addVertex(3)
+    assert gm.getNeighbors(1) == e1 + e2 and gm.getNeighbors(2) == e3 + e4
+    assert gm.getNeighbors(3) == [] and gm.getNeighbors(99) is None
+    gm.addVertex(1, e3)
+    assert gm.getNeighbors(1) == e1 + e2
+
+
+# ---- P0: load counts + first step (T-URW:33-86, T-VRW:32-85) ----------------------------------
+@pytest.mark.parametrize("cls", [srw.UniformRandomWalk, srw.VCutRandomWalk])
+def test_load_karate_and_first_step(cls):
+    for directed, ne in ((False, 156), (True, 78)):
+        rw = cls(srw.Params(input=KARATE, directed=directed))
+        paths = rw.loadGraph()
+        assert (rw.nEdges, rw.nVertices, len(paths)) == (ne, 34, 34)
+    rw = cls(srw.Params(input=TESTGRAPH, directed=True))
+    paths = rw.loadGraph()
+    res = rw.initFirstStep(paths, lambda: 0.5)
+    assert len(res) == len(paths)
+    assert sorted(p for _, (p, _) in res) == [[1, 2], [2]]
+
+
+def test_adjacency_matches_oracle(oracle):
+    for directed in (False, True):
+        og = oracle.Graph().load_file(KARATE, directed=directed)
+        g = srw.UniformRandomWalk(srw.Params(input=KARATE, directed=directed))
+        g.loadGraph()
+        assert g.graph.vertex_ids().tolist() == og.vertex_ids().tolist()
+        for v in og.vertex_ids():
+            assert g.graph.neighbors(int(v)) == og.neighbors(int(v))
+        assert g.graph.neighbors(1000) is None
+
+
+# ---- P0: constant-u walk scenarios (T-URW:181-291, T-VRW:189-299) -----------------------------
+SCENARIOS = [(False, 0.1, 1), (False, 0.1, 50), (False, 0.9, 50), (True, 0.9, 50), (True, 0.1, 50)]
+
+
+@pytest.mark.parametrize("cls", [srw.UniformRandomWalk, srw.VCutRandomWalk])
+@pytest.mark.parametrize("directed,u,wl", SCENARIOS)
+def test_constant_u_walks(oracle, cls, directed, u, wl):
+    cfg = srw.Params(input=KARATE, directed=directed, walkLength=wl, rddPartitions=8, numWalks=1)
+    rw = cls(cfg)
+    graph = rw.loadGraph()
+    paths = rw.randomWalk(graph, lambda: u)
+    assert paths.count() == rw.nVertices
+    og = oracle.Graph().load_file(KARATE, directed=directed, partitioned=cls.partitioned)
+    ids, offs = oracle.walk(og, walk_length=wl, num_walks=1, u_const=u)
+    assert paths.collect() == oracle.paths_as_lists(ids, offs)
+
+
+def test_derived_known_answers():
+    rw = srw.UniformRandomWalk(srw.Params(input=KARATE, walkLength=10, numWalks=1, p=0.5, q=2.0))
+    rw.loadGraph()
+    P = {p[0]: p for p in rw.randomWalk(None, lambda: 0.37).collect()}
+    assert P[1] == [1, 13] * 6
+    rw = srw.UniformRandomWalk(srw.Params(input=KARATE, walkLength=50, numWalks=1))
+    rw.loadGraph()
+    P = {p[0]: p for p in rw.randomWalk(None, lambda: 0.9).collect()}
+    assert P[1][:6] == [1, 3, 8, 4, 8, 4] and P[34][:5] == [34, 32, 33, 32, 33]
+
+
+# ---- graphs for P1 / P2 -----------------------------------------------------------------------
+def _rmat(scale, ef, weighted, seed=42):
+    s, d = synth.rmat_edges(scale, ef, seed=seed)
+    w = synth.edge_weights(len(s), seed=seed + 1) if weighted else None
+    return s, d, w
+
+
+CASES = [  # scale, ef, weighted, directed, p, q, seed
+    (8, 8, False, False, 1.0, 1.0, 1),
+    (8, 8, False, False, 0.5, 2.0, 2),
+    (9, 8, True, False, 0.5, 2.0, 3),
+    (9, 4, True, True, 0.25, 4.0, 4),
+    (10, 8, False, True, 2.0, 0.5, 5),
+    (10, 16, True, False, 4.0, 0.25, 6),
+]
+
+
+@pytest.mark.parametrize("scale,ef,weighted,directed,p,q,seed", CASES)
+def test_p1_exact_sampler_bit_equal(oracle, scale, ef, weighted, directed, p, q, seed):
+    s, d, w = _rmat(scale, ef, weighted)
+    og = oracle.Graph().load_edges(s, d, w, directed=directed)
+    g = srw.Graph.from_edges(s, d, w, directed=directed)
+    assert g.stats() == (og.num_vertices, og.num_edges)
+    ids, offs = oracle.walk(og, walk_length=20, num_walks=2, p=p, q=q, seed=seed)
+    got_ids, got_offs = g.walk(srw.Params(walkLength=20, numWalks=2, p=p, q=q, seed=seed, sampler="exact")).arrays()
+    assert (got_offs == offs).all()
+    assert (got_ids == ids).all()
+
+
+@pytest.mark.parametrize("scale,ef,weighted,directed,p,q,seed", CASES)
+def test_p2_alias_sampler_bit_equal(oracle, scale, ef, weighted, directed, p, q, seed):
+    s, d, w = _rmat(scale, ef, weighted)
+    og = oracle.Graph().load_edges(s, d, w, directed=directed)
+    twin = oracle.AliasGraph(og)
+    g = srw.Graph.from_edges(s, d, w, directed=directed)
+    # layout parity: offsets, sorted rows, Vose slots
+    tv, lay = twin.view(), g.layout()
+    assert (lay["offsets"] == tv["offsets"]).all() and (lay["col"] == tv["col"]).all()
+    assert lay["has_alias"] == twin.has_alias == weighted
+    if weighted:
+        assert (lay["thr"] == tv["thr"]).all() and (lay["alias"] == tv["alias"]).all()
+        assert (lay["own"].astype(np.int32) == tv["col"]).all()
+    ids, offs, st = twin.walk(walk_length=30, num_walks=3, p=p, q=q, seed=seed)
+    paths = g.walk(srw.Params(walkLength=30, numWalks=3, p=p, q=q, seed=seed, sampler="alias"))
+    got_ids, got_offs = paths.arrays()
+    assert (got_offs == offs).all()
+    assert (got_ids == ids).all()
+    assert paths.steps() == st.steps == len(ids) - (len(offs) - 1)
+
+
+def test_alias_karate_text_output_matches_twin(oracle, tmp_path):
+    """C1 through the native Main: 34 lines x 12 ids, same multiset of lines as the twin."""
+    out = str(tmp_path / "out")
+    rc = srw.Main.main(["--cmd", "randomwalk", "--input", KARATE, "--output", out, "--numWalks", "1", "--walkLength", "10", "--seed", "5"])
+    assert rc == 0
+    text = open(os.path.join(out, "path", "part-00000")).read()
+    lines = text.split("\n")
+    assert lines[-1] == "" and len(lines) == 35 and all(len(ln.split("\t")) == 12 for ln in lines[:-1])
+    assert os.path.exists(os.path.join(out, "path", "_SUCCESS"))
+    twin = oracle.AliasGraph(oracle.Graph().load_file(KARATE))
+    ids, offs, _ = twin.walk(walk_length=10, num_walks=1, seed=5)
+    assert sorted(lines[:-1]) == sorted(oracle.format_paths(ids, offs).decode().split("\n")[:-1])
+    # a second run into the same directory fails like Hadoop's saveAsTextFile
+    assert srw.Main.main(["--cmd", "randomwalk", "--input", KARATE, "--output", out]) != 0
+
+
+def test_ragged_and_edge_cases(oracle):
+    # arbitrary (negative, sparse) ids, self loops, duplicates, dead ends
+    txt = "-5 7\n7 7\n7 100000\n7 100000\n100000 -5\n3 -5\n"
+    for directed in (False, True):
+        og = oracle.Graph().load_text(txt, directed=directed)
+        s, d, w, _ = srw.parse_edges(txt)
+        g = srw.Graph.from_edges(s, d, w, directed=directed)
+        assert g.vertex_ids().tolist() == [-5, 3, 7, 100000]
+        for sampler, p, q in (("exact", 0.5, 2.0), ("alias", 0.5, 2.0)):
+            got = g.walk(srw.Params(walkLength=6, numWalks=4, p=p, q=q, seed=9, sampler=sampler)).collect()
+            if sampler == "exact":
+                ids, offs = oracle.walk(og, walk_length=6, num_walks=4, p=p, q=q, seed=9)
+            else:
+                ids, offs, _ = oracle.AliasGraph(og).walk(walk_length=6, num_walks=4, p=p, q=q, seed=9)
+            assert got == oracle.paths_as_lists(ids, offs)
+    # empty graph, zero walks
+    g = srw.Graph.from_edges(np.zeros(0, np.int32), np.zeros(0, np.int32))
+    assert g.stats() == (0, 0) and g.walk(srw.Params(walkLength=5, numWalks=2)).collect() == []
+    g = srw.Graph.from_edges([1], [2])
+    assert g.walk(srw.Params(walkLength=5, numWalks=0)).collect() == []
+    assert g.walk(srw.Params(walkLength=0, numWalks=1)).collect() == [[1, 2], [2, 1]]
+
+
+def test_device_rmat_generator_matches_numpy():
+    import torch
+    scale, ef = 10, 8
+    n = ef << scale
+    ds = torch.empty(n, dtype=torch.int32, device="cuda")
+    dd = torch.empty(n, dtype=torch.int32, device="cuda")
+    dw = torch.empty(n, dtype=torch.float32, device="cuda")
+    srw.check(srw.lib().srw_synth_rmat_device(scale, ef, 42, 0, n, ds.data_ptr(), dd.data_ptr()))
+    srw.check(srw.lib().srw_synth_weights_device(43, 0, n, dw.data_ptr()))
+    s, d = synth.rmat_edges(scale, ef, seed=42)
+    assert (ds.cpu().numpy() == s).all() and (dd.cpu().numpy() == d).all()
+    assert (dw.cpu().numpy() == synth.edge_weights(n, seed=43)).all()
+
+
+def test_full_size_properties():
+    """RMAT-20 (BASELINE config C2 size): size-independent properties of the device walk."""
+    import torch
+    scale, ef = 20, 16
+    n = ef << scale
+    ds = torch.empty(n, dtype=torch.int32, device="cuda")
+    dd = torch.empty(n, dtype=torch.int32, device="cuda")
+    srw.check(srw.lib().srw_synth_rmat_device(scale, ef, 42, 0, n, ds.data_ptr(), dd.data_ptr()))
+    g = srw.Graph.from_device_edges(n, ds.data_ptr(), dd.data_ptr())
+    nv, nnz = g.stats()
+    assert nnz == 2 * n and 600000 < nv < (1 << scale)
+    lay_off = g.layout()["offsets"]
+    assert lay_off[0] == 0 and lay_off[-1] == nnz and (np.diff(lay_off) > 0).all()   # undirected: no dead ends
+    L = 80
+    paths = torch.empty((nv, L + 2), dtype=torch.int32, device="cuda")
+    lens = torch.empty(nv, dtype=torch.int32, device="cuda")
+    cp = srw.Params(walkLength=L, numWalks=1, p=0.5, q=2.0, seed=1).to_c()
+    import ctypes as C
+    srw.check(srw.lib().srw_walk_device(g.h, C.byref(cp), 0, nv, paths.data_ptr(), lens.data_ptr(), None))
+    assert bool((lens == L + 2).all())                       # every walk is full length
+    vids = torch.from_numpy(g.vertex_ids()).cuda()
+    assert bool((paths[:, 0] == vids).all())                 # one walker per vertex, in id order
+    # every consecutive pair is an edge: check a sample of walkers against the sorted rows on the host
+    lay = g.layout()
+    rank = {int(v): i for i, v in enumerate(g.vertex_ids().tolist())} if nv < 2000000 else None
+    hp = paths[:: max(1, nv // 2000)].cpu().numpy()
+    for row in hp[:200]:
+        for a, b in zip(row[:-1], row[1:]):
+            ra, rb = rank[int(a)], rank[int(b)]
+            seg = lay["col"][lay["offsets"][ra]:lay["offsets"][ra + 1]]
+            k = np.searchsorted(seg, rb)
+            assert k < len(seg) and seg[k] == rb
+    # idempotence: same seed -> same paths; different launch split -> same paths
+    paths2 = torch.empty_like(paths)
+    half = nv // 2
+    srw.check(srw.lib().srw_walk_device(g.h, C.byref(cp), 0, half, paths2.data_ptr(), lens.data_ptr(), None))
+    srw.check(srw.lib().srw_walk_device(g.h, C.byref(cp), half, nv - half, paths2[half:].data_ptr(), lens[half:].data_ptr(), None))
+    assert bool((paths2 == paths).all())
+    wi = srw.last_walk_info()
+    assert wi.steps == (nv - half) * (L + 1) and wi.kernel_ms > 0
