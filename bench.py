@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py -- walk-steps/sec of the node2vec second-order walk hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scale S]
+
+One "step" = one walk round: one walker per present vertex, walkLength 80 (81 sampled transitions
+each) -- `--steps 10` is the reference's numWalks 10.  Workload: synthetic RMAT (Graph500
+parameters, edge factor 16), undirected, p = 0.5, q = 2.0 (BASELINE config C4's graph and bias).
+`value` is measured with the CSR resident in HBM and the paths left in HBM; `e2e` goes through the
+host-buffer C ABI (edge list H2D + CSR build + rounds + paths D2H inside the timed region).
+
+The oracle (oracle/) is used here only for the `cpu_baseline` object and the `--impl reference` arm.
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "walk-steps/sec"
+UNIT = "steps/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", type=int, default=int(os.environ.get("SRW_BENCH_SCALE", "26")))
+    ap.add_argument("--edge-factor", type=int, default=16)
+    ap.add_argument("--walk-length", type=int, default=80)
+    ap.add_argument("--p", type=float, default=0.5)
+    ap.add_argument("--q", type=float, default=2.0)
+    ap.add_argument("--weighted", type=int, default=0)
+    ap.add_argument("--mode", default="auto", choices=["auto", "sharded", "replicated"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--gen-seed", type=int, default=42)
+    ap.add_argument("--seed", type=int, default=1)
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "rmat-%d ef%d undirected %s p=%g q=%g walkLength=%d (one round = one walker per present vertex)" % (
+        a.scale, a.edge_factor, "weighted" if a.weighted else "unweighted", a.p, a.q, a.walk_length)
+
+
+def mem_available_gb():
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable"):
+                return int(ln.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 0.0
+
+
+def peaks():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        self.t0 = None
+
+    def launch(self):
+        """Start the nvidia-smi loop early (its start-up takes driver locks); only samples taken
+        after mark() -- i.e. during the timed region -- are reported."""
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=timestamp," + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "250"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def mark(self):
+        self.t0 = time.time()
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        t1 = time.time()
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        import datetime
+        for ln in self.f.read().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 10:
+                continue
+            try:
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if self.t0 is not None and not (self.t0 - 0.05 <= ts <= t1 + 0.05):
+                    continue
+                s_, m_ = float(c[2]), float(c[3])
+            except ValueError:
+                continue
+            sm.append(s_)
+            mx.append(m_)
+            for nme, v in zip(names, c[6:10]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        try:
+            os.unlink(self.f.name)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port) on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_walk_sample(oracle_lib, offsets, col, w, a, budget_s, phase=0):
+    """Times the literal reference algorithm on a strided walker sample of the CSR."""
+    L = oracle_lib.lib()
+    nv = len(offsets) - 1
+    cfg = oracle_lib.make_cfg(walk_length=a.walk_length, num_walks=1, p=a.p, q=a.q, seed=a.seed, threads=0)
+    elapsed, done, chk = C.c_double(), C.c_int64(), C.c_uint64()
+    fn = L.oracle_walk_csr_timed
+    fn.restype = C.c_int64
+    fn.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_double,
+                   C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_uint64)]
+    L.oracle_max_threads.restype = C.c_int
+    stride = max(1, nv // 4096)           # ~4096 sampled start vertices spread over the id range
+    steps = fn(nv, offsets.ctypes.data, col.ctypes.data, None if w is None else w.ctypes.data, C.addressof(cfg), stride, phase % stride,
+               budget_s, C.byref(elapsed), C.byref(done), C.byref(chk))
+    cores = int(L.oracle_max_threads())
+    return {"steps": int(steps), "elapsed_s": elapsed.value, "walkers": int(done.value), "cores": cores,
+            "value": steps / max(elapsed.value, 1e-9),
+            "sample": "C port of RandomSample/RandomWalk (oracle/), not Spark: %d strided start vertices of %d, %.0f s budget, "
+                      "%d OpenMP threads, row copies and hash lookups omitted" % (int(done.value), nv, budget_s, cores)}
+
+
+def run_reference(a):
+    """--impl reference: the reference's CPU algorithm (oracle port -- the reference itself is
+    Scala/Spark and cannot run in this image) on the host cores, on the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle_lib
+    L = oracle_lib.lib()
+    n_edges = a.edge_factor << a.scale
+    need_gb = (n_edges * 8 + 2 * n_edges * 4 + (1 << a.scale) * 16) / 1e9
+    if mem_available_gb() < need_gb * 1.5 + 8:
+        print(json.dumps({"impl": "reference", "unavailable": "host RAM too small for a CPU build of rmat-%d (%.0f GB needed)" % (a.scale, need_gb)}))
+        return
+    t0 = time.time()
+    src = np.empty(n_edges, np.int32)
+    dst = np.empty(n_edges, np.int32)
+    L.oracle_rmat_edges.argtypes = [C.c_int, C.c_uint64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
+    L.oracle_rmat_edges(a.scale, a.gen_seed, 0, n_edges, src.ctypes.data, dst.ctypes.data, 0)
+    n_ids = 1 << a.scale
+    offsets = np.empty(n_ids + 1, np.int64)
+    col = np.empty(2 * n_edges, np.int32)
+    L.oracle_csr_build.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.oracle_csr_build(n_ids, n_edges, src.ctypes.data, dst.ctypes.data, offsets.ctypes.data, col.ctypes.data, 0)
+    del src, dst
+    build_s = time.time() - t0
+    # each step: a bounded sample, sized so that steps+warmup end within a few minutes
+    per_step = max(2.0, min(a.cpu_budget, 150.0 / max(1, a.steps + a.warmup)))
+    for k in range(a.warmup):
+        cpu_walk_sample(oracle_lib, offsets, col, None, a, per_step, phase=k)
+    tot_steps, tot_s, res = 0, 0.0, None
+    for k in range(a.steps):
+        res = cpu_walk_sample(oracle_lib, offsets, col, None, a, per_step, phase=a.warmup + k)
+        tot_steps += res["steps"]
+        tot_s += res["elapsed_s"]
+    v = tot_steps / max(tot_s, 1e-9)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * tot_s / max(1, a.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 weights / f64 cdf (reference arithmetic)", "data": "synthetic",
+            "config": {"workload": workload_name(a), "cpu_graph_build_s": round(build_s, 1)},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": res["sample"]},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    srw = importlib.import_module("stellar-random-walk_b200")
+    lib = srw.lib()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream()
+    n_edges = a.edge_factor << a.scale
+    stride = a.walk_length + 2
+
+    def gen_edges():
+        s = torch.empty(n_edges, dtype=torch.int32, device=dev)
+        d = torch.empty(n_edges, dtype=torch.int32, device=dev)
+        srw.check(lib.srw_synth_rmat_device(a.scale, a.edge_factor, a.gen_seed, 0, n_edges, s.data_ptr(), d.data_ptr()))
+        w = None
+        if a.weighted:
+            w = torch.empty(n_edges, dtype=torch.float32, device=dev)
+            srw.check(lib.srw_synth_weights_device(a.gen_seed + 1, 0, n_edges, w.data_ptr()))
+        return s, d, w
+
+    def build(s, d, w):
+        torch.cuda.synchronize()
+        t = time.time()
+        g = srw.Graph.from_device_edges(n_edges, s.data_ptr(), d.data_ptr(), None if w is None else w.data_ptr(), False, srw.BUILD_ALIAS)
+        torch.cuda.synchronize()
+        return g, time.time() - t
+
+    d_src, d_dst, d_w = gen_edges()
+    want_e2e = (not a.no_e2e) and world == 1
+    h_edges = None
+    if want_e2e and mem_available_gb() > (n_edges * 8) / 1e9 * 2 + 16:
+        h_edges = [t.cpu().pin_memory() for t in (d_src, d_dst)] + ([d_w.cpu().pin_memory()] if d_w is not None else [])
+    g, build_s = build(d_src, d_dst, d_w)
+    del d_src, d_dst, d_w
+    torch.cuda.empty_cache()
+    nv, nnz = g.stats()
+
+    # walkers of one round are split across ranks (replicated graph) -- the sharded mode lives in shard.cu
+    lo, hi = nv * rank // world, nv * (rank + 1) // world
+    n_local = hi - lo
+    paths = torch.empty((n_local, stride), dtype=torch.int32, device=dev)
+    lens = torch.empty(n_local, dtype=torch.int32, device=dev)
+    prm = srw.Params(walkLength=a.walk_length, numWalks=1, p=a.p, q=a.q, seed=a.seed, sampler="alias")
+    cp = prm.to_c()
+
+    def one_round(r):
+        srw.check(lib.srw_walk_device(g.h, C.byref(cp), r * nv + lo, n_local, paths.data_ptr(), lens.data_ptr(), stream.cuda_stream))
+        return srw.last_walk_info()
+
+    # ---- proposal / membership statistics (untimed, instrumented kernel) on a bounded sample ----
+    lib.srw_walk_collect_stats(1)
+    n_stat = min(n_local, 1 << 22)
+    srw.check(lib.srw_walk_device(g.h, C.byref(cp), lo, n_stat, paths.data_ptr(), lens.data_ptr(), stream.cuda_stream))
+    st = srw.last_walk_info()
+    lib.srw_walk_collect_stats(0)
+    T_bar = st.proposals / max(1, st.steps)
+    probes_per_step = st.probes_log2 / max(1, st.steps)
+    L_bar = st.probes_log2 / max(1, st.member_tests)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    clocks = ClockSampler(local)
+    clocks.launch()
+    for r in range(a.warmup):
+        one_round(r)
+    barrier()
+    clocks.mark()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    kernel_ms, steps, launches = 0.0, 0, 0
+    for k in range(a.steps):
+        wi = one_round(a.warmup + k)
+        kernel_ms += wi.kernel_ms
+        steps += wi.steps
+        launches += wi.kernel_launches
+    e1.record(stream)
+    barrier()
+    clk = clocks.stop()
+    elapsed_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([elapsed_ms, float(steps)], dtype=torch.float64, device=dev)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        elapsed_ms, steps_all = float(tmax[0]), int(t[1])
+    else:
+        steps_all = steps
+    value = steps_all / (elapsed_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (walk_alias_kernel) ----
+    # algorithmic bytes per sampled transition (DESIGN.md "bytes per step"): row extent 8 B +
+    # T * (neighbour id 4 B [+ Vose slot 8 B when weighted]) + 4 B per binary-search probe + 4 B path write
+    per_prop = 4 + (8 if a.weighted else 0)
+    B = 8 + T_bar * per_prop + 4 * probes_per_step + 4
+    B_survey = T_bar * (20 + 4 * (st.probes_log2 / max(1, st.proposals))) + 4      # SURVEY 8(d) formula, same measurements
+    peak, peak_src = peaks()
+    kernel_s = kernel_ms * 1e-3
+    achieved = steps * B / kernel_s / 1e9
+    traffic = None
+    tj = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tj):
+        try:
+            traffic = json.load(open(tj)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "walk_alias_kernel", "kernel_ms_per_launch": kernel_ms / max(1, a.steps), "peak_source": peak_src,
+                "bytes_per_step": B, "bytes_per_step_survey_formula": B_survey, "proposals_per_step": T_bar,
+                "member_tests_per_step": st.member_tests / max(1, st.steps), "mean_probes_per_test": L_bar,
+                "kernel_share_of_step": kernel_ms / elapsed_ms}
+    if rank == 0 and world == 1:
+        gs, gg = C.c_double(), C.c_double()
+        try:
+            srw.check(lib.srw_gather_ceiling(8 << 30, 1 << 28, C.byref(gs), C.byref(gg)))
+            roofline["gather_ceiling_sectors_per_s"] = gs.value
+            roofline["gather_ceiling_GBps_of_32B_sectors"] = gg.value
+            # sectors the kernel must touch per step if nothing hits in cache
+            sect = 1 + T_bar + probes_per_step + 1
+            roofline["frac_of_gather_ceiling"] = (steps / kernel_s) * sect / gs.value
+        except Exception as ex:   # noqa: BLE001
+            roofline["gather_ceiling_error"] = str(ex)
+
+    # ---- e2e: host edge list -> H2D -> CSR build -> K rounds, every round's paths read back ----
+    e2e = None
+    if want_e2e and h_edges is not None:
+        g.free()
+        torch.cuda.empty_cache()
+        ring = [torch.empty(1 << 26, dtype=torch.int32).pin_memory() for _ in range(2)]   # 2 x 256 MiB staging ring
+        flat = paths.view(-1)
+        copy_stream = torch.cuda.Stream()
+        torch.cuda.synchronize()
+        t0 = time.time()
+        dd = [t.to(dev, non_blocking=True) for t in h_edges]
+        g2 = srw.Graph.from_device_edges(n_edges, dd[0].data_ptr(), dd[1].data_ptr(), dd[2].data_ptr() if len(dd) > 2 else None, False, srw.BUILD_ALIAS)
+        del dd
+        e_steps, d2h = 0, 0
+        for k in range(a.steps):
+            srw.check(lib.srw_walk_device(g2.h, C.byref(cp), (a.warmup + k) * nv, nv, paths.data_ptr(), lens.data_ptr(), stream.cuda_stream))
+            e_steps += srw.last_walk_info().steps
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_stream(stream)
+                for i, off in enumerate(range(0, flat.numel(), ring[0].numel())):
+                    n = min(ring[0].numel(), flat.numel() - off)
+                    ring[i & 1][:n].copy_(flat[off:off + n], non_blocking=True)
+                    d2h += n * 4
+            copy_stream.synchronize()
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        h2d = sum(t.numel() * t.element_size() for t in h_edges)
+        e2e = {"value": e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d // max(1, a.steps), "d2h_bytes_per_step": d2h // max(1, a.steps),
+               "seconds": dt, "includes": "edge-list H2D + CSR build (once) + %d rounds + D2H of every round's paths through a pinned ring" % a.steps}
+        g = g2
+
+    # ---- CPU baseline beside it (rank 0, N=1): oracle port on the same CSR ----
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        try:
+            import oracle_lib
+            lay_off = np.empty(nv + 1, np.int64)
+            lay_col = np.empty(nnz, np.int32)
+            srw.check(lib.srw_graph_layout(g.h, lay_off.ctypes.data, lay_col.ctypes.data, None, None))
+            r = cpu_walk_sample(oracle_lib, lay_off, lay_col, None, a, a.cpu_budget)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                   "sample": r["sample"] + "; CSR = the device build copied to the host (sorted rows; timing only)"}
+        except Exception as ex:   # noqa: BLE001
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %s" % ex}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": elapsed_ms / max(1, a.steps), "higher_is_better": True,
+                "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "u32 (integer thresholds; f64 only in the Vose build)",
+                "data": "synthetic",
+                "config": {"workload": workload_name(a), "vertices_present": nv, "adjacency_entries": nnz, "walkers_per_step": nv,
+                           "graph_bytes_hbm": int(lib.srw_graph_device_bytes(g.h)), "build_s": round(build_s, 3),
+                           "l2": "inputs larger than L2 (CSR %.1f GB >> 126 MB), no flush needed" % (nnz * 4 / 1e9),
+                           "parallelism": "1 GPU" if world == 1 else "replicated graph, walkers split %d ways" % world,
+                           "sampler": "alias"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

@@ -811,3 +811,138 @@ int64_t oracle_alias_walk(const oa_graph *a, const oracle_walk_cfg *cfg, int32_t
   if (overflow) { offsets[0] = total; return -1; }
   return n_paths;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* CPU-baseline helpers (bench.py only)                                                        */
+/* ------------------------------------------------------------------------------------------ */
+#include <time.h>
+static double now_s(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+int oracle_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+void oracle_rmat_edges(int scale, uint64_t seed, int64_t first, int64_t count, int32_t *src, int32_t *dst, int threads) {
+  const uint32_t A = (uint32_t)(0.57 * 4294967296.0), AB = (uint32_t)((0.57 + 0.19) * 4294967296.0),
+                 ABC = (uint32_t)((0.57 + 0.19 + 0.19) * 4294967296.0);
+  (void)threads;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(threads > 0 ? threads : omp_get_max_threads())
+#endif
+  for (int64_t i = 0; i < count; ++i) {
+    const uint64_t e = (uint64_t)(first + i);
+    uint32_t s = 0, d = 0;
+    for (int blk = 0; blk * 4 < scale; ++blk) {
+      uint32_t ctr[4] = {(uint32_t)e, (uint32_t)(e >> 32), (uint32_t)blk, 0x524D4154u}, key[2] = {(uint32_t)seed, 0u}, r[4];
+      oracle_philox4x32_10(ctr, key, r);
+      for (int k = 0; k < 4 && blk * 4 + k < scale; ++k) {
+        const uint32_t x = r[k];
+        s = (s << 1) | (x >= AB ? 1u : 0u);
+        d = (d << 1) | (((x >= A && x < AB) || x >= ABC) ? 1u : 0u);
+      }
+    }
+    src[i] = (int32_t)s;
+    dst[i] = (int32_t)d;
+  }
+}
+
+void oracle_csr_build(int64_t n_ids, int64_t n_edges, const int32_t *src, const int32_t *dst, int64_t *offsets,
+                      int32_t *col, int threads) {
+  (void)threads;
+  int64_t *cursor = (int64_t *)calloc((size_t)n_ids + 1, sizeof(int64_t));
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(threads > 0 ? threads : omp_get_max_threads())
+#endif
+  for (int64_t e = 0; e < n_edges; ++e) {
+#ifdef _OPENMP
+#pragma omp atomic
+#endif
+    cursor[src[e]]++;
+#ifdef _OPENMP
+#pragma omp atomic
+#endif
+    cursor[dst[e]]++;
+  }
+  offsets[0] = 0;
+  for (int64_t v = 0; v < n_ids; ++v) offsets[v + 1] = offsets[v] + cursor[v];
+  memcpy(cursor, offsets, (size_t)n_ids * sizeof(int64_t));
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(threads > 0 ? threads : omp_get_max_threads())
+#endif
+  for (int64_t e = 0; e < n_edges; ++e) {
+    int64_t k;
+#ifdef _OPENMP
+#pragma omp atomic capture
+#endif
+    k = cursor[src[e]]++;
+    col[k] = dst[e];
+#ifdef _OPENMP
+#pragma omp atomic capture
+#endif
+    k = cursor[dst[e]]++;
+    col[k] = src[e];
+  }
+  free(cursor);
+}
+
+int64_t oracle_walk_csr_timed(int64_t nv, const int64_t *offsets, const int32_t *col, const float *w,
+                              const oracle_walk_cfg *cfg, int64_t sample_stride, int64_t sample_phase,
+                              double budget_s, double *elapsed_s, int64_t *walkers_done, uint64_t *checksum) {
+  const float p = (float)cfg->p, q = (float)cfg->q;
+  const int32_t full = cfg->walk_length + 2;
+  if (sample_stride < 1) sample_stride = 1;
+  const int64_t n_samples = (nv - sample_phase + sample_stride - 1) / sample_stride;
+  int64_t steps = 0, done = 0;
+  uint64_t sum = 0;
+  const double t0 = now_s();
+#ifdef _OPENMP
+#pragma omp parallel num_threads(cfg->threads > 0 ? cfg->threads : omp_get_max_threads()) reduction(+ : steps, done, sum)
+#endif
+  {
+    int32_t *path = (int32_t *)malloc((size_t)full * sizeof(int32_t));
+    float *nw = NULL, *ones = NULL;
+    int64_t nw_cap = 0;
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 1)
+#endif
+    for (int64_t sidx = 0; sidx < n_samples; ++sidx) {
+      if (now_s() - t0 > budget_s) continue;
+      const int64_t v = sample_phase + sidx * sample_stride;
+      const uint64_t walker = (uint64_t)v;
+      int32_t len = 0;
+      path[len++] = (int32_t)v;
+      int64_t off = offsets[v], deg = offsets[v + 1] - off;
+      if (deg > 0) {
+        if (deg > nw_cap) { nw_cap = deg * 2; nw = (float *)realloc(nw, (size_t)nw_cap * 4); ones = (float *)realloc(ones, (size_t)nw_cap * 4); for (int64_t k = 0; k < nw_cap; ++k) ones[k] = 1.0f; }
+        path[len++] = col[off + oracle_sample(deg, w ? w + off : ones, oracle_u01(cfg->seed, walker, 0u))];
+        steps++;
+        while (len != full) {
+          const int32_t curr = path[len - 1], prev = path[len - 2];
+          off = offsets[curr]; deg = offsets[curr + 1] - off;
+          if (deg <= 0) break;
+          if (deg > nw_cap) { nw_cap = deg * 2; nw = (float *)realloc(nw, (size_t)nw_cap * 4); ones = (float *)realloc(ones, (size_t)nw_cap * 4); for (int64_t k = 0; k < nw_cap; ++k) ones[k] = 1.0f; }
+          const int64_t poff = offsets[prev], pdeg = offsets[prev + 1] - poff;
+          oracle_second_order_weights(p, q, prev, pdeg, col + poff, deg, col + off, w ? w + off : ones, nw);   /* RS:27-44 */
+          const float u = oracle_u01(cfg->seed, walker, (uint32_t)(len - 1));
+          path[len++] = col[off + oracle_sample(deg, nw, u)];                                                /* RS:12-25 */
+          steps++;
+          if (now_s() - t0 > budget_s) break;
+        }
+      }
+      for (int32_t k = 0; k < len; ++k) sum += (uint64_t)(uint32_t)path[k] * (uint64_t)(k + 1);
+      done++;
+    }
+    free(path); free(nw); free(ones);
+  }
+  if (elapsed_s) *elapsed_s = now_s() - t0;
+  if (walkers_done) *walkers_done = done;
+  if (checksum) *checksum = sum;
+  return steps;
+}

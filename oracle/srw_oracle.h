@@ -120,6 +120,23 @@ int64_t oracle_alias_walk(const oa_graph *a, const oracle_walk_cfg *cfg, int32_t
 /* acceptance thresholds, shared definition: T(f) = f>=M ? 2^32 : floor(f/M * 2^32) */
 void oracle_alias_thresholds(double p, double q, uint64_t *t_ret, uint64_t *t_common, uint64_t *t_far);
 
+/* ---- CPU-baseline helpers (bench.py only): dense CSR (vid == rank), no GraphMap hash lookups and
+ * no row copies -- both omissions favour the CPU.  The walk itself is walk_one's algorithm
+ * (RS:12-62 + RW:103-133) on the CSR rows. ---- */
+/* RMAT edges [first, first+count): C twin of stellar-random-walk_b200/synth.py::rmat_edges */
+void oracle_rmat_edges(int scale, uint64_t seed, int64_t first, int64_t count, int32_t *src, int32_t *dst, int threads);
+/* undirected CSR over ids [0, n_ids): offsets[n_ids+1], col[2*n_edges].  Parallel counting build;
+ * neighbour order within a row is arbitrary (timing only -- not a parity input). */
+void oracle_csr_build(int64_t n_ids, int64_t n_edges, const int32_t *src, const int32_t *dst, int64_t *offsets,
+                      int32_t *col, int threads);
+/* Walks a strided sample of walkers (start vertices with degree > 0, stride `sample_stride`) for at
+ * most budget_s seconds on `threads` OpenMP threads.  w may be NULL (all 1.0f).  Returns the number
+ * of sampled transitions; *elapsed_s = wall time, *walkers_done = walkers finished. */
+int64_t oracle_walk_csr_timed(int64_t nv, const int64_t *offsets, const int32_t *col, const float *w,
+                              const oracle_walk_cfg *cfg, int64_t sample_stride, int64_t sample_phase,
+                              double budget_s, double *elapsed_s, int64_t *walkers_done, uint64_t *checksum);
+int oracle_max_threads(void);
+
 #ifdef __cplusplus
 }
 #endif

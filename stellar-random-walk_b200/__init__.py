@@ -360,7 +360,7 @@ class Paths:
         check(lib().srw_paths_view(self.h, C.byref(n), C.byref(ids), C.byref(offs)))
         o = np.ctypeslib.as_array(offs, (n.value + 1,)).copy()
         tot = int(o[-1])
-        i = np.ctypeslib.as_array(ids, (max(tot, 1),))[:tot].copy()
+        i = np.ctypeslib.as_array(ids, (tot,)).copy() if tot > 0 else np.zeros(0, np.int32)
         return i, o
 
     def collect(self):

@@ -14,7 +14,11 @@
 // One walker per thread; a draw is Philox4x32-10 keyed by (seed; walker, step, trial).
 #include <cuda_runtime.h>
 
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 #include "philox.cuh"
@@ -130,6 +134,104 @@ __global__ void __launch_bounds__(256) walk_alias_kernel(WalkArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// K6 (v2): the same sampler as a per-lane state machine.  The v1 loop nest above leaves ~5 of 32
+// lanes active (ncu: smsp__thread_inst_executed_per_inst_executed = 4.8) because rejection loops and
+// binary searches of different lengths serialise inside a warp.  Here every lane performs exactly ONE
+// dependent memory access per iteration of a single convergent loop -- a row-extent load, a proposal
+// gather or a binary-search probe, whichever its walker needs next -- so a warp keeps 32 independent
+// gathers in flight.  Decisions are the same pure functions of (seed; walker, step, trial): the
+// output is bit-identical to v1 and to the CPU twin.
+// ------------------------------------------------------------------------------------------
+enum : int { ST_EXTENT = 0, ST_PROPOSE = 1, ST_SEARCH = 2, ST_DONE = 3 };
+
+template <bool HAS_ALIAS, bool STATS>
+__global__ void __launch_bounds__(256) walk_alias_sm_kernel(WalkArgs a) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= a.n_walkers) return;
+  const uint64_t walker = a.walker_first + (uint64_t)i;
+  int32_t curr = (int32_t)(walker % (uint64_t)a.nv), prev = -1;
+  int32_t *path = a.paths + i * a.stride;
+  path[0] = curr;
+  int32_t len = 1;
+  int64_t off = 0, poff = 0;
+  uint32_t deg = 0, pdeg = 0, trial = 0, lo = 0, hi = 0, y = 0;
+  int32_t x = 0;
+  uint64_t k = 0;              // proposal slot of the pending trial
+  uint32_t coin = 0;           // Vose coin of the pending trial
+  int state = ST_EXTENT;
+  unsigned long long n_prop = 0, n_mem = 0, n_log = 0;
+  const uint64_t t_lo = a.t_common < a.t_far ? a.t_common : a.t_far;
+  const uint64_t t_hi = a.t_common < a.t_far ? a.t_far : a.t_common;
+
+  while (state != ST_DONE) {
+    // ---- one memory access per lane ----
+    int64_t e0 = 0, e1 = 0;
+    int32_t v = 0, v_alias = 0;
+    uint32_t thr = 0xFFFFFFFFu;
+    if (state == ST_EXTENT) {
+      e0 = __ldg(a.off + curr);
+      e1 = __ldg(a.off + curr + 1);
+    } else if (state == ST_PROPOSE) {
+      if (HAS_ALIAS) {
+        const int4 raw = __ldg(reinterpret_cast<const int4 *>(a.slot + off + (int64_t)k));
+        thr = (uint32_t)raw.x; v = raw.y; v_alias = raw.z;
+      } else {
+        v = __ldg(a.col + off + (int64_t)k);
+      }
+    } else {
+      v = __ldg(a.col + poff + (int64_t)((lo + hi) >> 1));
+    }
+    // ---- consume it ----
+    int verdict = 0;           // 0 = nothing yet, 1 = accept x, 2 = reject (next trial)
+    if (state == ST_EXTENT) {
+      off = e0;
+      deg = (uint32_t)(e1 - e0);
+      if (deg == 0) { state = ST_DONE; continue; }              // RW:59-62 / RW:115-119 dead end
+      trial = 0;
+      verdict = 2;                                             // draw trial 0
+    } else if (state == ST_PROPOSE) {
+      x = (HAS_ALIAS && !(coin < thr)) ? v_alias : v;
+      if (STATS && len > 1) n_prop++;
+      if (len == 1 || deg == 1) verdict = 1;                   // first-order step (RW:57) / single choice
+      else if (x == prev) verdict = ((uint64_t)y < a.t_ret) ? 1 : 2;    // RS:36  w/p
+      else if ((uint64_t)y < t_lo) verdict = 1;                // below both bounds: accept without a test
+      else if ((uint64_t)y >= t_hi) verdict = 2;               // above both bounds: reject without a test
+      else {
+        if (STATS) { n_mem++; n_log += ceil_log2_p1(pdeg); }
+        lo = 0; hi = pdeg;
+        state = ST_SEARCH;
+      }
+    } else {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (v == x) verdict = ((uint64_t)y < a.t_common) ? 1 : 2;          // RS:38  x in N(prev): w
+      else {
+        if (v < x) lo = mid + 1; else hi = mid;
+        if (lo >= hi) verdict = ((uint64_t)y < a.t_far) ? 1 : 2;         // RS:34  not a neighbour: w/q
+      }
+    }
+    if (verdict == 1) {
+      path[len++] = x;                                         // RW:114
+      prev = curr; poff = off; pdeg = deg;
+      curr = x;
+      state = (len == a.stride) ? ST_DONE : ST_EXTENT;         // RW:103
+    } else if (verdict == 2) {
+      const Philox4 r = walker_rng(a.seed_lo, a.seed_hi, walker, (uint32_t)(len - 1), trial);
+      trial++;
+      k = __umul64hi(((uint64_t)r.x << 32) | (uint64_t)r.w, (uint64_t)deg);
+      coin = r.y;
+      y = r.z;
+      state = ST_PROPOSE;
+    }
+  }
+  a.lens[i] = len;
+  if (STATS) {
+    atomicAdd(a.stats + 1, n_prop);
+    atomicAdd(a.stats + 2, n_mem);
+    atomicAdd(a.stats + 3, n_log);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // K5: exact sampler (also used by the KAT entry points)
 // ------------------------------------------------------------------------------------------
 // RS:12-25 over weights produced by `wf(i)`: two passes, float64 accumulation, left to right.
@@ -198,14 +300,15 @@ __global__ void __launch_bounds__(128) walk_exact_kernel(WalkArgs a) {
 __global__ void finalize_paths_kernel(int64_t n_walkers, int32_t stride, const int32_t *__restrict__ vids,
                                       const int32_t *__restrict__ lens, int32_t *paths, unsigned long long *stats) {
   unsigned long long steps = 0;
-  const int64_t total = n_walkers * stride;
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t wk = t / stride;
-    const int32_t k = (int32_t)(t - wk * stride);
-    const int32_t len = lens[wk];
-    if (k < len) paths[t] = __ldg(vids + paths[t]);
-    else paths[t] = -1;
-    if (k == 0) steps += (unsigned long long)(len - 1);
+  // one warp per path row: coalesced, no 64-bit division
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t wk = warp; wk < n_walkers; wk += n_warps) {
+    const int32_t len = __ldg(lens + wk);
+    int32_t *row = paths + wk * stride;
+    for (int32_t k = lane; k < stride; k += 32) row[k] = k < len ? __ldg(vids + row[k]) : -1;
+    if (lane == 0) steps += (unsigned long long)(len - 1);
   }
   // warp-reduce then one atomic per warp
   for (int o = 16; o > 0; o >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, o);
@@ -230,10 +333,32 @@ __global__ void kat_philox_kernel(const uint32_t *ctr, const uint32_t *key, uint
 thread_local srw_walk_info t_info = {};
 thread_local int t_collect_stats = 0;
 
-struct EventPair {
+// Per-thread launch context, created once: no cudaMalloc / cudaFree / event creation on the call
+// path (those take driver-wide locks and serialise against other tools using the driver).
+struct LaunchCtx {
+  int device = -1;
   cudaEvent_t a = nullptr, b = nullptr;
-  ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+  unsigned long long *d_stats = nullptr;   // [4]
+  unsigned long long *h_stats = nullptr;   // pinned [4]
+  srw_status init(int dev) {
+    if (device == dev) return SRW_OK;
+    release();
+    SRW_CUDA(cudaEventCreate(&a));
+    SRW_CUDA(cudaEventCreate(&b));
+    SRW_CUDA(cudaMalloc(&d_stats, 4 * sizeof(unsigned long long)));
+    SRW_CUDA(cudaMallocHost(&h_stats, 4 * sizeof(unsigned long long)));
+    device = dev;
+    return SRW_OK;
+  }
+  void release() {
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+    if (d_stats) cudaFree(d_stats);
+    if (h_stats) cudaFreeHost(h_stats);
+    a = b = nullptr; d_stats = h_stats = nullptr; device = -1;
+  }
 };
+thread_local LaunchCtx t_ctx;
 
 }  // namespace
 
@@ -253,20 +378,22 @@ srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLa
   srw_alias_thresholds(p->p, p->q, &a.t_ret, &a.t_common, &a.t_far);
   a.p = (float)p->p; a.q = (float)p->q; a.u_mode = p->u_mode; a.u_const = p->u_const;
   a.paths = l.d_paths; a.lens = l.d_lens;
-  unsigned long long *d_stats = nullptr;
-  SRW_CUDA(cudaMalloc(&d_stats, 4 * sizeof(unsigned long long)));
+  SRW_TRY(t_ctx.init(g->device));
+  LaunchCtx &ev = t_ctx;
+  unsigned long long *d_stats = ev.d_stats;
   SRW_CUDA(cudaMemsetAsync(d_stats, 0, 4 * sizeof(unsigned long long), l.stream));
   a.stats = d_stats;
-  EventPair ev;
-  SRW_CUDA(cudaEventCreate(&ev.a));
-  SRW_CUDA(cudaEventCreate(&ev.b));
   SRW_CUDA(cudaEventRecord(ev.a, l.stream));
   if (exact) {
     walk_exact_kernel<<<(unsigned)((l.n_walkers + 127) / 128), 128, 0, l.stream>>>(a);
   } else {
     const unsigned grid = (unsigned)((l.n_walkers + 255) / 256);
     const bool st = t_collect_stats != 0;
-    if (g->has_alias) { if (st) walk_alias_kernel<true, true><<<grid, 256, 0, l.stream>>>(a); else walk_alias_kernel<true, false><<<grid, 256, 0, l.stream>>>(a); }
+    static const bool use_v1 = getenv("SRW_KERNEL") && !strcmp(getenv("SRW_KERNEL"), "v1");   // A/B switch
+    if (!use_v1) {
+      if (g->has_alias) { if (st) walk_alias_sm_kernel<true, true><<<grid, 256, 0, l.stream>>>(a); else walk_alias_sm_kernel<true, false><<<grid, 256, 0, l.stream>>>(a); }
+      else              { if (st) walk_alias_sm_kernel<false, true><<<grid, 256, 0, l.stream>>>(a); else walk_alias_sm_kernel<false, false><<<grid, 256, 0, l.stream>>>(a); }
+    } else if (g->has_alias) { if (st) walk_alias_kernel<true, true><<<grid, 256, 0, l.stream>>>(a); else walk_alias_kernel<true, false><<<grid, 256, 0, l.stream>>>(a); }
     else              { if (st) walk_alias_kernel<false, true><<<grid, 256, 0, l.stream>>>(a); else walk_alias_kernel<false, false><<<grid, 256, 0, l.stream>>>(a); }
   }
   SRW_CUDA(cudaEventRecord(ev.b, l.stream));
@@ -276,13 +403,12 @@ srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLa
     if (blocks > 148 * 32) blocks = 148 * 32;
     finalize_paths_kernel<<<(unsigned)blocks, 256, 0, l.stream>>>(l.n_walkers, a.stride, g->d_vids, l.d_lens, l.d_paths, d_stats);
   }
-  unsigned long long h_stats[4];
-  SRW_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, l.stream));
+  unsigned long long *h_stats = ev.h_stats;
+  SRW_CUDA(cudaMemcpyAsync(h_stats, d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, l.stream));
   SRW_CUDA(cudaStreamSynchronize(l.stream));
   SRW_CUDA(cudaGetLastError());
   float ms = 0.f;
   SRW_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));
-  cudaFree(d_stats);
   t_info.kernel_ms = ms;
   t_info.kernel_launches = 2;
   t_info.steps = (int64_t)h_stats[0];
