@@ -180,6 +180,36 @@ void srw_paths_free(srw_paths *paths);
  * Prints the reference's "edges:/vertices:" lines (URW:69-72).  Returns the process exit code. */
 int srw_main(int argc, const char *const *argv);
 
+/* ---- A10 / SURVEY 8(e): vertex-range shards.  Replaces the walker routing of URW:103-112 /
+ * VRW:121-134 and the per-super-step shuffle RW:186-192.  One srw_graph per rank holds the rows of a
+ * contiguous, edge-balanced vertex range; walkers travel as 32-byte tuples, path entries reach the
+ * walker's home shard (owner of its start vertex) as 16-byte records.  The library fills the send
+ * buffers; the caller performs the all-to-all (NCCL) between srw_shard_step calls -- see
+ * stellar-random-walk_b200/sharded.py for the loop (RW:91-162).  Alias sampler only. ---- */
+srw_status srw_graph_from_device_edges_sharded(int64_t n, const int32_t *d_src, const int32_t *d_dst, const float *d_w,
+                                               int directed, unsigned flags, int rank, int world, srw_graph **out);
+/* bounds: world+1 first-ranks of the shards (identical on every rank) */
+srw_status srw_graph_shard_info(const srw_graph *g, int *rank, int *world, int64_t *row_first, int64_t *row_last,
+                                int64_t *bounds, int64_t *nnz_local);
+int srw_walker_msg_bytes(void);   /* 32 */
+int srw_path_rec_bytes(void);     /* 16 */
+/* RW:81-87 initial walkers of rounds [round_first, round_first+n_rounds) for this shard's vertices;
+ * d_paths is [rows*n_rounds][walk_length+2], d_lens [rows*n_rounds] */
+srw_status srw_shard_seed(const srw_graph *g, const srw_params *params, int64_t round_first, int64_t n_rounds, void *d_inbox,
+                          int64_t cap, int64_t *n_seeded, int32_t *d_paths, int32_t *d_lens, void *stream);
+/* one super-step: advance the n_in resident tuples of d_inbox until each needs a remote row; outgoing
+ * tuples / records are left in d_send_msgs / d_send_recs as contiguous per-destination segments in
+ * rank order with h_msg_counts[world] / h_rec_counts[world] items each */
+srw_status srw_shard_step(const srw_graph *g, const srw_params *params, int64_t round_first, int64_t n_rounds,
+                          const void *d_inbox, int64_t n_in, void *d_send_msgs, void *d_send_recs, int64_t rec_cap,
+                          int32_t *d_paths, int32_t *d_lens, int64_t *h_msg_counts, int64_t *h_rec_counts, int64_t *steps_done,
+                          void *stream);
+srw_status srw_shard_apply(const srw_graph *g, const srw_params *params, int64_t round_first, int64_t n_rounds,
+                           const void *d_recs, int64_t n_recs, int32_t *d_paths, void *stream);
+/* ranks -> vertex ids over the home rows; *steps = sum(len - 1) */
+srw_status srw_shard_finalize(const srw_graph *g, const srw_params *params, int64_t n_rows, int32_t *d_paths,
+                              const int32_t *d_lens, int64_t *steps, void *stream);
+
 /* ---- synthetic inputs for the benchmark; device-resident, not on the walk path ---- */
 srw_status srw_synth_rmat_device(int scale, int edge_factor, uint64_t seed, int64_t first, int64_t count,
                                  int32_t *d_src, int32_t *d_dst);

@@ -38,8 +38,8 @@ ABI_SYMBOLS = [
     "srw_walk", "srw_walk_device", "srw_last_walk_info", "srw_walk_collect_stats", "srw_paths_view", "srw_paths_counts",
     "srw_save", "srw_paths_format", "srw_paths_free", "srw_main", "srw_synth_rmat_device", "srw_synth_weights_device",
     "srw_gather_ceiling",
-    "srw_shard_plan", "srw_shard_create", "srw_shard_free", "srw_shard_seed_walkers", "srw_shard_step",
-    "srw_shard_outbox", "srw_shard_deliver", "srw_shard_paths", "srw_shard_info",
+    "srw_graph_from_device_edges_sharded", "srw_graph_shard_info", "srw_walker_msg_bytes", "srw_path_rec_bytes",
+    "srw_shard_seed", "srw_shard_step", "srw_shard_apply", "srw_shard_finalize",
 ]
 
 

@@ -85,6 +85,49 @@ __global__ void k_entries(int64_t n, const int32_t *__restrict__ src, const int3
     }
   }
 }
+// ---- sharded build: every rank scans the whole edge list, counts global degrees, and
+// keeps only the adjacency entries whose row lies in its vertex range [row_first, row_last) ----
+__global__ void k_degrees(int64_t n, const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int directed,
+                          const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ wordrank, int32_t id_min,
+                          uint32_t *deg) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    atomicAdd(&deg[rank_of(bitmap, wordrank, id_min, src[e])], 1u);
+    if (!directed) atomicAdd(&deg[rank_of(bitmap, wordrank, id_min, dst[e])], 1u);
+  }
+}
+__device__ __forceinline__ uint32_t warp_reserve(bool want, unsigned long long *cursor) {
+  const unsigned m = __ballot_sync(0xffffffffu, want);
+  if (!m) return 0;
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  unsigned long long base = 0;
+  if (lane == leader) base = atomicAdd(cursor, (unsigned long long)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return (uint32_t)(base + __popc(m & ((1u << lane) - 1u)));
+}
+// compaction order is arbitrary; the global entry index (2e / 2e+1, or e when directed) is kept so
+// that a sort restores file-appearance order
+__global__ void k_entries_range(int64_t n, const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int directed,
+                                const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ wordrank, int32_t id_min,
+                                uint32_t row_first, uint32_t row_last, uint32_t *ent_row, uint32_t *ent_col,
+                                uint32_t *ent_gidx, unsigned long long *cursor) {
+  const int64_t n_pad = (n + 31) & ~(int64_t)31;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_pad; e += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t rs = 0, rd = 0;
+    const bool live = e < n;
+    if (live) { rs = rank_of(bitmap, wordrank, id_min, src[e]); rd = rank_of(bitmap, wordrank, id_min, dst[e]); }
+    const bool k0 = live && rs >= row_first && rs < row_last;
+    const bool k1 = live && !directed && rd >= row_first && rd < row_last;
+    const uint32_t p0 = warp_reserve(k0, cursor);
+    if (k0) { ent_row[p0] = rs - row_first; ent_col[p0] = rd; ent_gidx[p0] = (uint32_t)(directed ? e : 2 * e); }
+    const uint32_t p1 = warp_reserve(k1, cursor);
+    if (k1) { ent_row[p1] = rd - row_first; ent_col[p1] = rs; ent_gidx[p1] = (uint32_t)(2 * e + 1); }
+  }
+}
+__global__ void k_rebase_off(int64_t rows, const int64_t *__restrict__ goff, int64_t row_first, int64_t *off) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r <= rows; r += (int64_t)gridDim.x * blockDim.x)
+    off[r] = goff[row_first + r] - goff[row_first];
+}
+
 __global__ void k_iota(int64_t n, uint32_t *a) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a[i] = (uint32_t)i;
 }
@@ -92,9 +135,13 @@ __global__ void k_gather_u32(int64_t n, const uint32_t *__restrict__ idx, const 
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = table[idx[i]];
 }
 // entry index -> input edge weight (shift = 1 when each edge made two entries)
-__global__ void k_gather_w(int64_t n, const uint32_t *__restrict__ idx, const float *__restrict__ w, int shift, float *out) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    out[i] = w ? w[idx[i] >> shift] : 1.0f;
+// (gidx: local position -> global entry index, NULL = identity)
+__global__ void k_gather_w(int64_t n, const uint32_t *__restrict__ idx, const uint32_t *__restrict__ gidx,
+                           const float *__restrict__ w, int shift, float *out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t p = idx[i];
+    out[i] = w ? w[(gidx ? gidx[p] : p) >> shift] : 1.0f;
+  }
 }
 __global__ void k_any_non_unit(int64_t n, const float *__restrict__ w, int *flag) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -220,7 +267,8 @@ void srw_alias_thresholds(double p, double q, uint64_t *t_ret, uint64_t *t_commo
 }
 
 static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_dst, const float *d_w, const int32_t *d_pid,
-                             int directed, unsigned flags, int64_t n_extra, const int32_t *d_extra, srw_graph *g) {
+                             int directed, unsigned flags, int64_t n_extra, const int32_t *d_extra, srw_graph *g, int shard_rank = 0,
+                             int shard_world = 1) {
   g->directed = directed != 0;
   g->flags = flags;
   SRW_CUDA(cudaGetDevice(&g->device));
@@ -229,7 +277,7 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
     SRW_CUDA(cudaMemset(g->d_off, 0, sizeof(int64_t)));
     return SRW_OK;
   }
-  const int64_t nnz = directed ? n : 2 * n;
+  int64_t nnz = directed ? n : 2 * n;   // global; becomes this shard's count below
   if (nnz >= ((int64_t)1 << 32)) { srw_set_error("more than 2^32-1 adjacency entries are not supported"); return SRW_ERR_UNSUPPORTED; }
 
   // ---- id range and presence bitmap ----
@@ -272,24 +320,79 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
   k_vids<<<grid((int64_t)words), kThreads>>>(words, g->d_bitmap, g->d_wordrank, mn, g->d_vids);
 
   // ---- adjacency entries + degrees -> row offsets ----
-  DevBuf ent_row, ent_col, deg;
-  SRW_CUDA(ent_row.alloc((size_t)nnz * 4));
-  SRW_CUDA(ent_col.alloc((size_t)nnz * 4));
+  const bool sharded = shard_world > 1;
+  DevBuf ent_row, ent_col, ent_gidx, deg;
   SRW_CUDA(deg.alloc((size_t)(nv + 1) * 4));
   SRW_CUDA(cudaMemset(deg.p, 0, (size_t)(nv + 1) * 4));
-  if (n > 0)
-    k_entries<<<grid(n), kThreads>>>(n, d_src, d_dst, directed, g->d_bitmap, g->d_wordrank, mn, ent_row.as<uint32_t>(),
-                                     ent_col.as<uint32_t>(), deg.as<uint32_t>());
-  SRW_CUDA(cudaMalloc(&g->d_off, (size_t)(nv + 1) * 8));
-  {
+  auto scan_degrees = [&](int64_t *d_out) -> srw_status {
     cub::TransformInputIterator<int64_t, CastU32ToI64, uint32_t *> it(deg.as<uint32_t>(), CastU32ToI64());
     size_t tb = 0;
     DevBuf tmp;
-    SRW_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, it, g->d_off, nv + 1));
+    SRW_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, it, d_out, nv + 1));
     SRW_CUDA(tmp.alloc(tb));
-    SRW_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, it, g->d_off, nv + 1));
+    SRW_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, it, d_out, nv + 1));
+    SRW_CUDA(cudaDeviceSynchronize());
+    return SRW_OK;
+  };
+  g->shard_rank = shard_rank; g->shard_world = shard_world;
+  g->row_first = 0; g->row_last = nv; g->nnz_global = nnz;
+  g->bounds.assign((size_t)shard_world + 1, 0);
+  g->bounds[(size_t)shard_world] = nv;
+  int64_t nrows = nv;
+  if (!sharded) {
+    SRW_CUDA(ent_row.alloc((size_t)nnz * 4));
+    SRW_CUDA(ent_col.alloc((size_t)nnz * 4));
+    if (n > 0)
+      k_entries<<<grid(n), kThreads>>>(n, d_src, d_dst, directed, g->d_bitmap, g->d_wordrank, mn, ent_row.as<uint32_t>(),
+                                       ent_col.as<uint32_t>(), deg.as<uint32_t>());
+    SRW_CUDA(cudaMalloc(&g->d_off, (size_t)(nv + 1) * 8));
+    SRW_TRY(scan_degrees(g->d_off));
+  } else {
+    // global degrees -> global offsets -> edge-balanced contiguous vertex ranges (same on every rank)
+    if (n > 0) k_degrees<<<grid(n), kThreads>>>(n, d_src, d_dst, directed, g->d_bitmap, g->d_wordrank, mn, deg.as<uint32_t>());
+    DevBuf goff;
+    SRW_CUDA(goff.alloc((size_t)(nv + 1) * 8));
+    SRW_TRY(scan_degrees(goff.as<int64_t>()));
+    std::vector<int64_t> h_goff((size_t)nv + 1);
+    SRW_CUDA(cudaMemcpy(h_goff.data(), goff.p, (size_t)(nv + 1) * 8, cudaMemcpyDeviceToHost));
+    for (int r = 1; r < shard_world; ++r) {
+      const int64_t target = (int64_t)((__int128)nnz * r / shard_world);
+      g->bounds[(size_t)r] = (int64_t)(std::lower_bound(h_goff.begin(), h_goff.end(), target) - h_goff.begin());
+      if (g->bounds[(size_t)r] > nv) g->bounds[(size_t)r] = nv;
+      if (g->bounds[(size_t)r] < g->bounds[(size_t)r - 1]) g->bounds[(size_t)r] = g->bounds[(size_t)r - 1];
+    }
+    g->row_first = g->bounds[(size_t)shard_rank];
+    g->row_last = g->bounds[(size_t)shard_rank + 1];
+    nrows = g->row_last - g->row_first;
+    nnz = h_goff[(size_t)g->row_last] - h_goff[(size_t)g->row_first];     // this shard's entries
+    g->nnz = nnz;
+    SRW_CUDA(cudaMalloc(&g->d_off, (size_t)(nrows + 1) * 8));
+    k_rebase_off<<<grid(nrows + 1), kThreads>>>(nrows, goff.as<int64_t>(), g->row_first, g->d_off);
+    DevBuf raw_row, raw_col, raw_gidx, cursor, ka, va;
+    SRW_CUDA(raw_row.alloc((size_t)nnz * 4)); SRW_CUDA(raw_col.alloc((size_t)nnz * 4)); SRW_CUDA(raw_gidx.alloc((size_t)nnz * 4));
+    SRW_CUDA(cursor.alloc(8));
+    SRW_CUDA(cudaMemset(cursor.p, 0, 8));
+    if (n > 0)
+      k_entries_range<<<grid(n), kThreads>>>(n, d_src, d_dst, directed, g->d_bitmap, g->d_wordrank, mn, (uint32_t)g->row_first,
+                                             (uint32_t)g->row_last, raw_row.as<uint32_t>(), raw_col.as<uint32_t>(),
+                                             raw_gidx.as<uint32_t>(), cursor.as<unsigned long long>());
+    SRW_CUDA(cudaDeviceSynchronize());
+    if (nnz > 0) {
+      // restore file-appearance order: sort the kept entries by their global entry index
+      SRW_CUDA(ka.alloc((size_t)nnz * 4)); SRW_CUDA(va.alloc((size_t)nnz * 4));
+      DevBuf vb;
+      SRW_CUDA(vb.alloc((size_t)nnz * 4));
+      uint32_t *k_in = raw_gidx.as<uint32_t>(), *k_out = ka.as<uint32_t>(), *v_in = va.as<uint32_t>(), *v_out = vb.as<uint32_t>();
+      k_iota<<<grid(nnz), kThreads>>>(nnz, v_in);
+      SRW_TRY(sort_pairs(k_in, k_out, v_in, v_out, nnz, 32));
+      SRW_CUDA(ent_row.alloc((size_t)nnz * 4)); SRW_CUDA(ent_col.alloc((size_t)nnz * 4)); SRW_CUDA(ent_gidx.alloc((size_t)nnz * 4));
+      k_gather_u32<<<grid(nnz), kThreads>>>(nnz, v_in, raw_row.as<uint32_t>(), ent_row.as<uint32_t>());
+      k_gather_u32<<<grid(nnz), kThreads>>>(nnz, v_in, raw_col.as<uint32_t>(), ent_col.as<uint32_t>());
+      SRW_CUDA(cudaMemcpy(ent_gidx.p, k_in, (size_t)nnz * 4, cudaMemcpyDeviceToDevice));
+      SRW_CUDA(cudaDeviceSynchronize());
+    }
   }
-  SRW_CUDA(cudaDeviceSynchronize());
+  const uint32_t *gidx = sharded ? ent_gidx.as<uint32_t>() : nullptr;
   deg.alloc(0);
 
   if (d_pid) {  // GM:21,31
@@ -304,7 +407,7 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
   }
   if (nnz == 0) return SRW_OK;
 
-  const int rbits = bits_for(nv);
+  const int rbits = bits_for(nrows), cbits = bits_for(nv);
   const int wshift = directed ? 0 : 1;
   DevBuf kb0, kb1, vb0, vb1;
   SRW_CUDA(kb0.alloc((size_t)nnz * 4)); SRW_CUDA(kb1.alloc((size_t)nnz * 4));
@@ -319,20 +422,21 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
     SRW_CUDA(cudaMalloc(&g->d_col_app, (size_t)nnz * 4));
     SRW_CUDA(cudaMalloc(&g->d_w_app, (size_t)nnz * 4));
     k_gather_u32<<<grid(nnz), kThreads>>>(nnz, v_in, ent_col.as<uint32_t>(), (uint32_t *)g->d_col_app);
-    k_gather_w<<<grid(nnz), kThreads>>>(nnz, v_in, d_w, wshift, g->d_w_app);
+    k_gather_w<<<grid(nnz), kThreads>>>(nnz, v_in, gidx, d_w, wshift, g->d_w_app);
     SRW_CUDA(cudaDeviceSynchronize());
   }
 
   // ---- K2: neighbour-sorted rows = stable sort by column, then stable sort by row ----
   SRW_CUDA(cudaMemcpy(k_in, ent_col.p, (size_t)nnz * 4, cudaMemcpyDeviceToDevice));
   k_iota<<<grid(nnz), kThreads>>>(nnz, v_in);
-  SRW_TRY(sort_pairs(k_in, k_out, v_in, v_out, nnz, rbits));
+  SRW_TRY(sort_pairs(k_in, k_out, v_in, v_out, nnz, cbits));
   k_gather_u32<<<grid(nnz), kThreads>>>(nnz, v_in, ent_row.as<uint32_t>(), k_in);
   SRW_TRY(sort_pairs(k_in, k_out, v_in, v_out, nnz, rbits));
   SRW_CUDA(cudaMalloc(&g->d_col, (size_t)nnz * 4));
   k_gather_u32<<<grid(nnz), kThreads>>>(nnz, v_in, ent_col.as<uint32_t>(), (uint32_t *)g->d_col);
   SRW_CUDA(cudaDeviceSynchronize());
   ent_row.alloc(0); ent_col.alloc(0);
+  (void)ent_gidx;
 
   // ---- K3: Vose slots over the sorted rows (weighted graphs only) ----
   if ((flags & SRW_BUILD_ALIAS) && d_w) {
@@ -345,9 +449,9 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
     if (h) {
       DevBuf ws;
       SRW_CUDA(ws.alloc((size_t)nnz * 4));
-      k_gather_w<<<grid(nnz), kThreads>>>(nnz, v_in, d_w, wshift, ws.as<float>());
+      k_gather_w<<<grid(nnz), kThreads>>>(nnz, v_in, gidx, d_w, wshift, ws.as<float>());
       SRW_CUDA(cudaMalloc(&g->d_slot, (size_t)nnz * sizeof(AliasSlot)));
-      k_alias_rows<<<grid_for(nv, 64), 64>>>(nv, g->d_off, g->d_col, ws.as<float>(), g->d_slot);
+      k_alias_rows<<<grid_for(nrows, 64), 64>>>(nrows, g->d_off, g->d_col, ws.as<float>(), g->d_slot);
       SRW_CUDA(cudaDeviceSynchronize());
       g->has_alias = true;
     }
@@ -394,6 +498,20 @@ srw_status srw_build_graph_rows(int64_t n_rows, const int32_t *h_vids, const int
   srw_graph *g = new srw_graph();
   srw_status s = build_impl(n, ds.as<int32_t>(), dd.as<int32_t>(), dw.as<float>(), h_pid ? dp.as<int32_t>() : nullptr, 1,
                             flags ? flags : SRW_BUILD_ALL, n_rows, dx.as<int32_t>(), g);
+  if (s != SRW_OK) { srw_graph_free(g); return s; }
+  *out = g;
+  return SRW_OK;
+}
+
+srw_status srw_build_graph_device_sharded(int64_t n, const int32_t *d_src, const int32_t *d_dst, const float *d_w, int directed,
+                                          unsigned flags, int rank, int world, srw_graph **out) {
+  SRW_TRY(srw_require_device());
+  if (n < 0 || !out || (n > 0 && (!d_src || !d_dst)) || world < 1 || world > SRW_MAX_SHARDS || rank < 0 || rank >= world) {
+    srw_set_error("srw_graph_from_device_edges_sharded: bad argument");
+    return SRW_ERR_ARG;
+  }
+  srw_graph *g = new srw_graph();
+  srw_status s = build_impl(n, d_src, d_dst, d_w, nullptr, directed, flags ? flags : SRW_BUILD_ALIAS, 0, nullptr, g, rank, world);
   if (s != SRW_OK) { srw_graph_free(g); return s; }
   *out = g;
   return SRW_OK;

@@ -60,7 +60,18 @@ struct srw_graph {
   int64_t device_bytes = 0;
   mutable std::vector<int32_t> h_vids;  // lazy host copies for the query entry points
   mutable std::vector<int64_t> h_off;
+  // vertex-range shard: this handle holds rows [row_first, row_last) of a graph whose
+  // ranks run to nv; d_off / d_col / d_slot are indexed by (rank - row_first); neighbour ids stay global
+  int shard_rank = 0, shard_world = 1;
+  int64_t row_first = 0, row_last = 0, nnz_global = 0;
+  std::vector<int64_t> bounds;          // [world+1] first rank of every shard
+  struct ShardScratch *scratch = nullptr;
 };
+
+#define SRW_MAX_SHARDS 16
+srw_status srw_build_graph_device_sharded(int64_t n, const int32_t *d_src, const int32_t *d_dst, const float *d_w, int directed,
+                                          unsigned flags, int rank, int world, srw_graph **out);
+void srw_shard_scratch_free(struct ShardScratch *s);
 
 struct srw_paths {
   int64_t n_paths = 0, n_steps = 0;

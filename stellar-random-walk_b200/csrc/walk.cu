@@ -366,6 +366,7 @@ srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLa
   if (p->walk_length < 0 || l.n_walkers < 0) { srw_set_error("walkLength and the walker count must be >= 0"); return SRW_ERR_ARG; }
   if (!(p->p > 0.0) || !(p->q > 0.0)) { srw_set_error("p and q must be > 0"); return SRW_ERR_ARG; }
   t_info = srw_walk_info{};
+  if (g->shard_world > 1) { srw_set_error("this handle is one shard of %d: use the srw_shard_* calls", g->shard_world); return SRW_ERR_ARG; }
   if (l.n_walkers == 0 || g->nv == 0) return SRW_OK;
   const bool exact = p->sampler == SRW_SAMPLER_EXACT;
   if (exact && g->nnz > 0 && !g->d_col_app) { srw_set_error("graph was built without SRW_BUILD_EXACT"); return SRW_ERR_ARG; }
