@@ -54,6 +54,15 @@ def parse_args():
     return ap.parse_args()
 
 
+_T0 = time.time()
+
+
+def log(msg):
+    if os.environ.get("RANK", "0") == "0":
+        sys.stderr.write("[bench %7.1fs] %s\n" % (time.time() - _T0, msg))
+        sys.stderr.flush()
+
+
 def workload_name(a):
     return "rmat-%d ef%d undirected %s p=%g q=%g walkLength=%d (one round = one walker per present vertex)" % (
         a.scale, a.edge_factor, "weighted" if a.weighted else "unweighted", a.p, a.q, a.walk_length)
@@ -177,11 +186,13 @@ def run_reference(a):
     if mem_available_gb() < need_gb * 1.5 + 8:
         print(json.dumps({"impl": "reference", "unavailable": "host RAM too small for a CPU build of rmat-%d (%.0f GB needed)" % (a.scale, need_gb)}))
         return
+    log("reference arm: generating rmat-%d on the CPU" % a.scale)
     t0 = time.time()
     src = np.empty(n_edges, np.int32)
     dst = np.empty(n_edges, np.int32)
     L.oracle_rmat_edges.argtypes = [C.c_int, C.c_uint64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
     L.oracle_rmat_edges(a.scale, a.gen_seed, 0, n_edges, src.ctypes.data, dst.ctypes.data, 0)
+    log("reference arm: building the CSR on the CPU")
     n_ids = 1 << a.scale
     offsets = np.empty(n_ids + 1, np.int64)
     col = np.empty(2 * n_edges, np.int32)
@@ -189,6 +200,7 @@ def run_reference(a):
     L.oracle_csr_build(n_ids, n_edges, src.ctypes.data, dst.ctypes.data, offsets.ctypes.data, col.ctypes.data, 0)
     del src, dst
     build_s = time.time() - t0
+    log("reference arm: CPU build %.1f s; walking" % build_s)
     # each step: a bounded sample, sized so that steps+warmup end within a few minutes
     per_step = max(2.0, min(a.cpu_budget, 150.0 / max(1, a.steps + a.warmup)))
     for k in range(a.warmup):
@@ -246,12 +258,15 @@ def run_b200(a):
         torch.cuda.synchronize()
         return g, time.time() - t
 
+    log("generating %s" % workload_name(a))
     d_src, d_dst, d_w = gen_edges()
     want_e2e = (not a.no_e2e) and world == 1
     h_edges = None
     if want_e2e and mem_available_gb() > (n_edges * 8) / 1e9 * 2 + 16:
         h_edges = [t.cpu().pin_memory() for t in (d_src, d_dst)] + ([d_w.cpu().pin_memory()] if d_w is not None else [])
+    log("host copy of the edge list done (e2e=%s); building CSR" % (h_edges is not None))
     g, build_s = build(d_src, d_dst, d_w)
+    log("CSR built in %.2f s" % build_s)
     del d_src, d_dst, d_w
     torch.cuda.empty_cache()
     nv, nnz = g.stats()
@@ -285,9 +300,11 @@ def run_b200(a):
 
     clocks = ClockSampler(local)
     clocks.launch()
+    log("stats pass done: T=%.2f proposals/step; warm-up" % T_bar)
     for r in range(a.warmup):
         one_round(r)
     barrier()
+    log("timed region: %d rounds" % a.steps)
     clocks.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -310,6 +327,7 @@ def run_b200(a):
     else:
         steps_all = steps
     value = steps_all / (elapsed_ms * 1e-3)
+    log("timed region done: %.3e steps/s" % value)
 
     # ---- roofline of the dominant kernel (walk_alias_kernel) ----
     # algorithmic bytes per sampled transition (DESIGN.md "bytes per step"): row extent 8 B +
@@ -344,6 +362,7 @@ def run_b200(a):
         except Exception as ex:   # noqa: BLE001
             roofline["gather_ceiling_error"] = str(ex)
 
+    log("roofline done")
     # ---- e2e: host edge list -> H2D -> CSR build -> K rounds, every round's paths read back ----
     e2e = None
     if want_e2e and h_edges is not None:
@@ -375,6 +394,7 @@ def run_b200(a):
                "seconds": dt, "includes": "edge-list H2D + CSR build (once) + %d rounds + D2H of every round's paths through a pinned ring" % a.steps}
         g = g2
 
+    log("e2e done: %s" % (None if e2e is None else "%.3e steps/s" % e2e["value"]))
     # ---- CPU baseline beside it (rank 0, N=1): oracle port on the same CSR ----
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
@@ -389,6 +409,7 @@ def run_b200(a):
         except Exception as ex:   # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %s" % ex}
 
+    log("cpu baseline done")
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": elapsed_ms / max(1, a.steps), "higher_is_better": True,

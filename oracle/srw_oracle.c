@@ -929,7 +929,15 @@ int64_t oracle_walk_csr_timed(int64_t nv, const int64_t *offsets, const int32_t 
           if (deg <= 0) break;
           if (deg > nw_cap) { nw_cap = deg * 2; nw = (float *)realloc(nw, (size_t)nw_cap * 4); ones = (float *)realloc(ones, (size_t)nw_cap * 4); for (int64_t k = 0; k < nw_cap; ++k) ones[k] = 1.0f; }
           const int64_t poff = offsets[prev], pdeg = offsets[prev + 1] - poff;
-          oracle_second_order_weights(p, q, prev, pdeg, col + poff, deg, col + off, w ? w + off : ones, nw);   /* RS:27-44 */
+          /* RS:27-44, in slices of neighbours so that one hub-by-hub step (d_c*d_p ~ 1e12 compares on
+           * RMAT-26) cannot overrun the time budget: an unfinished step is abandoned and not counted */
+          int timed_out = 0;
+          for (int64_t c0 = 0; c0 < deg; c0 += 256) {
+            const int64_t c1 = c0 + 256 < deg ? c0 + 256 : deg;
+            oracle_second_order_weights(p, q, prev, pdeg, col + poff, c1 - c0, col + off + c0, (w ? w + off : ones) + c0, nw + c0);
+            if (now_s() - t0 > budget_s) { timed_out = 1; break; }
+          }
+          if (timed_out) break;
           const float u = oracle_u01(cfg->seed, walker, (uint32_t)(len - 1));
           path[len++] = col[off + oracle_sample(deg, nw, u)];                                                /* RS:12-25 */
           steps++;
