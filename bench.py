@@ -426,9 +426,97 @@ def run_b200(a):
         dist.destroy_process_group()
 
 
+def run_b200_sharded(a):
+    """N > 1: the graph is sharded by vertex range, one rank per GPU, walkers exchanged by an NCCL
+    all-to-all every super-step (BASELINE config C4).  The K timed rounds are walked as one batch
+    (rounds are independent), so `steps` rounds of work are timed exactly once."""
+    import torch
+    import torch.distributed as dist
+    srw = importlib.import_module("stellar-random-walk_b200")
+    sh = importlib.import_module("stellar-random-walk_b200.sharded")
+    lib = srw.lib()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    n_edges = a.edge_factor << a.scale
+    log("sharded: generating %s on every rank" % workload_name(a))
+    s = torch.empty(n_edges, dtype=torch.int32, device=dev)
+    d = torch.empty(n_edges, dtype=torch.int32, device=dev)
+    srw.check(lib.srw_synth_rmat_device(a.scale, a.edge_factor, a.gen_seed, 0, n_edges, s.data_ptr(), d.data_ptr()))
+    w = None
+    if a.weighted:
+        w = torch.empty(n_edges, dtype=torch.float32, device=dev)
+        srw.check(lib.srw_synth_weights_device(a.gen_seed + 1, 0, n_edges, w.data_ptr()))
+    torch.cuda.synchronize()
+    t0 = time.time()
+    shard = sh.Shard(n_edges, s.data_ptr(), d.data_ptr(), None if w is None else w.data_ptr(), rank, world, False, dev)
+    torch.cuda.synchronize()
+    build_s = time.time() - t0
+    del s, d, w
+    torch.cuda.empty_cache()
+    log("sharded: rank 0 owns ranks [%d, %d) of %d, %d entries, built in %.2f s" % (shard.row_first, shard.row_last, shard.nv, shard.nnz_local, build_s))
+    prm = srw.Params(walkLength=a.walk_length, numWalks=1, p=a.p, q=a.q, seed=a.seed, sampler="alias")
+    ex = sh.DistExchange(device=dev)
+    # the busiest rank holds about 1/world of the walkers (edge-balanced ranges make the stationary
+    # walker distribution balanced), plus slack
+    n_total = shard.nv * max(a.steps, a.warmup, 1)
+    cap = min(n_total, int(2.5 * n_total / world) + (1 << 20))
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    if a.warmup > 0:
+        wk = sh.ShardedWalker([shard], prm, a.warmup, ex, rec_cap=1 << 24, inbox_cap=cap)
+        wk.run(0)
+        del wk
+        torch.cuda.empty_cache()
+    walker = sh.ShardedWalker([shard], prm, a.steps, ex, rec_cap=1 << 24, inbox_cap=cap)
+    clocks = ClockSampler(local)
+    clocks.launch()
+    time.sleep(1.0)
+    barrier()
+    log("sharded: timed region, %d rounds as one batch" % a.steps)
+    clocks.mark()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out, stats = walker.run(a.warmup)
+    e1.record()
+    barrier()
+    clk = clocks.stop()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t[0])
+    tot = torch.tensor([stats["steps"], stats["tuples_sent"], stats["records_sent"], int((out[0][1].long() - 1).clamp(min=0).sum())],
+                       dtype=torch.int64, device=dev)
+    dist.all_reduce(tot)
+    steps_all, tuples, recs, steps_check = (int(x) for x in tot.tolist())
+    value = steps_all / (elapsed_ms * 1e-3)
+    log("sharded: %.3e steps/s, %d super-steps" % (value, stats["super_steps"]))
+    if rank == 0:
+        peak, peak_src = peaks()
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": elapsed_ms / max(1, a.steps), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "u32 (integer thresholds; f64 only in the Vose build)", "data": "synthetic",
+                "config": {"workload": workload_name(a), "vertices_present": shard.nv, "walkers_per_step": shard.nv,
+                           "parallelism": "graph sharded into %d edge-balanced vertex ranges, NCCL all-to-all of 32-byte walker tuples "
+                                          "and 16-byte path records every super-step" % world,
+                           "build_s": round(build_s, 3), "super_steps": stats["super_steps"], "tuples_exchanged": tuples,
+                           "records_exchanged": recs, "nvlink_bytes": tuples * 32 + recs * 16, "steps_cross_check": steps_check == steps_all,
+                           "l2": "inputs larger than L2, no flush needed", "sampler": "alias"},
+                "roofline": {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
+                             "note": "single-GPU kernel roofline is reported by the N=1 line; the sharded step adds the exchange"},
+                "cpu_baseline": None, "e2e": None, "gpu_launches": stats["super_steps"] * 3, "clocks": clk}
+        print(json.dumps(line))
+    dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.mode != "replicated":
+        run_b200_sharded(args)
     else:
         run_b200(args)

@@ -69,9 +69,12 @@ __device__ __forceinline__ int owner_of(const ShardArgs &a, int32_t v) {
   while (o + 1 < a.world && (int64_t)v >= a.bounds[o + 1]) o++;
   return o;
 }
+// Path rows are homed round-robin (home(v) = v mod world) so that every rank stores ~|V|/world rows per
+// round even though the edge-balanced vertex ranges hold very different numbers of vertices.
+__device__ __forceinline__ int64_t home_rows(const ShardArgs &a) { return (a.nv - a.rank + a.world - 1) / a.world; }
 __device__ __forceinline__ int64_t home_row(const ShardArgs &a, uint64_t walker) {
   const int64_t round = (int64_t)(walker / (uint64_t)a.nv), v = (int64_t)(walker % (uint64_t)a.nv);
-  return (round - a.round_first) * (a.row_last - a.row_first) + (v - a.row_first);
+  return (round - a.round_first) * home_rows(a) + v / a.world;
 }
 
 template <bool HAS_ALIAS>
@@ -86,7 +89,7 @@ __global__ void __launch_bounds__(256) shard_walk_kernel(ShardArgs a) {
   int64_t off = 0, poff = 0;
   uint64_t k = 0;
   bool have_ext = false;
-  const int home = owner_of(a, (int32_t)(walker % (uint64_t)a.nv));
+  const int home = (int)((walker % (uint64_t)a.nv) % (uint64_t)a.world);
   const uint64_t t_lo = a.t_common < a.t_far ? a.t_common : a.t_far;
   const uint64_t t_hi = a.t_common < a.t_far ? a.t_far : a.t_common;
   unsigned long long steps = 0;
@@ -103,8 +106,12 @@ __global__ void __launch_bounds__(256) shard_walk_kernel(ShardArgs a) {
   if (m.state == MSG_FIN) {          // home: RW:132 completed path
     a.lens[home_row(a, walker)] = len;
     st = L_EXIT;
+  } else if (m.state == MSG_STEP) {
+    const int co = owner_of(a, curr);          // freshly seeded walkers start on their home rank
+    if (co == a.rank) st = L_EXT_CURR;
+    else { emit(co, MSG_STEP); st = L_EXIT; }
   } else {
-    st = m.state == MSG_STEP ? L_EXT_CURR : L_EXT_PREV;
+    st = L_EXT_PREV;
   }
 
   while (st != L_EXIT) {
@@ -215,9 +222,9 @@ __global__ void __launch_bounds__(256) shard_walk_kernel(ShardArgs a) {
 }
 
 __global__ void shard_seed_kernel(ShardArgs a, WalkerMsg *inbox) {
-  const int64_t rows = a.row_last - a.row_first, total = rows * a.n_rounds;
+  const int64_t rows = home_rows(a), total = rows * a.n_rounds;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t round = a.round_first + i / rows, v = a.row_first + i % rows;
+    const int64_t round = a.round_first + i / rows, v = a.rank + (i % rows) * a.world;
     WalkerMsg m;
     m.walker = (uint64_t)round * (uint64_t)a.nv + (uint64_t)v;
     m.curr = (int32_t)v; m.prev = -1; m.x = 0; m.y = 0; m.trial = 0; m.len = 1; m.state = MSG_STEP; m.pad = 0;
@@ -329,13 +336,13 @@ extern "C" srw_status srw_graph_shard_info(const srw_graph *g, int *rank, int *w
 extern "C" int srw_walker_msg_bytes(void) { return (int)sizeof(WalkerMsg); }
 extern "C" int srw_path_rec_bytes(void) { return (int)sizeof(PathRec); }
 
-// RW:81-87 + URW:81-87: one walker per local vertex and round, path = [v]
+// RW:81-87 + URW:81-87: one walker per homed vertex (v mod world == rank) and round, path = [v]
 extern "C" srw_status srw_shard_seed(const srw_graph *g, const srw_params *params, int64_t round_first, int64_t n_rounds,
                                      void *d_inbox, int64_t cap, int64_t *n_seeded, int32_t *d_paths, int32_t *d_lens, void *stream) {
   SRW_TRY(srw_require_device());
   ShardArgs a;
   SRW_TRY(fill_args(g, params, round_first, n_rounds, &a));
-  const int64_t total = (g->row_last - g->row_first) * n_rounds;
+  const int64_t total = ((g->nv - g->shard_rank + g->shard_world - 1) / g->shard_world) * n_rounds;
   if (total > cap) { srw_set_error("srw_shard_seed: inbox capacity %lld < %lld walkers", (long long)cap, (long long)total); return SRW_ERR_ARG; }
   a.paths = d_paths; a.lens = d_lens;
   if (total > 0) shard_seed_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(a, (WalkerMsg *)d_inbox);

@@ -88,7 +88,16 @@ class Shard:
 
     @property
     def rows(self):
+        """vertices whose adjacency rows this shard owns"""
         return self.row_last - self.row_first
+
+    @property
+    def home_rows(self):
+        """path rows per round stored here: vertices v with v mod world == rank (round-robin homes)"""
+        return (self.nv - self.rank + self.world - 1) // self.world
+
+    def home_vertices(self):
+        return range(self.rank, self.nv, self.world)
 
 
 class LocalExchange:
@@ -97,7 +106,12 @@ class LocalExchange:
     def __init__(self, world):
         self.world = world
 
-    def exchange(self, sends, counts, item_bytes):
+    def plan(self, counts):
+        """counts[r] = what local rank r sends to every destination (any number of count kinds,
+        concatenated).  Returns the full [world][len] matrix every rank would see."""
+        return [list(c) for c in counts]
+
+    def exchange(self, sends, counts, item_bytes, all_counts=None, outs=None):
         """sends[r]: uint8 tensor of rank r's send buffer (segments in destination order);
         counts[r][d]: items rank r sends to d.  Returns (recv tensors, recv totals) per rank."""
         out, tot = [], []
@@ -106,109 +120,135 @@ class LocalExchange:
             for r in range(self.world):
                 first = sum(counts[r][:d]) * item_bytes
                 parts.append(sends[r][first:first + counts[r][d] * item_bytes])
-            out.append(torch.cat(parts) if parts else sends[d][:0])
-            tot.append(sum(counts[r][d] for r in range(self.world)))
+            n = sum(counts[r][d] for r in range(self.world))
+            cat = torch.cat(parts) if parts else sends[d][:0]
+            if outs is not None:
+                # sends[d] may alias nothing in outs[d]; copy after the concatenation is materialised
+                outs[d][:n * item_bytes].copy_(cat)
+                cat = outs[d]
+            out.append(cat)
+            tot.append(n)
         return out, tot
-
-    def total(self, values):
-        return sum(values)
 
 
 class DistExchange:
-    """One shard per process: all-to-all of the counts, then of the payload (NCCL over NVLink on
-    GPUs; the same calls run over gloo in the CPU tests)."""
+    """One shard per process: ONE all-gather of every rank's count vector per super-step (gives the
+    receive counts and the global termination test), then all-to-all of the payloads (NCCL over
+    NVLink on GPUs; the same calls run over gloo in the CPU tests)."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, device=None):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
         self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self._dev = device if device is not None else torch.device("cpu")
 
-    def exchange(self, sends, counts, item_bytes):
+    def plan(self, counts):
+        mine = torch.tensor(counts[0], dtype=torch.int64, device=self._dev)
+        flat = torch.empty(self.world * mine.numel(), dtype=torch.int64, device=self._dev)
+        self.dist.all_gather_into_tensor(flat, mine, group=self.group)
+        return flat.view(self.world, mine.numel()).tolist()
+
+    def exchange(self, sends, counts, item_bytes, all_counts=None, outs=None):
         dist = self.dist
         send, cnt = sends[0], counts[0]
-        dev = send.device
-        c_out = torch.tensor(cnt, dtype=torch.int64, device=dev)
-        c_in = torch.empty_like(c_out)
-        dist.all_to_all_single(c_in, c_out, group=self.group)
-        c_in_l = [int(v) for v in c_in.tolist()]
-        recv = torch.empty(sum(c_in_l) * item_bytes, dtype=torch.uint8, device=dev)
-        dist.all_to_all_single(recv, send[:sum(cnt) * item_bytes], output_split_sizes=[c * item_bytes for c in c_in_l],
+        if all_counts is None:
+            all_counts = self.plan([cnt])
+        c_in = [int(all_counts[r][self.rank]) for r in range(self.world)]
+        n_in = sum(c_in)
+        recv = outs[0][:n_in * item_bytes] if outs is not None else torch.empty(n_in * item_bytes, dtype=torch.uint8, device=send.device)
+        dist.all_to_all_single(recv, send[:sum(cnt) * item_bytes], output_split_sizes=[c * item_bytes for c in c_in],
                                input_split_sizes=[c * item_bytes for c in cnt], group=self.group)
-        return [recv], [sum(c_in_l)]
+        return [recv], [n_in]
 
-    def total(self, values):
-        t = torch.tensor([sum(values)], dtype=torch.int64, device=self._dev)
-        self.dist.all_reduce(t, group=self.group)
-        return int(t.item())
 
-    _dev = torch.device("cpu")
+class ShardedWalker:
+    """Owns the device buffers of the local shard(s) and runs batches of rounds (RW:82 `for (_ <- 0 until
+    numWalks)`; rounds are independent under the counter RNG, so a batch walks them concurrently)."""
+
+    def __init__(self, shards, params, n_rounds=1, exchange=None, rec_cap=1 << 22, inbox_cap=None, stream=None):
+        self.L = _bind()
+        self.shards = shards
+        self.params = params
+        self.n_rounds = n_rounds
+        self.world = shards[0].world
+        if exchange is None:
+            exchange = LocalExchange(self.world) if len(shards) == self.world else DistExchange()
+        if isinstance(exchange, DistExchange) and shards[0].device.type == "cuda":
+            exchange._dev = shards[0].device
+        self.exchange = exchange
+        self.cp = params.to_c()
+        self.stride = params.walkLength + 2
+        self.st = 0 if stream is None else stream
+        self.rec_cap = rec_cap
+        n_total = shards[0].nv * n_rounds
+        self.state = []
+        for s in shards:
+            n_home = s.home_rows * n_rounds
+            cap = inbox_cap or n_total
+            self.state.append({
+                "paths": torch.empty((max(n_home, 1), self.stride), dtype=torch.int32, device=s.device),
+                "lens": torch.zeros(max(n_home, 1), dtype=torch.int32, device=s.device),
+                "inbox": torch.empty(max(cap, 1) * MSG_BYTES, dtype=torch.uint8, device=s.device),
+                "send_msgs": torch.empty(max(cap, 1) * MSG_BYTES, dtype=torch.uint8, device=s.device),
+                "send_recs": torch.empty(rec_cap * REC_BYTES, dtype=torch.uint8, device=s.device),
+                "n_in": 0, "cap": cap, "n_home": n_home,
+            })
+
+    def run(self, round_first=0):
+        """Walks rounds [round_first, round_first + n_rounds).  Returns per local shard
+        (paths [home_rows * n_rounds, walkLength + 2] int32 vertex ids, lens int32) and a stats dict
+        (super-steps, tuples and records this process sent, sampled transitions it decided)."""
+        L, cp, st, world, n_rounds = self.L, self.cp, self.st, self.world, self.n_rounds
+        for s, d in zip(self.shards, self.state):
+            n = C.c_int64()
+            check(L.srw_shard_seed(s.h, C.byref(cp), round_first, n_rounds, d["inbox"].data_ptr(), d["cap"], C.byref(n),
+                                   d["paths"].data_ptr(), d["lens"].data_ptr(), st))
+            d["n_in"] = n.value
+        stats = {"super_steps": 0, "tuples_sent": 0, "records_sent": 0, "steps": 0}
+        while True:
+            msg_counts, rec_counts = [], []
+            for s, d in zip(self.shards, self.state):
+                mc, rc = (C.c_int64 * world)(), (C.c_int64 * world)()
+                steps = C.c_int64()
+                check(L.srw_shard_step(s.h, C.byref(cp), round_first, n_rounds, d["inbox"].data_ptr(), d["n_in"],
+                                       d["send_msgs"].data_ptr(), d["send_recs"].data_ptr(), self.rec_cap, d["paths"].data_ptr(),
+                                       d["lens"].data_ptr(), mc, rc, C.byref(steps), st))
+                msg_counts.append(list(mc))
+                rec_counts.append(list(rc))
+                stats["steps"] += steps.value
+            stats["super_steps"] += 1
+            stats["tuples_sent"] += sum(sum(c) for c in msg_counts)
+            stats["records_sent"] += sum(sum(c) for c in rec_counts)
+            # every rank learns every rank's counts: receive sizes + RW:162 `remainingWalkers != 0`
+            allc = self.exchange.plan([m + r for m, r in zip(msg_counts, rec_counts)])
+            if sum(sum(row[:world]) for row in allc) == 0:
+                break
+            all_m = [row[:world] for row in allc]
+            all_r = [row[world:] for row in allc]
+            recv_r, tot_r = self.exchange.exchange([d["send_recs"] for d in self.state], rec_counts, REC_BYTES, all_r)
+            need = [sum(all_m[r][s.rank] for r in range(world)) for s in self.shards] if len(allc) == world else None
+            for s, d, nm in zip(self.shards, self.state, need):
+                if nm > d["cap"]:
+                    raise RuntimeError("shard %d inbox overflow: %d tuples > capacity %d" % (s.rank, nm, d["cap"]))
+            # the step kernel has consumed the inbox: receive the next tuples straight into it
+            recv_m, tot_m = self.exchange.exchange([d["send_msgs"] for d in self.state], msg_counts, MSG_BYTES, all_m,
+                                                   outs=[d["inbox"] for d in self.state])
+            for s, d, nm, rr, nr in zip(self.shards, self.state, tot_m, recv_r, tot_r):
+                if nr:
+                    rr = rr.contiguous()
+                    check(L.srw_shard_apply(s.h, C.byref(cp), round_first, n_rounds, rr.data_ptr(), nr, d["paths"].data_ptr(), st))
+                d["n_in"] = nm
+            torch.cuda.synchronize()
+        out = []
+        for s, d in zip(self.shards, self.state):
+            steps = C.c_int64()
+            check(L.srw_shard_finalize(s.h, C.byref(cp), d["n_home"], d["paths"].data_ptr(), d["lens"].data_ptr(), C.byref(steps), st))
+            out.append((d["paths"][:d["n_home"]], d["lens"][:d["n_home"]]))
+        return out, stats
 
 
 def run_sharded(shards, params, round_first=0, n_rounds=1, exchange=None, rec_cap=1 << 22, stream=None, inbox_cap=None):
-    """Walks rounds [round_first, round_first + n_rounds) over `shards` (all W shards of the graph in
-    this process with LocalExchange, or this process's single shard with DistExchange).
-
-    Returns per local shard: (paths [rows * n_rounds, walkLength + 2] int32 vertex ids, lens int32),
-    plus a stats dict (super-steps, tuples and records exchanged, sampled transitions)."""
-    L = _bind()
-    world = shards[0].world
-    if exchange is None:
-        exchange = LocalExchange(world) if len(shards) == world else DistExchange()
-    if isinstance(exchange, DistExchange):
-        exchange._dev = shards[0].device
-    cp = params.to_c()
-    stride = params.walkLength + 2
-    st = 0 if stream is None else stream
-    n_total = shards[0].nv * n_rounds
-    state = []
-    for s in shards:
-        n_home = s.rows * n_rounds
-        cap = inbox_cap or n_total
-        state.append({
-            "paths": torch.empty((max(n_home, 1), stride), dtype=torch.int32, device=s.device),
-            "lens": torch.zeros(max(n_home, 1), dtype=torch.int32, device=s.device),
-            "inbox": torch.empty(max(cap, 1) * MSG_BYTES, dtype=torch.uint8, device=s.device),
-            "send_msgs": torch.empty(max(cap, 1) * MSG_BYTES, dtype=torch.uint8, device=s.device),
-            "send_recs": torch.empty(rec_cap * REC_BYTES, dtype=torch.uint8, device=s.device),
-            "n_in": 0, "cap": cap, "n_home": n_home,
-        })
-        n = C.c_int64()
-        check(L.srw_shard_seed(s.h, C.byref(cp), round_first, n_rounds, state[-1]["inbox"].data_ptr(), cap, C.byref(n),
-                               state[-1]["paths"].data_ptr(), state[-1]["lens"].data_ptr(), st))
-        state[-1]["n_in"] = n.value
-    stats = {"super_steps": 0, "tuples_sent": 0, "records_sent": 0, "steps": 0}
-    while True:
-        msg_counts, rec_counts = [], []
-        for s, d in zip(shards, state):
-            mc, rc = (C.c_int64 * world)(), (C.c_int64 * world)()
-            steps = C.c_int64()
-            check(L.srw_shard_step(s.h, C.byref(cp), round_first, n_rounds, d["inbox"].data_ptr(), d["n_in"], d["send_msgs"].data_ptr(),
-                                   d["send_recs"].data_ptr(), rec_cap, d["paths"].data_ptr(), d["lens"].data_ptr(), mc, rc,
-                                   C.byref(steps), st))
-            msg_counts.append(list(mc))
-            rec_counts.append(list(rc))
-            stats["steps"] += steps.value
-        stats["super_steps"] += 1
-        sent = sum(sum(c) for c in msg_counts)
-        stats["tuples_sent"] += sent
-        stats["records_sent"] += sum(sum(c) for c in rec_counts)
-        if exchange.total([sent]) == 0:           # RW:162 remainingWalkers == 0
-            break
-        recv_m, tot_m = exchange.exchange([d["send_msgs"] for d in state], msg_counts, MSG_BYTES)
-        recv_r, tot_r = exchange.exchange([d["send_recs"] for d in state], rec_counts, REC_BYTES)
-        for s, d, rm, nm, rr, nr in zip(shards, state, recv_m, tot_m, recv_r, tot_r):
-            if nm > d["cap"]:
-                raise RuntimeError("shard %d inbox overflow: %d tuples > capacity %d" % (s.rank, nm, d["cap"]))
-            if nr:
-                rr = rr.contiguous()
-                check(L.srw_shard_apply(s.h, C.byref(cp), round_first, n_rounds, rr.data_ptr(), nr, d["paths"].data_ptr(), st))
-            d["inbox"][:nm * MSG_BYTES].copy_(rm[:nm * MSG_BYTES])
-            d["n_in"] = nm
-        torch.cuda.synchronize()
-    out = []
-    for s, d in zip(shards, state):
-        steps = C.c_int64()
-        check(L.srw_shard_finalize(s.h, C.byref(cp), d["n_home"], d["paths"].data_ptr(), d["lens"].data_ptr(), C.byref(steps), st))
-        out.append((d["paths"][:d["n_home"]], d["lens"][:d["n_home"]]))
-    return out, stats
+    """One-shot convenience wrapper around ShardedWalker."""
+    return ShardedWalker(shards, params, n_rounds, exchange, rec_cap, inbox_cap, stream).run(round_first)

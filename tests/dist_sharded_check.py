@@ -47,8 +47,12 @@ def exchange_only():
             seg = got[pos:pos + n]
             assert (seg[:, 0] == src).all() and (seg[:, 2] == np.arange(n)).all()
             pos += n
-        total = ex.total([sum(counts)])
-        assert total == sum(sum(c) for c in all_counts)
+        allc = ex.plan([counts])
+        assert allc == all_counts
+        # receiving straight into a preallocated buffer
+        buf = torch.zeros(64 * 32 * world, dtype=torch.uint8)
+        recv2, tot2 = ex.exchange([send], [counts], 32, allc, outs=[buf])
+        assert tot2 == tot and bytes(recv2[0].numpy()) == bytes(recv[0].numpy())
     # plan / owner helpers
     deg = rng.randint(0, 9, size=1000)
     pre = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
@@ -86,9 +90,9 @@ def full():
         want = oracle_lib.paths_as_lists(ids, offs)
         P, Ln = out[0][0].cpu().numpy(), out[0][1].cpu().numpy()
         for rnd in range(2):
-            for k in range(shard.rows):
-                row = rnd * shard.rows + k
-                if P[row, :Ln[row]].tolist() != want[rnd * twin.nv + shard.row_first + k]:
+            for k, v in enumerate(shard.home_vertices()):
+                row = rnd * shard.home_rows + k
+                if P[row, :Ln[row]].tolist() != want[rnd * twin.nv + v]:
                     ok = False
         t = torch.tensor([stats["steps"]], dtype=torch.int64, device="cuda")
         dist.all_reduce(t)

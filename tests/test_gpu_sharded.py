@@ -44,9 +44,9 @@ def test_sharded_equals_twin(oracle, world, weighted, directed, p, q):
     for x, (paths, lens) in zip(shards, out):
         P, Ln = paths.cpu().numpy(), lens.cpu().numpy()
         for rnd in range(3):
-            for k in range(x.rows):
-                row = rnd * x.rows + k
-                got[rnd * nv + x.row_first + k] = P[row, :Ln[row]].tolist()
+            for k, v in enumerate(x.home_vertices()):
+                row = rnd * x.home_rows + k
+                got[rnd * nv + v] = P[row, :Ln[row]].tolist()
     assert got == want
     assert stats["steps"] == st.steps
     if world > 1:
@@ -69,6 +69,6 @@ def test_sharded_matches_single_gpu_kernel():
     for x, (paths, lens) in zip(shards, out):
         P = paths.cpu().numpy()
         for rnd in range(2):
-            rows[rnd * nv + x.row_first: rnd * nv + x.row_last] = P[rnd * x.rows:(rnd + 1) * x.rows]
+            rows[rnd * nv + x.rank: (rnd + 1) * nv: x.world] = P[rnd * x.home_rows:(rnd + 1) * x.home_rows]
     assert (np.diff(ref_offs) == 42).all()
     assert (rows.reshape(-1) == ref_ids).all()
