@@ -458,10 +458,9 @@ def run_b200_sharded(a):
     log("sharded: rank 0 owns ranks [%d, %d) of %d, %d entries, built in %.2f s" % (shard.row_first, shard.row_last, shard.nv, shard.nnz_local, build_s))
     prm = srw.Params(walkLength=a.walk_length, numWalks=1, p=a.p, q=a.q, seed=a.seed, sampler="alias")
     ex = sh.DistExchange(device=dev)
-    # the busiest rank holds about 1/world of the walkers (edge-balanced ranges make the stationary
-    # walker distribution balanced), plus slack
-    n_total = shard.nv * max(a.steps, a.warmup, 1)
-    cap = min(n_total, int(2.5 * n_total / world) + (1 << 20))
+    # worst case every walker of the batch sits on one rank (after the first hop the owner of the
+    # low-degree vertex range briefly holds most of them): size the inbox for all of them
+    cap = shard.nv * max(a.steps, a.warmup, 1)
 
     def barrier():
         dist.barrier()

@@ -291,6 +291,14 @@ void og_load_edges(og_graph *g, int64_t n, const int32_t *src, const int32_t *ds
     if (pid) og_add_vertex_pid(g, vids[v], adst + off[v], apid + off[v], aw + off[v], deg[v]);
     else     og_add_vertex(g, vids[v], adst + off[v], aw + off[v], deg[v]);
   }
+  /* GM:31 `vertexPartitionMap.put(dst, pId)`: the surviving value depends on the order in which
+   * Spark hands vertices to addVertex (hash-partition order: unpinned).  This build pins it to FILE
+   * order: the partition id of the last input line in which the vertex is a neighbour. */
+  if (pid)
+    for (int64_t i = 0; i < n; ++i) {
+      imap_put(&g->vertex_partition_map, dst[i], pid[i]);
+      if (!directed) imap_put(&g->vertex_partition_map, src[i], pid[i]);
+    }
 #undef TMP_INDEX
   free(fill); free(aw); free(apid); free(adst); free(off); free(deg); free(vids);
   imap_destroy(&tmp);

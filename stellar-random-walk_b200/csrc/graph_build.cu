@@ -213,6 +213,45 @@ __global__ void k_alias_rows(int64_t nv, const int64_t *__restrict__ off, const 
   }
 }
 
+// ---- per-row neighbour hash sets + packed row descriptors ----
+__global__ void k_hash_sizes(int64_t rows, const int64_t *__restrict__ off, uint32_t *nb) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r <= rows; r += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t v = 0;
+    if (r < rows) {
+      const int64_t d = off[r + 1] - off[r];
+      if (d > (int64_t)kHashMinDeg) v = (uint32_t)((d + kHashLoadNum - 1) / kHashLoadNum);
+    }
+    nb[r] = v;
+  }
+}
+__global__ void k_row_meta(int64_t rows, const int64_t *__restrict__ off, const uint32_t *__restrict__ nb,
+                           const int64_t *__restrict__ hoff, RowMeta *meta) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    RowMeta m;
+    m.off = off[r]; m.hoff = hoff[r]; m.deg = (uint32_t)(off[r + 1] - off[r]); m.nb = nb[r]; m.pad0 = 0; m.pad1 = 0;
+    meta[r] = m;
+  }
+}
+// one thread per adjacency entry (row keys come from the sort that produced d_col)
+__global__ void k_hash_insert(int64_t nnz, const uint32_t *__restrict__ row_of, const int32_t *__restrict__ col,
+                              const RowMeta *__restrict__ meta, int32_t *hash) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+    const RowMeta m = meta[row_of[i]];
+    if (m.nb == 0) continue;
+    const int32_t x = col[i];
+    uint32_t b = __umulhi(srw_hash32((uint32_t)x), m.nb);
+    bool done = false;
+    while (!done) {
+      int32_t *bucket = hash + (m.hoff + b) * 8;
+      for (int s = 0; s < 8 && !done; ++s) {
+        const int32_t old = atomicCAS(bucket + s, -1, x);
+        if (old == -1 || old == x) done = true;       // inserted, or a parallel edge already did
+      }
+      b = b + 1 == m.nb ? 0 : b + 1;
+    }
+  }
+}
+
 struct CastU32ToI64 {
   __host__ __device__ int64_t operator()(uint32_t x) const { return (int64_t)x; }
 };
@@ -438,6 +477,31 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
   ent_row.alloc(0); ent_col.alloc(0);
   (void)ent_gidx;
 
+  // ---- packed row descriptors + neighbour hash sets (membership test of the alias sampler) ----
+  if (flags & SRW_BUILD_ALIAS) {
+    DevBuf nb, hoff;
+    SRW_CUDA(nb.alloc((size_t)(nrows + 1) * 4));
+    SRW_CUDA(hoff.alloc((size_t)(nrows + 1) * 8));
+    k_hash_sizes<<<grid(nrows + 1), kThreads>>>(nrows, g->d_off, nb.as<uint32_t>());
+    {
+      cub::TransformInputIterator<int64_t, CastU32ToI64, uint32_t *> it(nb.as<uint32_t>(), CastU32ToI64());
+      size_t tb = 0;
+      DevBuf tmp;
+      SRW_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, it, hoff.as<int64_t>(), nrows + 1));
+      SRW_CUDA(tmp.alloc(tb));
+      SRW_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, it, hoff.as<int64_t>(), nrows + 1));
+    }
+    SRW_CUDA(cudaMemcpy(&g->hash_buckets, hoff.as<int64_t>() + nrows, 8, cudaMemcpyDeviceToHost));
+    SRW_CUDA(cudaMalloc(&g->d_meta, (size_t)(nrows ? nrows : 1) * sizeof(RowMeta)));
+    k_row_meta<<<grid(nrows), kThreads>>>(nrows, g->d_off, nb.as<uint32_t>(), hoff.as<int64_t>(), g->d_meta);
+    if (g->hash_buckets > 0) {
+      SRW_CUDA(cudaMalloc(&g->d_hash, (size_t)g->hash_buckets * 32));
+      SRW_CUDA(cudaMemset(g->d_hash, 0xFF, (size_t)g->hash_buckets * 32));
+      k_hash_insert<<<grid(nnz), kThreads>>>(nnz, k_in, g->d_col, g->d_meta, g->d_hash);   // k_in = row keys in d_col order
+    }
+    SRW_CUDA(cudaDeviceSynchronize());
+  }
+
   // ---- K3: Vose slots over the sorted rows (weighted graphs only) ----
   if ((flags & SRW_BUILD_ALIAS) && d_w) {
     DevBuf flag;
@@ -458,7 +522,7 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
   }
   SRW_CUDA(cudaGetLastError());
   g->device_bytes = (int64_t)(words * 8 + (size_t)nv * 12 + (size_t)nnz * 4) + (g->d_col_app ? nnz * 8 : 0) +
-                    (g->d_slot ? nnz * 16 : 0) + (g->d_vpid ? nv * 4 : 0);
+                    (g->d_slot ? nnz * 16 : 0) + (g->d_vpid ? nv * 4 : 0) + (g->d_meta ? nrows * 32 : 0) + g->hash_buckets * 32;
   return SRW_OK;
 }
 

@@ -41,6 +41,23 @@ struct __align__(16) AliasSlot {
   uint32_t alias_index;   // row-relative index of the alias slot
 };
 
+// Row descriptor read once per walk step.  Rows with more than kHashMinDeg neighbours also own a hash
+// set of their neighbour ids (`nb` buckets of 8 slots starting at bucket `hoff`): the d(t,x)=1
+// membership test of node2vec becomes ~1 sector instead of a ~log2(deg) binary search.
+struct __align__(32) RowMeta {
+  int64_t off;     // first entry in d_col / d_slot
+  int64_t hoff;    // first bucket in d_hash
+  uint32_t deg;
+  uint32_t nb;     // 0: no hash set (short row: binary search in d_col)
+  uint32_t pad0, pad1;
+};
+constexpr uint32_t kHashMinDeg = 16;
+constexpr uint32_t kHashLoadNum = 6;   // <= 6 of 8 slots used on average
+__host__ __device__ inline uint32_t srw_hash32(uint32_t x) {
+  x *= 0x9E3779B1u; x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 12;
+  return x;
+}
+
 struct srw_graph {
   int device = 0;
   int64_t nv = 0, nnz = 0;
@@ -57,6 +74,9 @@ struct srw_graph {
   int32_t *d_col = nullptr;       // [nnz] neighbour ranks, ascending per row (membership + unweighted proposals)
   AliasSlot *d_slot = nullptr;    // [nnz] iff has_alias                              (SRW_BUILD_ALIAS)
   int32_t *d_vpid = nullptr;      // [nv] GM:21 vertexPartitionMap (-1 = absent)
+  struct RowMeta *d_meta = nullptr;  // [rows] packed row descriptor: one 32-byte load per step   (SRW_BUILD_ALIAS)
+  int32_t *d_hash = nullptr;         // per-row neighbour hash sets, 8-slot (32-byte) buckets, -1 = empty
+  int64_t hash_buckets = 0;
   int64_t device_bytes = 0;
   mutable std::vector<int32_t> h_vids;  // lazy host copies for the query entry points
   mutable std::vector<int64_t> h_off;

@@ -232,6 +232,105 @@ __global__ void __launch_bounds__(256) walk_alias_sm_kernel(WalkArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// K6 (v3): v2's state machine over packed row descriptors and per-row neighbour hash sets.
+// ncu on v2 (RMAT-24): 865 B of DRAM traffic per step, about half of it the ~10-probe binary search
+// for "is x a neighbour of prev" (RS:38).  Here that test is one 32-byte bucket probe (rows longer
+// than kHashMinDeg), and the row extent is one aligned 32-byte RowMeta load.  Same decisions, same bits.
+// ------------------------------------------------------------------------------------------
+enum : int { ST_HASH = 4 };
+
+template <bool HAS_ALIAS, bool STATS>
+__global__ void __launch_bounds__(256) walk_alias_hash_kernel(WalkArgs a, const RowMeta *__restrict__ meta,
+                                                              const int32_t *__restrict__ hash) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= a.n_walkers) return;
+  const uint64_t walker = a.walker_first + (uint64_t)i;
+  int32_t curr = (int32_t)(walker % (uint64_t)a.nv), prev = -1;
+  int32_t *path = a.paths + i * a.stride;
+  path[0] = curr;
+  int32_t len = 1;
+  int64_t off = 0, hoff = 0, poff = 0, phoff = 0;
+  uint32_t deg = 0, nb = 0, pdeg = 0, pnb = 0, trial = 0, lo = 0, hi = 0, y = 0, coin = 0, bkt = 0;
+  int32_t x = 0;
+  uint64_t k = 0;
+  int state = ST_EXTENT;
+  unsigned long long n_prop = 0, n_mem = 0, n_log = 0;
+  const uint64_t t_lo = a.t_common < a.t_far ? a.t_common : a.t_far;
+  const uint64_t t_hi = a.t_common < a.t_far ? a.t_far : a.t_common;
+
+  while (state != ST_DONE) {
+    // ---- one memory access per lane ----
+    int4 q0 = make_int4(0, 0, 0, 0), q1 = make_int4(0, 0, 0, 0);
+    int32_t v = 0;
+    if (state == ST_EXTENT) {
+      const int4 *m = reinterpret_cast<const int4 *>(meta + curr);
+      q0 = __ldg(m); q1 = __ldg(m + 1);
+    } else if (state == ST_PROPOSE) {
+      if (HAS_ALIAS) q0 = __ldg(reinterpret_cast<const int4 *>(a.slot + off + (int64_t)k));
+      else v = __ldg(a.col + off + (int64_t)k);
+    } else if (state == ST_HASH) {
+      const int4 *b = reinterpret_cast<const int4 *>(hash + (phoff + (int64_t)bkt) * 8);
+      q0 = __ldg(b); q1 = __ldg(b + 1);
+    } else {
+      v = __ldg(a.col + poff + (int64_t)((lo + hi) >> 1));
+    }
+    // ---- consume it ----
+    int verdict = 0;           // 1 = accept x, 2 = reject (next trial)
+    if (state == ST_EXTENT) {
+      off = ((int64_t)(uint32_t)q0.x) | ((int64_t)q0.y << 32);
+      hoff = ((int64_t)(uint32_t)q0.z) | ((int64_t)q0.w << 32);
+      deg = (uint32_t)q1.x; nb = (uint32_t)q1.y;
+      if (deg == 0) { state = ST_DONE; continue; }              // dead end (RW:59-62, RW:115-119)
+      trial = 0;
+      verdict = 2;
+    } else if (state == ST_PROPOSE) {
+      if (HAS_ALIAS) x = (coin < (uint32_t)q0.x) ? q0.y : q0.z; else x = v;
+      if (STATS && len > 1) n_prop++;
+      if (len == 1 || deg == 1) verdict = 1;                   // first-order step (RW:57) / single choice
+      else if (x == prev) verdict = ((uint64_t)y < a.t_ret) ? 1 : 2;    // RS:36  w/p
+      else if ((uint64_t)y < t_lo) verdict = 1;
+      else if ((uint64_t)y >= t_hi) verdict = 2;
+      else {
+        if (STATS) { n_mem++; n_log += ceil_log2_p1(pdeg); }
+        if (pnb) { bkt = __umulhi(srw_hash32((uint32_t)x), pnb); state = ST_HASH; }
+        else { lo = 0; hi = pdeg; state = ST_SEARCH; }
+      }
+    } else if (state == ST_HASH) {
+      const bool found = q0.x == x || q0.y == x || q0.z == x || q0.w == x || q1.x == x || q1.y == x || q1.z == x || q1.w == x;
+      if (found) verdict = ((uint64_t)y < a.t_common) ? 1 : 2;           // RS:38  x in N(prev): w
+      else if (q1.w == -1) verdict = ((uint64_t)y < a.t_far) ? 1 : 2;    // bucket not full: x is absent (RS:34 w/q)
+      else bkt = bkt + 1 == pnb ? 0 : bkt + 1;                           // full bucket: linear probing
+    } else {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (v == x) verdict = ((uint64_t)y < a.t_common) ? 1 : 2;
+      else {
+        if (v < x) lo = mid + 1; else hi = mid;
+        if (lo >= hi) verdict = ((uint64_t)y < a.t_far) ? 1 : 2;
+      }
+    }
+    if (verdict == 1) {
+      path[len++] = x;                                         // RW:114
+      prev = curr; poff = off; pdeg = deg; phoff = hoff; pnb = nb;
+      curr = x;
+      state = (len == a.stride) ? ST_DONE : ST_EXTENT;         // RW:103
+    } else if (verdict == 2) {
+      const Philox4 r = walker_rng(a.seed_lo, a.seed_hi, walker, (uint32_t)(len - 1), trial);
+      trial++;
+      k = __umul64hi(((uint64_t)r.x << 32) | (uint64_t)r.w, (uint64_t)deg);
+      coin = r.y;
+      y = r.z;
+      state = ST_PROPOSE;
+    }
+  }
+  a.lens[i] = len;
+  if (STATS) {
+    atomicAdd(a.stats + 1, n_prop);
+    atomicAdd(a.stats + 2, n_mem);
+    atomicAdd(a.stats + 3, n_log);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // K5: exact sampler (also used by the KAT entry points)
 // ------------------------------------------------------------------------------------------
 // RS:12-25 over weights produced by `wf(i)`: two passes, float64 accumulation, left to right.
@@ -390,8 +489,14 @@ srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLa
   } else {
     const unsigned grid = (unsigned)((l.n_walkers + 255) / 256);
     const bool st = t_collect_stats != 0;
-    static const bool use_v1 = getenv("SRW_KERNEL") && !strcmp(getenv("SRW_KERNEL"), "v1");   // A/B switch
-    if (!use_v1) {
+    static const bool use_v1 = getenv("SRW_KERNEL") && !strcmp(getenv("SRW_KERNEL"), "v1");   // A/B switches
+    static const bool use_v2 = getenv("SRW_KERNEL") && !strcmp(getenv("SRW_KERNEL"), "v2");
+    if (!use_v1 && !use_v2 && g->d_meta) {
+      const RowMeta *mt = g->d_meta;
+      const int32_t *hs = g->d_hash;
+      if (g->has_alias) { if (st) walk_alias_hash_kernel<true, true><<<grid, 256, 0, l.stream>>>(a, mt, hs); else walk_alias_hash_kernel<true, false><<<grid, 256, 0, l.stream>>>(a, mt, hs); }
+      else              { if (st) walk_alias_hash_kernel<false, true><<<grid, 256, 0, l.stream>>>(a, mt, hs); else walk_alias_hash_kernel<false, false><<<grid, 256, 0, l.stream>>>(a, mt, hs); }
+    } else if (!use_v1) {
       if (g->has_alias) { if (st) walk_alias_sm_kernel<true, true><<<grid, 256, 0, l.stream>>>(a); else walk_alias_sm_kernel<true, false><<<grid, 256, 0, l.stream>>>(a); }
       else              { if (st) walk_alias_sm_kernel<false, true><<<grid, 256, 0, l.stream>>>(a); else walk_alias_sm_kernel<false, false><<<grid, 256, 0, l.stream>>>(a); }
     } else if (g->has_alias) { if (st) walk_alias_kernel<true, true><<<grid, 256, 0, l.stream>>>(a); else walk_alias_kernel<true, false><<<grid, 256, 0, l.stream>>>(a); }

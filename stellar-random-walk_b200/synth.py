@@ -67,6 +67,32 @@ def edge_weights(n_edges, seed=43, first=0):
     return (np.float32(1.0) + (r0 % np.uint64(1000)).astype(np.float32) / np.float32(1000.0)).astype(np.float32)
 
 
+ZIPF_TAG = 0x5A495046
+ZIPF_DST_TAG = 0x5A445354
+
+
+def zipf_stub_counts(n_vertices, cap=1000000, seed=7):
+    """Out-stub count per vertex: min(cap, floor(1 / (1 - U))), U = r / 2^32 -> integer 2^32 // (2^32 - r)
+    (P(count >= k) = 1/k: Zipf exponent 2 on the pmf; config C5)."""
+    v = np.arange(n_vertices, dtype=np.uint64)
+    r, _, _, _ = philox4x32_10(v & _MASK, v >> np.uint64(32), np.zeros(n_vertices, np.uint64),
+                               np.full(n_vertices, ZIPF_TAG, np.uint64), seed, 0)
+    cnt = np.uint64(1 << 32) // (np.uint64(1 << 32) - r)
+    return np.minimum(cnt, np.uint64(cap)).astype(np.int64)
+
+
+def zipf_edges(n_vertices, cap=1000000, seed=7):
+    """Edge e of vertex v's stub block: (v, uniform target) -- self-loops and duplicates kept."""
+    cnt = zipf_stub_counts(n_vertices, cap, seed)
+    n_edges = int(cnt.sum())
+    src = np.repeat(np.arange(n_vertices, dtype=np.int32), cnt)
+    e = np.arange(n_edges, dtype=np.uint64)
+    r, _, _, _ = philox4x32_10(e & _MASK, e >> np.uint64(32), np.zeros(n_edges, np.uint64),
+                               np.full(n_edges, ZIPF_DST_TAG, np.uint64), seed, 0)
+    dst = ((r * np.uint64(n_vertices)) >> np.uint64(32)).astype(np.int32)
+    return src, dst
+
+
 def edges_to_text(src, dst, w=None, pid=None):
     cols = [src, dst]
     if pid is not None:

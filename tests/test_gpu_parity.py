@@ -267,3 +267,85 @@ def test_full_size_properties():
     assert bool((paths2 == paths).all())
     wi = srw.last_walk_info()
     assert wi.steps == (nv - half) * (L + 1) and wi.kernel_ms > 0
+
+
+# ---- BASELINE config C5 shape at test scale: Zipf hub graph, p=0.25 q=4 (membership stress) ----
+@pytest.mark.parametrize("sampler", ["alias", "exact"])
+def test_c5_zipf_hub_graph(oracle, sampler):
+    s, d = synth.zipf_edges(2048, cap=1500, seed=7)
+    assert np.bincount(s).max() == 1500                      # a hub with the capped stub count exists
+    og = oracle.Graph().load_edges(s, d)
+    g = srw.Graph.from_edges(s, d)
+    kw = dict(walk_length=12 if sampler == "exact" else 40, num_walks=1 if sampler == "exact" else 3, p=0.25, q=4.0, seed=31)
+    prm = srw.Params(walkLength=kw["walk_length"], numWalks=kw["num_walks"], p=0.25, q=4.0, seed=31, sampler=sampler)
+    got_ids, got_offs = g.walk(prm).arrays()
+    if sampler == "exact":
+        ids, offs = oracle.walk(og, **kw)
+    else:
+        ids, offs, _ = oracle.AliasGraph(og).walk(**kw)
+    assert (got_offs == offs).all() and (got_ids == ids).all()
+
+
+# ---- BASELINE config C3 shape at test scale: weighted RMAT, p=0.5 q=2 (alias build + biased step) ----
+def test_c3_weighted_rmat_layout_and_walk(oracle):
+    s, d = synth.rmat_edges(13, 16, seed=42)
+    w = synth.edge_weights(len(s), seed=43)
+    og = oracle.Graph().load_edges(s, d, w)
+    twin = oracle.AliasGraph(og)
+    g = srw.Graph.from_edges(s, d, w, flags=srw.BUILD_ALIAS)
+    tv, lay = twin.view(), g.layout()
+    assert (lay["offsets"] == tv["offsets"]).all() and (lay["col"] == tv["col"]).all()
+    assert (lay["thr"] == tv["thr"]).all() and (lay["alias"] == tv["alias"]).all()
+    ids, offs, st = twin.walk(walk_length=80, num_walks=1, p=0.5, q=2.0, seed=1)
+    got_ids, got_offs = g.walk(srw.Params(walkLength=80, numWalks=1, p=0.5, q=2.0, seed=1)).arrays()
+    assert (got_offs == offs).all() and (got_ids == ids).all()
+
+
+# ---- every alias kernel generation produces the same bits (A/B switch SRW_KERNEL) ----
+def test_kernel_generations_agree(tmp_path):
+    import subprocess, sys, json
+    script = tmp_path / "run.py"
+    script.write_text('''
+import importlib, sys, hashlib
+sys.path.insert(0, %r)
+srw = importlib.import_module("stellar-random-walk_b200")
+synth = importlib.import_module("stellar-random-walk_b200.synth")
+s, d = synth.rmat_edges(12, 16, seed=3)
+out = []
+for w in (None, synth.edge_weights(len(s), seed=4)):
+    g = srw.Graph.from_edges(s, d, w)
+    ids, offs = g.walk(srw.Params(walkLength=60, numWalks=2, p=0.5, q=2.0, seed=9)).arrays()
+    out.append(hashlib.sha256(ids.tobytes() + offs.tobytes()).hexdigest())
+print(",".join(out))
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    res = {}
+    for k in ("v1", "v2", "v3"):
+        env = dict(os.environ, SRW_KERNEL=k)
+        r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[k] = r.stdout.strip().splitlines()[-1]
+    assert res["v1"] == res["v2"] == res["v3"], res
+
+
+# ---- VCut input format through the native Main (--partitioned true, 3rd column = partition id) ----
+def test_vcut_cli_partitioned_input(oracle, tmp_path):
+    rows = [ln.split() for ln in open(KARATE).read().split("\n") if ln]
+    txt = "".join("%s %s %d %.2f\n" % (a, b, i % 4, 1.0 + (i % 7) / 4.0) for i, (a, b) in enumerate(rows))
+    inp = tmp_path / "karate_vcut.txt"
+    inp.write_text(txt)
+    out = str(tmp_path / "o")
+    rc = srw.Main.main(["--cmd", "randomwalk", "--input", str(inp), "--output", out, "--partitioned", "true", "--numWalks", "2",
+                        "--walkLength", "15", "--p", "0.5", "--q", "2.0", "--seed", "8", "--singleOutput", "false", "--rddPartitions", "4"])
+    assert rc == 0
+    files = sorted(f for f in os.listdir(os.path.join(out, "path")) if f.startswith("part-"))
+    assert files == ["part-0000%d" % k for k in range(4)]
+    lines = []
+    for f in files:
+        lines += open(os.path.join(out, "path", f)).read().split("\n")[:-1]
+    og = oracle.Graph().load_text(txt, weighted=True, partitioned=True)
+    ids, offs, _ = oracle.AliasGraph(og).walk(walk_length=15, num_walks=2, p=0.5, q=2.0, seed=8)
+    assert sorted(lines) == sorted(oracle.format_paths(ids, offs).decode().split("\n")[:-1])
+    # GraphMap.getPartition analogue
+    rw = srw.VCutRandomWalk(srw.Params(input=str(inp), partitioned=True))
+    rw.loadGraph()
+    assert rw.graph.partition(2) == og.partition(2) and rw.graph.partition(12345) is None
