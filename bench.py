@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--q", type=float, default=2.0)
     ap.add_argument("--weighted", type=int, default=0)
     ap.add_argument("--mode", default="auto", choices=["auto", "sharded", "replicated"])
+    ap.add_argument("--sampler", default="fold", choices=["fold", "alias"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
@@ -276,7 +277,7 @@ def run_b200(a):
     n_local = hi - lo
     paths = torch.empty((n_local, stride), dtype=torch.int32, device=dev)
     lens = torch.empty(n_local, dtype=torch.int32, device=dev)
-    prm = srw.Params(walkLength=a.walk_length, numWalks=1, p=a.p, q=a.q, seed=a.seed, sampler="alias")
+    prm = srw.Params(walkLength=a.walk_length, numWalks=1, p=a.p, q=a.q, seed=a.seed, sampler=a.sampler)
     cp = prm.to_c()
 
     def one_round(r):
@@ -346,7 +347,7 @@ def run_b200(a):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "walk_alias_kernel", "kernel_ms_per_launch": kernel_ms / max(1, a.steps), "peak_source": peak_src,
+                "kernel": "walk_fold_kernel" if (a.sampler == "fold" and not a.weighted) else "walk_alias_hash_kernel", "kernel_ms_per_launch": kernel_ms / max(1, a.steps), "peak_source": peak_src,
                 "bytes_per_step": B, "bytes_per_step_survey_formula": B_survey, "proposals_per_step": T_bar,
                 "member_tests_per_step": st.member_tests / max(1, st.steps), "mean_probes_per_test": L_bar,
                 "kernel_share_of_step": kernel_ms / elapsed_ms}
@@ -419,7 +420,7 @@ def run_b200(a):
                            "graph_bytes_hbm": int(lib.srw_graph_device_bytes(g.h)), "build_s": round(build_s, 3),
                            "l2": "inputs larger than L2 (CSR %.1f GB >> 126 MB), no flush needed" % (nnz * 4 / 1e9),
                            "parallelism": "1 GPU" if world == 1 else "replicated graph, walkers split %d ways" % world,
-                           "sampler": "alias"},
+                           "sampler": "alias-fold (SRW_SAMPLER_ALIAS_FOLD; classic alias rejection when the graph is weighted/directed)" if a.sampler == "fold" else "alias"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk}
         print(json.dumps(line))
     if world > 1:

@@ -41,7 +41,11 @@ typedef enum srw_status {
 enum { SRW_TASK_NODE2VEC = 0, SRW_TASK_RANDOMWALK = 1, SRW_TASK_EMBEDDING = 2 };
 /* sampler: ALIAS = Vose proposal + p/q rejection (throughput path); EXACT = RS:12-62 literal
  * float32/float64 inverse-CDF (bit-parity path) */
-enum { SRW_SAMPLER_ALIAS = 0, SRW_SAMPLER_EXACT = 1 };
+enum { SRW_SAMPLER_ALIAS = 0, SRW_SAMPLER_EXACT = 1,
+       /* ALIAS with the return edge folded out of the rejection envelope (undirected, unweighted graphs
+        * with 1/p > max(1, 1/q); anything else runs as ALIAS).  Same distribution, about half the
+        * proposals per step; bit-identical to its own CPU twin (oracle cfg.fold = 1). */
+       SRW_SAMPLER_ALIAS_FOLD = 2 };
 /* where a draw comes from: Philox4x32-10 keyed by (seed; walker, step, trial), or the constant
  * generator the reference's tests inject (`nextFloat = () => rValue`, RS:5, T-URW:183-185) */
 enum { SRW_U_PHILOX = 0, SRW_U_CONST = 1 };
@@ -69,7 +73,7 @@ typedef struct srw_params {
   int32_t cmd;             /* cmd = node2vec */
   /* ---- additive ---- */
   uint64_t seed;           /* --seed (default 1): the reference has no seed at all */
-  int32_t sampler;         /* --sampler alias|exact (default alias) */
+  int32_t sampler;         /* --sampler alias|fold|exact (default alias) */
   int32_t u_mode;          /* SRW_U_PHILOX; SRW_U_CONST for the reference's constant-u tests */
   float u_const;
   int32_t num_gpus;        /* --gpus (default 1) */

@@ -609,7 +609,9 @@ struct oa_graph {
   float *w;
   uint32_t *thr;      /* Vose bucket threshold (NULL when every weight is 1.0f) */
   uint32_t *alias;    /* row-relative alias slot */
+  uint32_t *mult;     /* parallel-edge multiplicity of every entry */
   int has_alias;
+  int directed;       /* set by the caller: folding is defined for undirected graphs only */
 };
 
 typedef struct { int32_t c; float w; int64_t pos; } oa_ent;
@@ -689,6 +691,16 @@ oa_graph *oa_build(const og_graph *g) {
     free(e);
   }
   a->has_alias = has;
+  a->mult = (uint32_t *)malloc((size_t)(nnz ? nnz : 1) * 4);
+  for (int64_t v = 0; v < a->nv; ++v) {
+    const int64_t lo = a->offsets[v], hi = a->offsets[v + 1];
+    for (int64_t i = lo; i < hi;) {
+      int64_t j = i;
+      while (j < hi && a->col[j] == a->col[i]) j++;
+      for (int64_t k = i; k < j; ++k) a->mult[k] = (uint32_t)(j - i);
+      i = j;
+    }
+  }
   if (has) {
     a->thr = (uint32_t *)malloc((size_t)(nnz ? nnz : 1) * 4);
     a->alias = (uint32_t *)malloc((size_t)(nnz ? nnz : 1) * 4);
@@ -701,10 +713,12 @@ oa_graph *oa_build(const og_graph *g) {
 }
 void oa_free(oa_graph *a) {
   if (!a) return;
-  free(a->vids); free(a->offsets); free(a->col); free(a->w); free(a->thr); free(a->alias); free(a);
+  free(a->vids); free(a->offsets); free(a->col); free(a->w); free(a->thr); free(a->alias); free(a->mult); free(a);
 }
 int64_t oa_num_vertices(const oa_graph *a) { return a->nv; }
 int oa_has_alias(const oa_graph *a) { return a->has_alias; }
+const uint32_t *oa_mult(const oa_graph *a) { return a->mult; }
+void oa_set_directed(oa_graph *a, int directed) { a->directed = directed; }
 void oa_view(const oa_graph *a, const int32_t **vids, const int64_t **offsets, const int32_t **col,
              const float **w, const uint32_t **thr, const uint32_t **alias) {
   if (vids) *vids = a->vids;
@@ -724,6 +738,17 @@ void oracle_alias_thresholds(double p, double q, uint64_t *t_ret, uint64_t *t_co
   *t_common = THR(1.0);
   *t_far = THR(inv_q);
 #undef THR
+}
+
+void oracle_fold_thresholds(double p, double q, uint64_t *t_common, uint64_t *t_far, double *a, double *mp) {
+  const double inv_p = 1.0 / (double)(float)p, inv_q = 1.0 / (double)(float)q;
+  const double M = inv_q > 1.0 ? inv_q : 1.0;
+#define THR(f) ((f) >= M ? 4294967296ULL : (uint64_t)(((f) / M) * 4294967296.0))
+  *t_common = THR(1.0);
+  *t_far = THR(inv_q);
+#undef THR
+  *a = inv_p - M;
+  *mp = M;
 }
 
 static inline uint64_t mulhi64(uint64_t a, uint64_t b) {
@@ -752,6 +777,13 @@ int64_t oracle_alias_walk(const oa_graph *a, const oracle_walk_cfg *cfg, int32_t
   const int32_t stride = cfg->walk_length + 2;
   uint64_t t_ret, t_common, t_far;
   oracle_alias_thresholds(cfg->p, cfg->q, &t_ret, &t_common, &t_far);
+  double fold_a = 0.0, fold_mp = 1.0;
+  int fold = 0;
+  if (cfg->fold && !a->has_alias && !a->directed) {
+    uint64_t fc, ff;
+    oracle_fold_thresholds(cfg->p, cfg->q, &fc, &ff, &fold_a, &fold_mp);
+    if (fold_a > 0.0) { fold = 1; t_common = fc; t_far = ff; t_ret = 4294967296ULL; }
+  }
   int32_t *tmp = (int32_t *)malloc((size_t)(nv ? nv : 1) * (size_t)stride * 4);
   int32_t *lens = (int32_t *)malloc((size_t)(nv ? nv : 1) * 4);
   int64_t n_paths = 0, total = 0, st_steps = 0, st_prop = 0, st_log = 0, st_mem = 0;
@@ -774,7 +806,9 @@ int64_t oracle_alias_walk(const oa_graph *a, const oracle_walk_cfg *cfg, int32_t
       uint32_t r[4];
       if (deg > 0) {
         walker_rng(cfg->seed, walker, 0u, 0u, r);           /* first-order step: proposal accepted */
-        path[len++] = a->col[off + alias_pick(a, off, deg, r)];
+        int64_t kk = alias_pick(a, off, deg, r);
+        uint32_t m_ret = a->mult[off + kk];                  /* parallel edges start<->first (undirected: symmetric) */
+        path[len++] = a->col[off + kk];
         st_steps++;
         while (len != stride) {
           int32_t curr = path[len - 1], prev = path[len - 2];
@@ -782,9 +816,18 @@ int64_t oracle_alias_walk(const oa_graph *a, const oracle_walk_cfg *cfg, int32_t
           if (deg <= 0) break;
           const int64_t poff = a->offsets[prev], pdeg = a->offsets[prev + 1] - poff;
           int32_t x = -1;
+          /* fold: one trial picks the return-excess component with probability
+           * a*m / (Mp*deg + a*m) (always accepted), else a uniform entry under the envelope Mp */
+          uint64_t thr_ret = 0;
+          if (fold) {
+            const double t1 = fold_a * (double)m_ret, t2 = fold_mp * (double)deg;
+            thr_ret = (uint64_t)((t1 / (t2 + t1)) * 4294967296.0);
+          }
           for (uint32_t trial = 0;; ++trial) {
             walker_rng(cfg->seed, walker, (uint32_t)(len - 1), trial, r);
-            x = a->col[off + alias_pick(a, off, deg, r)];
+            if (fold && (uint64_t)r[1] < thr_ret) { x = prev; kk = -1; st_prop++; break; }
+            kk = alias_pick(a, off, deg, r);
+            x = a->col[off + kk];
             st_prop++;
             uint64_t t;
             if (x == prev) t = t_ret;
@@ -796,6 +839,14 @@ int64_t oracle_alias_walk(const oa_graph *a, const oracle_walk_cfg *cfg, int32_t
               t = row_contains(a->col + poff, pdeg, x) ? t_common : t_far;
             }
             if ((uint64_t)r[2] < t) break;
+          }
+          if (fold) {
+            if (kk >= 0) m_ret = a->mult[off + kk];
+            else {                                            /* direct return: multiplicity of prev in N(curr) */
+              int64_t lo = 0, hi = deg;
+              while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (a->col[off + mid] < x) lo = mid + 1; else hi = mid; }
+              m_ret = a->mult[off + lo];
+            }
           }
           path[len++] = x;
           st_steps++;

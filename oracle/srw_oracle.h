@@ -86,6 +86,11 @@ typedef struct oracle_walk_cfg {
   /* optional walker subset for bounded CPU-baseline timing: walkers w with
    * (w % sample_mod) == 0 only (sample_mod <= 1: all walkers) */
   int64_t sample_mod;
+  /* alias twin only: 1 = "alias-fold" (the product's SRW_SAMPLER_ALIAS_FOLD): on an undirected,
+   * unweighted graph with 1/p > max(1, 1/q) the return edge's excess weight is sampled as its own
+   * mixture component, so the rejection envelope is max(1, 1/q) instead of 1/p.  Ignored (classic
+   * rejection) when the graph or (p, q) do not qualify. */
+  int32_t fold;
 } oracle_walk_cfg;
 
 /* Runs all rounds.  Paths are emitted in (round, ascending vertex id) order into a ragged array:
@@ -119,6 +124,11 @@ int64_t oracle_alias_walk(const oa_graph *a, const oracle_walk_cfg *cfg, int32_t
                           int64_t *offsets, oracle_alias_stats *stats);
 /* acceptance thresholds, shared definition: T(f) = f>=M ? 2^32 : floor(f/M * 2^32) */
 void oracle_alias_thresholds(double p, double q, uint64_t *t_ret, uint64_t *t_common, uint64_t *t_far);
+/* fold mode: envelope Mp = max(1, 1/q); *a = 1/p - Mp (> 0 iff folding applies) */
+void oracle_fold_thresholds(double p, double q, uint64_t *t_common, uint64_t *t_far, double *a, double *mp);
+/* per-entry multiplicity (number of parallel edges to the same neighbour), sorted-row order */
+const uint32_t *oa_mult(const oa_graph *a);
+void oa_set_directed(oa_graph *a, int directed);   /* folding needs mult(prev->curr) == mult(curr->prev) */
 
 /* ---- CPU-baseline helpers (bench.py only): dense CSR (vid == rank), no GraphMap hash lookups and
  * no row copies -- both omissions favour the CPU.  The walk itself is walk_one's algorithm

@@ -23,7 +23,7 @@ LIB_PATH = os.path.join(_HERE, "libsrw.so")
 
 SRW_OK, SRW_ERR_ARG, SRW_ERR_USAGE, SRW_ERR_PARSE, SRW_ERR_IO, SRW_ERR_CUDA, SRW_ERR_NO_DEVICE, SRW_ERR_UNSUPPORTED = range(8)
 TASK_NODE2VEC, TASK_RANDOMWALK, TASK_EMBEDDING = 0, 1, 2
-SAMPLER_ALIAS, SAMPLER_EXACT = 0, 1
+SAMPLER_ALIAS, SAMPLER_EXACT, SAMPLER_ALIAS_FOLD = 0, 1, 2
 U_PHILOX, U_CONST = 0, 1
 BUILD_EXACT, BUILD_ALIAS, BUILD_ALL = 1, 2, 3
 
@@ -174,7 +174,7 @@ class Params:
         c.rdd_partitions, c.single_output, c.partitioned = self.rddPartitions, int(self.singleOutput), int(self.partitioned)
         c.cmd = self._TASKS.index(self.cmd)
         c.seed = self.seed
-        c.sampler = SAMPLER_EXACT if self.sampler == "exact" else SAMPLER_ALIAS
+        c.sampler = {"exact": SAMPLER_EXACT, "fold": SAMPLER_ALIAS_FOLD}.get(self.sampler, SAMPLER_ALIAS)
         c.num_gpus = self.gpus
         if u_const is not None:
             c.u_mode, c.u_const, c.sampler = U_CONST, u_const, SAMPLER_EXACT
@@ -186,7 +186,7 @@ class Params:
                    walkLength=c.walk_length, numWalks=c.num_walks, p=c.p, q=c.q, weighted=bool(c.weighted),
                    directed=bool(c.directed), input=c.input.decode() or None, output=c.output.decode() or None,
                    rddPartitions=c.rdd_partitions, singleOutput=bool(c.single_output), partitioned=bool(c.partitioned),
-                   cmd=cls._TASKS[c.cmd], seed=int(c.seed), sampler="exact" if c.sampler == SAMPLER_EXACT else "alias",
+                   cmd=cls._TASKS[c.cmd], seed=int(c.seed), sampler={SAMPLER_EXACT: "exact", SAMPLER_ALIAS_FOLD: "fold"}.get(c.sampler, "alias"),
                    gpus=c.num_gpus)
 
 

@@ -214,22 +214,28 @@ __global__ void k_alias_rows(int64_t nv, const int64_t *__restrict__ off, const 
 }
 
 // ---- per-row neighbour hash sets + packed row descriptors ----
-__global__ void k_hash_sizes(int64_t rows, const int64_t *__restrict__ off, uint32_t *nb) {
-  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r <= rows; r += (int64_t)gridDim.x * blockDim.x) {
-    uint32_t v = 0;
-    if (r < rows) {
-      const int64_t d = off[r + 1] - off[r];
-      if (d > (int64_t)kHashMinDeg) v = (uint32_t)((d + kHashLoadNum - 1) / kHashLoadNum);
-    }
-    nb[r] = v;
-  }
-}
-__global__ void k_row_meta(int64_t rows, const int64_t *__restrict__ off, const uint32_t *__restrict__ nb,
-                           const int64_t *__restrict__ hoff, RowMeta *meta) {
+__global__ void k_row_meta(int64_t rows, const int64_t *__restrict__ off, RowMeta *meta) {
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
     RowMeta m;
-    m.off = off[r]; m.hoff = hoff[r]; m.deg = (uint32_t)(off[r + 1] - off[r]); m.nb = nb[r]; m.pad0 = 0; m.pad1 = 0;
+    m.off = off[r]; m.deg = (uint32_t)(off[r + 1] - off[r]);
+    m.hoff = srw_hash_first(m.off); m.nb = srw_hash_buckets(m.off, m.deg); m.pad0 = 0; m.pad1 = 0;
     meta[r] = m;
+  }
+}
+// 16-byte neighbour entries: (x, deg(x), off(x), multiplicity of x in this row)
+__global__ void k_nbr_entries(int64_t nnz, const uint32_t *__restrict__ row_of, const int32_t *__restrict__ col,
+                              const int64_t *__restrict__ off, NbrEntry *ent, int *overflow) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t lo = off[row_of[i]], hi = off[row_of[i] + 1];
+    const int32_t x = col[i];
+    int64_t a = i, b = i;
+    while (a > lo && col[a - 1] == x) a--;
+    while (b + 1 < hi && col[b + 1] == x) b++;
+    const int64_t mult = b - a + 1, xo = off[x], xd = off[x + 1] - xo;
+    if (mult >= (1 << 24) || xo >= ((int64_t)1 << 40)) *overflow = 1;
+    NbrEntry e;
+    e.x = x; e.deg = (uint32_t)xd; e.off_lo = (uint32_t)xo; e.off_hi_mult = (uint32_t)((xo >> 32) & 0xFF) | ((uint32_t)mult << 8);
+    ent[i] = e;
   }
 }
 // one thread per adjacency entry (row keys come from the sort that produced d_col)
@@ -477,40 +483,41 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
   ent_row.alloc(0); ent_col.alloc(0);
   (void)ent_gidx;
 
-  // ---- packed row descriptors + neighbour hash sets (membership test of the alias sampler) ----
-  if (flags & SRW_BUILD_ALIAS) {
-    DevBuf nb, hoff;
-    SRW_CUDA(nb.alloc((size_t)(nrows + 1) * 4));
-    SRW_CUDA(hoff.alloc((size_t)(nrows + 1) * 8));
-    k_hash_sizes<<<grid(nrows + 1), kThreads>>>(nrows, g->d_off, nb.as<uint32_t>());
-    {
-      cub::TransformInputIterator<int64_t, CastU32ToI64, uint32_t *> it(nb.as<uint32_t>(), CastU32ToI64());
-      size_t tb = 0;
-      DevBuf tmp;
-      SRW_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, it, hoff.as<int64_t>(), nrows + 1));
-      SRW_CUDA(tmp.alloc(tb));
-      SRW_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, it, hoff.as<int64_t>(), nrows + 1));
-    }
-    SRW_CUDA(cudaMemcpy(&g->hash_buckets, hoff.as<int64_t>() + nrows, 8, cudaMemcpyDeviceToHost));
-    SRW_CUDA(cudaMalloc(&g->d_meta, (size_t)(nrows ? nrows : 1) * sizeof(RowMeta)));
-    k_row_meta<<<grid(nrows), kThreads>>>(nrows, g->d_off, nb.as<uint32_t>(), hoff.as<int64_t>(), g->d_meta);
-    if (g->hash_buckets > 0) {
-      SRW_CUDA(cudaMalloc(&g->d_hash, (size_t)g->hash_buckets * 32));
-      SRW_CUDA(cudaMemset(g->d_hash, 0xFF, (size_t)g->hash_buckets * 32));
-      k_hash_insert<<<grid(nnz), kThreads>>>(nnz, k_in, g->d_col, g->d_meta, g->d_hash);   // k_in = row keys in d_col order
-    }
-    SRW_CUDA(cudaDeviceSynchronize());
-  }
-
-  // ---- K3: Vose slots over the sorted rows (weighted graphs only) ----
-  if ((flags & SRW_BUILD_ALIAS) && d_w) {
+  bool weighted_graph = false;     // any weight != 1.0f (RS semantics are weight-relative; 1.0f rows need no table)
+  if (d_w) {
     DevBuf flag;
     SRW_CUDA(flag.alloc(4));
     SRW_CUDA(cudaMemset(flag.p, 0, 4));
     k_any_non_unit<<<grid(n), kThreads>>>(n, d_w, flag.as<int>());
     int h = 0;
     SRW_CUDA(cudaMemcpy(&h, flag.p, 4, cudaMemcpyDeviceToHost));
-    if (h) {
+    weighted_graph = h != 0;
+  }
+
+  // ---- packed row descriptors + neighbour hash sets (membership test of the alias sampler) ----
+  if (flags & SRW_BUILD_ALIAS) {
+    g->hash_buckets = (nnz >> 2) + 1;
+    SRW_CUDA(cudaMalloc(&g->d_meta, (size_t)(nrows ? nrows : 1) * sizeof(RowMeta)));
+    k_row_meta<<<grid(nrows), kThreads>>>(nrows, g->d_off, g->d_meta);
+    SRW_CUDA(cudaMalloc(&g->d_hash, (size_t)g->hash_buckets * 32));
+    SRW_CUDA(cudaMemset(g->d_hash, 0xFF, (size_t)g->hash_buckets * 32));
+    k_hash_insert<<<grid(nnz), kThreads>>>(nnz, k_in, g->d_col, g->d_meta, g->d_hash);   // k_in = row keys in d_col order
+    SRW_CUDA(cudaDeviceSynchronize());
+    if (!sharded && !weighted_graph) {
+      DevBuf ovf;
+      SRW_CUDA(ovf.alloc(4));
+      SRW_CUDA(cudaMemset(ovf.p, 0, 4));
+      SRW_CUDA(cudaMalloc(&g->d_ent, (size_t)nnz * sizeof(NbrEntry)));
+      k_nbr_entries<<<grid(nnz), kThreads>>>(nnz, k_in, g->d_col, g->d_off, g->d_ent, ovf.as<int>());
+      int h = 0;
+      SRW_CUDA(cudaMemcpy(&h, ovf.p, 4, cudaMemcpyDeviceToHost));
+      if (h) { cudaFree(g->d_ent); g->d_ent = nullptr; }    // absurd multiplicities: fold sampler unavailable
+    }
+  }
+
+  // ---- K3: Vose slots over the sorted rows (weighted graphs only) ----
+  if ((flags & SRW_BUILD_ALIAS) && weighted_graph) {
+    {
       DevBuf ws;
       SRW_CUDA(ws.alloc((size_t)nnz * 4));
       k_gather_w<<<grid(nnz), kThreads>>>(nnz, v_in, gidx, d_w, wshift, ws.as<float>());
@@ -522,7 +529,7 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
   }
   SRW_CUDA(cudaGetLastError());
   g->device_bytes = (int64_t)(words * 8 + (size_t)nv * 12 + (size_t)nnz * 4) + (g->d_col_app ? nnz * 8 : 0) +
-                    (g->d_slot ? nnz * 16 : 0) + (g->d_vpid ? nv * 4 : 0) + (g->d_meta ? nrows * 32 : 0) + g->hash_buckets * 32;
+                    (g->d_slot ? nnz * 16 : 0) + (g->d_vpid ? nv * 4 : 0) + (g->d_meta ? nrows * 32 : 0) + (g->d_hash ? g->hash_buckets * 32 : 0) + (g->d_ent ? nnz * 16 : 0);
   return SRW_OK;
 }
 

@@ -162,7 +162,7 @@ extern "C" void srw_graph_free(srw_graph *g) {
   if (!g) return;
   cudaFree(g->d_bitmap); cudaFree(g->d_wordrank); cudaFree(g->d_vids); cudaFree(g->d_off);
   cudaFree(g->d_col_app); cudaFree(g->d_w_app); cudaFree(g->d_col); cudaFree(g->d_slot); cudaFree(g->d_vpid);
-  cudaFree(g->d_meta); cudaFree(g->d_hash);
+  cudaFree(g->d_meta); cudaFree(g->d_hash); cudaFree(g->d_ent);
   srw_shard_scratch_free(g->scratch);
   delete g;
 }
@@ -240,7 +240,7 @@ extern "C" int srw_main(int argc, const char *const *argv) {
     fprintf(stderr, "Error: --cmd %s is not supported by this engine (only randomwalk)\n", prm.cmd == SRW_TASK_NODE2VEC ? "node2vec" : "embedding");
     return 1;
   }
-  const unsigned flags = prm.sampler == SRW_SAMPLER_EXACT ? SRW_BUILD_EXACT : SRW_BUILD_ALIAS;
+  const unsigned flags = prm.sampler == SRW_SAMPLER_EXACT ? SRW_BUILD_EXACT : SRW_BUILD_ALIAS;   // alias and fold share a layout
   srw_graph *g = nullptr;
   auto t0 = std::chrono::steady_clock::now();
   if (srw_graph_load(&prm, flags, &g) != SRW_OK) { fprintf(stderr, "Exception: %s\n", srw_last_error()); return 2; }

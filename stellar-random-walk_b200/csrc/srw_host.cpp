@@ -68,7 +68,7 @@ extern "C" const char *srw_usage(void) {
          "  --dim <value>            Number of dimensions in word2vec: 128\n"
          "  --window <value>         Window size in word2vec: 10\n"
          "  --seed <value>           [b200] Philox seed: 1\n"
-         "  --sampler <value>        [b200] alias | exact: alias\n"
+         "  --sampler <value>        [b200] alias | fold | exact: alias\n"
          "  --gpus <value>           [b200] number of GPUs: 1\n";
 }
 
@@ -141,6 +141,7 @@ extern "C" srw_status srw_params_parse_argv(int argc, const char *const *argv, s
     else if (name == "seed") { char *ep; errno = 0; o->seed = strtoull(v, &ep, 10); ok = !errno && *v && !*ep; }
     else if (name == "sampler") {
       if (val == "alias") o->sampler = SRW_SAMPLER_ALIAS;
+      else if (val == "fold") o->sampler = SRW_SAMPLER_ALIAS_FOLD;
       else if (val == "exact") o->sampler = SRW_SAMPLER_EXACT;
       else ok = false;
     }

@@ -51,8 +51,22 @@ struct __align__(32) RowMeta {
   uint32_t nb;     // 0: no hash set (short row: binary search in d_col)
   uint32_t pad0, pad1;
 };
-constexpr uint32_t kHashMinDeg = 16;
-constexpr uint32_t kHashLoadNum = 6;   // <= 6 of 8 slots used on average
+// Hash-set placement is DERIVED from the row extent, so nothing but (off, deg) is needed to probe it:
+// row r owns buckets [off >> 2, (off + deg) >> 2) -- about deg/4 buckets of 8 slots (load <= ~0.5).
+// Rows shorter than kHashMinDeg have no set (8 * nb >= 2*deg - 6 >= deg + 1 needs deg >= 7).
+constexpr uint32_t kHashMinDeg = 8;
+__host__ __device__ inline int64_t srw_hash_first(int64_t off) { return off >> 2; }
+__host__ __device__ inline uint32_t srw_hash_buckets(int64_t off, uint32_t deg) {
+  return deg >= kHashMinDeg ? (uint32_t)(((off + (int64_t)deg) >> 2) - (off >> 2)) : 0u;
+}
+// Neighbour entry of the fold sampler (unweighted graphs): one 16-byte gather yields the neighbour AND
+// its row extent AND the multiplicity of the edge, so a walk step needs no separate row-descriptor load.
+struct __align__(16) NbrEntry {
+  int32_t x;             // neighbour rank
+  uint32_t deg;          // deg(x)
+  uint32_t off_lo;       // row offset of x, low 32 bits
+  uint32_t off_hi_mult;  // [7:0] row offset bits 39:32, [31:8] number of parallel edges to x in this row
+};
 __host__ __device__ inline uint32_t srw_hash32(uint32_t x) {
   x *= 0x9E3779B1u; x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 12;
   return x;
@@ -77,6 +91,7 @@ struct srw_graph {
   struct RowMeta *d_meta = nullptr;  // [rows] packed row descriptor: one 32-byte load per step   (SRW_BUILD_ALIAS)
   int32_t *d_hash = nullptr;         // per-row neighbour hash sets, 8-slot (32-byte) buckets, -1 = empty
   int64_t hash_buckets = 0;
+  NbrEntry *d_ent = nullptr;         // [nnz] unweighted, unsharded graphs (fold sampler)
   int64_t device_bytes = 0;
   mutable std::vector<int32_t> h_vids;  // lazy host copies for the query entry points
   mutable std::vector<int64_t> h_off;

@@ -331,6 +331,155 @@ __global__ void __launch_bounds__(256) walk_alias_hash_kernel(WalkArgs a, const 
 }
 
 // ------------------------------------------------------------------------------------------
+// K6 (v4, SRW_SAMPLER_ALIAS_FOLD): fewer memory requests per step.  ncu on v3 (RMAT-26): the kernel runs
+// at the memory system's random-request ceiling (~46 G requests/s, profiles/README.md) with 6.1 requests
+// per step: 3.7 proposals, 1 row descriptor, ~1 hash probe, 1 path write.  v4 removes most of them:
+//   * fold: for 1/p > max(1, 1/q) the return edge's excess weight (1/p - Mp) * mult is its own mixture
+//     component, picked with probability a*m / (Mp*deg + a*m) and always accepted; everything else is
+//     rejection under the envelope Mp = max(1, 1/q) instead of 1/p  (3.7 -> ~1.8 proposals per step);
+//   * the 16-byte neighbour entry carries deg/off/multiplicity of the neighbour: no row-descriptor load;
+//   * the hash set of prev is addressed from (poff, pdeg) alone;
+//   * path ids are staged in shared memory and flushed as 8-byte stores, 16 ids at a time.
+// Defined for undirected, unweighted graphs (multiplicity of prev in N(curr) == multiplicity of the edge
+// just taken); otherwise the launch falls back to v3.  CPU twin: oracle_alias_walk with cfg.fold = 1.
+// ------------------------------------------------------------------------------------------
+struct FoldArgs {
+  const NbrEntry *__restrict__ ent;
+  const int32_t *__restrict__ hash;
+  double a, mp;              // a = 1/p - Mp > 0, Mp = max(1, 1/q)
+  uint64_t t_common, t_far;  // thresholds under the envelope Mp
+};
+
+constexpr int kStage = 16;
+
+template <bool STATS>
+__global__ void __launch_bounds__(256) walk_fold_kernel(WalkArgs a, FoldArgs f) {
+  __shared__ int32_t sbuf[kStage * 256];
+  const int tid = threadIdx.x;
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + tid;
+  if (i >= a.n_walkers) return;
+  const uint64_t walker = a.walker_first + (uint64_t)i;
+  int32_t curr = (int32_t)(walker % (uint64_t)a.nv), prev = -1;
+  int32_t *path = a.paths + i * a.stride;
+  const bool vec2 = ((a.stride & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.paths) & 7) == 0);
+  int32_t len = 0, staged = 0, flushed = 0;
+  auto flush = [&]() {
+    int32_t *dst = path + flushed;
+    int j = 0;
+    if (vec2) for (; j + 1 < staged; j += 2) *reinterpret_cast<int2 *>(dst + j) = make_int2(sbuf[j * 256 + tid], sbuf[(j + 1) * 256 + tid]);
+    for (; j < staged; ++j) dst[j] = sbuf[j * 256 + tid];
+    flushed += staged; staged = 0;
+  };
+  auto push = [&](int32_t v) {
+    sbuf[staged * 256 + tid] = v;
+    staged++; len++;
+    if (staged == kStage) flush();
+  };
+  push(curr);
+  int64_t off = 0, poff = 0, xoff = 0;
+  uint32_t deg = 0, pdeg = 0, m = 1, xdeg = 0, xm = 1, trial = 0, lo = 0, hi = 0, y = 0, bkt = 0, pnb = 0;
+  int32_t x = 0;
+  uint64_t k = 0, thr_ret = 0;
+  int state = ST_EXTENT;      // only for the start vertex
+  unsigned long long n_prop = 0, n_mem = 0, n_log = 0;
+  const uint64_t t_lo = f.t_common < f.t_far ? f.t_common : f.t_far;
+  const uint64_t t_hi = f.t_common < f.t_far ? f.t_far : f.t_common;
+
+  while (state != ST_DONE) {
+    // ---- one memory access per lane ----
+    int4 q0 = make_int4(0, 0, 0, 0), q1 = make_int4(0, 0, 0, 0);
+    int64_t e0 = 0, e1 = 0;
+    int32_t v = 0;
+    if (state == ST_EXTENT) {
+      e0 = __ldg(a.off + curr); e1 = __ldg(a.off + curr + 1);
+    } else if (state == ST_PROPOSE) {
+      q0 = __ldg(reinterpret_cast<const int4 *>(f.ent + off + (int64_t)k));
+    } else if (state == ST_HASH) {
+      const int4 *b = reinterpret_cast<const int4 *>(f.hash + (srw_hash_first(poff) + (int64_t)bkt) * 8);
+      q0 = __ldg(b); q1 = __ldg(b + 1);
+    } else {
+      v = __ldg(&f.ent[poff + (int64_t)((lo + hi) >> 1)].x);
+    }
+    // ---- consume it ----
+    int verdict = 0;           // 1 = accept entry x, 2 = reject (next trial), 3 = new step: draw trial 0, 4 = direct return
+    if (state == ST_EXTENT) {
+      off = e0; deg = (uint32_t)(e1 - e0);
+      if (deg == 0) { state = ST_DONE; continue; }              // dead end (RW:59-62)
+      verdict = 3;
+    } else if (state == ST_PROPOSE) {
+      x = q0.x; xdeg = (uint32_t)q0.y;
+      xoff = (int64_t)(uint32_t)q0.z | ((int64_t)((uint32_t)q0.w & 0xFFu) << 32);
+      xm = (uint32_t)q0.w >> 8;
+      if (STATS && len > 1) n_prop++;
+      if (len == 1 || x == prev) verdict = 1;                  // first-order step (RW:57); return entry: mass Mp of Mp
+      else if ((uint64_t)y < t_lo) verdict = 1;
+      else if ((uint64_t)y >= t_hi) verdict = 2;
+      else {
+        if (STATS) { n_mem++; n_log += ceil_log2_p1(pdeg); }
+        pnb = srw_hash_buckets(poff, pdeg);
+        if (pnb) { bkt = __umulhi(srw_hash32((uint32_t)x), pnb); state = ST_HASH; }
+        else { lo = 0; hi = pdeg; state = ST_SEARCH; }
+      }
+    } else if (state == ST_HASH) {
+      const bool found = q0.x == x || q0.y == x || q0.z == x || q0.w == x || q1.x == x || q1.y == x || q1.z == x || q1.w == x;
+      if (found) verdict = ((uint64_t)y < f.t_common) ? 1 : 2;           // RS:38
+      else if (q1.w == -1) verdict = ((uint64_t)y < f.t_far) ? 1 : 2;    // RS:34
+      else bkt = bkt + 1 == pnb ? 0 : bkt + 1;
+    } else {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (v == x) verdict = ((uint64_t)y < f.t_common) ? 1 : 2;
+      else {
+        if (v < x) lo = mid + 1; else hi = mid;
+        if (lo >= hi) verdict = ((uint64_t)y < f.t_far) ? 1 : 2;
+      }
+    }
+    bool draw = false;
+    if (verdict == 1) {                                        // move along entry (x, xoff, xdeg, xm)
+      push(x);                                                 // RW:114
+      prev = curr; poff = off; pdeg = deg;
+      curr = x; off = xoff; deg = xdeg; m = xm;
+      verdict = 3;
+    }
+    if (verdict == 3) {                                        // a new step starts at curr
+      if (len == a.stride || deg == 0) { state = ST_DONE; continue; }   // RW:103 / RW:115-119
+      trial = 0;
+      draw = true;
+    } else if (verdict == 2) {
+      trial++;
+      draw = true;
+    }
+    while (draw) {
+      if (trial == 0 && len > 1) {                             // per step: P(return-excess component)
+        const double t1 = __dmul_rn(f.a, (double)m), t2 = __dmul_rn(f.mp, (double)deg);
+        thr_ret = __double2ull_rz(__dmul_rn(__ddiv_rn(t1, __dadd_rn(t2, t1)), 4294967296.0));
+      }
+      const Philox4 r = walker_rng(a.seed_lo, a.seed_hi, walker, (uint32_t)(len - 1), trial);
+      if (len > 1 && (uint64_t)r.y < thr_ret) {                // return-excess component: always accepted, no memory access
+        if (STATS) n_prop++;
+        push(prev);
+        const int32_t c = curr; curr = prev; prev = c;
+        const int64_t o = off; off = poff; poff = o;
+        const uint32_t d = deg; deg = pdeg; pdeg = d;          // m unchanged: the same bundle of parallel edges
+        if (len == a.stride) { state = ST_DONE; break; }
+        trial = 0;
+        continue;                                              // draw trial 0 of the next step
+      }
+      k = __umul64hi(((uint64_t)r.x << 32) | (uint64_t)r.w, (uint64_t)deg);
+      y = r.z;
+      state = ST_PROPOSE;
+      draw = false;
+    }
+  }
+  flush();
+  a.lens[i] = len;
+  if (STATS) {
+    atomicAdd(a.stats + 1, n_prop);
+    atomicAdd(a.stats + 2, n_mem);
+    atomicAdd(a.stats + 3, n_log);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // K5: exact sampler (also used by the KAT entry points)
 // ------------------------------------------------------------------------------------------
 // RS:12-25 over weights produced by `wf(i)`: two passes, float64 accumulation, left to right.
@@ -468,6 +617,7 @@ srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLa
   if (g->shard_world > 1) { srw_set_error("this handle is one shard of %d: use the srw_shard_* calls", g->shard_world); return SRW_ERR_ARG; }
   if (l.n_walkers == 0 || g->nv == 0) return SRW_OK;
   const bool exact = p->sampler == SRW_SAMPLER_EXACT;
+  if (p->sampler != SRW_SAMPLER_EXACT && p->sampler != SRW_SAMPLER_ALIAS && p->sampler != SRW_SAMPLER_ALIAS_FOLD) { srw_set_error("unknown sampler %d", p->sampler); return SRW_ERR_ARG; }
   if (exact && g->nnz > 0 && !g->d_col_app) { srw_set_error("graph was built without SRW_BUILD_EXACT"); return SRW_ERR_ARG; }
   if (!exact && p->u_mode == SRW_U_CONST) { srw_set_error("the constant-u generator is defined for --sampler exact only"); return SRW_ERR_ARG; }
   SRW_CUDA(cudaSetDevice(g->device));
@@ -491,7 +641,20 @@ srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLa
     const bool st = t_collect_stats != 0;
     static const bool use_v1 = getenv("SRW_KERNEL") && !strcmp(getenv("SRW_KERNEL"), "v1");   // A/B switches
     static const bool use_v2 = getenv("SRW_KERNEL") && !strcmp(getenv("SRW_KERNEL"), "v2");
-    if (!use_v1 && !use_v2 && g->d_meta) {
+    // SRW_SAMPLER_ALIAS_FOLD: undirected + unweighted + 1/p > max(1, 1/q), else the classic sampler
+    // (the CPU twin applies the same rule, oracle_alias_walk)
+    FoldArgs f{};
+    bool fold = false;
+    if (p->sampler == SRW_SAMPLER_ALIAS_FOLD && g->d_ent && g->d_hash && !g->directed && !g->has_alias) {
+      const double inv_p = 1.0 / (double)(float)p->p, inv_q = 1.0 / (double)(float)p->q;
+      const double M = inv_q > 1.0 ? inv_q : 1.0;
+      auto thr = [M](double v) -> uint64_t { return v >= M ? 4294967296ULL : (uint64_t)((v / M) * 4294967296.0); };
+      f.ent = g->d_ent; f.hash = g->d_hash; f.a = inv_p - M; f.mp = M; f.t_common = thr(1.0); f.t_far = thr(inv_q);
+      fold = f.a > 0.0;
+    }
+    if (fold) {
+      if (st) walk_fold_kernel<true><<<grid, 256, 0, l.stream>>>(a, f); else walk_fold_kernel<false><<<grid, 256, 0, l.stream>>>(a, f);
+    } else if (!use_v1 && !use_v2 && g->d_meta) {
       const RowMeta *mt = g->d_meta;
       const int32_t *hs = g->d_hash;
       if (g->has_alias) { if (st) walk_alias_hash_kernel<true, true><<<grid, 256, 0, l.stream>>>(a, mt, hs); else walk_alias_hash_kernel<true, false><<<grid, 256, 0, l.stream>>>(a, mt, hs); }

@@ -25,7 +25,7 @@ def build(force=False):
 class WalkCfg(C.Structure):
     _fields_ = [("walk_length", C.c_int32), ("num_walks", C.c_int32), ("p", C.c_double), ("q", C.c_double),
                 ("u_mode", C.c_int32), ("u_const", C.c_float), ("seed", C.c_uint64), ("threads", C.c_int32),
-                ("sample_mod", C.c_int64)]
+                ("sample_mod", C.c_int64), ("fold", C.c_int32)]
 
 
 class AliasStats(C.Structure):
@@ -217,9 +217,9 @@ def second_order_sample(p, q, prev, prev_neighbors, curr_neighbors, u):
     return (int(cd[k]), float(wo.value))
 
 
-def make_cfg(walk_length=80, num_walks=10, p=1.0, q=1.0, u_const=None, seed=1, threads=0, sample_mod=0):
+def make_cfg(walk_length=80, num_walks=10, p=1.0, q=1.0, u_const=None, seed=1, threads=0, sample_mod=0, fold=0):
     return WalkCfg(walk_length, num_walks, p, q, 0 if u_const is not None else 1,
-                   0.0 if u_const is None else u_const, seed, threads, sample_mod)
+                   0.0 if u_const is None else u_const, seed, threads, sample_mod, fold)
 
 
 def _run_walk(fn, handle, cfg, n_vertices, extra=()):
@@ -256,9 +256,11 @@ def format_paths(ids, offs):
 class AliasGraph:
     """CPU twin of the product's alias-mode layout (sorted CSR + Vose tables)."""
 
-    def __init__(self, graph):
+    def __init__(self, graph, directed=False):
         self.h = lib().oa_build(graph.h)
         self.nv = int(lib().oa_num_vertices(self.h))
+        lib().oa_set_directed.argtypes = [C.c_void_p, C.c_int]
+        lib().oa_set_directed(self.h, int(directed))
 
     def __del__(self):
         try:

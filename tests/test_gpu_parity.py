@@ -349,3 +349,33 @@ def test_vcut_cli_partitioned_input(oracle, tmp_path):
     rw = srw.VCutRandomWalk(srw.Params(input=str(inp), partitioned=True))
     rw.loadGraph()
     assert rw.graph.partition(2) == og.partition(2) and rw.graph.partition(12345) is None
+
+
+# ---- SRW_SAMPLER_ALIAS_FOLD (kernel v4) == its CPU twin, bit for bit; falls back to alias when not applicable ----
+@pytest.mark.parametrize("scale,ef,p,q,seed", [(8, 8, 0.5, 2.0, 1), (10, 16, 0.25, 4.0, 2), (11, 4, 0.1, 0.5, 3), (9, 8, 0.5, 1.0, 4)])
+def test_fold_sampler_bit_equal(oracle, scale, ef, p, q, seed):
+    s, d = synth.rmat_edges(scale, ef, seed=42)
+    og = oracle.Graph().load_edges(s, d)
+    twin = oracle.AliasGraph(og)
+    g = srw.Graph.from_edges(s, d, None, flags=srw.BUILD_ALIAS)
+    ids, offs, st = twin.walk(walk_length=60, num_walks=3, p=p, q=q, seed=seed, fold=1)
+    paths = g.walk(srw.Params(walkLength=60, numWalks=3, p=p, q=q, seed=seed, sampler="fold"))
+    got_ids, got_offs = paths.arrays()
+    assert (got_offs == offs).all()
+    assert (got_ids == ids).all()
+    # odd stride (scalar path flush) and a text-loaded (weights all 1.0) graph
+    ids, offs, _ = twin.walk(walk_length=7, num_walks=2, p=p, q=q, seed=seed, fold=1)
+    w1 = np.ones(len(s), np.float32)
+    g1 = srw.Graph.from_edges(s, d, w1, flags=srw.BUILD_ALIAS)
+    got_ids, got_offs = g1.walk(srw.Params(walkLength=7, numWalks=2, p=p, q=q, seed=seed, sampler="fold")).arrays()
+    assert (got_offs == offs).all() and (got_ids == ids).all()
+
+
+def test_fold_sampler_fallbacks(oracle):
+    s, d = synth.rmat_edges(9, 8, seed=42)
+    w = synth.edge_weights(len(s), seed=43)
+    for kw, prm in ((dict(w=None, directed=True), (0.5, 2.0)), (dict(w=w, directed=False), (0.5, 2.0)), (dict(w=None, directed=False), (2.0, 0.5))):
+        g = srw.Graph.from_edges(s, d, kw["w"], directed=kw["directed"], flags=srw.BUILD_ALIAS)
+        a = g.walk(srw.Params(walkLength=30, numWalks=2, p=prm[0], q=prm[1], seed=5, sampler="fold")).arrays()
+        b = g.walk(srw.Params(walkLength=30, numWalks=2, p=prm[0], q=prm[1], seed=5, sampler="alias")).arrays()
+        assert (a[0] == b[0]).all() and (a[1] == b[1]).all()

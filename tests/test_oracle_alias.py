@@ -109,3 +109,54 @@ def test_rmat_generator_shape():
     assert (s < 128).mean() > 0.7
     w = synth.edge_weights(1000)
     assert w.dtype == np.float32 and w.min() >= 1.0 and w.max() < 2.0
+
+
+@pytest.mark.parametrize("p,q", [(0.5, 2.0), (0.25, 4.0), (0.1, 0.5)])
+def test_alias_fold_distribution(oracle, p, q):
+    """alias-fold (return edge folded out of the envelope) samples the same exact distribution;
+    karate has a parallel edge (9-33 twice), so the multiplicity path is exercised."""
+    g = oracle.Graph().load_file(KARATE)
+    a = oracle.AliasGraph(g)
+    ids, offs, st = a.walk(walk_length=40, num_walks=300, p=p, q=q, seed=12, fold=1)
+    ids0, _, st0 = a.walk(walk_length=40, num_walks=300, p=p, q=q, seed=12, fold=0)
+    assert not np.array_equal(ids, ids0)                   # a different (cheaper) sampler ...
+    assert st.proposals < 0.8 * st0.proposals              # ... with fewer proposals per step
+    paths = ids.reshape(-1, 42)
+    ctx = {}
+    for k in range(2, 42):
+        for a_, b_, c_ in zip(paths[:, k - 2], paths[:, k - 1], paths[:, k]):
+            ctx.setdefault((int(a_), int(b_)), {}).setdefault(int(c_), 0)
+            ctx[(int(a_), int(b_))][int(c_)] += 1
+    chi2, dof = 0.0, 0
+    for (pv, cu), cnt in ctx.items():
+        n = sum(cnt.values())
+        if n < 400:
+            continue
+        probs = _exact_transition(oracle, g, pv, cu, p, q)
+        assert set(cnt) <= set(probs)
+        for d, pr in probs.items():
+            e = n * pr
+            if e >= 5:
+                chi2 += (cnt.get(d, 0) - e) ** 2 / e
+                dof += 1
+        dof -= 1
+    assert dof > 50
+    assert abs(chi2 - dof) < 5.0 * (2.0 * dof) ** 0.5, (chi2, dof)
+
+
+def test_alias_fold_falls_back_when_not_applicable(oracle):
+    g = oracle.Graph().load_file(KARATE)
+    a = oracle.AliasGraph(g)
+    for p, q in ((2.0, 0.5), (1.0, 1.0)):                 # 1/p <= max(1, 1/q): nothing to fold
+        i1, o1, _ = a.walk(walk_length=20, num_walks=2, p=p, q=q, seed=3, fold=1)
+        i0, o0, _ = a.walk(walk_length=20, num_walks=2, p=p, q=q, seed=3, fold=0)
+        assert np.array_equal(i1, i0)
+    d = oracle.AliasGraph(oracle.Graph().load_file(KARATE, directed=True), directed=True)   # directed: no symmetry
+    i1, _, _ = d.walk(walk_length=20, num_walks=2, p=0.5, q=2.0, seed=3, fold=1)
+    i0, _, _ = d.walk(walk_length=20, num_walks=2, p=0.5, q=2.0, seed=3, fold=0)
+    assert np.array_equal(i1, i0)
+    w = _weighted_karate(oracle)
+    aw = oracle.AliasGraph(w)
+    i1, _, _ = aw.walk(walk_length=20, num_walks=2, p=0.5, q=2.0, seed=3, fold=1)
+    i0, _, _ = aw.walk(walk_length=20, num_walks=2, p=0.5, q=2.0, seed=3, fold=0)
+    assert np.array_equal(i1, i0)
