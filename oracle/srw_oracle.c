@@ -818,14 +818,17 @@ int64_t oracle_alias_walk(const oa_graph *a, const oracle_walk_cfg *cfg, int32_t
           int32_t x = -1;
           /* fold: one trial picks the return-excess component with probability
            * a*m / (Mp*deg + a*m) (always accepted), else a uniform entry under the envelope Mp */
-          uint64_t thr_ret = 0;
+          /* division-free form: return iff r1 * (Mp*deg + a*m) < a*m * 2^32 (IEEE double, one
+           * rounding per operation; the kernel evaluates the same expression) */
+          double ret_lhs = 0.0, ret_rhs = 0.0;
           if (fold) {
             const double t1 = fold_a * (double)m_ret, t2 = fold_mp * (double)deg;
-            thr_ret = (uint64_t)((t1 / (t2 + t1)) * 4294967296.0);
+            ret_lhs = t2 + t1;
+            ret_rhs = t1 * 4294967296.0;
           }
           for (uint32_t trial = 0;; ++trial) {
             walker_rng(cfg->seed, walker, (uint32_t)(len - 1), trial, r);
-            if (fold && (uint64_t)r[1] < thr_ret) { x = prev; kk = -1; st_prop++; break; }
+            if (fold && (double)r[1] * ret_lhs < ret_rhs) { x = prev; kk = -1; st_prop++; break; }
             kk = alias_pick(a, off, deg, r);
             x = a->col[off + kk];
             st_prop++;

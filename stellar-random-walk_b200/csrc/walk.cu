@@ -379,7 +379,8 @@ __global__ void __launch_bounds__(256) walk_fold_kernel(WalkArgs a, FoldArgs f) 
   int64_t off = 0, poff = 0, xoff = 0;
   uint32_t deg = 0, pdeg = 0, m = 1, xdeg = 0, xm = 1, trial = 0, lo = 0, hi = 0, y = 0, bkt = 0, pnb = 0;
   int32_t x = 0;
-  uint64_t k = 0, thr_ret = 0;
+  uint64_t k = 0;
+  double ret_lhs = 0.0, ret_rhs = 0.0;
   int state = ST_EXTENT;      // only for the start vertex
   unsigned long long n_prop = 0, n_mem = 0, n_log = 0;
   const uint64_t t_lo = f.t_common < f.t_far ? f.t_common : f.t_far;
@@ -449,12 +450,13 @@ __global__ void __launch_bounds__(256) walk_fold_kernel(WalkArgs a, FoldArgs f) 
       draw = true;
     }
     while (draw) {
-      if (trial == 0 && len > 1) {                             // per step: P(return-excess component)
+      if (trial == 0 && len > 1) {                             // per step: P(return-excess component) = a*m / (Mp*deg + a*m)
         const double t1 = __dmul_rn(f.a, (double)m), t2 = __dmul_rn(f.mp, (double)deg);
-        thr_ret = __double2ull_rz(__dmul_rn(__ddiv_rn(t1, __dadd_rn(t2, t1)), 4294967296.0));
+        ret_lhs = __dadd_rn(t2, t1);
+        ret_rhs = __dmul_rn(t1, 4294967296.0);
       }
       const Philox4 r = walker_rng(a.seed_lo, a.seed_hi, walker, (uint32_t)(len - 1), trial);
-      if (len > 1 && (uint64_t)r.y < thr_ret) {                // return-excess component: always accepted, no memory access
+      if (len > 1 && __dmul_rn((double)r.y, ret_lhs) < ret_rhs) {   // return-excess component: always accepted, no memory access
         if (STATS) n_prop++;
         push(prev);
         const int32_t c = curr; curr = prev; prev = c;
