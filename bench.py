@@ -271,6 +271,7 @@ def run_b200(a):
     del d_src, d_dst, d_w
     torch.cuda.empty_cache()
     nv, nnz = g.stats()
+    graph_bytes = int(lib.srw_graph_device_bytes(g.h))
 
     # walkers of one round are split across ranks (replicated graph) -- the sharded mode lives in shard.cu
     lo, hi = nv * rank // world, nv * (rank + 1) // world
@@ -433,26 +434,44 @@ def run_b200(a):
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %s" % ex}
 
     log("cpu baseline done")
+    sharded_line = None
+    if world > 1 and a.mode == "auto":
+        # also measure the vertex-range-sharded walk (BASELINE config C4) on the same ranks
+        del paths, lens
+        g.free()
+        torch.cuda.empty_cache()
+        sub = argparse.Namespace(**vars(a))
+        sub.steps, sub.warmup = min(a.steps, 4), min(a.warmup, 1)
+        try:
+            sharded_line = run_b200_sharded(sub, own_group=False)
+        except Exception as ex:   # noqa: BLE001
+            sharded_line = {"error": str(ex)}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": elapsed_ms / max(1, a.steps), "higher_is_better": True,
                 "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "u32 (integer thresholds; f64 only in the Vose build)",
                 "data": "synthetic",
                 "config": {"workload": workload_name(a), "vertices_present": nv, "adjacency_entries": nnz, "walkers_per_step": nv,
-                           "graph_bytes_hbm": int(lib.srw_graph_device_bytes(g.h)), "build_s": round(build_s, 3),
+                           "graph_bytes_hbm": graph_bytes, "build_s": round(build_s, 3),
                            "l2": "inputs larger than L2 (CSR %.1f GB >> 126 MB), no flush needed" % (nnz * 4 / 1e9),
-                           "parallelism": "1 GPU" if world == 1 else "replicated graph, walkers split %d ways" % world,
+                           "parallelism": "1 GPU" if world == 1 else
+                           "walkers (the independent units) split %d ways, no data-path collective; every rank holds the whole CSR "
+                           "(%.0f GB fits one B200: the ABI's 2^32-entry limit is ~120 GB).  The vertex-range-sharded walk with the NCCL "
+                           "walker all-to-all is measured beside it in `sharded_c4`" % (world, graph_bytes / 1e9),
                            "sampler": "alias-fold (SRW_SAMPLER_ALIAS_FOLD; classic alias rejection when the graph is weighted/directed)" if a.sampler == "fold" else "alias"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk}
+        if sharded_line is not None:
+            line["sharded_c4"] = {k: sharded_line.get(k) for k in ("value", "unit", "steps", "ms_per_step", "config", "error") if k in sharded_line}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_b200_sharded(a):
-    """N > 1: the graph is sharded by vertex range, one rank per GPU, walkers exchanged by an NCCL
+def run_b200_sharded(a, own_group=True):
+    """The graph is sharded by vertex range, one rank per GPU, walkers exchanged by an NCCL
     all-to-all every super-step (BASELINE config C4).  The K timed rounds are walked as one batch
-    (rounds are independent), so `steps` rounds of work are timed exactly once."""
+    (rounds are independent), so `steps` rounds of work are timed exactly once.  Returns the JSON
+    line (rank 0) or None."""
     import torch
     import torch.distributed as dist
     srw = importlib.import_module("stellar-random-walk_b200")
@@ -461,7 +480,8 @@ def run_b200_sharded(a):
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    if own_group:
+        dist.init_process_group("nccl", device_id=dev)
     n_edges = a.edge_factor << a.scale
     log("sharded: generating %s on every rank" % workload_name(a))
     s = torch.empty(n_edges, dtype=torch.int32, device=dev)
@@ -490,11 +510,13 @@ def run_b200_sharded(a):
         torch.cuda.synchronize()
 
     if a.warmup > 0:
-        wk = sh.ShardedWalker([shard], prm, a.warmup, ex, rec_cap=1 << 24, inbox_cap=cap)
+        wk = sh.ShardedWalker([shard], prm, a.warmup, ex, rec_cap=max(1 << 22, shard.nv * a.warmup), inbox_cap=cap)
         wk.run(0)
         del wk
         torch.cuda.empty_cache()
-    walker = sh.ShardedWalker([shard], prm, a.steps, ex, rec_cap=1 << 24, inbox_cap=cap)
+    # one record slot per walker of the batch: a super-step rarely decides more than one step per walker
+    # on a non-home rank, and an overflow only parks the walker for the next super-step
+    walker = sh.ShardedWalker([shard], prm, a.steps, ex, rec_cap=max(1 << 22, shard.nv * a.steps), inbox_cap=cap)
     clocks = ClockSampler(local)
     clocks.launch()
     time.sleep(1.0)
@@ -530,15 +552,23 @@ def run_b200_sharded(a):
                 "roofline": {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
                              "note": "single-GPU kernel roofline is reported by the N=1 line; the sharded step adds the exchange"},
                 "cpu_baseline": None, "e2e": None, "gpu_launches": stats["super_steps"] * 3, "clocks": clk}
-        print(json.dumps(line))
-    dist.destroy_process_group()
+    else:
+        line = None
+    del walker, out
+    shard.free()
+    torch.cuda.empty_cache()
+    if own_group:
+        if line is not None:
+            print(json.dumps(line))
+        dist.destroy_process_group()
+    return line
 
 
 if __name__ == "__main__":
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
-    elif int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.mode != "replicated":
+    elif int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.mode == "sharded":
         run_b200_sharded(args)
     else:
         run_b200(args)

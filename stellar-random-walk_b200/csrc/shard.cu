@@ -40,12 +40,13 @@ struct __align__(16) PathRec {     // 16 bytes
 static_assert(sizeof(WalkerMsg) == 32 && sizeof(PathRec) == 16, "wire formats");
 
 enum : int { MSG_STEP = 0, MSG_SEARCH = 1, MSG_FIN = 2 };
-enum : int { L_EXT_CURR = 0, L_PROPOSE = 1, L_EXT_PREV = 2, L_SEARCH = 3, L_EXIT = 4 };
+enum : int { L_EXT_CURR = 0, L_PROPOSE = 1, L_EXT_PREV = 2, L_SEARCH = 3, L_EXIT = 4, L_HASH = 5 };
 
 struct ShardArgs {
   const int64_t *__restrict__ off;
   const int32_t *__restrict__ col;
   const AliasSlot *__restrict__ slot;
+  const int32_t *__restrict__ hash;   // per-row neighbour hash sets (derived placement, srw_internal.h)
   int64_t nv, row_first, row_last;
   int world, rank;
   int64_t bounds[SRW_MAX_SHARDS + 1];
@@ -79,12 +80,21 @@ __device__ __forceinline__ int64_t home_row(const ShardArgs &a, uint64_t walker)
 
 template <bool HAS_ALIAS>
 __global__ void __launch_bounds__(256) shard_walk_kernel(ShardArgs a) {
+  // per-block tallies (message / record counts per destination, steps): same-address global atomics
+  // from every lane serialise (~1 per ns chip-wide) and dominated the first version of this kernel
+  __shared__ unsigned int s_msg[SRW_MAX_SHARDS], s_rec[SRW_MAX_SHARDS];
+  __shared__ unsigned long long s_steps;
+  if (threadIdx.x < SRW_MAX_SHARDS) { s_msg[threadIdx.x] = 0; s_rec[threadIdx.x] = 0; }
+  if (threadIdx.x == 0) s_steps = 0;
+  __syncthreads();
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= a.n_in) return;
-  const WalkerMsg m = a.inbox[i];
+  const bool live = i < a.n_in;
+  WalkerMsg m;
+  if (live) m = a.inbox[i];
+  else { m.walker = 0; m.curr = m.prev = m.x = 0; m.y = m.trial = 0; m.len = 0; m.state = MSG_FIN + 1; m.pad = 0; }
   const uint64_t walker = m.walker;
   int32_t curr = m.curr, prev = m.prev, x = m.x;
-  uint32_t y = m.y, trial = m.trial, coin = 0, lo = 0, hi = 0, deg = 0, pdeg = 0;
+  uint32_t y = m.y, trial = m.trial, coin = 0, lo = 0, hi = 0, deg = 0, pdeg = 0, pnb = 0, bkt = 0;
   int32_t len = m.len;
   int64_t off = 0, poff = 0;
   uint64_t k = 0;
@@ -103,7 +113,8 @@ __global__ void __launch_bounds__(256) shard_walk_kernel(ShardArgs a) {
   };
 
   int st;
-  if (m.state == MSG_FIN) {          // home: RW:132 completed path
+  if (!live) st = L_EXIT;
+  else if (m.state == MSG_FIN) {     // home: RW:132 completed path
     a.lens[home_row(a, walker)] = len;
     st = L_EXIT;
   } else if (m.state == MSG_STEP) {
@@ -119,7 +130,11 @@ __global__ void __launch_bounds__(256) shard_walk_kernel(ShardArgs a) {
     int64_t e0 = 0, e1 = 0;
     int32_t v = 0, v_alias = 0;
     uint32_t thr = 0xFFFFFFFFu;
-    if (st == L_EXT_CURR) {
+    int4 h0 = make_int4(0, 0, 0, 0), h1 = make_int4(0, 0, 0, 0);
+    if (st == L_HASH) {
+      const int4 *b = reinterpret_cast<const int4 *>(a.hash + (srw_hash_first(poff) + (int64_t)bkt) * 8);
+      h0 = __ldg(b); h1 = __ldg(b + 1);
+    } else if (st == L_EXT_CURR) {
       e0 = __ldg(a.off + (curr - a.row_first));
       e1 = __ldg(a.off + (curr - a.row_first) + 1);
     } else if (st == L_EXT_PREV) {
@@ -148,7 +163,8 @@ __global__ void __launch_bounds__(256) shard_walk_kernel(ShardArgs a) {
     } else if (st == L_EXT_PREV) {
       poff = e0; pdeg = (uint32_t)(e1 - e0);
       lo = 0; hi = pdeg;
-      st = L_SEARCH;
+      pnb = a.hash ? srw_hash_buckets(poff, pdeg) : 0u;
+      if (pnb) { bkt = __umulhi(srw_hash32((uint32_t)x), pnb); st = L_HASH; } else st = L_SEARCH;
       if (pdeg == 0) verdict = ((uint64_t)y < a.t_far) ? 1 : 2;     // directed: prev may have no out-row here
     } else if (st == L_PROPOSE) {
       x = (HAS_ALIAS && !(coin < thr)) ? v_alias : v;
@@ -161,6 +177,11 @@ __global__ void __launch_bounds__(256) shard_walk_kernel(ShardArgs a) {
         if (po == a.rank) st = L_EXT_PREV;
         else { emit(po, MSG_SEARCH); st = L_EXIT; continue; }
       }
+    } else if (st == L_HASH) {
+      const bool found = h0.x == x || h0.y == x || h0.z == x || h0.w == x || h1.x == x || h1.y == x || h1.z == x || h1.w == x;
+      if (found) verdict = ((uint64_t)y < a.t_common) ? 1 : 2;
+      else if (h1.w == -1) verdict = ((uint64_t)y < a.t_far) ? 1 : 2;
+      else bkt = bkt + 1 == pnb ? 0 : bkt + 1;
     } else {
       const uint32_t mid = (lo + hi) >> 1;
       if (v == x) verdict = ((uint64_t)y < a.t_common) ? 1 : 2;
@@ -174,18 +195,24 @@ __global__ void __launch_bounds__(256) shard_walk_kernel(ShardArgs a) {
       if (home == a.rank) {
         a.paths[home_row(a, walker) * a.stride + len] = x;
       } else {
-        const unsigned long long slot = atomicAdd(a.counters + 0, 1ULL);
+        // warp-aggregated slot reservation: one global atomic per group of lanes that reach this point together
+        const unsigned act = __activemask();
+        const int lane = threadIdx.x & 31, leader = __ffs(act) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(a.counters + 0, (unsigned long long)__popc(act));
+        base = __shfl_sync(act, base, leader);
+        const unsigned long long slot = base + __popc(act & ((1u << lane) - 1u));
         if (slot >= (unsigned long long)a.rec_cap) {
           // record buffer full: park the walker on this rank in its pre-decision state; the next
           // super-step recomputes the same decision (pure function of walker/step/trial)
-          emit(a.rank, st == L_PROPOSE ? MSG_STEP : MSG_SEARCH);
+          emit(a.rank, st == L_PROPOSE ? MSG_STEP : MSG_SEARCH);   // L_SEARCH / L_HASH / L_EXT_PREV re-run the membership test
           st = L_EXIT;
           continue;
         }
         PathRec r; r.walker = walker; r.pos = len; r.value = x;
         a.stage_recs[slot] = r;
         a.rec_dest[slot] = home;
-        atomicAdd(a.counters + 2 + a.world + home, 1ULL);
+        atomicAdd(&s_rec[home], 1u);
       }
       steps++;
       len++;
@@ -213,12 +240,20 @@ __global__ void __launch_bounds__(256) shard_walk_kernel(ShardArgs a) {
       st = L_PROPOSE;
     }
   }
-  a.stage_dest[i] = out_dest;
-  if (out_dest >= 0) {
-    a.stage_msgs[i] = out;
-    atomicAdd(a.counters + 2 + out_dest, 1ULL);
+  if (live) {
+    a.stage_dest[i] = out_dest;
+    if (out_dest >= 0) {
+      a.stage_msgs[i] = out;
+      atomicAdd(&s_msg[out_dest], 1u);
+    }
+    if (steps) atomicAdd(&s_steps, steps);
   }
-  if (steps) atomicAdd(a.counters + 1, steps);
+  __syncthreads();
+  if (threadIdx.x < a.world) {
+    if (s_msg[threadIdx.x]) atomicAdd(a.counters + 2 + threadIdx.x, (unsigned long long)s_msg[threadIdx.x]);
+    if (s_rec[threadIdx.x]) atomicAdd(a.counters + 2 + a.world + threadIdx.x, (unsigned long long)s_rec[threadIdx.x]);
+  }
+  if (threadIdx.x == 0 && s_steps) atomicAdd(a.counters + 1, s_steps);
 }
 
 __global__ void shard_seed_kernel(ShardArgs a, WalkerMsg *inbox) {
@@ -238,10 +273,22 @@ __global__ void shard_seed_kernel(ShardArgs a, WalkerMsg *inbox) {
 template <class T>
 __global__ void shard_scatter_kernel(int64_t n, const T *__restrict__ stage, const int32_t *__restrict__ dest,
                                      const unsigned long long *__restrict__ seg_first, unsigned long long *seg_cursor, T *out) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int d = dest[i];
-    if (d < 0) continue;
-    out[seg_first[d] + atomicAdd(seg_cursor + d, 1ULL)] = stage[i];
+  // per tile of blockDim items: shared histogram -> one global reservation per destination -> local ranks
+  __shared__ unsigned int s_cnt[SRW_MAX_SHARDS], s_pos[SRW_MAX_SHARDS];
+  __shared__ unsigned long long s_base[SRW_MAX_SHARDS];
+  const int64_t tiles = (n + blockDim.x - 1) / blockDim.x;
+  for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    if (threadIdx.x < SRW_MAX_SHARDS) { s_cnt[threadIdx.x] = 0; s_pos[threadIdx.x] = 0; }
+    __syncthreads();
+    const int64_t i = t * blockDim.x + threadIdx.x;
+    const int d = i < n ? dest[i] : -1;
+    if (d >= 0) atomicAdd(&s_cnt[d], 1u);
+    __syncthreads();
+    if (threadIdx.x < SRW_MAX_SHARDS && s_cnt[threadIdx.x])
+      s_base[threadIdx.x] = seg_first[threadIdx.x] + atomicAdd(seg_cursor + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
+    __syncthreads();
+    if (d >= 0) out[s_base[d] + atomicAdd(&s_pos[d], 1u)] = stage[i];
+    __syncthreads();
   }
 }
 
@@ -276,7 +323,7 @@ srw_status fill_args(const srw_graph *g, const srw_params *p, int64_t round_firs
   if (!(p->p > 0.0) || !(p->q > 0.0)) { srw_set_error("p and q must be > 0"); return SRW_ERR_ARG; }
   SRW_CUDA(cudaSetDevice(g->device));
   memset(a, 0, sizeof(*a));
-  a->off = g->d_off; a->col = g->d_col; a->slot = g->d_slot;
+  a->off = g->d_off; a->col = g->d_col; a->slot = g->d_slot; a->hash = g->d_hash;
   a->nv = g->nv; a->row_first = g->row_first; a->row_last = g->row_last; a->world = g->shard_world; a->rank = g->shard_rank;
   for (int r = 0; r <= g->shard_world; ++r) a->bounds[r] = g->bounds[(size_t)r];
   a->stride = p->walk_length + 2;
