@@ -344,7 +344,10 @@ def run_b200(a):
     tj = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tj):
         try:
-            traffic = json.load(open(tj)).get("dram_bytes_per_launch")
+            tjd = json.load(open(tj))
+            # only meaningful for the launch it was captured on: same kernel, one GPU, full round of the default workload
+            if world == 1 and a.scale == 26 and not a.weighted and tjd.get("kernel") == ("walk_fold_kernel" if a.sampler == "fold" else "walk_alias_hash_kernel"):
+                traffic = tjd.get("dram_bytes_per_launch")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
