@@ -213,9 +213,19 @@ extern "C" srw_status srw_walk(const srw_graph *g, const srw_params *params, srw
     props += wi.proposals; mem += wi.member_tests; logs += wi.probes_log2;
     SRW_CUDA(cudaMemcpy(h_paths.data(), d_paths.p, (size_t)n * stride * 4, cudaMemcpyDeviceToHost));
     SRW_CUDA(cudaMemcpy(h_lens.data(), d_lens.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
-    for (int64_t i = 0; i < n; ++i) {
-      P->ids.insert(P->ids.end(), h_paths.begin() + i * stride, h_paths.begin() + i * stride + h_lens[i]);
-      P->offsets.push_back((int64_t)P->ids.size());
+    // full-length paths (every walk on an undirected graph): one bulk append instead of a copy per row
+    bool all_full = true;
+    for (int64_t i = 0; i < n && all_full; ++i) all_full = h_lens[i] == stride;
+    if (all_full) {
+      const int64_t base = (int64_t)P->ids.size();
+      P->ids.insert(P->ids.end(), h_paths.begin(), h_paths.begin() + n * stride);
+      P->offsets.reserve(P->offsets.size() + (size_t)n);
+      for (int64_t i = 1; i <= n; ++i) P->offsets.push_back(base + i * stride);
+    } else {
+      for (int64_t i = 0; i < n; ++i) {
+        P->ids.insert(P->ids.end(), h_paths.begin() + i * stride, h_paths.begin() + i * stride + h_lens[i]);
+        P->offsets.push_back((int64_t)P->ids.size());
+      }
     }
   }
   P->n_paths = total;
