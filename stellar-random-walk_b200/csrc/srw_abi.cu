@@ -250,7 +250,8 @@ extern "C" int srw_main(int argc, const char *const *argv) {
     fprintf(stderr, "Error: --cmd %s is not supported by this engine (only randomwalk)\n", prm.cmd == SRW_TASK_NODE2VEC ? "node2vec" : "embedding");
     return 1;
   }
-  const unsigned flags = prm.sampler == SRW_SAMPLER_EXACT ? SRW_BUILD_EXACT : SRW_BUILD_ALIAS;   // alias and fold share a layout
+  // alias and fold share a layout; the exact sampler also uses the neighbour hash sets of the alias layout
+  const unsigned flags = prm.sampler == SRW_SAMPLER_EXACT ? SRW_BUILD_ALL : SRW_BUILD_ALIAS;
   srw_graph *g = nullptr;
   auto t0 = std::chrono::steady_clock::now();
   if (srw_graph_load(&prm, flags, &g) != SRW_OK) { fprintf(stderr, "Exception: %s\n", srw_last_error()); return 2; }

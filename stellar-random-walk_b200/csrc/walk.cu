@@ -546,6 +546,83 @@ __global__ void __launch_bounds__(128) walk_exact_kernel(WalkArgs a) {
   a.lens[i] = len;
 }
 
+// ------------------------------------------------------------------------------------------
+// K5 (v2): the exact sampler with one WARP per walker.  RS:27-44 is embarrassingly parallel over the
+// neighbours of curr (one membership test each), RS:14 / RS:19 are not: float64 addition does not
+// associate, so the sum and the running CDF stay strictly left-to-right.  Each lane therefore computes the
+// biased weight (and, in pass 2, the float64 quotient w'/sum) of one neighbour per 32-wide chunk -- a hash
+// probe in prev's neighbour set, or a binary search in its sorted row when no set was built -- and the 32
+// values are then folded in order through warp shuffles, every lane carrying the same accumulator.
+// Bit-identical to walk_exact_kernel and to the oracle; O(d_c/32) chunk rounds per pass instead of O(d_c).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool hash_contains(const int32_t *__restrict__ hash, int64_t poff, uint32_t pnb, int32_t x) {
+  uint32_t b = __umulhi(srw_hash32((uint32_t)x), pnb);
+  for (;;) {
+    const int4 *q = reinterpret_cast<const int4 *>(hash + (srw_hash_first(poff) + (int64_t)b) * 8);
+    const int4 q0 = __ldg(q), q1 = __ldg(q + 1);
+    if (q0.x == x || q0.y == x || q0.z == x || q0.w == x || q1.x == x || q1.y == x || q1.z == x || q1.w == x) return true;
+    if (q1.w == -1) return false;
+    b = b + 1 == pnb ? 0 : b + 1;
+  }
+}
+
+__global__ void __launch_bounds__(256) walk_exact_warp_kernel(WalkArgs a, const int32_t *__restrict__ hash) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;     // one warp per walker
+  if (i >= a.n_walkers) return;
+  const uint64_t walker = a.walker_first + (uint64_t)i;
+  int32_t curr = (int32_t)(walker % (uint64_t)a.nv), prev = -1;
+  int32_t *path = a.paths + i * a.stride;
+  if (lane == 0) path[0] = curr;
+  int32_t len = 1;
+  int64_t poff = 0;
+  uint32_t pdeg = 0;
+  const bool biased = a.p != 1.0f || a.q != 1.0f;
+  while (len != a.stride) {                                                     // RW:103
+    const int64_t off = __ldg(a.off + curr);
+    const uint32_t deg = (uint32_t)(__ldg(a.off + curr + 1) - off);
+    if (deg == 0) break;                                                        // RW:59-62 / RW:115-119
+    const int32_t *cd = a.col_app + off;
+    const float *cw = a.w_app + off;
+    const float u = draw_u(a, walker, (uint32_t)(len - 1));
+    const bool second = len > 1;
+    const uint32_t pnb = (second && biased && hash) ? srw_hash_buckets(poff, pdeg) : 0u;
+    auto weight_of = [&](uint32_t j) -> float {                                 // RS:33-41 for neighbour j (first step: RS:12 plain weights)
+      const float w = __ldg(cw + j);
+      if (!second) return w;
+      const int32_t d = __ldg(cd + j);
+      bool in_prev = false;
+      if (biased && d != prev) in_prev = pnb ? hash_contains(hash, poff, pnb, d) : row_contains(a.col, poff, pdeg, d);
+      return biased_weight(a.p, a.q, prev, d, w, in_prev);
+    };
+    // pass 1 (RS:14): sum, strictly left to right
+    double sum = 0.0;
+    for (uint32_t base = 0; base < deg; base += 32) {
+      const uint32_t j = base + lane, n = min(32u, deg - base);
+      const float wv = j < deg ? weight_of(j) : 0.0f;
+      for (uint32_t l = 0; l < n; ++l) sum = __dadd_rn(sum, (double)__shfl_sync(0xffffffffu, wv, (int)l));
+    }
+    // pass 2 (RS:16-22): acc += w / sum; first index with acc >= u
+    double acc = 0.0;
+    int64_t pick = 0;                                                           // RS:24 edges.head
+    bool found = false;
+    for (uint32_t base = 0; base < deg && !found; base += 32) {
+      const uint32_t j = base + lane, n = min(32u, deg - base);
+      const double qv = j < deg ? __ddiv_rn((double)weight_of(j), sum) : 0.0;
+      for (uint32_t l = 0; l < n; ++l) {
+        acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, qv, (int)l));
+        if (acc >= (double)u) { pick = base + l; found = true; break; }
+      }
+    }
+    const int32_t nxt = __ldg(cd + pick);
+    if (lane == 0) path[len] = nxt;                                             // RW:114
+    len++;
+    prev = curr; poff = off; pdeg = deg;
+    curr = nxt;
+  }
+  if (lane == 0) a.lens[i] = len;
+}
+
 // ranks -> original vertex ids, and the step count
 __global__ void finalize_paths_kernel(int64_t n_walkers, int32_t stride, const int32_t *__restrict__ vids,
                                       const int32_t *__restrict__ lens, int32_t *paths, unsigned long long *stats) {
@@ -637,7 +714,9 @@ srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLa
   a.stats = d_stats;
   SRW_CUDA(cudaEventRecord(ev.a, l.stream));
   if (exact) {
-    walk_exact_kernel<<<(unsigned)((l.n_walkers + 127) / 128), 128, 0, l.stream>>>(a);
+    static const bool per_thread = getenv("SRW_EXACT") && !strcmp(getenv("SRW_EXACT"), "thread");   // A/B switch
+    if (per_thread) walk_exact_kernel<<<(unsigned)((l.n_walkers + 127) / 128), 128, 0, l.stream>>>(a);
+    else walk_exact_warp_kernel<<<(unsigned)((l.n_walkers + 7) / 8), 256, 0, l.stream>>>(a, g->d_hash);
   } else {
     const unsigned grid = (unsigned)((l.n_walkers + 255) / 256);
     const bool st = t_collect_stats != 0;
