@@ -214,6 +214,18 @@ srw_status srw_shard_apply(const srw_graph *g, const srw_params *params, int64_t
 srw_status srw_shard_finalize(const srw_graph *g, const srw_params *params, int64_t n_rows, int32_t *d_paths,
                               const int32_t *d_lens, int64_t *steps, void *stream);
 
+/* ---- A10, peer-gather variant.  The same vertex-range shards, but no walker ever moves: every shard's row
+ * arrays are made addressable from every GPU of the box (CUDA IPC mappings between the per-GPU processes,
+ * plain pointers inside one process) and the walk kernel loads remote rows over NVLink.  This is what the
+ * reference's "ship prevNeighbors with the walker" (RW:135) and its per-super-step shuffle (RW:186-192)
+ * collapse to on an NVSwitch box.  Once every peer is attached, srw_walk_device(g = any shard handle, ...)
+ * walks ANY range of walkers against the whole graph; output is bit-identical to the unsharded graph's.
+ * Undirected, unweighted graphs (SRW_BUILD_ALIAS), samplers alias | fold. ---- */
+int srw_shard_ipc_bytes(void);                                       /* size of the export blob */
+srw_status srw_shard_ipc_export(const srw_graph *g, void *h_blob);  /* this shard's row arrays as IPC handles */
+srw_status srw_shard_ipc_attach(srw_graph *g, const void *h_blob);  /* map another process's shard (own blob: no-op) */
+srw_status srw_shard_attach_local(srw_graph *g, const srw_graph *peer);   /* peer handle lives in this process */
+
 /* ---- synthetic inputs for the benchmark; device-resident, not on the walk path ---- */
 srw_status srw_synth_rmat_device(int scale, int edge_factor, uint64_t seed, int64_t first, int64_t count,
                                  int32_t *d_src, int32_t *d_dst);

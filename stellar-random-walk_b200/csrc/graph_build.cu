@@ -222,19 +222,37 @@ __global__ void k_row_meta(int64_t rows, const int64_t *__restrict__ off, RowMet
     meta[r] = m;
   }
 }
-// 16-byte neighbour entries: (x, deg(x), off(x), multiplicity of x in this row)
+// 16-byte neighbour entries: (x, deg(x), off(x) inside owner(x)'s arrays, owner(x), multiplicity of x in this row).
+// Unsharded: goff == nullptr, owner 0, offsets from `off`.  Sharded: `off` holds this shard's local offsets
+// (row_of is a local row), goff the global ones, sb the vertex ranges and the global offset of every range.
+struct ShardBounds {
+  int world;
+  int64_t first[SRW_MAX_SHARDS + 1];   // first rank of every shard
+  int64_t base[SRW_MAX_SHARDS];        // global offset of the shard's first entry
+};
 __global__ void k_nbr_entries(int64_t nnz, const uint32_t *__restrict__ row_of, const int32_t *__restrict__ col,
-                              const int64_t *__restrict__ off, NbrEntry *ent, int *overflow) {
+                              const int64_t *__restrict__ off, const int64_t *__restrict__ goff, ShardBounds sb, NbrEntry *ent,
+                              int *overflow) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t lo = off[row_of[i]], hi = off[row_of[i] + 1];
     const int32_t x = col[i];
     int64_t a = i, b = i;
     while (a > lo && col[a - 1] == x) a--;
     while (b + 1 < hi && col[b + 1] == x) b++;
-    const int64_t mult = b - a + 1, xo = off[x], xd = off[x + 1] - xo;
-    if (mult >= (1 << 24) || xo >= ((int64_t)1 << 40)) *overflow = 1;
+    const int64_t mult = b - a + 1;
+    int64_t xo, xd;
+    uint32_t owner = 0;
+    if (goff) {
+      while ((int)owner + 1 < sb.world && (int64_t)x >= sb.first[owner + 1]) owner++;
+      xo = goff[x] - sb.base[owner];
+      xd = goff[x + 1] - goff[x];
+    } else {
+      xo = off[x];
+      xd = off[x + 1] - xo;
+    }
+    if (mult >= (1 << 24) || xo >= ((int64_t)1 << 32)) *overflow = 1;
     NbrEntry e;
-    e.x = x; e.deg = (uint32_t)xd; e.off_lo = (uint32_t)xo; e.off_hi_mult = (uint32_t)((xo >> 32) & 0xFF) | ((uint32_t)mult << 8);
+    e.x = x; e.deg = (uint32_t)xd; e.off_lo = (uint32_t)xo; e.off_hi_mult = owner | ((uint32_t)mult << 8);
     ent[i] = e;
   }
 }
@@ -384,6 +402,9 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
   g->bounds.assign((size_t)shard_world + 1, 0);
   g->bounds[(size_t)shard_world] = nv;
   int64_t nrows = nv;
+  DevBuf goff;                 // sharded: global row offsets (kept for the neighbour entries below)
+  ShardBounds sb{};
+  sb.world = shard_world;
   if (!sharded) {
     SRW_CUDA(ent_row.alloc((size_t)nnz * 4));
     SRW_CUDA(ent_col.alloc((size_t)nnz * 4));
@@ -395,7 +416,6 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
   } else {
     // global degrees -> global offsets -> edge-balanced contiguous vertex ranges (same on every rank)
     if (n > 0) k_degrees<<<grid(n), kThreads>>>(n, d_src, d_dst, directed, g->d_bitmap, g->d_wordrank, mn, deg.as<uint32_t>());
-    DevBuf goff;
     SRW_CUDA(goff.alloc((size_t)(nv + 1) * 8));
     SRW_TRY(scan_degrees(goff.as<int64_t>()));
     std::vector<int64_t> h_goff((size_t)nv + 1);
@@ -406,6 +426,8 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
       if (g->bounds[(size_t)r] > nv) g->bounds[(size_t)r] = nv;
       if (g->bounds[(size_t)r] < g->bounds[(size_t)r - 1]) g->bounds[(size_t)r] = g->bounds[(size_t)r - 1];
     }
+    for (int r = 0; r <= shard_world; ++r) sb.first[r] = g->bounds[(size_t)r];
+    for (int r = 0; r < shard_world; ++r) sb.base[r] = h_goff[(size_t)g->bounds[(size_t)r]];
     g->row_first = g->bounds[(size_t)shard_rank];
     g->row_last = g->bounds[(size_t)shard_rank + 1];
     nrows = g->row_last - g->row_first;
@@ -503,12 +525,13 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
     SRW_CUDA(cudaMemset(g->d_hash, 0xFF, (size_t)g->hash_buckets * 32));
     k_hash_insert<<<grid(nnz), kThreads>>>(nnz, k_in, g->d_col, g->d_meta, g->d_hash);   // k_in = row keys in d_col order
     SRW_CUDA(cudaDeviceSynchronize());
-    if (!sharded && !weighted_graph) {
+    if (!weighted_graph) {
       DevBuf ovf;
       SRW_CUDA(ovf.alloc(4));
       SRW_CUDA(cudaMemset(ovf.p, 0, 4));
       SRW_CUDA(cudaMalloc(&g->d_ent, (size_t)nnz * sizeof(NbrEntry)));
-      k_nbr_entries<<<grid(nnz), kThreads>>>(nnz, k_in, g->d_col, g->d_off, g->d_ent, ovf.as<int>());
+      k_nbr_entries<<<grid(nnz), kThreads>>>(nnz, k_in, g->d_col, g->d_off, sharded ? goff.as<int64_t>() : nullptr, sb, g->d_ent,
+                                             ovf.as<int>());
       int h = 0;
       SRW_CUDA(cudaMemcpy(&h, ovf.p, 4, cudaMemcpyDeviceToHost));
       if (h) { cudaFree(g->d_ent); g->d_ent = nullptr; }    // absurd multiplicities: fold sampler unavailable
@@ -584,6 +607,8 @@ srw_status srw_build_graph_device_sharded(int64_t n, const int32_t *d_src, const
   srw_graph *g = new srw_graph();
   srw_status s = build_impl(n, d_src, d_dst, d_w, nullptr, directed, flags ? flags : SRW_BUILD_ALIAS, 0, nullptr, g, rank, world);
   if (s != SRW_OK) { srw_graph_free(g); return s; }
+  g->peer_off[rank] = g->d_off; g->peer_ent[rank] = g->d_ent; g->peer_hash[rank] = g->d_hash;
+  g->peer_attached[rank] = true;
   *out = g;
   return SRW_OK;
 }

@@ -497,3 +497,82 @@ extern "C" srw_status srw_shard_finalize(const srw_graph *g, const srw_params *p
   if (steps) *steps = (int64_t)s->h_counters[0];
   return SRW_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// Peer-gather mode: instead of moving walkers to the rows (super-steps above), make every shard's rows
+// addressable from every GPU and let the walk kernel (walk.cu, walk_fold_kernel<PEER>) load remote rows
+// over NVLink.  One process per GPU exchanges CUDA IPC handles of the three row arrays; shards living in
+// one process (tests, or one process driving several GPUs) hand over plain pointers.
+// ------------------------------------------------------------------------------------------
+namespace {
+struct ShardIpcBlob {
+  uint32_t magic;
+  int32_t rank, world, device;
+  int64_t rows, nnz, hash_buckets;
+  uint32_t has_off, has_ent, has_hash, pad;
+  cudaIpcMemHandle_t off, ent, hash;
+};
+constexpr uint32_t kIpcMagic = 0x53525749u;   // "SRWI"
+}  // namespace
+
+extern "C" int srw_shard_ipc_bytes(void) { return (int)sizeof(ShardIpcBlob); }
+
+extern "C" srw_status srw_shard_ipc_export(const srw_graph *g, void *h_blob) {
+  SRW_TRY(srw_require_device());
+  if (!g || !h_blob || g->shard_world < 1) { srw_set_error("srw_shard_ipc_export: bad argument"); return SRW_ERR_ARG; }
+  SRW_CUDA(cudaSetDevice(g->device));
+  ShardIpcBlob b;
+  memset(&b, 0, sizeof(b));
+  b.magic = kIpcMagic; b.rank = g->shard_rank; b.world = g->shard_world; b.device = g->device;
+  b.rows = g->row_last - g->row_first; b.nnz = g->nnz; b.hash_buckets = g->hash_buckets;
+  if (g->d_off) { SRW_CUDA(cudaIpcGetMemHandle(&b.off, g->d_off)); b.has_off = 1; }
+  if (g->d_ent) { SRW_CUDA(cudaIpcGetMemHandle(&b.ent, g->d_ent)); b.has_ent = 1; }
+  if (g->d_hash) { SRW_CUDA(cudaIpcGetMemHandle(&b.hash, g->d_hash)); b.has_hash = 1; }
+  memcpy(h_blob, &b, sizeof(b));
+  return SRW_OK;
+}
+
+extern "C" srw_status srw_shard_ipc_attach(srw_graph *g, const void *h_blob) {
+  SRW_TRY(srw_require_device());
+  if (!g || !h_blob) { srw_set_error("srw_shard_ipc_attach: bad argument"); return SRW_ERR_ARG; }
+  ShardIpcBlob b;
+  memcpy(&b, h_blob, sizeof(b));
+  if (b.magic != kIpcMagic || b.world != g->shard_world || b.rank < 0 || b.rank >= g->shard_world) {
+    srw_set_error("srw_shard_ipc_attach: blob does not describe a shard of this graph (world %d)", g->shard_world);
+    return SRW_ERR_ARG;
+  }
+  if (b.rank == g->shard_rank || g->peer_attached[b.rank]) return SRW_OK;     // own rows / already mapped
+  if (b.nnz > 0 && !b.has_ent) { srw_set_error("shard %d has no neighbour entries (weighted graph?): the peer-gather walk needs an unweighted SRW_BUILD_ALIAS build", b.rank); return SRW_ERR_UNSUPPORTED; }
+  SRW_CUDA(cudaSetDevice(g->device));
+  void *p = nullptr;
+  if (b.has_off) { SRW_CUDA(cudaIpcOpenMemHandle(&p, b.off, cudaIpcMemLazyEnablePeerAccess)); g->peer_off[b.rank] = (const int64_t *)p; }
+  if (b.has_ent) { SRW_CUDA(cudaIpcOpenMemHandle(&p, b.ent, cudaIpcMemLazyEnablePeerAccess)); g->peer_ent[b.rank] = (const NbrEntry *)p; }
+  if (b.has_hash) { SRW_CUDA(cudaIpcOpenMemHandle(&p, b.hash, cudaIpcMemLazyEnablePeerAccess)); g->peer_hash[b.rank] = (const int32_t *)p; }
+  g->peer_ipc[b.rank] = true;
+  g->peer_attached[b.rank] = true;
+  return SRW_OK;
+}
+
+extern "C" srw_status srw_shard_attach_local(srw_graph *g, const srw_graph *peer) {
+  SRW_TRY(srw_require_device());
+  if (!g || !peer || peer->shard_world != g->shard_world || peer->nv != g->nv || peer->bounds != g->bounds) {
+    srw_set_error("srw_shard_attach_local: not two shards of the same graph");
+    return SRW_ERR_ARG;
+  }
+  const int r = peer->shard_rank;
+  if (r == g->shard_rank) return SRW_OK;
+  if (peer->nnz > 0 && !peer->d_ent) { srw_set_error("shard %d has no neighbour entries (weighted graph?): the peer-gather walk needs an unweighted SRW_BUILD_ALIAS build", r); return SRW_ERR_UNSUPPORTED; }
+  if (peer->device != g->device) {
+    int can = 0;
+    SRW_CUDA(cudaDeviceCanAccessPeer(&can, g->device, peer->device));
+    if (!can) { srw_set_error("device %d cannot address device %d", g->device, peer->device); return SRW_ERR_UNSUPPORTED; }
+    SRW_CUDA(cudaSetDevice(g->device));
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) SRW_CUDA(e);
+    cudaGetLastError();
+  }
+  g->peer_off[r] = peer->d_off; g->peer_ent[r] = peer->d_ent; g->peer_hash[r] = peer->d_hash;
+  g->peer_ipc[r] = false;
+  g->peer_attached[r] = true;
+  return SRW_OK;
+}

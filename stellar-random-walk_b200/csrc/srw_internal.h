@@ -64,14 +64,15 @@ __host__ __device__ inline uint32_t srw_hash_buckets(int64_t off, uint32_t deg) 
 struct __align__(16) NbrEntry {
   int32_t x;             // neighbour rank
   uint32_t deg;          // deg(x)
-  uint32_t off_lo;       // row offset of x, low 32 bits
-  uint32_t off_hi_mult;  // [7:0] row offset bits 39:32, [31:8] number of parallel edges to x in this row
+  uint32_t off_lo;       // row offset of x inside its owner's arrays (< 2^32: the ABI caps nnz at 2^32 - 1)
+  uint32_t off_hi_mult;  // [7:0] owner shard of x (0 on an unsharded graph), [31:8] number of parallel edges to x in this row
 };
 __host__ __device__ inline uint32_t srw_hash32(uint32_t x) {
   x *= 0x9E3779B1u; x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 12;
   return x;
 }
 
+#define SRW_MAX_SHARDS 16
 struct srw_graph {
   int device = 0;
   int64_t nv = 0, nnz = 0;
@@ -101,9 +102,16 @@ struct srw_graph {
   int64_t row_first = 0, row_last = 0, nnz_global = 0;
   std::vector<int64_t> bounds;          // [world+1] first rank of every shard
   struct ShardScratch *scratch = nullptr;
+  // peer-gather mode (SURVEY 8(e) "NVLink peer loads"): the row arrays of every shard, addressable from
+  // this device -- own pointers for shard_rank, cudaIpcOpenMemHandle mappings (or same-process pointers)
+  // for the others.  The walk kernel then reads remote rows directly; no walker ever migrates.
+  const int64_t *peer_off[SRW_MAX_SHARDS] = {};
+  const NbrEntry *peer_ent[SRW_MAX_SHARDS] = {};
+  const int32_t *peer_hash[SRW_MAX_SHARDS] = {};
+  bool peer_attached[SRW_MAX_SHARDS] = {};
+  bool peer_ipc[SRW_MAX_SHARDS] = {};   // mapping opened with cudaIpcOpenMemHandle (closed on free)
 };
 
-#define SRW_MAX_SHARDS 16
 srw_status srw_build_graph_device_sharded(int64_t n, const int32_t *d_src, const int32_t *d_dst, const float *d_w, int directed,
                                           unsigned flags, int rank, int world, srw_graph **out);
 void srw_shard_scratch_free(struct ShardScratch *s);

@@ -346,16 +346,34 @@ __global__ void __launch_bounds__(256) walk_alias_hash_kernel(WalkArgs a, const 
 struct FoldArgs {
   const NbrEntry *__restrict__ ent;
   const int32_t *__restrict__ hash;
-  double a, mp;              // a = 1/p - Mp > 0, Mp = max(1, 1/q)
-  uint64_t t_common, t_far;  // thresholds under the envelope Mp
+  double a, mp;              // a = 1/p - Mp > 0, Mp = max(1, 1/q)   (a = 0: no return component, plain rejection under mp)
+  uint64_t t_ret, t_common, t_far;  // thresholds under the envelope (t_ret = 2^32 when the return edge is folded out)
+};
+
+// Peer-gather mode: the graph is cut into vertex ranges, shard s lives in the HBM of GPU s, and
+// every GPU can address every shard (NVLink peer mappings).  A neighbour entry names the owner of the
+// neighbour's row, so the kernel picks the base pointer per access and a walker never migrates: the
+// "exchange" of the reference's super-step shuffle (RW:186-192) becomes 16/32-byte loads over NVLink.
+struct PeerTable {
+  int world;
+  int64_t first[SRW_MAX_SHARDS + 1];          // first rank of every shard
+  const int64_t *off[SRW_MAX_SHARDS];         // shard-local row offsets
+  const NbrEntry *ent[SRW_MAX_SHARDS];
+  const int32_t *hash[SRW_MAX_SHARDS];
 };
 
 constexpr int kStage = 16;
 
-template <bool STATS>
-__global__ void __launch_bounds__(256) walk_fold_kernel(WalkArgs a, FoldArgs f) {
+template <bool STATS, bool PEER>
+__global__ void __launch_bounds__(256) walk_fold_kernel(WalkArgs a, FoldArgs f, const PeerTable pt) {
   __shared__ int32_t sbuf[kStage * 256];
+  __shared__ const NbrEntry *s_ent[SRW_MAX_SHARDS];
+  __shared__ const int32_t *s_hash[SRW_MAX_SHARDS];
   const int tid = threadIdx.x;
+  if (PEER) {
+    if (tid < SRW_MAX_SHARDS) { s_ent[tid] = pt.ent[tid]; s_hash[tid] = pt.hash[tid]; }
+    __syncthreads();
+  }
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + tid;
   if (i >= a.n_walkers) return;
   const uint64_t walker = a.walker_first + (uint64_t)i;
@@ -378,6 +396,7 @@ __global__ void __launch_bounds__(256) walk_fold_kernel(WalkArgs a, FoldArgs f) 
   push(curr);
   int64_t off = 0, poff = 0, xoff = 0;
   uint32_t deg = 0, pdeg = 0, m = 1, xdeg = 0, xm = 1, trial = 0, lo = 0, hi = 0, y = 0, bkt = 0, pnb = 0;
+  uint32_t cown = 0, pown = 0, xown = 0;   // PEER: shards that hold the rows of curr / prev / x
   int32_t x = 0;
   uint64_t k = 0;
   double ret_lhs = 0.0, ret_rhs = 0.0;
@@ -392,14 +411,20 @@ __global__ void __launch_bounds__(256) walk_fold_kernel(WalkArgs a, FoldArgs f) 
     int64_t e0 = 0, e1 = 0;
     int32_t v = 0;
     if (state == ST_EXTENT) {
-      e0 = __ldg(a.off + curr); e1 = __ldg(a.off + curr + 1);
+      if (PEER) {
+        while ((int)cown + 1 < pt.world && (int64_t)curr >= pt.first[cown + 1]) cown++;
+        const int64_t *o = pt.off[cown] + ((int64_t)curr - pt.first[cown]);
+        e0 = __ldg(o); e1 = __ldg(o + 1);
+      } else {
+        e0 = __ldg(a.off + curr); e1 = __ldg(a.off + curr + 1);
+      }
     } else if (state == ST_PROPOSE) {
-      q0 = __ldg(reinterpret_cast<const int4 *>(f.ent + off + (int64_t)k));
+      q0 = __ldg(reinterpret_cast<const int4 *>((PEER ? s_ent[cown] : f.ent) + off + (int64_t)k));
     } else if (state == ST_HASH) {
-      const int4 *b = reinterpret_cast<const int4 *>(f.hash + (srw_hash_first(poff) + (int64_t)bkt) * 8);
+      const int4 *b = reinterpret_cast<const int4 *>((PEER ? s_hash[pown] : f.hash) + (srw_hash_first(poff) + (int64_t)bkt) * 8);
       q0 = __ldg(b); q1 = __ldg(b + 1);
     } else {
-      v = __ldg(&f.ent[poff + (int64_t)((lo + hi) >> 1)].x);
+      v = __ldg(&(PEER ? s_ent[pown] : f.ent)[poff + (int64_t)((lo + hi) >> 1)].x);
     }
     // ---- consume it ----
     int verdict = 0;           // 1 = accept entry x, 2 = reject (next trial), 3 = new step: draw trial 0, 4 = direct return
@@ -409,10 +434,12 @@ __global__ void __launch_bounds__(256) walk_fold_kernel(WalkArgs a, FoldArgs f) 
       verdict = 3;
     } else if (state == ST_PROPOSE) {
       x = q0.x; xdeg = (uint32_t)q0.y;
-      xoff = (int64_t)(uint32_t)q0.z | ((int64_t)((uint32_t)q0.w & 0xFFu) << 32);
+      xoff = (int64_t)(uint32_t)q0.z;
+      xown = (uint32_t)q0.w & 0xFFu;
       xm = (uint32_t)q0.w >> 8;
       if (STATS && len > 1) n_prop++;
-      if (len == 1 || x == prev) verdict = 1;                  // first-order step (RW:57); return entry: mass Mp of Mp
+      if (len == 1 || deg == 1) verdict = 1;                   // first-order step (RW:57) / single choice
+      else if (x == prev) verdict = ((uint64_t)y < f.t_ret) ? 1 : 2;   // RS:36; folded: mass Mp of Mp, t_ret = 2^32
       else if ((uint64_t)y < t_lo) verdict = 1;
       else if ((uint64_t)y >= t_hi) verdict = 2;
       else {
@@ -437,8 +464,8 @@ __global__ void __launch_bounds__(256) walk_fold_kernel(WalkArgs a, FoldArgs f) 
     bool draw = false;
     if (verdict == 1) {                                        // move along entry (x, xoff, xdeg, xm)
       push(x);                                                 // RW:114
-      prev = curr; poff = off; pdeg = deg;
-      curr = x; off = xoff; deg = xdeg; m = xm;
+      prev = curr; poff = off; pdeg = deg; pown = cown;
+      curr = x; off = xoff; deg = xdeg; m = xm; cown = xown;
       verdict = 3;
     }
     if (verdict == 3) {                                        // a new step starts at curr
@@ -462,6 +489,7 @@ __global__ void __launch_bounds__(256) walk_fold_kernel(WalkArgs a, FoldArgs f) 
         const int32_t c = curr; curr = prev; prev = c;
         const int64_t o = off; off = poff; poff = o;
         const uint32_t d = deg; deg = pdeg; pdeg = d;          // m unchanged: the same bundle of parallel edges
+        const uint32_t w = cown; cown = pown; pown = w;
         if (len == a.stride) { state = ST_DONE; break; }
         trial = 0;
         continue;                                              // draw trial 0 of the next step
@@ -623,6 +651,126 @@ __global__ void __launch_bounds__(256) walk_exact_warp_kernel(WalkArgs a, const 
   if (lane == 0) a.lens[i] = len;
 }
 
+// ------------------------------------------------------------------------------------------
+// K5 (v3): the exact sampler with a CERTIFIED parallel inverse-CDF search.  Still bit-identical to RS:12-25,
+// but the two float64 chains of the reference (sum, then acc += w/sum) are not replayed element by element
+// unless they have to be.  For non-negative weights, ANY summation order of k terms is within
+// k * 2^-53 * (exact sum) of the exact sum (Higham, gamma_k), and fl(w/sum) is within 2^-53 relative of w/sum.
+// Hence, with S = a parallel (tree) sum of the row and P_k = a parallel prefix sum,
+//        | acc_k(reference, sequential) - P_k / S |  <=  (3k + 2) * 2^-53 * (1 + tiny)
+// and the reference's answer "first k with acc_k >= u" is decided by comparing P_k with (u -+ delta) * S,
+// delta = (4n + 64) * 2^-52, whenever no prefix falls inside the +-delta band around u.  The first prefix
+// certainly above the band is then the reference's pick -- every earlier one is certainly below.  If some
+// earlier prefix lands inside the band (probability ~ n * 2 * delta per step, < 2^-8 for a million-entry
+// row), or a weight is negative / non-finite, or the sum is not a positive finite number, the step is
+// replayed with the in-order chains of walk_exact_warp_kernel.  O(d_c / 32) warp scans per step instead of
+// d_c dependent float64 additions.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_scan_incl(double v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v = __dadd_rn(v, t);
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(256) walk_exact_cert_kernel(WalkArgs a, const int32_t *__restrict__ hash) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;     // one warp per walker
+  if (i >= a.n_walkers) return;
+  const uint64_t walker = a.walker_first + (uint64_t)i;
+  int32_t curr = (int32_t)(walker % (uint64_t)a.nv), prev = -1;
+  int32_t *path = a.paths + i * a.stride;
+  if (lane == 0) path[0] = curr;
+  int32_t len = 1;
+  int64_t poff = 0;
+  uint32_t pdeg = 0;
+  unsigned long long n_replay = 0;
+  const bool biased = a.p != 1.0f || a.q != 1.0f;
+  while (len != a.stride) {                                                     // RW:103
+    const int64_t off = __ldg(a.off + curr);
+    const uint32_t deg = (uint32_t)(__ldg(a.off + curr + 1) - off);
+    if (deg == 0) break;                                                        // RW:59-62 / RW:115-119
+    const int32_t *cd = a.col_app + off;
+    const float *cw = a.w_app + off;
+    const float u = draw_u(a, walker, (uint32_t)(len - 1));
+    const bool second = len > 1;
+    const uint32_t pnb = (second && biased && hash) ? srw_hash_buckets(poff, pdeg) : 0u;
+    auto weight_of = [&](uint32_t j) -> float {                                 // RS:33-41 for neighbour j (first step: RS:12 plain weights)
+      const float w = __ldg(cw + j);
+      if (!second) return w;
+      const int32_t d = __ldg(cd + j);
+      bool in_prev = false;
+      if (biased && d != prev) in_prev = pnb ? hash_contains(hash, poff, pnb, d) : row_contains(a.col, poff, pdeg, d);
+      return biased_weight(a.p, a.q, prev, d, w, in_prev);
+    };
+    int64_t pick = -1;
+    // ---- certified parallel search ----
+    {
+      double part = 0.0;
+      bool bad = false;
+      for (uint32_t j = lane; j < deg; j += 32) {
+        const float wv = weight_of(j);
+        bad |= !(wv >= 0.0f) || !(wv <= 3.0e38f);
+        part = __dadd_rn(part, (double)wv);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part = __dadd_rn(part, __shfl_xor_sync(0xffffffffu, part, o));
+      bad = __any_sync(0xffffffffu, bad) || !(part > 0.0) || !(part <= 1.0e300);
+      if (!bad) {
+        const double delta = (4.0 * (double)deg + 64.0) * 2.220446049250313e-16;        // 2^-52
+        const double uu = (double)u;
+        const double t_hi = (uu + delta) * part * (1.0 + 1e-15), t_lo = (uu - delta) * part;   // t_lo < 0: every prefix is above it
+        double carry = 0.0;
+        for (uint32_t base = 0; base < deg; base += 32) {
+          const uint32_t j = base + lane;
+          const double wv = j < deg ? (double)weight_of(j) : 0.0;
+          const double P = __dadd_rn(carry, warp_scan_incl(wv, lane));
+          const unsigned valid = (deg - base >= 32u) ? 0xffffffffu : ((1u << (deg - base)) - 1u);
+          const unsigned hi = __ballot_sync(0xffffffffu, P >= t_hi) & valid;
+          const unsigned band = __ballot_sync(0xffffffffu, P > t_lo) & valid;     // includes the hi lanes
+          const unsigned below_first_hi = hi ? ((1u << (__ffs(hi) - 1)) - 1u) : 0xffffffffu;
+          if (band & ~hi & below_first_hi) break;                                  // a prefix inside the band: replay in order
+          if (hi) { pick = base + (__ffs(hi) - 1); break; }
+          carry = __shfl_sync(0xffffffffu, P, 31);
+          if (base + 32 >= deg) pick = 0;                                          // never reached u, certainly: RS:24 edges.head
+        }
+      }
+    }
+    if (pick < 0) {
+      // ---- in-order replay (RS:14, RS:16-22 literally) ----
+      n_replay++;
+      double sum = 0.0;
+      for (uint32_t base = 0; base < deg; base += 32) {
+        const uint32_t j = base + lane, n = min(32u, deg - base);
+        const float wv = j < deg ? weight_of(j) : 0.0f;
+        for (uint32_t l = 0; l < n; ++l) sum = __dadd_rn(sum, (double)__shfl_sync(0xffffffffu, wv, (int)l));
+      }
+      double acc = 0.0;
+      pick = 0;                                                                 // RS:24 edges.head
+      bool found = false;
+      for (uint32_t base = 0; base < deg && !found; base += 32) {
+        const uint32_t j = base + lane, n = min(32u, deg - base);
+        const double qv = j < deg ? __ddiv_rn((double)weight_of(j), sum) : 0.0;
+        for (uint32_t l = 0; l < n; ++l) {
+          acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, qv, (int)l));
+          if (acc >= (double)u) { pick = base + l; found = true; break; }
+        }
+      }
+    }
+    const int32_t nxt = __ldg(cd + pick);
+    if (lane == 0) path[len] = nxt;                                             // RW:114
+    len++;
+    prev = curr; poff = off; pdeg = deg;
+    curr = nxt;
+  }
+  if (lane == 0) {
+    a.lens[i] = len;
+    if (n_replay) atomicAdd(a.stats + 2, n_replay);                             // reported as member_tests: in-order replays
+  }
+}
+
 // ranks -> original vertex ids, and the step count
 __global__ void finalize_paths_kernel(int64_t n_walkers, int32_t stride, const int32_t *__restrict__ vids,
                                       const int32_t *__restrict__ lens, int32_t *paths, unsigned long long *stats) {
@@ -693,7 +841,14 @@ srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLa
   if (p->walk_length < 0 || l.n_walkers < 0) { srw_set_error("walkLength and the walker count must be >= 0"); return SRW_ERR_ARG; }
   if (!(p->p > 0.0) || !(p->q > 0.0)) { srw_set_error("p and q must be > 0"); return SRW_ERR_ARG; }
   t_info = srw_walk_info{};
-  if (g->shard_world > 1) { srw_set_error("this handle is one shard of %d: use the srw_shard_* calls", g->shard_world); return SRW_ERR_ARG; }
+  const bool peer = g->shard_world > 1;
+  if (peer) {
+    // one shard of several: only the peer-gather walk runs through this entry point (the tuple-exchange
+    // walk is driven per super-step through srw_shard_step)
+    for (int r = 0; r < g->shard_world; ++r)
+      if (!g->peer_attached[r]) { srw_set_error("this handle is shard %d of %d and shard %d is not attached: attach every peer (srw_shard_attach_*) for the peer-gather walk, or use the srw_shard_* super-step calls", g->shard_rank, g->shard_world, r); return SRW_ERR_ARG; }
+    if (p->sampler == SRW_SAMPLER_EXACT || g->directed || g->has_alias) { srw_set_error("the peer-gather walk covers undirected, unweighted graphs with --sampler alias|fold"); return SRW_ERR_UNSUPPORTED; }
+  }
   if (l.n_walkers == 0 || g->nv == 0) return SRW_OK;
   const bool exact = p->sampler == SRW_SAMPLER_EXACT;
   if (p->sampler != SRW_SAMPLER_EXACT && p->sampler != SRW_SAMPLER_ALIAS && p->sampler != SRW_SAMPLER_ALIAS_FOLD) { srw_set_error("unknown sampler %d", p->sampler); return SRW_ERR_ARG; }
@@ -714,9 +869,10 @@ srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLa
   a.stats = d_stats;
   SRW_CUDA(cudaEventRecord(ev.a, l.stream));
   if (exact) {
-    static const bool per_thread = getenv("SRW_EXACT") && !strcmp(getenv("SRW_EXACT"), "thread");   // A/B switch
-    if (per_thread) walk_exact_kernel<<<(unsigned)((l.n_walkers + 127) / 128), 128, 0, l.stream>>>(a);
-    else walk_exact_warp_kernel<<<(unsigned)((l.n_walkers + 7) / 8), 256, 0, l.stream>>>(a, g->d_hash);
+    static const char *ex = getenv("SRW_EXACT");                                // A/B switch: thread | warp | cert (default)
+    if (ex && !strcmp(ex, "thread")) walk_exact_kernel<<<(unsigned)((l.n_walkers + 127) / 128), 128, 0, l.stream>>>(a);
+    else if (ex && !strcmp(ex, "warp")) walk_exact_warp_kernel<<<(unsigned)((l.n_walkers + 7) / 8), 256, 0, l.stream>>>(a, g->d_hash);
+    else walk_exact_cert_kernel<<<(unsigned)((l.n_walkers + 7) / 8), 256, 0, l.stream>>>(a, g->d_hash);
   } else {
     const unsigned grid = (unsigned)((l.n_walkers + 255) / 256);
     const bool st = t_collect_stats != 0;
@@ -726,15 +882,26 @@ srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLa
     // (the CPU twin applies the same rule, oracle_alias_walk)
     FoldArgs f{};
     bool fold = false;
-    if (p->sampler == SRW_SAMPLER_ALIAS_FOLD && g->d_ent && g->d_hash && !g->directed && !g->has_alias) {
+    if ((peer || p->sampler == SRW_SAMPLER_ALIAS_FOLD) && (peer || (g->d_ent && g->d_hash)) && !g->directed && !g->has_alias) {
       const double inv_p = 1.0 / (double)(float)p->p, inv_q = 1.0 / (double)(float)p->q;
       const double M = inv_q > 1.0 ? inv_q : 1.0;
       auto thr = [M](double v) -> uint64_t { return v >= M ? 4294967296ULL : (uint64_t)((v / M) * 4294967296.0); };
-      f.ent = g->d_ent; f.hash = g->d_hash; f.a = inv_p - M; f.mp = M; f.t_common = thr(1.0); f.t_far = thr(inv_q);
-      fold = f.a > 0.0;
+      f.ent = g->d_ent; f.hash = g->d_hash; f.a = inv_p - M; f.mp = M; f.t_ret = 4294967296ULL; f.t_common = thr(1.0); f.t_far = thr(inv_q);
+      fold = f.a > 0.0 && p->sampler == SRW_SAMPLER_ALIAS_FOLD;
+      if (peer && !fold) {
+        // classic rejection under M = max(1/p, 1, 1/q) through the same kernel: no return component
+        f.a = 0.0; f.mp = 1.0; f.t_ret = a.t_ret; f.t_common = a.t_common; f.t_far = a.t_far;
+      }
     }
-    if (fold) {
-      if (st) walk_fold_kernel<true><<<grid, 256, 0, l.stream>>>(a, f); else walk_fold_kernel<false><<<grid, 256, 0, l.stream>>>(a, f);
+    if (peer) {
+      PeerTable pt{};
+      pt.world = g->shard_world;
+      for (int r = 0; r <= g->shard_world; ++r) pt.first[r] = g->bounds[(size_t)r];
+      for (int r = 0; r < g->shard_world; ++r) { pt.off[r] = g->peer_off[r]; pt.ent[r] = g->peer_ent[r]; pt.hash[r] = g->peer_hash[r]; }
+      if (st) walk_fold_kernel<true, true><<<grid, 256, 0, l.stream>>>(a, f, pt); else walk_fold_kernel<false, true><<<grid, 256, 0, l.stream>>>(a, f, pt);
+    } else if (fold) {
+      const PeerTable pt{};
+      if (st) walk_fold_kernel<true, false><<<grid, 256, 0, l.stream>>>(a, f, pt); else walk_fold_kernel<false, false><<<grid, 256, 0, l.stream>>>(a, f, pt);
     } else if (!use_v1 && !use_v2 && g->d_meta) {
       const RowMeta *mt = g->d_meta;
       const int32_t *hs = g->d_hash;

@@ -31,6 +31,9 @@ def _bind():
     L.srw_shard_step.argtypes = [vp, vp, C.c_int64, C.c_int64, vp, C.c_int64, vp, vp, C.c_int64, vp, vp, i64p, i64p, i64p, vp]
     L.srw_shard_apply.argtypes = [vp, vp, C.c_int64, C.c_int64, vp, C.c_int64, vp, vp]
     L.srw_shard_finalize.argtypes = [vp, vp, C.c_int64, vp, vp, i64p, vp]
+    L.srw_shard_ipc_export.argtypes = [vp, vp]
+    L.srw_shard_ipc_attach.argtypes = [vp, vp]
+    L.srw_shard_attach_local.argtypes = [vp, vp]
     assert L.srw_walker_msg_bytes() == MSG_BYTES and L.srw_path_rec_bytes() == REC_BYTES
     L._shard_bound = True
     return L
@@ -85,6 +88,49 @@ class Shard:
             self.free()
         except Exception:
             pass
+
+    # ---- peer-gather mode: every shard addressable from every GPU, no walker migration ----
+    def attach_local(self, shards):
+        """All shards live in this process (tests; one process driving several GPUs)."""
+        for o in shards:
+            if o is not self:
+                check(lib().srw_shard_attach_local(self.h, o.h))
+        return self
+
+    def attach_dist(self, group=None):
+        """One shard per process: all-gather the CUDA IPC handles of the row arrays and map every peer's."""
+        import torch.distributed as dist
+        L = lib()
+        nb = L.srw_shard_ipc_bytes()
+        blob = (C.c_uint8 * nb)()
+        check(L.srw_shard_ipc_export(self.h, blob))
+        mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8).clone()
+        dev = self.device if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        mine = mine.to(dev)
+        allb = torch.empty(self.world * nb, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allb, mine, group=group)
+        allb = allb.cpu().numpy()
+        err = None
+        try:
+            for r in range(self.world):
+                if r != self.rank:
+                    buf = (C.c_uint8 * nb).from_buffer_copy(allb[r * nb:(r + 1) * nb].tobytes())
+                    check(L.srw_shard_ipc_attach(self.h, buf))
+        except Exception as e:   # noqa: BLE001  -- agree on the outcome before anyone walks (or waits in a barrier)
+            err = e
+        ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            raise RuntimeError("peer attach failed on at least one rank%s" % ("" if err is None else ": %s" % err))
+        return self
+
+    def walk_device(self, params, walker_first, n_walkers, d_paths, d_lens, stream=0):
+        """srw_walk_device on this shard handle: walkers [walker_first, walker_first + n) against the whole
+        (peer-attached) graph.  Returns the WalkInfo of the launch."""
+        from . import last_walk_info
+        cp = params.to_c()
+        check(lib().srw_walk_device(self.h, C.byref(cp), walker_first, n_walkers, d_paths, d_lens, stream))
+        return last_walk_info()
 
     @property
     def rows(self):

@@ -97,6 +97,26 @@ def full():
         t = torch.tensor([stats["steps"]], dtype=torch.int64, device="cuda")
         dist.all_reduce(t)
         ok = ok and int(t.item()) == st.steps
+        if not weighted:
+            # peer-gather mode over CUDA IPC: this rank walks its slice of the walkers against the whole graph
+            shard.attach_dist()
+            for sampler, fold in (("fold", 1), ("alias", 0)):
+                ids, offs, st = twin.walk(walk_length=30, num_walks=2, p=p, q=q, seed=23, fold=fold)
+                want = oracle_lib.paths_as_lists(ids, offs)
+                total = 2 * twin.nv
+                lo, hi = total * rank // world, total * (rank + 1) // world
+                pp = torch.full((hi - lo, 32), -7, dtype=torch.int32, device="cuda")
+                ll = torch.zeros(hi - lo, dtype=torch.int32, device="cuda")
+                wi = shard.walk_device(srw.Params(walkLength=30, numWalks=2, p=p, q=q, seed=23, sampler=sampler), lo, hi - lo,
+                                       pp.data_ptr(), ll.data_ptr())
+                P, Ln = pp.cpu().numpy(), ll.cpu().numpy()
+                for i in range(hi - lo):
+                    if P[i, :Ln[i]].tolist() != want[lo + i]:
+                        ok = False
+                t = torch.tensor([wi.steps], dtype=torch.int64, device="cuda")
+                dist.all_reduce(t)
+                ok = ok and int(t.item()) == st.steps
+            dist.barrier()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -379,3 +379,72 @@ def test_fold_sampler_fallbacks(oracle):
         a = g.walk(srw.Params(walkLength=30, numWalks=2, p=prm[0], q=prm[1], seed=5, sampler="fold")).arrays()
         b = g.walk(srw.Params(walkLength=30, numWalks=2, p=prm[0], q=prm[1], seed=5, sampler="alias")).arrays()
         assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+
+
+# ---- exact sampler, certified parallel CDF search (walk_exact_cert_kernel): adversarial rows ----
+def test_exact_cert_prefix_on_the_boundary(oracle):
+    """Unit weights, power-of-two degree, constant u = k/deg: a prefix equals u exactly, so the +-delta band is
+    hit and the step must be replayed in order (RS:20 `acc >= u` picks that very prefix)."""
+    n = 9                                               # K9: every vertex has 8 unit-weight neighbours
+    s, d = np.array([(i, j) for i in range(n) for j in range(i + 1, n)], dtype=np.int32).T
+    og = oracle.Graph().load_edges(s, d)
+    g = srw.Graph.from_edges(s, d)
+    for u in (0.0, 0.125, 0.25, 0.5, 0.875, 0.99999994):
+        for p, q in ((1.0, 1.0), (0.5, 2.0)):
+            ids, offs = oracle.walk(og, walk_length=12, num_walks=1, p=p, q=q, u_const=u)
+            got = g.walk(srw.Params(walkLength=12, numWalks=1, p=p, q=q, sampler="exact"), u_const=u).arrays()
+            assert (got[1] == offs).all() and (got[0] == ids).all(), (u, p, q)
+
+
+@pytest.mark.parametrize("kind", ["wide", "zeros", "tiny", "allzero"])
+def test_exact_cert_adversarial_weights(oracle, kind):
+    """Weights over 40 orders of magnitude, zero weights (RS:20 can pick a zero-weight edge when u == 0; an all-zero
+    row makes sum == 0 and falls through to edges.head), denormal-sized weights."""
+    rng = np.random.RandomState(5)
+    s, d = synth.rmat_edges(9, 16, seed=11)
+    m = len(s)
+    if kind == "wide":
+        w = (10.0 ** rng.uniform(-20, 20, m)).astype(np.float32)
+    elif kind == "zeros":
+        w = np.where(rng.rand(m) < 0.4, 0.0, rng.rand(m)).astype(np.float32)
+    elif kind == "tiny":
+        w = (rng.rand(m) * 1e-38).astype(np.float32)
+    else:
+        w = np.zeros(m, np.float32)
+    og = oracle.Graph().load_edges(s, d, w)
+    g = srw.Graph.from_edges(s, d, w)
+    for p, q, seed in ((1.0, 1.0, 1), (0.5, 2.0, 2), (4.0, 0.25, 3)):
+        ids, offs = oracle.walk(og, walk_length=15, num_walks=2, p=p, q=q, seed=seed)
+        got = g.walk(srw.Params(walkLength=15, numWalks=2, p=p, q=q, seed=seed, sampler="exact")).arrays()
+        assert (got[1] == offs).all() and (got[0] == ids).all(), (kind, p, q)
+
+
+def test_exact_kernel_generations_agree(tmp_path):
+    """thread (one walker per thread), warp (in-order fold through shuffles) and cert (certified parallel
+    search) produce the same bits on a weighted hub graph."""
+    import subprocess, sys
+    script = tmp_path / "run.py"
+    script.write_text('''
+import importlib, sys, hashlib
+sys.path.insert(0, %r)
+srw = importlib.import_module("stellar-random-walk_b200")
+synth = importlib.import_module("stellar-random-walk_b200.synth")
+out = []
+s, d = synth.rmat_edges(12, 16, seed=3)
+for w in (None, synth.edge_weights(len(s), seed=4)):
+    g = srw.Graph.from_edges(s, d, w)
+    ids, offs = g.walk(srw.Params(walkLength=20, numWalks=1, p=0.5, q=2.0, seed=9, sampler="exact")).arrays()
+    out.append(hashlib.sha256(ids.tobytes() + offs.tobytes()).hexdigest())
+s, d = synth.zipf_edges(4096, cap=3000, seed=7)
+g = srw.Graph.from_edges(s, d)
+ids, offs = g.walk(srw.Params(walkLength=20, numWalks=1, p=0.25, q=4.0, seed=2, sampler="exact")).arrays()
+out.append(hashlib.sha256(ids.tobytes() + offs.tobytes()).hexdigest())
+print(",".join(out))
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    res = {}
+    for k in ("thread", "warp", "cert"):
+        env = dict(os.environ, SRW_EXACT=k)
+        r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[k] = r.stdout.strip().splitlines()[-1]
+    assert res["thread"] == res["warp"] == res["cert"], res

@@ -72,3 +72,51 @@ def test_sharded_matches_single_gpu_kernel():
             rows[rnd * nv + x.rank: (rnd + 1) * nv: x.world] = P[rnd * x.home_rows:(rnd + 1) * x.home_rows]
     assert (np.diff(ref_offs) == 42).all()
     assert (rows.reshape(-1) == ref_ids).all()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("sampler,p,q", [("fold", 0.5, 2.0), ("fold", 0.25, 4.0), ("alias", 0.5, 2.0), ("fold", 2.0, 0.5), ("alias", 1.0, 1.0)])
+def test_peer_gather_equals_twin(oracle, world, sampler, p, q):
+    """Peer-gather mode: W shards on one device, every shard attached to every other; each shard handle walks
+    a slice of the walkers against the whole graph.  Output == CPU twin (== the unsharded kernel)."""
+    import torch
+    sh = importlib.import_module("stellar-random-walk_b200.sharded")
+    s, d = synth.rmat_edges(10, 8, seed=42)
+    ds, dd, _ = _device_edges(s, d, None)
+    shards = [sh.Shard(len(s), ds.data_ptr(), dd.data_ptr(), None, r, world) for r in range(world)]
+    for x in shards:
+        x.attach_local(shards)
+    twin = oracle.AliasGraph(oracle.Graph().load_edges(s, d, None))
+    ids, offs, st = twin.walk(walk_length=30, num_walks=2, p=p, q=q, seed=9, fold=1 if sampler == "fold" else 0)
+    nv = twin.nv
+    prm = srw.Params(walkLength=30, numWalks=2, p=p, q=q, seed=9, sampler=sampler)
+    total = 2 * nv
+    paths = torch.full((total, 32), -7, dtype=torch.int32, device="cuda")
+    lens = torch.zeros(total, dtype=torch.int32, device="cuda")
+    steps = 0
+    for r, x in enumerate(shards):             # walker slices deliberately not aligned with the vertex ranges
+        lo, hi = total * r // world, total * (r + 1) // world
+        wi = x.walk_device(prm, lo, hi - lo, paths[lo:].data_ptr(), lens[lo:].data_ptr())
+        steps += wi.steps
+    P, Ln = paths.cpu().numpy(), lens.cpu().numpy()
+    got = [P[i, :Ln[i]].tolist() for i in range(total)]
+    assert got == oracle.paths_as_lists(ids, offs)
+    assert steps == st.steps
+
+
+def test_peer_gather_requires_every_peer():
+    import torch
+    sh = importlib.import_module("stellar-random-walk_b200.sharded")
+    s, d = synth.rmat_edges(8, 4, seed=1)
+    ds, dd, _ = _device_edges(s, d, None)
+    shards = [sh.Shard(len(s), ds.data_ptr(), dd.data_ptr(), None, r, 2) for r in range(2)]
+    paths = torch.zeros((4, 12), dtype=torch.int32, device="cuda")
+    lens = torch.zeros(4, dtype=torch.int32, device="cuda")
+    with pytest.raises(srw.SrwError):
+        shards[0].walk_device(srw.Params(walkLength=10, numWalks=1), 0, 4, paths.data_ptr(), lens.data_ptr())
+    # weighted shards carry no neighbour entries: attaching is refused
+    w = synth.edge_weights(len(s), seed=2)
+    dw = torch.from_numpy(w).cuda()
+    ws = [sh.Shard(len(s), ds.data_ptr(), dd.data_ptr(), dw.data_ptr(), r, 2) for r in range(2)]
+    with pytest.raises(srw.SrwError):
+        ws[0].attach_local(ws)
