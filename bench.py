@@ -618,6 +618,32 @@ def run_peer_gather(a, srw, sh, shard, rank, world, dev, barrier):
     stream = torch.cuda.current_stream()
     a = argparse.Namespace(**vars(a))
     a.steps, a.warmup = getattr(a, "peer_steps", a.steps), getattr(a, "peer_warmup", a.warmup)
+    # bounded probe first: the whole measurement must fit a time budget whatever a peer load costs on this box
+    probe_n = min(n_local, 1 << 20)
+    shard.walk_device(prm, lo, min(probe_n, 1 << 14), paths.data_ptr(), lens.data_ptr(), stream.cuda_stream)
+    wi = shard.walk_device(prm, lo, probe_n, paths.data_ptr(), lens.data_ptr(), stream.cuda_stream)
+    est = torch.tensor([wi.kernel_ms * 1e-3 * n_local / max(1, probe_n)], dtype=torch.float64, device=dev)
+    dist.all_reduce(est, op=dist.ReduceOp.MAX)
+    est_round_s = float(est[0])
+    budget_s = float(os.environ.get("SRW_PEER_BUDGET_S", "60"))
+    sampled = None
+    if est_round_s * (a.steps + a.warmup) > budget_s:
+        k = int(budget_s / max(est_round_s, 1e-9))
+        if k >= 2:
+            a.steps, a.warmup = k - 1, 1
+        else:
+            # even one full round does not fit: report the probe (a strided... no: the first probe_n walkers of this rank's slice)
+            t = torch.tensor([wi.kernel_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tot = torch.tensor([wi.steps], dtype=torch.int64, device=dev)
+            dist.all_reduce(tot)
+            value = int(tot[0]) / (float(t[0]) * 1e-3)
+            log("sharded: peer-gather %.3e steps/s on a %d-walker probe per rank (a full round would take %.0f s)" % (value, probe_n, est_round_s))
+            del paths, lens
+            torch.cuda.empty_cache()
+            return {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": 0, "warmup": 0, "ms_per_step": est_round_s * 1e3,
+                    "scaling": "strong", "sampled": "first %d walkers of every rank's slice, one launch; full rounds skipped (time budget %.0f s)" % (probe_n, budget_s),
+                    "config": {"workload": workload_name(a), "vertices_present": nv, "sampler": a.sampler, "ipc_attach_s": round(attach_s, 3)}}
     for r in range(a.warmup):
         shard.walk_device(prm, r * nv + lo, n_local, paths.data_ptr(), lens.data_ptr(), stream.cuda_stream)
     barrier()
@@ -652,8 +678,9 @@ def run_peer_gather(a, srw, sh, shard, rank, world, dev, barrier):
             "scaling": "strong", "path_checksum": int(chk[0]),
             "config": {"workload": workload_name(a), "vertices_present": nv, "walkers_per_step": nv,
                        "parallelism": "graph sharded into %d edge-balanced vertex ranges (one per GPU, %d adjacency entries on rank 0); "
-                                      "every GPU maps every shard through CUDA IPC and walk_fold_kernel<PEER> loads remote rows over "
+                                      "every GPU maps every shard (symmetric-memory blocks, CUDA VMM) and walk_fold_kernel<PEER> loads remote rows over "
                                       "NVLink; walkers split evenly, never migrate, no collective on the data path" % (world, shard.nnz_local),
+                       "peer_mapping": os.environ.get("SRW_PEER_MAP", "symm"),
                        "sampler": a.sampler, "ipc_attach_s": round(attach_s, 3)},
             "clocks": clk}
 

@@ -225,6 +225,13 @@ int srw_shard_ipc_bytes(void);                                       /* size of 
 srw_status srw_shard_ipc_export(const srw_graph *g, void *h_blob);  /* this shard's row arrays as IPC handles */
 srw_status srw_shard_ipc_attach(srw_graph *g, const void *h_blob);  /* map another process's shard (own blob: no-op) */
 srw_status srw_shard_attach_local(srw_graph *g, const srw_graph *peer);   /* peer handle lives in this process */
+/* One process per GPU, the fast way: the host runtime allocates one symmetric-memory block per rank (CUDA VMM
+ * allocations whose handles it exchanges; torch.distributed._symmetric_memory in sharded.py), the shard moves
+ * its row arrays into its block, and every peer's block pointer is attached.  block layout: see shard.cu. */
+srw_status srw_shard_rows_info(const srw_graph *g, int64_t *rows, int64_t *nnz, int64_t *hash_buckets, int64_t *block_bytes);
+srw_status srw_shard_rows_relocate(srw_graph *g, void *d_block, int64_t block_bytes);   /* block must outlive g */
+srw_status srw_shard_attach_block(srw_graph *g, int peer_rank, const void *d_block, int64_t rows, int64_t nnz,
+                                  int64_t hash_buckets);
 
 /* ---- synthetic inputs for the benchmark; device-resident, not on the walk path ---- */
 srw_status srw_synth_rmat_device(int scale, int edge_factor, uint64_t seed, int64_t first, int64_t count,

@@ -41,6 +41,7 @@ ABI_SYMBOLS = [
     "srw_graph_from_device_edges_sharded", "srw_graph_shard_info", "srw_walker_msg_bytes", "srw_path_rec_bytes",
     "srw_shard_seed", "srw_shard_step", "srw_shard_apply", "srw_shard_finalize",
     "srw_shard_ipc_bytes", "srw_shard_ipc_export", "srw_shard_ipc_attach", "srw_shard_attach_local",
+    "srw_shard_rows_info", "srw_shard_rows_relocate", "srw_shard_attach_block",
 ]
 
 

@@ -576,3 +576,69 @@ extern "C" srw_status srw_shard_attach_local(srw_graph *g, const srw_graph *peer
   g->peer_attached[r] = true;
   return SRW_OK;
 }
+
+// ---- the same, over a caller-provided block per shard.  One process per GPU: the block is a symmetric-memory
+// allocation (CUDA VMM handles exchanged by the host runtime -- torch.distributed._symmetric_memory in
+// sharded.py), whose peer mappings are ordinary NVLink peer pointers.  (Legacy cudaIpc mappings of
+// cudaMalloc memory, srw_shard_ipc_* above, were measured ~35x slower for random 16-byte loads on this
+// platform: profiles/README.md.)  Layout of a block, every part 256-byte aligned:
+//   [ off: (rows + 1) * 8 ][ ent: nnz * 16 ][ hash: hash_buckets * 32 ]
+namespace {
+inline int64_t up256(int64_t x) { return (x + 255) & ~(int64_t)255; }
+inline void block_layout(int64_t rows, int64_t nnz, int64_t hash_buckets, int64_t *o_ent, int64_t *o_hash, int64_t *total) {
+  const int64_t e = up256((rows + 1) * 8), h = e + up256(nnz * (int64_t)sizeof(NbrEntry));
+  if (o_ent) *o_ent = e;
+  if (o_hash) *o_hash = h;
+  if (total) *total = h + up256(hash_buckets * 32);
+}
+}  // namespace
+
+extern "C" srw_status srw_shard_rows_info(const srw_graph *g, int64_t *rows, int64_t *nnz, int64_t *hash_buckets, int64_t *block_bytes) {
+  if (!g) return SRW_ERR_ARG;
+  const int64_t r = g->row_last - g->row_first, hb = g->d_hash ? g->hash_buckets : 0;
+  if (rows) *rows = r;
+  if (nnz) *nnz = g->nnz;
+  if (hash_buckets) *hash_buckets = hb;
+  block_layout(r, g->nnz, hb, nullptr, nullptr, block_bytes);
+  return SRW_OK;
+}
+
+extern "C" srw_status srw_shard_rows_relocate(srw_graph *g, void *d_block, int64_t block_bytes) {
+  SRW_TRY(srw_require_device());
+  if (!g || !d_block || g->rows_external) { srw_set_error("srw_shard_rows_relocate: bad argument (or already relocated)"); return SRW_ERR_ARG; }
+  if (g->nnz > 0 && (!g->d_ent || !g->d_hash)) { srw_set_error("this shard has no neighbour entries (weighted graph?): the peer-gather walk needs an unweighted SRW_BUILD_ALIAS build"); return SRW_ERR_UNSUPPORTED; }
+  const int64_t rows = g->row_last - g->row_first, hb = g->d_hash ? g->hash_buckets : 0;
+  int64_t o_ent, o_hash, total;
+  block_layout(rows, g->nnz, hb, &o_ent, &o_hash, &total);
+  if (block_bytes < total) { srw_set_error("srw_shard_rows_relocate: block of %lld bytes < %lld needed", (long long)block_bytes, (long long)total); return SRW_ERR_ARG; }
+  SRW_CUDA(cudaSetDevice(g->device));
+  char *b = (char *)d_block;
+  SRW_CUDA(cudaMemcpy(b, g->d_off, (size_t)(rows + 1) * 8, cudaMemcpyDeviceToDevice));
+  if (g->d_ent) SRW_CUDA(cudaMemcpy(b + o_ent, g->d_ent, (size_t)g->nnz * sizeof(NbrEntry), cudaMemcpyDeviceToDevice));
+  if (g->d_hash) SRW_CUDA(cudaMemcpy(b + o_hash, g->d_hash, (size_t)hb * 32, cudaMemcpyDeviceToDevice));
+  SRW_CUDA(cudaDeviceSynchronize());
+  cudaFree(g->d_off); cudaFree(g->d_ent); cudaFree(g->d_hash);
+  g->d_off = (int64_t *)b;
+  g->d_ent = g->nnz > 0 ? (NbrEntry *)(b + o_ent) : nullptr;
+  g->d_hash = hb > 0 ? (int32_t *)(b + o_hash) : nullptr;
+  g->rows_external = true;
+  const int r = g->shard_rank;
+  g->peer_off[r] = g->d_off; g->peer_ent[r] = g->d_ent; g->peer_hash[r] = g->d_hash;
+  return SRW_OK;
+}
+
+extern "C" srw_status srw_shard_attach_block(srw_graph *g, int peer_rank, const void *d_block, int64_t rows, int64_t nnz,
+                                             int64_t hash_buckets) {
+  if (!g || !d_block || peer_rank < 0 || peer_rank >= g->shard_world) { srw_set_error("srw_shard_attach_block: bad argument"); return SRW_ERR_ARG; }
+  if (peer_rank == g->shard_rank) return SRW_OK;
+  if (rows != g->bounds[(size_t)peer_rank + 1] - g->bounds[(size_t)peer_rank]) { srw_set_error("srw_shard_attach_block: shard %d has %lld rows, expected %lld", peer_rank, (long long)rows, (long long)(g->bounds[(size_t)peer_rank + 1] - g->bounds[(size_t)peer_rank])); return SRW_ERR_ARG; }
+  int64_t o_ent, o_hash;
+  block_layout(rows, nnz, hash_buckets, &o_ent, &o_hash, nullptr);
+  const char *b = (const char *)d_block;
+  g->peer_off[peer_rank] = (const int64_t *)b;
+  g->peer_ent[peer_rank] = nnz > 0 ? (const NbrEntry *)(b + o_ent) : nullptr;
+  g->peer_hash[peer_rank] = hash_buckets > 0 ? (const int32_t *)(b + o_hash) : nullptr;
+  g->peer_ipc[peer_rank] = false;
+  g->peer_attached[peer_rank] = true;
+  return SRW_OK;
+}

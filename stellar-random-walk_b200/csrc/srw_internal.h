@@ -110,6 +110,7 @@ struct srw_graph {
   const int32_t *peer_hash[SRW_MAX_SHARDS] = {};
   bool peer_attached[SRW_MAX_SHARDS] = {};
   bool peer_ipc[SRW_MAX_SHARDS] = {};   // mapping opened with cudaIpcOpenMemHandle (closed on free)
+  bool rows_external = false;           // d_off / d_ent / d_hash live in a caller-owned block (srw_shard_rows_relocate)
 };
 
 srw_status srw_build_graph_device_sharded(int64_t n, const int32_t *d_src, const int32_t *d_dst, const float *d_w, int directed,

@@ -10,6 +10,7 @@ Two deployments share this code:
   * several shards inside one process on one device (tests): `LocalExchange` -- tensor slicing.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -34,6 +35,9 @@ def _bind():
     L.srw_shard_ipc_export.argtypes = [vp, vp]
     L.srw_shard_ipc_attach.argtypes = [vp, vp]
     L.srw_shard_attach_local.argtypes = [vp, vp]
+    L.srw_shard_rows_info.argtypes = [vp, i64p, i64p, i64p, i64p]
+    L.srw_shard_rows_relocate.argtypes = [vp, vp, C.c_int64]
+    L.srw_shard_attach_block.argtypes = [vp, C.c_int, vp, C.c_int64, C.c_int64, C.c_int64]
     assert L.srw_walker_msg_bytes() == MSG_BYTES and L.srw_path_rec_bytes() == REC_BYTES
     L._shard_bound = True
     return L
@@ -77,11 +81,13 @@ class Shard:
         check(L.srw_graph_stats(self.h, C.byref(nv), None))
         self.nv = nv.value
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self._block = self._symm = None
 
     def free(self):
         if self.h:
             lib().srw_graph_free(self.h)
             self.h = None
+        self._block = self._symm = None     # the rows lived there (srw_shard_rows_relocate): release after the handle
 
     def __del__(self):
         try:
@@ -97,20 +103,67 @@ class Shard:
                 check(lib().srw_shard_attach_local(self.h, o.h))
         return self
 
-    def attach_dist(self, group=None):
-        """One shard per process: all-gather the CUDA IPC handles of the row arrays and map every peer's."""
+    def rows_info(self):
+        r, n, hb, nb = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        check(lib().srw_shard_rows_info(self.h, C.byref(r), C.byref(n), C.byref(hb), C.byref(nb)))
+        return r.value, n.value, hb.value, nb.value
+
+    def attach_blocks_local(self, shards):
+        """Same-process variant of attach_dist (tests): every shard moves its rows into a block, then maps the others'."""
+        for o in shards:
+            if getattr(o, "_block", None) is None:
+                nb = o.rows_info()[3]
+                o._block = torch.empty(nb, dtype=torch.uint8, device=o.device)
+                check(lib().srw_shard_rows_relocate(o.h, o._block.data_ptr(), nb))
+        for o in shards:
+            if o is not self:
+                r, n, hb, _ = o.rows_info()
+                check(lib().srw_shard_attach_block(self.h, o.rank, o._block.data_ptr(), r, n, hb))
+        return self
+
+    def attach_dist(self, group=None, mode=None):
+        """One shard per process.  mode "symm" (default): the row arrays move into a torch symmetric-memory block
+        (CUDA VMM allocation; torch exchanges the handles) and every peer's block is attached as an NVLink peer
+        pointer.  mode "ipc": legacy cudaIpc handles of the cudaMalloc'ed arrays (kept for comparison: ~35x slower
+        random loads on this platform)."""
         import torch.distributed as dist
         L = lib()
+        mode = mode or os.environ.get("SRW_PEER_MAP", "symm")
+        dev = self.device if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        err = None
+        if mode == "symm":
+            import torch.distributed._symmetric_memory as symm
+            mine = torch.tensor(self.rows_info(), dtype=torch.int64, device=dev)
+            meta = torch.empty(self.world * 4, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(meta, mine, group=group)
+            meta = meta.view(self.world, 4).tolist()
+            size = max(m[3] for m in meta)
+            try:
+                blk = symm.empty(size, dtype=torch.uint8, device=self.device)
+                hdl = symm.rendezvous(blk, group if group is not None else dist.group.WORLD)
+                check(L.srw_shard_rows_relocate(self.h, blk.data_ptr(), size))
+                self._block, self._symm = blk, hdl
+            except Exception as e:   # noqa: BLE001
+                err = e
+            ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)     # also orders "everyone relocated" before any attach
+            if int(ok.item()) == 0:
+                raise RuntimeError("symmetric-memory block setup failed on at least one rank%s" % ("" if err is None else ": %s" % err))
+            ptrs = list(self._symm.buffer_ptrs)
+            for r in range(self.world):
+                if r != self.rank:
+                    check(L.srw_shard_attach_block(self.h, r, ptrs[r], meta[r][0], meta[r][1], meta[r][2]))
+            torch.cuda.synchronize()
+            dist.barrier(group=group)
+            return self
         nb = L.srw_shard_ipc_bytes()
         blob = (C.c_uint8 * nb)()
         check(L.srw_shard_ipc_export(self.h, blob))
         mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8).clone()
-        dev = self.device if dist.get_backend(group) == "nccl" else torch.device("cpu")
         mine = mine.to(dev)
         allb = torch.empty(self.world * nb, dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(allb, mine, group=group)
         allb = allb.cpu().numpy()
-        err = None
         try:
             for r in range(self.world):
                 if r != self.rank:
