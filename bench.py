@@ -56,6 +56,15 @@ def parse_args():
 
 
 _T0 = time.time()
+_OUT = None
+
+
+def emit(obj):
+    """The ONE JSON line of this run, on the real stdout (fd 1 is pointed at stderr for everything else: NCCL
+    prints its version banner on stdout, libraries may print warnings)."""
+    out = _OUT if _OUT is not None else sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
 
 
 def log(msg):
@@ -185,7 +194,7 @@ def run_reference(a):
     n_edges = a.edge_factor << a.scale
     need_gb = (n_edges * 8 + 2 * n_edges * 4 + (1 << a.scale) * 16) / 1e9
     if mem_available_gb() < need_gb * 1.5 + 8:
-        print(json.dumps({"impl": "reference", "unavailable": "host RAM too small for a CPU build of rmat-%d (%.0f GB needed)" % (a.scale, need_gb)}))
+        emit({"impl": "reference", "unavailable": "host RAM too small for a CPU build of rmat-%d (%.0f GB needed)" % (a.scale, need_gb)})
         return
     log("reference arm: generating rmat-%d on the CPU" % a.scale)
     t0 = time.time()
@@ -218,7 +227,7 @@ def run_reference(a):
             "config": {"workload": workload_name(a), "cpu_graph_build_s": round(build_s, 1)},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": res["sample"]},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -261,10 +270,15 @@ def run_b200(a):
 
     log("generating %s" % workload_name(a))
     d_src, d_dst, d_w = gen_edges()
-    want_e2e = (not a.no_e2e) and world == 1
+    want_e2e = not a.no_e2e
     h_edges = None
-    if want_e2e and mem_available_gb() > (n_edges * 8) / 1e9 * 2 + 16:
+    if want_e2e and mem_available_gb() > world * ((n_edges * 8) / 1e9 * 2 + 2) + 16:
         h_edges = [t.cpu().pin_memory() for t in (d_src, d_dst)] + ([d_w.cpu().pin_memory()] if d_w is not None else [])
+    if world > 1:      # all ranks or none (the e2e region holds collectives)
+        fl = torch.tensor([1 if h_edges is not None else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(fl, op=dist.ReduceOp.MIN)
+        if int(fl.item()) == 0:
+            h_edges = None
     log("host copy of the edge list done (e2e=%s); building CSR" % (h_edges is not None))
     g, build_s = build(d_src, d_dst, d_w)
     log("CSR built in %.2f s" % build_s)
@@ -378,7 +392,7 @@ def run_b200(a):
         bufs = [paths, torch.empty_like(paths)]
         copy_stream = torch.cuda.Stream()
         copied = [None, None]
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.time()
         dd = [t.to(dev, non_blocking=True) for t in h_edges]
         g2 = srw.Graph.from_device_edges(n_edges, dd[0].data_ptr(), dd[1].data_ptr(), dd[2].data_ptr() if len(dd) > 2 else None, False, srw.BUILD_ALIAS)
@@ -389,7 +403,7 @@ def run_b200(a):
             if copied[b] is not None:
                 copied[b].synchronize()            # the buffer's previous contents have left the device
             flat = bufs[b].view(-1)
-            srw.check(lib.srw_walk_device(g2.h, C.byref(cp), (a.warmup + k) * nv, nv, bufs[b].data_ptr(), lens.data_ptr(), stream.cuda_stream))
+            srw.check(lib.srw_walk_device(g2.h, C.byref(cp), (a.warmup + k) * nv + lo, n_local, bufs[b].data_ptr(), lens.data_ptr(), stream.cuda_stream))
             e_steps += srw.last_walk_info().steps
             with torch.cuda.stream(copy_stream):
                 for i, off in enumerate(range(0, flat.numel(), ring[0].numel())):
@@ -415,9 +429,16 @@ def run_b200(a):
         torch.cuda.synchronize()
         d2h_gbps = min(flat.numel(), 16 * ring[0].numel()) * 4 / (time.time() - tb) / 1e9
         h2d = sum(t.numel() * t.element_size() for t in h_edges)
+        if world > 1:
+            # whole job: every rank copied the edge list in, built its replica, walked and read back its slice
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            cc = torch.tensor([e_steps, h2d, d2h, 1 if e2e_ok else 0], dtype=torch.int64, device=dev)
+            dist.all_reduce(cc)
+            dt, e_steps, h2d, d2h, e2e_ok = float(tt[0]), int(cc[0]), int(cc[1]), int(cc[2]), int(cc[3]) == world
         e2e = {"value": e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d // max(1, a.steps), "d2h_bytes_per_step": d2h // max(1, a.steps),
-               "seconds": dt, "last_chunk_verified": e2e_ok, "d2h_GBps_standalone": d2h_gbps, "includes": "edge-list H2D + CSR build (once) + %d rounds + D2H of every round's paths through a pinned ring "
-                           "(the copy of round r overlaps the walk of round r+1)" % a.steps}
+               "seconds": dt, "last_chunk_verified": e2e_ok, "d2h_GBps_standalone": d2h_gbps, "includes": "edge-list H2D + CSR build (once%s) + %d rounds + D2H of every round's paths through a pinned ring "
+                           "(the copy of round r overlaps the walk of round r+1); wall clock, max over ranks" % (", on every rank" if world > 1 else "", a.steps)}
         del bufs
         g = g2
 
@@ -476,7 +497,7 @@ def run_b200(a):
                 line["sharded_c4"] = tup
                 if pg:
                     line["sharded_c4_peer_gather_error"] = pg.get("error")
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -534,7 +555,7 @@ def run_b200_sharded(a, own_group=True):
         torch.cuda.empty_cache()
         if own_group:
             if line is not None:
-                print(json.dumps(line))
+                emit(line)
             dist.destroy_process_group()
         return line
 
@@ -595,7 +616,7 @@ def run_b200_sharded(a, own_group=True):
     torch.cuda.empty_cache()
     if own_group:
         if line is not None:
-            print(json.dumps(line))
+            emit(line)
         dist.destroy_process_group()
     return line
 
@@ -687,6 +708,9 @@ def run_peer_gather(a, srw, sh, shard, rank, world, dev, barrier):
 
 if __name__ == "__main__":
     args = parse_args()
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     elif int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.mode in ("sharded", "peer"):

@@ -364,8 +364,8 @@ struct PeerTable {
 
 constexpr int kStage = 16;
 
-template <bool STATS, bool PEER>
-__global__ void __launch_bounds__(256) walk_fold_kernel(WalkArgs a, FoldArgs f, const PeerTable pt) {
+template <bool STATS, bool PEER, int MINB = 4>
+__global__ void __launch_bounds__(256, MINB) walk_fold_kernel(WalkArgs a, FoldArgs f, const PeerTable pt) {
   __shared__ int32_t sbuf[kStage * 256];
   __shared__ const NbrEntry *s_ent[SRW_MAX_SHARDS];
   __shared__ const int32_t *s_hash[SRW_MAX_SHARDS];
@@ -880,6 +880,7 @@ srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLa
     static const bool use_v2 = getenv("SRW_KERNEL") && !strcmp(getenv("SRW_KERNEL"), "v2");
     // SRW_SAMPLER_ALIAS_FOLD: undirected + unweighted + 1/p > max(1, 1/q), else the classic sampler
     // (the CPU twin applies the same rule, oracle_alias_walk)
+    static const int occ = getenv("SRW_FOLD_OCC") ? atoi(getenv("SRW_FOLD_OCC")) : 0;   // A/B: resident blocks per SM the fold kernel is compiled for
     FoldArgs f{};
     bool fold = false;
     if ((peer || p->sampler == SRW_SAMPLER_ALIAS_FOLD) && (peer || (g->d_ent && g->d_hash)) && !g->directed && !g->has_alias) {
@@ -898,10 +899,20 @@ srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLa
       pt.world = g->shard_world;
       for (int r = 0; r <= g->shard_world; ++r) pt.first[r] = g->bounds[(size_t)r];
       for (int r = 0; r < g->shard_world; ++r) { pt.off[r] = g->peer_off[r]; pt.ent[r] = g->peer_ent[r]; pt.hash[r] = g->peer_hash[r]; }
-      if (st) walk_fold_kernel<true, true><<<grid, 256, 0, l.stream>>>(a, f, pt); else walk_fold_kernel<false, true><<<grid, 256, 0, l.stream>>>(a, f, pt);
+      if (st) walk_fold_kernel<true, true><<<grid, 256, 0, l.stream>>>(a, f, pt);
+      else if (occ == 2) walk_fold_kernel<false, true, 2><<<grid, 256, 0, l.stream>>>(a, f, pt);
+      else if (occ == 5) walk_fold_kernel<false, true, 5><<<grid, 256, 0, l.stream>>>(a, f, pt);
+      else if (occ == 6) walk_fold_kernel<false, true, 6><<<grid, 256, 0, l.stream>>>(a, f, pt);
+      else if (occ == 8) walk_fold_kernel<false, true, 8><<<grid, 256, 0, l.stream>>>(a, f, pt);
+      else walk_fold_kernel<false, true><<<grid, 256, 0, l.stream>>>(a, f, pt);
     } else if (fold) {
       const PeerTable pt{};
-      if (st) walk_fold_kernel<true, false><<<grid, 256, 0, l.stream>>>(a, f, pt); else walk_fold_kernel<false, false><<<grid, 256, 0, l.stream>>>(a, f, pt);
+      if (st) walk_fold_kernel<true, false><<<grid, 256, 0, l.stream>>>(a, f, pt);
+      else if (occ == 2) walk_fold_kernel<false, false, 2><<<grid, 256, 0, l.stream>>>(a, f, pt);
+      else if (occ == 5) walk_fold_kernel<false, false, 5><<<grid, 256, 0, l.stream>>>(a, f, pt);
+      else if (occ == 6) walk_fold_kernel<false, false, 6><<<grid, 256, 0, l.stream>>>(a, f, pt);
+      else if (occ == 8) walk_fold_kernel<false, false, 8><<<grid, 256, 0, l.stream>>>(a, f, pt);
+      else walk_fold_kernel<false, false><<<grid, 256, 0, l.stream>>>(a, f, pt);
     } else if (!use_v1 && !use_v2 && g->d_meta) {
       const RowMeta *mt = g->d_meta;
       const int32_t *hs = g->d_hash;
