@@ -33,46 +33,8 @@ struct srw_edges {
   bool has_pid = false;
 };
 
-// Vose slot, one 16-byte gather per proposal: own and alias target vertex are both inline.
-struct __align__(16) AliasSlot {
-  uint32_t thr;           // take `own` iff r < thr
-  int32_t own;            // neighbour rank stored at this slot
-  int32_t alias_vertex;   // neighbour rank of the alias slot
-  uint32_t alias_index;   // row-relative index of the alias slot
-};
+#include "layout.h"
 
-// Row descriptor read once per walk step.  Rows with more than kHashMinDeg neighbours also own a hash
-// set of their neighbour ids (`nb` buckets of 8 slots starting at bucket `hoff`): the d(t,x)=1
-// membership test of node2vec becomes ~1 sector instead of a ~log2(deg) binary search.
-struct __align__(32) RowMeta {
-  int64_t off;     // first entry in d_col / d_slot
-  int64_t hoff;    // first bucket in d_hash
-  uint32_t deg;
-  uint32_t nb;     // 0: no hash set (short row: binary search in d_col)
-  uint32_t pad0, pad1;
-};
-// Hash-set placement is DERIVED from the row extent, so nothing but (off, deg) is needed to probe it:
-// row r owns buckets [off >> 2, (off + deg) >> 2) -- about deg/4 buckets of 8 slots (load <= ~0.5).
-// Rows shorter than kHashMinDeg have no set (8 * nb >= 2*deg - 6 >= deg + 1 needs deg >= 7).
-constexpr uint32_t kHashMinDeg = 8;
-__host__ __device__ inline int64_t srw_hash_first(int64_t off) { return off >> 2; }
-__host__ __device__ inline uint32_t srw_hash_buckets(int64_t off, uint32_t deg) {
-  return deg >= kHashMinDeg ? (uint32_t)(((off + (int64_t)deg) >> 2) - (off >> 2)) : 0u;
-}
-// Neighbour entry of the fold sampler (unweighted graphs): one 16-byte gather yields the neighbour AND
-// its row extent AND the multiplicity of the edge, so a walk step needs no separate row-descriptor load.
-struct __align__(16) NbrEntry {
-  int32_t x;             // neighbour rank
-  uint32_t deg;          // deg(x)
-  uint32_t off_lo;       // row offset of x inside its owner's arrays (< 2^32: the ABI caps nnz at 2^32 - 1)
-  uint32_t off_hi_mult;  // [7:0] owner shard of x (0 on an unsharded graph), [31:8] number of parallel edges to x in this row
-};
-__host__ __device__ inline uint32_t srw_hash32(uint32_t x) {
-  x *= 0x9E3779B1u; x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 12;
-  return x;
-}
-
-#define SRW_MAX_SHARDS 16
 struct srw_graph {
   int device = 0;
   int64_t nv = 0, nnz = 0;

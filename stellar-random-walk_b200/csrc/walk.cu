@@ -26,26 +26,7 @@
 
 namespace {
 
-struct WalkArgs {
-  const int64_t *__restrict__ off;
-  const int32_t *__restrict__ col;        // sorted rows
-  const AliasSlot *__restrict__ slot;     // Vose slots (weighted) or nullptr
-  const int32_t *__restrict__ col_app;    // appearance-order rows (exact sampler)
-  const float *__restrict__ w_app;
-  const int32_t *__restrict__ vids;
-  int64_t nv;
-  uint64_t walker_first;
-  int64_t n_walkers;
-  int32_t stride;                         // walk_length + 2 (RW:103)
-  uint32_t seed_lo, seed_hi;
-  uint64_t t_ret, t_common, t_far;        // alias acceptance thresholds
-  float p, q;                             // exact sampler (RW:112-113 .toFloat)
-  int32_t u_mode;
-  float u_const;
-  int32_t *paths;
-  int32_t *lens;
-  unsigned long long *stats;              // [steps, proposals, member_tests, probes_log2]
-};
+#include "walk_conv.cuh"   // WalkArgs, FoldArgs, PeerTable, the state enum and the convergent kernels (v5)
 
 // x in sorted row [lo, lo+n)?
 __device__ __forceinline__ bool row_contains(const int32_t *__restrict__ col, int64_t lo, int64_t n, int32_t x) {
@@ -57,7 +38,6 @@ __device__ __forceinline__ bool row_contains(const int32_t *__restrict__ col, in
   return a < n && __ldg(col + lo + a) == x;
 }
 
-__device__ __forceinline__ int ceil_log2_p1(int64_t d) { return d <= 0 ? 0 : 64 - __clzll(d); }
 
 // alias proposal from row [off, off+deg): slot index from 64 random bits, Vose coin from r.y
 template <bool HAS_ALIAS>
@@ -142,7 +122,6 @@ __global__ void __launch_bounds__(256) walk_alias_kernel(WalkArgs a) {
 // gathers in flight.  Decisions are the same pure functions of (seed; walker, step, trial): the
 // output is bit-identical to v1 and to the CPU twin.
 // ------------------------------------------------------------------------------------------
-enum : int { ST_EXTENT = 0, ST_PROPOSE = 1, ST_SEARCH = 2, ST_DONE = 3 };
 
 template <bool HAS_ALIAS, bool STATS>
 __global__ void __launch_bounds__(256) walk_alias_sm_kernel(WalkArgs a) {
@@ -237,7 +216,6 @@ __global__ void __launch_bounds__(256) walk_alias_sm_kernel(WalkArgs a) {
 // for "is x a neighbour of prev" (RS:38).  Here that test is one 32-byte bucket probe (rows longer
 // than kHashMinDeg), and the row extent is one aligned 32-byte RowMeta load.  Same decisions, same bits.
 // ------------------------------------------------------------------------------------------
-enum : int { ST_HASH = 4 };
 
 template <bool HAS_ALIAS, bool STATS>
 __global__ void __launch_bounds__(256) walk_alias_hash_kernel(WalkArgs a, const RowMeta *__restrict__ meta,
@@ -343,27 +321,6 @@ __global__ void __launch_bounds__(256) walk_alias_hash_kernel(WalkArgs a, const 
 // Defined for undirected, unweighted graphs (multiplicity of prev in N(curr) == multiplicity of the edge
 // just taken); otherwise the launch falls back to v3.  CPU twin: oracle_alias_walk with cfg.fold = 1.
 // ------------------------------------------------------------------------------------------
-struct FoldArgs {
-  const NbrEntry *__restrict__ ent;
-  const int32_t *__restrict__ hash;
-  double a, mp;              // a = 1/p - Mp > 0, Mp = max(1, 1/q)   (a = 0: no return component, plain rejection under mp)
-  uint64_t t_ret, t_common, t_far;  // thresholds under the envelope (t_ret = 2^32 when the return edge is folded out)
-};
-
-// Peer-gather mode: the graph is cut into vertex ranges, shard s lives in the HBM of GPU s, and
-// every GPU can address every shard (NVLink peer mappings).  A neighbour entry names the owner of the
-// neighbour's row, so the kernel picks the base pointer per access and a walker never migrates: the
-// "exchange" of the reference's super-step shuffle (RW:186-192) becomes 16/32-byte loads over NVLink.
-struct PeerTable {
-  int world;
-  int64_t first[SRW_MAX_SHARDS + 1];          // first rank of every shard
-  const int64_t *off[SRW_MAX_SHARDS];         // shard-local row offsets
-  const NbrEntry *ent[SRW_MAX_SHARDS];
-  const int32_t *hash[SRW_MAX_SHARDS];
-};
-
-constexpr int kStage = 16;
-
 template <bool STATS, bool PEER, int MINB = 4>
 __global__ void __launch_bounds__(256, MINB) walk_fold_kernel(WalkArgs a, FoldArgs f, const PeerTable pt) {
   __shared__ int32_t sbuf[kStage * 256];
@@ -884,17 +841,35 @@ srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLa
     FoldArgs f{};
     bool fold = false;
     if ((peer || p->sampler == SRW_SAMPLER_ALIAS_FOLD) && (peer || (g->d_ent && g->d_hash)) && !g->directed && !g->has_alias) {
-      const double inv_p = 1.0 / (double)(float)p->p, inv_q = 1.0 / (double)(float)p->q;
-      const double M = inv_q > 1.0 ? inv_q : 1.0;
-      auto thr = [M](double v) -> uint64_t { return v >= M ? 4294967296ULL : (uint64_t)((v / M) * 4294967296.0); };
-      f.ent = g->d_ent; f.hash = g->d_hash; f.a = inv_p - M; f.mp = M; f.t_ret = 4294967296ULL; f.t_common = thr(1.0); f.t_far = thr(inv_q);
-      fold = f.a > 0.0 && p->sampler == SRW_SAMPLER_ALIAS_FOLD;
+      fold = srw_fold_args(p->p, p->q, p->sampler == SRW_SAMPLER_ALIAS_FOLD, &f);
+      f.ent = g->d_ent; f.hash = g->d_hash;
       if (peer && !fold) {
         // classic rejection under M = max(1/p, 1, 1/q) through the same kernel: no return component
         f.a = 0.0; f.mp = 1.0; f.t_ret = a.t_ret; f.t_common = a.t_common; f.t_far = a.t_far;
       }
     }
-    if (peer) {
+    // A/B: SRW_FOLD=v4 runs the pre-convergence kernel; SRW_FOLD_VAR bit 0 = L2::64B loads in v5
+    static const bool fold_v4 = getenv("SRW_FOLD") && !strcmp(getenv("SRW_FOLD"), "v4");
+    constexpr int kFoldVarDefault = 0;   // v5 load flavour used when SRW_FOLD_VAR is unset
+    static const int fold_var = getenv("SRW_FOLD_VAR") ? atoi(getenv("SRW_FOLD_VAR")) : kFoldVarDefault;
+    if ((peer || fold) && !fold_v4) {
+      PeerTable pt{};
+      if (peer) {
+        pt.world = g->shard_world;
+        for (int r = 0; r <= g->shard_world; ++r) pt.first[r] = g->bounds[(size_t)r];
+        for (int r = 0; r < g->shard_world; ++r) { pt.off[r] = g->peer_off[r]; pt.ent[r] = g->peer_ent[r]; pt.hash[r] = g->peer_hash[r]; }
+      }
+      const bool v64 = (fold_var & 1) != 0;
+      if (peer) {
+        if (st) walk_fold_conv_kernel<true, true, 0><<<grid, 256, 0, l.stream>>>(a, f, pt);
+        else if (v64) walk_fold_conv_kernel<false, true, 1><<<grid, 256, 0, l.stream>>>(a, f, pt);
+        else walk_fold_conv_kernel<false, true, 0><<<grid, 256, 0, l.stream>>>(a, f, pt);
+      } else {
+        if (st) walk_fold_conv_kernel<true, false, 0><<<grid, 256, 0, l.stream>>>(a, f, pt);
+        else if (v64) walk_fold_conv_kernel<false, false, 1><<<grid, 256, 0, l.stream>>>(a, f, pt);
+        else walk_fold_conv_kernel<false, false, 0><<<grid, 256, 0, l.stream>>>(a, f, pt);
+      }
+    } else if (peer) {
       PeerTable pt{};
       pt.world = g->shard_world;
       for (int r = 0; r <= g->shard_world; ++r) pt.first[r] = g->bounds[(size_t)r];

@@ -1,0 +1,112 @@
+// emu_walk.cpp -- TEST INFRASTRUCTURE: runs the product's walk_fold_conv_kernel SOURCE on the host
+// (tests/emu/cuda_emu.h) over a CSR handed in by the test, after laying the rows out exactly as
+// graph_build.cu does (16-byte neighbour entries, derived-placement hash sets, optional vertex-range
+// shards for the PEER variant).  The test compares the paths with the CPU twin (oracle_alias_walk).
+#include "cuda_emu.h"
+
+#include <vector>
+
+#include "../../stellar-random-walk_b200/csrc/walk_conv.cuh"
+
+namespace {
+
+struct ShardRows {
+  std::vector<int64_t> off;        // shard-local offsets, rows+1
+  std::vector<NbrEntry> ent;
+  std::vector<int32_t> hash;       // 8-slot buckets, -1 = empty
+};
+
+void hash_insert(std::vector<int32_t> &hash, int64_t off, uint32_t deg, int32_t x) {
+  const uint32_t nb = srw_hash_buckets(off, deg);
+  if (!nb) return;
+  uint32_t b = __umulhi(srw_hash32((uint32_t)x), nb);
+  for (;;) {
+    int32_t *bucket = hash.data() + (srw_hash_first(off) + b) * 8;
+    for (int s = 0; s < 8; ++s) {
+      if (bucket[s] == x) return;
+      if (bucket[s] == -1) { bucket[s] = x; return; }
+    }
+    b = b + 1 == nb ? 0 : b + 1;
+  }
+}
+
+}  // namespace
+
+// Lays the graph out for `shards` vertex ranges (bounds[shards+1], first rank of every range; shards == 1:
+// the unsharded layout) and walks n_walkers walkers.  var: VAR template value; extra: see cuda_emu.h.
+// fold != 0: alias-fold arguments from (p, q); fold == 0: classic thresholds through the same kernel.
+extern "C" int emu_fold_walk(int64_t nv, const int64_t *off, const int32_t *col, const uint32_t *mult, int shards,
+                             const int64_t *bounds, double p, double q, int fold, uint64_t t_ret, uint64_t t_common,
+                             uint64_t t_far, uint64_t seed, int32_t walk_length, uint64_t walker_first, int64_t n_walkers,
+                             int32_t *paths, int32_t *lens, int var, int extra, int stats, unsigned long long *stats_out) {
+  if (shards < 1 || shards > SRW_MAX_SHARDS) return -1;
+  std::vector<ShardRows> sh((size_t)shards);
+  std::vector<int64_t> base((size_t)shards);
+  for (int s = 0; s < shards; ++s) {
+    const int64_t r0 = bounds[s], r1 = bounds[s + 1];
+    base[(size_t)s] = off[r0];
+    ShardRows &R = sh[(size_t)s];
+    R.off.resize((size_t)(r1 - r0 + 1));
+    for (int64_t r = r0; r <= r1; ++r) R.off[(size_t)(r - r0)] = off[r] - off[r0];
+    const int64_t n = off[r1] - off[r0];
+    R.ent.resize((size_t)n);
+    R.hash.assign((size_t)(((n >> 2) + 1) * 8), -1);
+  }
+  auto owner_of = [&](int64_t v) { int o = 0; while (o + 1 < shards && v >= bounds[o + 1]) o++; return o; };
+  for (int s = 0; s < shards; ++s) {
+    ShardRows &R = sh[(size_t)s];
+    for (int64_t r = bounds[s]; r < bounds[s + 1]; ++r) {
+      const int64_t lo = off[r] - base[(size_t)s];
+      const uint32_t deg = (uint32_t)(off[r + 1] - off[r]);
+      for (int64_t e = off[r]; e < off[r + 1]; ++e) {
+        const int32_t x = col[e];
+        const int ox = owner_of(x);
+        NbrEntry ne;
+        ne.x = x; ne.deg = (uint32_t)(off[x + 1] - off[x]); ne.off_lo = (uint32_t)(off[x] - base[(size_t)ox]);
+        ne.off_hi_mult = (uint32_t)ox | (mult[e] << 8);
+        R.ent[(size_t)(e - base[(size_t)s])] = ne;
+        hash_insert(R.hash, lo, deg, x);
+      }
+    }
+  }
+  WalkArgs a{};
+  a.off = sh[0].off.data(); a.nv = nv; a.walker_first = walker_first; a.n_walkers = n_walkers; a.stride = walk_length + 2;
+  a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
+  a.paths = paths; a.lens = lens;
+  unsigned long long st[4] = {0, 0, 0, 0};
+  a.stats = st;
+  FoldArgs f{};
+  const bool folded = srw_fold_args(p, q, fold != 0, &f);
+  if (!folded) { f.a = 0.0; f.mp = 1.0; f.t_ret = t_ret; f.t_common = t_common; f.t_far = t_far; }
+  f.ent = sh[0].ent.data(); f.hash = sh[0].hash.data();
+  PeerTable pt{};
+  pt.world = shards;
+  for (int s = 0; s <= shards; ++s) pt.first[s] = bounds[s];
+  for (int s = 0; s < shards; ++s) { pt.off[s] = sh[(size_t)s].off.data(); pt.ent[s] = sh[(size_t)s].ent.data(); pt.hash[s] = sh[(size_t)s].hash.data(); }
+  emu_extra_iters = extra;
+  blockDim.x = 256; blockDim.y = blockDim.z = 1;
+  const int64_t n_blocks = (n_walkers + 255) / 256;
+  const bool peer = shards > 1;
+  for (int64_t b = 0; b < n_blocks; ++b) {
+    blockIdx.x = (unsigned)b;
+    for (int pass = peer ? 0 : 1; pass < 2; ++pass) {      // pass 0: every lane only publishes the shard tables (s_ent / s_hash)
+      WalkArgs aa = a;
+      if (pass == 0) aa.n_walkers = 0;
+      for (unsigned t = 0; t < 256; ++t) {
+        threadIdx.x = t;
+        emu_linger = 0;
+        if (peer) {
+          if (var & 1) walk_fold_conv_kernel<false, true, 1>(aa, f, pt);
+          else if (stats) walk_fold_conv_kernel<true, true, 0>(aa, f, pt);
+          else walk_fold_conv_kernel<false, true, 0>(aa, f, pt);
+        } else {
+          if (var & 1) walk_fold_conv_kernel<false, false, 1>(aa, f, pt);
+          else if (stats) walk_fold_conv_kernel<true, false, 0>(aa, f, pt);
+          else walk_fold_conv_kernel<false, false, 0>(aa, f, pt);
+        }
+      }
+    }
+  }
+  if (stats_out) memcpy(stats_out, st, sizeof(st));
+  return folded ? 1 : 0;
+}

@@ -1,0 +1,150 @@
+"""The walk kernel SOURCE (csrc/walk_conv.cuh, walk_fold_conv_kernel) compiled for the host with
+tests/emu/cuda_emu.h and run lane by lane against the CPU twin (oracle_alias_walk).  This is a CPU-side check
+of the kernel's decision logic -- row layout, hash placement, thresholds, the draw/load/consume phases, the
+staged path stores, the vertex-range (PEER) addressing -- so that a logic slip is caught before GPU time is
+spent; the parity tests proper are the `-m gpu` tests, which run the same source on the device.
+"""
+import ctypes as C
+import importlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import KARATE, ROOT
+
+synth = importlib.import_module("stellar-random-walk_b200.synth")
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+EMU_SO = os.path.join(EMU_DIR, "libsrw_emu.so")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    srcs = [os.path.join(EMU_DIR, "emu_walk.cpp"), os.path.join(EMU_DIR, "cuda_emu.h")]
+    csrc = os.path.join(ROOT, "stellar-random-walk_b200", "csrc")
+    srcs += [os.path.join(csrc, f) for f in ("walk_conv.cuh", "layout.h", "philox.cuh")]
+    if not os.path.exists(EMU_SO) or any(os.path.getmtime(s) > os.path.getmtime(EMU_SO) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-Wno-unknown-pragmas", "-shared", "-fPIC",
+                               srcs[0], "-o", EMU_SO])
+    lib = C.CDLL(EMU_SO)
+    lib.emu_fold_walk.restype = C.c_int
+    lib.emu_fold_walk.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_int,
+                                  C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p,
+                                  C.c_int, C.c_int, C.c_int, C.c_void_p]
+    return lib
+
+
+def _mult(col, offsets):
+    """Number of parallel edges to the same neighbour, per entry of the sorted rows (graph_build.cu k_nbr_entries)."""
+    m = np.ones(len(col), dtype=np.uint32)
+    for r in range(len(offsets) - 1):
+        lo, hi = int(offsets[r]), int(offsets[r + 1])
+        if hi - lo > 1:
+            _, inv, cnt = np.unique(col[lo:hi], return_inverse=True, return_counts=True)
+            m[lo:hi] = cnt[inv]
+    return m
+
+
+def _bounds(offsets, shards):
+    """Edge-balanced vertex ranges on the degree prefix sum (sharded.py / graph_build.cu rule is not needed here:
+    any monotone cut must give the same paths)."""
+    nv, nnz = len(offsets) - 1, int(offsets[-1])
+    b = [0]
+    for s in range(1, shards):
+        b.append(int(np.searchsorted(offsets, nnz * s // shards, side="left")))
+    b.append(nv)
+    return np.maximum.accumulate(np.array(b, dtype=np.int64))
+
+
+def _emu_walk(emu, oracle, tw, *, walk_length, p, q, seed, fold, shards=1, var=0, extra=2, first=0, n=None, rounds=1, stats=False):
+    v = tw.view()
+    off = np.ascontiguousarray(v["offsets"], np.int64)
+    col = np.ascontiguousarray(v["col"], np.int32)
+    mult = _mult(col, off)
+    nv = len(off) - 1
+    n = nv * rounds - first if n is None else n
+    stride = walk_length + 2
+    paths = np.full((n, stride), -7, np.int32)
+    lens = np.zeros(n, np.int32)
+    bounds = _bounds(off, shards)
+    t_ret, t_common, t_far = oracle.alias_thresholds(p, q)
+    st = np.zeros(4, np.uint64)
+    rc = emu.emu_fold_walk(nv, off.ctypes.data, col.ctypes.data, mult.ctypes.data, shards, bounds.ctypes.data, p, q, int(fold),
+                           t_ret, t_common, t_far, seed, walk_length, first, n, paths.ctypes.data, lens.ctypes.data, var, extra,
+                           int(stats), st.ctypes.data)
+    assert rc >= 0
+    vids = v["vids"]
+    out = [vids[paths[i, :lens[i]]].tolist() for i in range(n)]
+    # nothing may be written past a path's end
+    for i in range(n):
+        assert (paths[i, lens[i]:] == -7).all()
+    return out, rc, st
+
+
+def _twin_paths(oracle, tw, **kw):
+    ids, offs, st = tw.walk(**kw)
+    return oracle.paths_as_lists(ids, offs), st
+
+
+def _rmat_twin(oracle, scale, ef, seed=42):
+    s, d = synth.rmat_edges(scale, ef, seed=seed)
+    return oracle.AliasGraph(oracle.Graph().load_edges(s, d))
+
+
+@pytest.mark.parametrize("p,q", [(0.5, 2.0), (0.25, 4.0), (0.5, 0.5), (1.0, 1.0), (2.0, 0.5)])
+def test_emulated_kernel_equals_twin_karate(emu, oracle, p, q):
+    tw = oracle.AliasGraph(oracle.Graph().load_file(KARATE))
+    want, _ = _twin_paths(oracle, tw, walk_length=30, num_walks=3, p=p, q=q, seed=11, fold=1)
+    got, folded, _ = _emu_walk(emu, oracle, tw, walk_length=30, p=p, q=q, seed=11, fold=True, rounds=3)
+    assert folded == (1 if 1.0 / p > max(1.0, 1.0 / q) else 0)
+    assert got == want
+
+
+@pytest.mark.parametrize("walk_length", [0, 1, 2, 13, 14, 15, 16, 17, 80])
+def test_emulated_kernel_path_staging_boundaries(emu, oracle, walk_length):
+    """Stage of 16 ids, first flush cut at a 16-byte boundary: every stride parity and every tail length."""
+    tw = _rmat_twin(oracle, 8, 8)
+    want, _ = _twin_paths(oracle, tw, walk_length=walk_length, num_walks=2, p=0.5, q=2.0, seed=5, fold=1)
+    got, _, _ = _emu_walk(emu, oracle, tw, walk_length=walk_length, p=0.5, q=2.0, seed=5, fold=True, rounds=2)
+    assert got == want
+
+
+@pytest.mark.parametrize("shards", [1, 2, 3, 8])
+@pytest.mark.parametrize("fold", [True, False])
+def test_emulated_kernel_equals_twin_rmat_sharded(emu, oracle, shards, fold):
+    """PEER addressing (shard-local offsets, owner byte in the entry) must not change a single id; fold=False
+    drives the classic thresholds through the same kernel (what a peer-gather walk does when 1/p <= max(1, 1/q))."""
+    tw = _rmat_twin(oracle, 10, 8)
+    p, q = (0.5, 2.0) if fold else (2.0, 0.5)
+    want, wst = _twin_paths(oracle, tw, walk_length=40, num_walks=1, p=p, q=q, seed=9, fold=1)
+    got, _, st = _emu_walk(emu, oracle, tw, walk_length=40, p=p, q=q, seed=9, fold=True, shards=shards, stats=True)
+    assert got == want
+    if fold:   # (classic thresholds: the kernel takes a degree-1 row's only entry at once, the twin counts its rejected trials)
+        assert int(st[1]) == wst.proposals and int(st[2]) == wst.member_tests and int(st[3]) == wst.probes_log2
+
+
+def test_emulated_kernel_walker_window_and_lingering_lanes(emu, oracle):
+    """A launch over a window of walkers (walker_first, n not a multiple of the block) gives the same paths as the
+    full launch; finished lanes driven through extra iterations stay inert; the L2::64B load flavour is the same code."""
+    tw = _rmat_twin(oracle, 9, 8)
+    want, _ = _twin_paths(oracle, tw, walk_length=20, num_walks=2, p=0.5, q=2.0, seed=3, fold=1)
+    nv = tw.nv
+    first, n = nv // 3, nv + 77
+    for extra, var in ((0, 0), (5, 0), (3, 1)):
+        got, _, _ = _emu_walk(emu, oracle, tw, walk_length=20, p=0.5, q=2.0, seed=3, fold=True, first=first, n=n, extra=extra, var=var)
+        assert got == want[first:first + n]
+
+
+def test_emulated_kernel_hub_and_multi_edges(emu, oracle):
+    """Zipf hubs (long rows -> hash probes with full buckets), parallel edges (multiplicity in the return component)
+    and self-loops."""
+    zs, zd = synth.zipf_edges(2048, seed=7, cap=600)
+    extra_s = np.array([0, 0, 0, 5, 5, 9], np.int32)
+    extra_d = np.array([1, 1, 1, 5, 6, 9], np.int32)
+    s, d = np.concatenate([zs, extra_s]), np.concatenate([zd, extra_d])
+    tw = oracle.AliasGraph(oracle.Graph().load_edges(s, d))
+    for p, q in ((0.25, 4.0), (0.5, 2.0)):
+        want, _ = _twin_paths(oracle, tw, walk_length=25, num_walks=1, p=p, q=q, seed=21, fold=1)
+        got, _, _ = _emu_walk(emu, oracle, tw, walk_length=25, p=p, q=q, seed=21, fold=True, shards=2)
+        assert got == want
