@@ -102,6 +102,10 @@ srw_status srw_edges_parse_buffer(const char *buf, size_t len, int weighted, int
 srw_status srw_edges_view(const srw_edges *e, int64_t *n, const int32_t **h_src, const int32_t **h_dst,
                           const float **h_w, const int32_t **h_pid);
 void srw_edges_free(srw_edges *e);
+/* The same rules applied ON THE DEVICE (text_io.cu: one thread per line; weight tokens outside the exact float fast
+ * path are re-parsed on the host), returned as the same host handle.  srw_graph_load uses this parser and keeps the
+ * arrays in HBM.  Identical output to srw_edges_parse_buffer, including the first error and its line number. */
+srw_status srw_edges_parse_buffer_device(const char *buf, size_t len, int weighted, int partitioned, srw_edges **out);
 
 /* ---- A1+A2: adjacency build (URW:35-43 + GM:41-64 semantics) on the device ---- */
 #define SRW_BUILD_EXACT 1u   /* keep the file-appearance-order rows (needed by SRW_SAMPLER_EXACT) */
@@ -179,6 +183,15 @@ srw_status srw_save(srw_paths *paths, const srw_params *params);
 /* the same text into a caller buffer; *needed = bytes required */
 srw_status srw_paths_format(srw_paths *paths, char *h_buf, int64_t cap, int64_t *needed);
 void srw_paths_free(srw_paths *paths);
+/* RW:234-241 on the device: the text of n_paths rows of a [n_paths][stride] path matrix (row i holds d_lens[i] ids,
+ * as srw_walk_device leaves it) -- `ids.mkString("\t") + "\n"` per row, rows in order -- into d_text (device
+ * memory, cap bytes).  *needed = bytes of the text; pass d_text = NULL to size the buffer first. */
+srw_status srw_paths_format_device(const int32_t *d_paths, const int32_t *d_lens, int64_t n_paths, int32_t stride,
+                                   char *d_text, int64_t cap, int64_t *needed, void *stream);
+/* execute() + save() streamed (RW:31-33, RW:234-241, Main:53-62): every round is walked, formatted on the device and
+ * written to <output>/path/part-NNNNN in walker order, so neither the paths nor their text have to fit in host
+ * memory.  Same files as srw_walk + srw_save.  srw_last_walk_info() then holds the totals of the call. */
+srw_status srw_walk_save(const srw_graph *g, const srw_params *params);
 
 /* Main.main / runJob for --cmd randomwalk (Main:18-27, 109-127): parse, load, walk, save.
  * Prints the reference's "edges:/vertices:" lines (URW:69-72).  Returns the process exit code. */

@@ -37,7 +37,7 @@ ABI_SYMBOLS = [
     "srw_graphmap_free", "srw_sample", "srw_second_order_weights", "srw_second_order_sample", "srw_philox4x32_10",
     "srw_walk", "srw_walk_device", "srw_last_walk_info", "srw_walk_collect_stats", "srw_paths_view", "srw_paths_counts",
     "srw_save", "srw_paths_format", "srw_paths_free", "srw_main", "srw_synth_rmat_device", "srw_synth_weights_device",
-    "srw_gather_ceiling",
+    "srw_gather_ceiling", "srw_edges_parse_buffer_device", "srw_paths_format_device", "srw_walk_save",
     "srw_graph_from_device_edges_sharded", "srw_graph_shard_info", "srw_walker_msg_bytes", "srw_path_rec_bytes",
     "srw_shard_seed", "srw_shard_step", "srw_shard_apply", "srw_shard_finalize",
     "srw_shard_ipc_bytes", "srw_shard_ipc_export", "srw_shard_ipc_attach", "srw_shard_attach_local",
@@ -87,6 +87,9 @@ def lib():
     L.srw_params_parse_argv.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(CParams)]
     L.srw_edges_parse_file.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(vp)]
     L.srw_edges_parse_buffer.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(vp)]
+    L.srw_edges_parse_buffer_device.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(vp)]
+    L.srw_paths_format_device.argtypes = [vp, vp, C.c_int64, C.c_int32, vp, C.c_int64, i64p, vp]
+    L.srw_walk_save.argtypes = [vp, C.POINTER(CParams)]
     L.srw_edges_view.argtypes = [vp, i64p, C.POINTER(i32p), C.POINTER(i32p), C.POINTER(f32p), C.POINTER(i32p)]
     L.srw_edges_free.argtypes = [vp]
     L.srw_graph_from_edges.argtypes = [C.c_int64, vp, vp, vp, vp, C.c_int, C.c_uint, C.POINTER(vp)]
@@ -217,10 +220,18 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def parse_edges(data=None, path=None, weighted=True, partitioned=False):
-    """URW:23-34 / VRW:19-34 line rules -> (src, dst, w, pid|None) numpy arrays (host only)."""
+def parse_edges(data=None, path=None, weighted=True, partitioned=False, device=False):
+    """URW:23-34 / VRW:19-34 line rules -> (src, dst, w, pid|None) numpy arrays.  device=False: the serial host
+    parser (no GPU needed); device=True: the CUDA parser srw_graph_load uses (text_io.cu), same result."""
     h = C.c_void_p()
-    if path is not None:
+    if device:
+        if path is not None:
+            with open(path, "rb") as f:
+                data = f.read()
+        if isinstance(data, str):
+            data = data.encode()
+        check(lib().srw_edges_parse_buffer_device(data, len(data), int(weighted), int(partitioned), C.byref(h)))
+    elif path is not None:
         check(lib().srw_edges_parse_file(path.encode(), int(weighted), int(partitioned), C.byref(h)))
     else:
         if isinstance(data, str):
@@ -334,6 +345,20 @@ class Graph:
         h = C.c_void_p()
         check(lib().srw_walk(self.h, C.byref(cp), C.byref(h)))
         return Paths(h)
+
+    def walk_save(self, params):
+        """execute() + save() streamed through the device formatter (srw_walk_save): writes <output>/path/part-NNNNN."""
+        cp = params.to_c()
+        check(lib().srw_walk_save(self.h, C.byref(cp)))
+        return last_walk_info()
+
+
+def format_paths_device(d_paths, d_lens, n_paths, stride, d_text=None, cap=0, stream=None):
+    """RW:234-241 on the device (srw_paths_format_device).  Pointers are raw device addresses (e.g. tensor.data_ptr()).
+    Returns the number of text bytes; with d_text=None only sizes the buffer."""
+    need = C.c_int64()
+    check(lib().srw_paths_format_device(d_paths, d_lens, n_paths, stride, d_text, cap, C.byref(need), stream))
+    return need.value
 
 
 def last_walk_info():

@@ -88,12 +88,9 @@ extern "C" srw_status srw_graph_from_edges(int64_t n, const int32_t *h_src, cons
 
 extern "C" srw_status srw_graph_load(const srw_params *params, unsigned flags, srw_graph **out) {
   if (!params || !out) return SRW_ERR_ARG;
-  srw_edges *e = nullptr;
-  SRW_TRY(srw_edges_parse_file(params->input, params->weighted, params->partitioned, &e));   // URW:23-34 | VRW:19-34
-  srw_status s = srw_graph_from_edges((int64_t)e->src.size(), e->src.data(), e->dst.data(), e->w.data(),
-                                      e->has_pid ? e->pid.data() : nullptr, params->directed, flags, out);
-  srw_edges_free(e);
-  return s;
+  SRW_TRY(srw_require_device());
+  // URW:23-34 | VRW:19-34 on the device: the file is parsed in HBM and the edge arrays never exist on the host
+  return srw_graph_load_device(params, flags, out);
 }
 
 extern "C" srw_status srw_graph_stats(const srw_graph *g, int64_t *nv, int64_t *ne) {
@@ -267,19 +264,16 @@ extern "C" int srw_main(int argc, const char *const *argv) {
   srw_graph_stats(g, &nv, &ne);
   printf("edges: %lld\nvertices: %lld\n", (long long)ne, (long long)nv);   // URW:71-72
   auto t1 = std::chrono::steady_clock::now();
-  srw_paths *paths = nullptr;
-  if (srw_walk(g, &prm, &paths) != SRW_OK) { fprintf(stderr, "Exception: %s\n", srw_last_error()); srw_graph_free(g); return 2; }
+  // execute() + save() (Main:53-62) streamed through the device formatter
+  int rc = 0;
+  if (srw_walk_save(g, &prm) != SRW_OK) { fprintf(stderr, "Exception: %s\n", srw_last_error()); srw_graph_free(g); return 2; }
   auto t2 = std::chrono::steady_clock::now();
   printf("Unfinished Walkers: 0\n");                                        // RW:154 (last super-step)
-  int rc = 0;
-  if (srw_save(paths, &prm) != SRW_OK) { fprintf(stderr, "Exception: %s\n", srw_last_error()); rc = 2; }   // Main:59-60
-  auto t3 = std::chrono::steady_clock::now();
   srw_walk_info wi;
   srw_last_walk_info(&wi);
   auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-  fprintf(stderr, "[srw] load+build %.1f ms, walk %.1f ms (kernels %.2f ms, %lld steps), save %.1f ms\n", ms(t0, t1), ms(t1, t2),
-          wi.kernel_ms, (long long)wi.steps, ms(t2, t3));
-  srw_paths_free(paths);
+  fprintf(stderr, "[srw] load+build %.1f ms, walk+save %.1f ms (walk kernels %.2f ms, %lld steps)\n", ms(t0, t1), ms(t1, t2),
+          wi.kernel_ms, (long long)wi.steps);
   srw_graph_free(g);
   return rc;
 }

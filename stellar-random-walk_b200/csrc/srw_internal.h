@@ -114,3 +114,8 @@ srw_status srw_build_graph_rows(int64_t n_rows, const int32_t *h_vids, const int
                                 const int32_t *h_dst, const int32_t *h_pid, const float *h_w, unsigned flags,
                                 srw_graph **out);
 void srw_alias_thresholds(double p, double q, uint64_t *t_ret, uint64_t *t_common, uint64_t *t_far);
+
+// text_io.cu
+srw_status srw_parse_text_device(const char *h_text, size_t len, int weighted, int partitioned, int64_t *n_out, int32_t **d_src,
+                                 int32_t **d_dst, float **d_w, int32_t **d_pid);
+srw_status srw_graph_load_device(const srw_params *params, unsigned flags, srw_graph **out);

@@ -837,7 +837,7 @@ srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLa
     static const bool use_v2 = getenv("SRW_KERNEL") && !strcmp(getenv("SRW_KERNEL"), "v2");
     // SRW_SAMPLER_ALIAS_FOLD: undirected + unweighted + 1/p > max(1, 1/q), else the classic sampler
     // (the CPU twin applies the same rule, oracle_alias_walk)
-    static const int occ = getenv("SRW_FOLD_OCC") ? atoi(getenv("SRW_FOLD_OCC")) : 0;   // A/B: resident blocks per SM the fold kernel is compiled for
+    const int occ = getenv("SRW_FOLD_OCC") ? atoi(getenv("SRW_FOLD_OCC")) : 0;   // A/B (read per launch): resident blocks per SM the fold kernel is compiled for
     FoldArgs f{};
     bool fold = false;
     if ((peer || p->sampler == SRW_SAMPLER_ALIAS_FOLD) && (peer || (g->d_ent && g->d_hash)) && !g->directed && !g->has_alias) {
@@ -848,10 +848,11 @@ srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLa
         f.a = 0.0; f.mp = 1.0; f.t_ret = a.t_ret; f.t_common = a.t_common; f.t_far = a.t_far;
       }
     }
-    // A/B: SRW_FOLD=v4 runs the pre-convergence kernel; SRW_FOLD_VAR bit 0 = L2::64B loads in v5
-    static const bool fold_v4 = getenv("SRW_FOLD") && !strcmp(getenv("SRW_FOLD"), "v4");
+    // A/B (read per launch, so one process can time every variant on one graph): SRW_FOLD=v4 runs the
+    // pre-convergence kernel; SRW_FOLD_VAR bit 0 = L2::64B loads in v5; SRW_FOLD_OCC = 5 | 6 blocks per SM
+    const bool fold_v4 = getenv("SRW_FOLD") && !strcmp(getenv("SRW_FOLD"), "v4");
     constexpr int kFoldVarDefault = 0;   // v5 load flavour used when SRW_FOLD_VAR is unset
-    static const int fold_var = getenv("SRW_FOLD_VAR") ? atoi(getenv("SRW_FOLD_VAR")) : kFoldVarDefault;
+    const int fold_var = getenv("SRW_FOLD_VAR") ? atoi(getenv("SRW_FOLD_VAR")) : kFoldVarDefault;
     if ((peer || fold) && !fold_v4) {
       PeerTable pt{};
       if (peer) {
@@ -866,7 +867,11 @@ srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLa
         else walk_fold_conv_kernel<false, true, 0><<<grid, 256, 0, l.stream>>>(a, f, pt);
       } else {
         if (st) walk_fold_conv_kernel<true, false, 0><<<grid, 256, 0, l.stream>>>(a, f, pt);
+        else if (v64 && occ == 5) walk_fold_conv_kernel<false, false, 1, 5><<<grid, 256, 0, l.stream>>>(a, f, pt);
+        else if (v64 && occ == 6) walk_fold_conv_kernel<false, false, 1, 6><<<grid, 256, 0, l.stream>>>(a, f, pt);
         else if (v64) walk_fold_conv_kernel<false, false, 1><<<grid, 256, 0, l.stream>>>(a, f, pt);
+        else if (occ == 5) walk_fold_conv_kernel<false, false, 0, 5><<<grid, 256, 0, l.stream>>>(a, f, pt);
+        else if (occ == 6) walk_fold_conv_kernel<false, false, 0, 6><<<grid, 256, 0, l.stream>>>(a, f, pt);
         else walk_fold_conv_kernel<false, false, 0><<<grid, 256, 0, l.stream>>>(a, f, pt);
       }
     } else if (peer) {

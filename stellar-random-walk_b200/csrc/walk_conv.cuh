@@ -107,8 +107,8 @@ __device__ __forceinline__ void gather32(const int4 *p, int4 &lo, int4 &hi) {   
 #endif
 }
 
-template <bool STATS, bool PEER, int VAR>
-__global__ void __launch_bounds__(256, 4) walk_fold_conv_kernel(WalkArgs a, FoldArgs f, const PeerTable pt) {
+template <bool STATS, bool PEER, int VAR, int MINB = 4>
+__global__ void __launch_bounds__(256, MINB) walk_fold_conv_kernel(WalkArgs a, FoldArgs f, const PeerTable pt) {
   __shared__ int32_t sbuf[kStage * 256];
   __shared__ const NbrEntry *s_ent[SRW_MAX_SHARDS];
   __shared__ const int32_t *s_hash[SRW_MAX_SHARDS];

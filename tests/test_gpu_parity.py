@@ -448,3 +448,22 @@ print(",".join(out))
         assert r.returncode == 0, r.stderr[-2000:]
         res[k] = r.stdout.strip().splitlines()[-1]
     assert res["thread"] == res["warp"] == res["cert"], res
+
+
+# ---- the alias-fold kernel generations and load flavours produce the same bits (switches are read per launch) ----
+def test_fold_kernel_generations_agree(oracle, monkeypatch):
+    s, d = synth.rmat_edges(13, 16, seed=3)
+    g = srw.Graph.from_edges(s, d, None, flags=srw.BUILD_ALIAS)
+    twin = oracle.AliasGraph(oracle.Graph().load_edges(s, d))
+    res = {}
+    for wl in (80, 13, 0):       # even and odd strides: both alignments of the staged path stores
+        want_ids, want_offs, _ = twin.walk(walk_length=wl, num_walks=2, p=0.5, q=2.0, seed=9, fold=1)
+        for name, env in (("v4", {"SRW_FOLD": "v4"}), ("v5", {}), ("v5-64B", {"SRW_FOLD_VAR": "1"}), ("v5-occ5", {"SRW_FOLD_OCC": "5"}),
+                          ("v5-occ6", {"SRW_FOLD_OCC": "6"}), ("v5-64B-occ6", {"SRW_FOLD_VAR": "1", "SRW_FOLD_OCC": "6"})):
+            for k in ("SRW_FOLD", "SRW_FOLD_VAR", "SRW_FOLD_OCC"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            ids, offs = g.walk(srw.Params(walkLength=wl, numWalks=2, p=0.5, q=2.0, seed=9, sampler="fold")).arrays()
+            res[(wl, name)] = bool(np.array_equal(ids, want_ids) and np.array_equal(offs, want_offs))
+    assert all(res.values()), res

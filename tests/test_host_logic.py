@@ -101,6 +101,11 @@ def test_product_fails_loudly_without_gpu():
     assert e.value.status == srw.SRW_ERR_NO_DEVICE
     with pytest.raises(srw.SrwError):
         srw.RandomSample(lambda: 0.5).sample([(1, 1.0)])
+    for call in (lambda: srw.parse_edges(data="1 2\n", device=True), lambda: srw.Graph.load(srw.Params(input=KARATE)),
+                 lambda: srw.format_paths_device(None, None, 0, 2)):
+        with pytest.raises(srw.SrwError) as e:
+            call()
+        assert e.value.status == srw.SRW_ERR_NO_DEVICE
     rc = srw.Main.main(["--cmd", "randomwalk", "--input", KARATE, "--output", "/tmp/srw_should_not_exist"])
     assert rc != 0 and not os.path.exists("/tmp/srw_should_not_exist")
     assert srw.Main.main(["--cmd", "randomwalk"]) == 1          # Main:25 sys.exit(1)
