@@ -211,6 +211,7 @@ extern "C" srw_status srw_walk_save(const srw_graph *g, const srw_params *params
   SRW_TRY(srw_require_device());
   if (!g || !params || !params->output[0]) { srw_set_error("srw_walk_save: no graph / output path"); return SRW_ERR_ARG; }
   if (params->num_walks < 0) { srw_set_error("numWalks must be >= 0"); return SRW_ERR_ARG; }
+  if (params->num_gpus > 1) { srw_set_error("srw_walk_save is single-GPU; the sharded walk is driven per rank (see shard API)"); return SRW_ERR_UNSUPPORTED; }
   const std::string dir = std::string(params->output) + "/path";          // Property.pathSuffix
   struct stat stt;
   if (stat(dir.c_str(), &stt) == 0) {   // Hadoop saveAsTextFile refuses an existing directory
@@ -352,7 +353,7 @@ namespace {
 
 struct IsLineStart {
   const char *buf;
-  __host__ __device__ bool operator()(uint32_t i) const {
+  __host__ __device__ unsigned long long operator()(uint32_t i) const {   // 0 / 1: a select flag and a countable value
     if (i == 0) return true;
     const char p = buf[i - 1];
     return p == '\n' || (p == '\r' && buf[i] != '\n');
@@ -420,6 +421,10 @@ srw_status srw_parse_text_device(const char *h_text, size_t len, int weighted, i
   std::vector<ChunkOut> outs;
   auto free_outs = [&]() { for (auto &c : outs) { cudaFree(c.src); cudaFree(c.dst); cudaFree(c.w); cudaFree(c.pid); } outs.clear(); };
   DBuf text, starts, nsel, sel_tmp, flag, status;
+  const bool timing = getenv("SRW_IO_TIMING") != nullptr;     // stderr: where the parse time goes (profiles/run_io.py)
+  double t_h2d = 0, t_split = 0, t_parse = 0;
+  auto now = []() { return std::chrono::steady_clock::now(); };
+  auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
   SRW_CUDA(nsel.alloc(8));
   SRW_CUDA(status.alloc(sizeof(ParseStatus)));
   int64_t lines_before = 0;
@@ -429,10 +434,12 @@ srw_status srw_parse_text_device(const char *h_text, size_t len, int weighted, i
     const size_t clen = c1 - c0;
     if (clen >= ((size_t)1 << 32) - 1) { free_outs(); srw_set_error("a single line of %zu bytes cannot be parsed", clen); return SRW_ERR_PARSE; }
     if (text.bytes < clen + 1) SRW_CUDA(text.alloc(clen + 1));
+    auto t0 = now();
     SRW_CUDA(cudaMemcpy(text.p, h_text + c0, clen, cudaMemcpyHostToDevice));
+    auto t1 = now();
     // line starts: every position whose predecessor ends a line
     cub::CountingInputIterator<uint32_t> pos(0);
-    cub::TransformInputIterator<bool, IsLineStart, cub::CountingInputIterator<uint32_t>> is_start(pos, IsLineStart{text.as<char>()});
+    cub::TransformInputIterator<unsigned long long, IsLineStart, cub::CountingInputIterator<uint32_t>> is_start(pos, IsLineStart{text.as<char>()});
     // empty lines are 1 byte each, so the number of starts can reach clen: count first, then size the array
     size_t tb = 0;
     SRW_CUDA(cub::DeviceReduce::Sum(nullptr, tb, is_start, nsel.as<unsigned long long>(), (int64_t)clen));
@@ -447,6 +454,8 @@ srw_status srw_parse_text_device(const char *h_text, size_t len, int weighted, i
     if (starts.bytes < (size_t)(n_lines + 1) * 4) SRW_CUDA(starts.alloc((size_t)(n_lines + 1) * 4));
     tb2 = sel_tmp.bytes;
     SRW_CUDA(cub::DeviceSelect::Flagged(sel_tmp.p, tb2, pos, is_start, starts.as<uint32_t>(), nsel.as<unsigned long long>(), (int64_t)clen));
+    if (timing) SRW_CUDA(cudaDeviceSynchronize());
+    auto t2 = now();
     ChunkOut co;
     co.n = n_lines;
     outs.push_back(co);
@@ -465,6 +474,8 @@ srw_status srw_parse_text_device(const char *h_text, size_t len, int weighted, i
       SRW_CUDA(cudaGetLastError());
     }
     SRW_CUDA(cudaMemcpy(&hs, status.p, sizeof(hs), cudaMemcpyDeviceToHost));
+    auto t3 = now();
+    t_h2d += secs(t0, t1); t_split += secs(t1, t2); t_parse += secs(t2, t3);
     if (hs.first_error != ~0ULL) {
       // the reference throws from the executor that meets the bad line; here the FIRST bad line is reported, with
       // the message of the host parser (same rules) and its line number in the file
@@ -515,6 +526,9 @@ srw_status srw_parse_text_device(const char *h_text, size_t len, int weighted, i
   // concatenate the chunks (a single chunk is handed over as it is)
   int64_t n = 0;
   for (auto &c : outs) n += c.n;
+  if (timing)
+    fprintf(stderr, "[srw io] parse: %zu bytes, %lld lines, %zu chunk(s): H2D %.3f s, line split %.3f s, alloc+parse kernel %.3f s\n", len,
+            (long long)n, outs.size(), t_h2d, t_split, t_parse);
   *n_out = n;
   *d_src = *d_dst = nullptr;
   if (d_w) *d_w = nullptr;

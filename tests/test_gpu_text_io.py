@@ -125,10 +125,10 @@ def test_device_formatter_equals_join(stride):
 
 
 def test_device_formatter_long_lines():
-    """walkLength 3000: one line (36 KB of staging) per block with opt-in shared memory."""
+    """walkLength 5000: one line (60 KB of staging) per block with opt-in shared memory."""
     rng = np.random.RandomState(1)
-    paths = rng.randint(-2**31, 2**31 - 1, (40, 3002)).astype(np.int32)
-    lens = np.full(40, 3002, np.int32)
+    paths = rng.randint(-2**31, 2**31 - 1, (40, 5002)).astype(np.int32)
+    lens = np.full(40, 5002, np.int32)
     lens[3] = 17
     want = "".join("\t".join(str(int(v)) for v in paths[i, :lens[i]]) + "\n" for i in range(40)).encode()
     assert _format_on_device(paths, lens) == want
