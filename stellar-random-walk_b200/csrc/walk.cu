@@ -835,6 +835,7 @@ srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLa
     const bool st = t_collect_stats != 0;
     static const bool use_v1 = getenv("SRW_KERNEL") && !strcmp(getenv("SRW_KERNEL"), "v1");   // A/B switches
     static const bool use_v2 = getenv("SRW_KERNEL") && !strcmp(getenv("SRW_KERNEL"), "v2");
+    static const bool use_v3 = getenv("SRW_KERNEL") && !strcmp(getenv("SRW_KERNEL"), "v3");
     // SRW_SAMPLER_ALIAS_FOLD: undirected + unweighted + 1/p > max(1, 1/q), else the classic sampler
     // (the CPU twin applies the same rule, oracle_alias_walk)
     const int occ = getenv("SRW_FOLD_OCC") ? atoi(getenv("SRW_FOLD_OCC")) : 0;   // A/B (read per launch): resident blocks per SM the fold kernel is compiled for
@@ -893,6 +894,20 @@ srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLa
       else if (occ == 6) walk_fold_kernel<false, false, 6><<<grid, 256, 0, l.stream>>>(a, f, pt);
       else if (occ == 8) walk_fold_kernel<false, false, 8><<<grid, 256, 0, l.stream>>>(a, f, pt);
       else walk_fold_kernel<false, false><<<grid, 256, 0, l.stream>>>(a, f, pt);
+    } else if (!use_v1 && !use_v2 && !use_v3 && g->d_meta && g->d_hash) {
+      // v5: the classic alias sampler in the warp-convergent layout (walk_conv.cuh)
+      const RowMeta *mt = g->d_meta;
+      const int32_t *hs = g->d_hash;
+      const bool v64 = (fold_var & 1) != 0;
+      if (g->has_alias) {
+        if (st) walk_alias_conv_kernel<true, true, 0><<<grid, 256, 0, l.stream>>>(a, mt, hs);
+        else if (v64) walk_alias_conv_kernel<true, false, 1><<<grid, 256, 0, l.stream>>>(a, mt, hs);
+        else walk_alias_conv_kernel<true, false, 0><<<grid, 256, 0, l.stream>>>(a, mt, hs);
+      } else {
+        if (st) walk_alias_conv_kernel<false, true, 0><<<grid, 256, 0, l.stream>>>(a, mt, hs);
+        else if (v64) walk_alias_conv_kernel<false, false, 1><<<grid, 256, 0, l.stream>>>(a, mt, hs);
+        else walk_alias_conv_kernel<false, false, 0><<<grid, 256, 0, l.stream>>>(a, mt, hs);
+      }
     } else if (!use_v1 && !use_v2 && g->d_meta) {
       const RowMeta *mt = g->d_meta;
       const int32_t *hs = g->d_hash;

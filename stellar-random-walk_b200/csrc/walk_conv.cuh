@@ -267,3 +267,138 @@ __global__ void __launch_bounds__(256, MINB) walk_fold_conv_kernel(WalkArgs a, F
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// K6 (v5, classic alias sampler: weighted or directed graphs, or (p, q) where folding does not apply).
+// The decisions of walk_alias_hash_kernel (v3) in the convergent three-phase layout of walk_fold_conv_kernel:
+//   A  draw      lanes in ST_WAIT run Philox together (draw(walker, step, trial), then trial++);
+//   B  load      ST_EXTENT and ST_HASH take one 256-bit load (row descriptor / hash bucket), ST_PROPOSE one
+//                16-byte Vose slot (weighted) or one 4-byte neighbour id, ST_SEARCH one 4-byte id;
+//   C  consume   verdicts, the single push site (ids staged in shared memory, 16-byte stores).
+// The hash set of prev is addressed from (poff, pdeg) alone (layout.h), so a lane carries two row extents and
+// nothing else.  Same bits as v3 and as the CPU twin (oracle_alias_walk, fold = 0).
+// ------------------------------------------------------------------------------------------
+template <bool HAS_ALIAS, bool STATS, int VAR>
+__global__ void __launch_bounds__(256, 4) walk_alias_conv_kernel(WalkArgs a, const RowMeta *__restrict__ meta,
+                                                                 const int32_t *__restrict__ hash) {
+  __shared__ int32_t sbuf[kStage * 256];
+  const int tid = threadIdx.x;
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + tid;
+  const bool live = i < a.n_walkers;
+  const uint64_t walker = a.walker_first + (uint64_t)(live ? i : 0);
+  int32_t curr = (int32_t)(walker % (uint64_t)a.nv), prev = -1;
+  int32_t *path = a.paths + (live ? i : 0) * a.stride;
+  int32_t len = 0, staged = 0, flushed = 0;
+  const int head = (int)(((16u - (uint32_t)(reinterpret_cast<uintptr_t>(path) & 15u)) & 15u) >> 2);
+  int lim = head ? kStage - 4 + head : kStage;
+  auto flush = [&]() {
+    int32_t *dst = path + flushed;
+    if (staged == kStage && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+      for (int j = 0; j < kStage; j += 4)
+        *reinterpret_cast<int4 *>(dst + j) = make_int4(sbuf[j * 256 + tid], sbuf[(j + 1) * 256 + tid], sbuf[(j + 2) * 256 + tid], sbuf[(j + 3) * 256 + tid]);
+    } else {
+      int j = 0;
+      if ((reinterpret_cast<uintptr_t>(dst) & 4) && staged >= 1) { dst[0] = sbuf[tid]; j = 1; }
+      if ((reinterpret_cast<uintptr_t>(dst + j) & 8) && j + 1 < staged) {
+        *reinterpret_cast<int2 *>(dst + j) = make_int2(sbuf[j * 256 + tid], sbuf[(j + 1) * 256 + tid]);
+        j += 2;
+      }
+#pragma unroll 1
+      for (; j + 3 < staged; j += 4)
+        *reinterpret_cast<int4 *>(dst + j) = make_int4(sbuf[j * 256 + tid], sbuf[(j + 1) * 256 + tid], sbuf[(j + 2) * 256 + tid], sbuf[(j + 3) * 256 + tid]);
+#pragma unroll 1
+      for (; j + 1 < staged; j += 2) *reinterpret_cast<int2 *>(dst + j) = make_int2(sbuf[j * 256 + tid], sbuf[(j + 1) * 256 + tid]);
+#pragma unroll 1
+      for (; j < staged; ++j) dst[j] = sbuf[j * 256 + tid];
+    }
+    flushed += staged; staged = 0; lim = kStage;
+  };
+  int64_t off = 0, poff = 0;
+  uint32_t deg = 0, pdeg = 0, trial = 0, lo = 0, hi = 0, y = 0, coin = 0, bkt = 0, pnb = 0;
+  uint64_t k = 0;
+  int32_t x = 0;
+  unsigned long long n_prop = 0, n_mem = 0, n_log = 0;
+  const uint64_t t_lo = a.t_common < a.t_far ? a.t_common : a.t_far;
+  const uint64_t t_hi = a.t_common < a.t_far ? a.t_far : a.t_common;
+  int state = ST_DONE;
+  if (live) { sbuf[tid] = curr; staged = 1; len = 1; state = ST_EXTENT; }
+
+  while (__any_sync(0xffffffffu, state != ST_DONE)) {
+    // ---- A: draw ----
+    if (state == ST_WAIT) {
+      const Philox4 r = walker_rng(a.seed_lo, a.seed_hi, walker, (uint32_t)(len - 1), trial);
+      trial++;
+      k = __umul64hi(((uint64_t)r.x << 32) | (uint64_t)r.w, (uint64_t)deg);
+      coin = r.y;
+      y = r.z;
+      state = ST_PROPOSE;
+    }
+    __syncwarp();
+    // ---- B: one memory access per lane ----
+    int4 q0 = make_int4(0, 0, 0, 0), q1 = make_int4(0, 0, 0, 0);
+    int32_t v = 0;
+    if (state == ST_EXTENT || state == ST_HASH) {
+      const int4 *P = state == ST_EXTENT ? reinterpret_cast<const int4 *>(meta + curr)
+                                         : reinterpret_cast<const int4 *>(hash + (srw_hash_first(poff) + (int64_t)bkt) * 8);
+      gather32<VAR>(P, q0, q1);
+    } else if (HAS_ALIAS && state == ST_PROPOSE) {
+      q0 = gather16<VAR>(reinterpret_cast<const int4 *>(a.slot + off + (int64_t)k));
+    } else if (state == ST_PROPOSE || state == ST_SEARCH) {
+      v = __ldg(state == ST_PROPOSE ? a.col + off + (int64_t)k : a.col + poff + (int64_t)((lo + hi) >> 1));
+    }
+    __syncwarp();
+    // ---- C: consume it ----
+    int verdict = 0;           // 1 = accept x, 2 = reject (next trial)
+    if (state == ST_EXTENT) {
+      off = ((int64_t)(uint32_t)q0.x) | ((int64_t)q0.y << 32);
+      deg = (uint32_t)q1.x;
+      trial = 0;
+      state = deg == 0 ? ST_DONE : ST_WAIT;                    // dead end (RW:59-62, RW:115-119)
+    } else if (state == ST_PROPOSE) {
+      if (HAS_ALIAS) x = (coin < (uint32_t)q0.x) ? q0.y : q0.z; else x = v;
+      if (STATS && len > 1) n_prop++;
+      if (len == 1 || deg == 1) verdict = 1;                   // first-order step (RW:57) / single choice
+      else if (x == prev) verdict = ((uint64_t)y < a.t_ret) ? 1 : 2;    // RS:36  w/p
+      else if ((uint64_t)y < t_lo) verdict = 1;
+      else if ((uint64_t)y >= t_hi) verdict = 2;
+      else {
+        if (STATS) { n_mem++; n_log += ceil_log2_p1(pdeg); }
+        pnb = srw_hash_buckets(poff, pdeg);
+        if (pnb) { bkt = __umulhi(srw_hash32((uint32_t)x), pnb); state = ST_HASH; }
+        else { lo = 0; hi = pdeg; state = ST_SEARCH; }
+      }
+    } else if (state == ST_HASH) {
+      const bool found = q0.x == x || q0.y == x || q0.z == x || q0.w == x || q1.x == x || q1.y == x || q1.z == x || q1.w == x;
+      if (found) verdict = ((uint64_t)y < a.t_common) ? 1 : 2;           // RS:38  x in N(prev): w
+      else if (q1.w == -1) verdict = ((uint64_t)y < a.t_far) ? 1 : 2;    // bucket not full: x is absent (RS:34 w/q)
+      else bkt = bkt + 1 == pnb ? 0 : bkt + 1;                           // full bucket: linear probing
+    } else if (state == ST_SEARCH) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (v == x) verdict = ((uint64_t)y < a.t_common) ? 1 : 2;
+      else {
+        if (v < x) lo = mid + 1; else hi = mid;
+        if (lo >= hi) verdict = ((uint64_t)y < a.t_far) ? 1 : 2;
+      }
+    }
+    if (verdict == 1) {                                        // RW:114, then RW:103
+      sbuf[staged * 256 + tid] = x;
+      staged++; len++;
+      if (staged == lim) flush();
+      prev = curr; poff = off; pdeg = deg;
+      curr = x;
+      state = (len == a.stride) ? ST_DONE : ST_EXTENT;
+    } else if (verdict == 2) {
+      state = ST_WAIT;
+    }
+  }
+  if (live) {
+    flush();
+    a.lens[i] = len;
+  }
+  if (STATS) {
+    atomicAdd(a.stats + 1, n_prop);
+    atomicAdd(a.stats + 2, n_mem);
+    atomicAdd(a.stats + 3, n_log);
+  }
+}

@@ -110,3 +110,58 @@ extern "C" int emu_fold_walk(int64_t nv, const int64_t *off, const int32_t *col,
   if (stats_out) memcpy(stats_out, st, sizeof(st));
   return folded ? 1 : 0;
 }
+
+// The classic alias sampler (walk_alias_conv_kernel): sorted CSR + optional Vose tables (thr / row-relative alias
+// index, as the twin's oa_view returns them) laid out as graph_build.cu does: RowMeta per row, hash sets placed
+// from the row extent, 16-byte AliasSlot per entry.
+extern "C" int emu_alias_walk(int64_t nv, const int64_t *off, const int32_t *col, const uint32_t *thr, const uint32_t *alias,
+                              uint64_t t_ret, uint64_t t_common, uint64_t t_far, uint64_t seed, int32_t walk_length,
+                              uint64_t walker_first, int64_t n_walkers, int32_t *paths, int32_t *lens, int var, int extra,
+                              unsigned long long *stats_out) {
+  const int64_t nnz = off[nv];
+  std::vector<RowMeta> meta((size_t)nv);
+  std::vector<int32_t> hash((size_t)(((nnz >> 2) + 1) * 8), -1);
+  std::vector<AliasSlot> slot;
+  for (int64_t r = 0; r < nv; ++r) {
+    RowMeta m;
+    m.off = off[r]; m.deg = (uint32_t)(off[r + 1] - off[r]);
+    m.hoff = srw_hash_first(m.off); m.nb = srw_hash_buckets(m.off, m.deg); m.pad0 = m.pad1 = 0;
+    meta[(size_t)r] = m;
+    for (int64_t e = off[r]; e < off[r + 1]; ++e) hash_insert(hash, m.off, m.deg, col[e]);
+  }
+  if (thr) {
+    slot.resize((size_t)nnz);
+    for (int64_t r = 0; r < nv; ++r)
+      for (int64_t e = off[r]; e < off[r + 1]; ++e) {
+        AliasSlot s;
+        s.thr = thr[e]; s.own = col[e]; s.alias_index = alias[e]; s.alias_vertex = col[off[r] + alias[e]];
+        slot[(size_t)e] = s;
+      }
+  }
+  WalkArgs a{};
+  a.off = off; a.col = col; a.slot = thr ? slot.data() : nullptr; a.nv = nv; a.walker_first = walker_first; a.n_walkers = n_walkers;
+  a.stride = walk_length + 2; a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
+  a.t_ret = t_ret; a.t_common = t_common; a.t_far = t_far;
+  a.paths = paths; a.lens = lens;
+  unsigned long long st[4] = {0, 0, 0, 0};
+  a.stats = st;
+  emu_extra_iters = extra;
+  blockDim.x = 256; blockDim.y = blockDim.z = 1;
+  const int64_t n_blocks = (n_walkers + 255) / 256;
+  for (int64_t b = 0; b < n_blocks; ++b) {
+    blockIdx.x = (unsigned)b;
+    for (unsigned t = 0; t < 256; ++t) {
+      threadIdx.x = t;
+      emu_linger = 0;
+      if (thr) {
+        if (var & 1) walk_alias_conv_kernel<true, false, 1>(a, meta.data(), hash.data());
+        else walk_alias_conv_kernel<true, true, 0>(a, meta.data(), hash.data());
+      } else {
+        if (var & 1) walk_alias_conv_kernel<false, false, 1>(a, meta.data(), hash.data());
+        else walk_alias_conv_kernel<false, true, 0>(a, meta.data(), hash.data());
+      }
+    }
+  }
+  if (stats_out) memcpy(stats_out, st, sizeof(st));
+  return 0;
+}

@@ -319,12 +319,12 @@ for w in (None, synth.edge_weights(len(s), seed=4)):
 print(",".join(out))
 ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     res = {}
-    for k in ("v1", "v2", "v3"):
+    for k in ("v1", "v2", "v3", "v5"):
         env = dict(os.environ, SRW_KERNEL=k)
         r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, env=env)
         assert r.returncode == 0, r.stderr[-2000:]
         res[k] = r.stdout.strip().splitlines()[-1]
-    assert res["v1"] == res["v2"] == res["v3"], res
+    assert res["v1"] == res["v2"] == res["v3"] == res["v5"], res
 
 
 # ---- VCut input format through the native Main (--partitioned true, 3rd column = partition id) ----

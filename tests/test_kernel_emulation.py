@@ -32,6 +32,9 @@ def emu():
     lib.emu_fold_walk.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_int,
                                   C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.emu_alias_walk.restype = C.c_int
+    lib.emu_alias_walk.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
+                                   C.c_int32, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     return lib
 
 
@@ -147,4 +150,53 @@ def test_emulated_kernel_hub_and_multi_edges(emu, oracle):
     for p, q in ((0.25, 4.0), (0.5, 2.0)):
         want, _ = _twin_paths(oracle, tw, walk_length=25, num_walks=1, p=p, q=q, seed=21, fold=1)
         got, _, _ = _emu_walk(emu, oracle, tw, walk_length=25, p=p, q=q, seed=21, fold=True, shards=2)
+        assert got == want
+
+
+# ---- the classic alias sampler in the convergent layout (walk_alias_conv_kernel) ----
+def _emu_alias_walk(emu, oracle, tw, *, walk_length, p, q, seed, var=0, extra=2, rounds=1):
+    v = tw.view()
+    off = np.ascontiguousarray(v["offsets"], np.int64)
+    col = np.ascontiguousarray(v["col"], np.int32)
+    thr = np.ascontiguousarray(v["thr"], np.uint32) if "thr" in v else None
+    al = np.ascontiguousarray(v["alias"], np.uint32) if "alias" in v else None
+    nv = len(off) - 1
+    n = nv * rounds
+    stride = walk_length + 2
+    paths = np.full((n, stride), -7, np.int32)
+    lens = np.zeros(n, np.int32)
+    t_ret, t_common, t_far = oracle.alias_thresholds(p, q)
+    st = np.zeros(4, np.uint64)
+    rc = emu.emu_alias_walk(nv, off.ctypes.data, col.ctypes.data, None if thr is None else thr.ctypes.data,
+                            None if al is None else al.ctypes.data, t_ret, t_common, t_far, seed, walk_length, 0, n,
+                            paths.ctypes.data, lens.ctypes.data, var, extra, st.ctypes.data)
+    assert rc == 0
+    for i in range(n):
+        assert (paths[i, lens[i]:] == -7).all()
+    vids = v["vids"]
+    return [vids[paths[i, :lens[i]]].tolist() for i in range(n)], st
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+@pytest.mark.parametrize("directed", [False, True])
+@pytest.mark.parametrize("p,q", [(0.5, 2.0), (2.0, 0.5), (1.0, 1.0), (0.25, 4.0)])
+def test_emulated_alias_kernel_equals_twin(emu, oracle, weighted, directed, p, q):
+    s, d = synth.rmat_edges(9, 8, seed=42)
+    w = synth.edge_weights(len(s), seed=43) if weighted else None
+    tw = oracle.AliasGraph(oracle.Graph().load_edges(s, d, w, directed=directed), directed=directed)
+    assert tw.has_alias == weighted
+    for wl in (30, 13):
+        want, wst = _twin_paths(oracle, tw, walk_length=wl, num_walks=2, p=p, q=q, seed=17)
+        for var, extra in ((0, 2), (1, 0)):
+            got, st = _emu_alias_walk(emu, oracle, tw, walk_length=wl, p=p, q=q, seed=17, var=var, extra=extra, rounds=2)
+            assert got == want
+
+
+def test_emulated_alias_kernel_hubs(emu, oracle):
+    zs, zd = synth.zipf_edges(2048, seed=7, cap=600)
+    w = synth.edge_weights(len(zs), seed=5)
+    for ww in (None, w):
+        tw = oracle.AliasGraph(oracle.Graph().load_edges(zs, zd, ww))
+        want, _ = _twin_paths(oracle, tw, walk_length=25, num_walks=1, p=0.25, q=4.0, seed=21)
+        got, _ = _emu_alias_walk(emu, oracle, tw, walk_length=25, p=0.25, q=4.0, seed=21)
         assert got == want
