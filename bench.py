@@ -345,7 +345,7 @@ def run_b200(a):
     value = steps_all / (elapsed_ms * 1e-3)
     log("timed region done: %.3e steps/s" % value)
 
-    # ---- roofline of the dominant kernel (walk_alias_kernel) ----
+    # ---- roofline of the dominant kernel ----
     # algorithmic bytes per sampled transition (DESIGN.md "bytes per step"): row extent 8 B +
     # T * (neighbour id 4 B [+ Vose slot 8 B when weighted]) + 4 B per binary-search probe + 4 B path write
     per_prop = 4 + (8 if a.weighted else 0)
@@ -354,30 +354,39 @@ def run_b200(a):
     peak, peak_src = peaks()
     kernel_s = kernel_ms * 1e-3
     achieved = steps * B / kernel_s / 1e9
-    traffic = None
+    traffic, l2_requests = None, None
+    kernel_name = "walk_fold_conv_kernel" if (a.sampler == "fold" and not a.weighted) else "walk_alias_conv_kernel"
     tj = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tj):
         try:
             tjd = json.load(open(tj))
             # only meaningful for the launch it was captured on: same kernel, one GPU, full round of the default workload
-            if world == 1 and a.scale == 26 and not a.weighted and tjd.get("kernel") == ("walk_fold_kernel" if a.sampler == "fold" else "walk_alias_hash_kernel"):
+            if world == 1 and a.scale == 26 and not a.weighted and tjd.get("kernel") == kernel_name:
                 traffic = tjd.get("dram_bytes_per_launch")
+                l2_requests = tjd.get("l2_requests_per_launch")
         except Exception:
             traffic = None
+    steps_per_launch = steps / max(1, a.steps)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "walk_fold_kernel" if (a.sampler == "fold" and not a.weighted) else "walk_alias_hash_kernel", "kernel_ms_per_launch": kernel_ms / max(1, a.steps), "peak_source": peak_src,
+                "kernel": kernel_name, "kernel_ms_per_launch": kernel_ms / max(1, a.steps), "peak_source": peak_src,
                 "bytes_per_step": B, "bytes_per_step_survey_formula": B_survey, "proposals_per_step": T_bar,
                 "member_tests_per_step": st.member_tests / max(1, st.steps), "mean_probes_per_test": L_bar,
-                "kernel_share_of_step": kernel_ms / elapsed_ms}
+                "kernel_share_of_step": kernel_ms / elapsed_ms,
+                "note": "the kernel is a random gather: what bounds it is the memory system's random-request rate (gather_ceiling_*), "
+                        "not streaming bandwidth -- a 4..32-byte gather that misses moves a whole 128-byte line (traffic / algorithmic bytes)"}
+    if traffic and l2_requests:
+        roofline["traffic_bytes_per_step_ncu"] = traffic / steps_per_launch
+        roofline["l2_requests_per_step_ncu"] = l2_requests / steps_per_launch
     if rank == 0 and world == 1:
         gs, gg = C.c_double(), C.c_double()
         try:
             srw.check(lib.srw_gather_ceiling(8 << 30, 1 << 28, C.byref(gs), C.byref(gg)))
-            roofline["gather_ceiling_sectors_per_s"] = gs.value
-            roofline["gather_ceiling_GBps_of_32B_sectors"] = gg.value
-            # sectors the kernel must touch per step if nothing hits in cache
-            sect = 1 + T_bar + probes_per_step + 1
-            roofline["frac_of_gather_ceiling"] = (steps / kernel_s) * sect / gs.value
+            roofline["gather_ceiling_requests_per_s"] = gs.value
+            # memory requests the kernel cannot avoid, per step: one neighbour-entry gather per proposal, one hash bucket per
+            # membership test (rows shorter than 8 use a <= 3-probe search instead), 1/8 of a 32-byte sector for the path id
+            req = T_bar + st.member_tests / max(1, st.steps) + 0.125
+            roofline["requests_per_step_model"] = req
+            roofline["frac_of_gather_ceiling"] = (steps / kernel_s) * req / gs.value
         except Exception as ex:   # noqa: BLE001
             roofline["gather_ceiling_error"] = str(ex)
 
@@ -699,7 +708,7 @@ def run_peer_gather(a, srw, sh, shard, rank, world, dev, barrier):
             "scaling": "strong", "path_checksum": int(chk[0]),
             "config": {"workload": workload_name(a), "vertices_present": nv, "walkers_per_step": nv,
                        "parallelism": "graph sharded into %d edge-balanced vertex ranges (one per GPU, %d adjacency entries on rank 0); "
-                                      "every GPU maps every shard (symmetric-memory blocks, CUDA VMM) and walk_fold_kernel<PEER> loads remote rows over "
+                                      "every GPU maps every shard (symmetric-memory blocks, CUDA VMM) and walk_fold_conv_kernel<PEER> loads remote rows over "
                                       "NVLink; walkers split evenly, never migrate, no collective on the data path" % (world, shard.nnz_local),
                        "peer_mapping": os.environ.get("SRW_PEER_MAP", "symm"),
                        "sampler": a.sampler, "ipc_attach_s": round(attach_s, 3)},

@@ -485,7 +485,8 @@ srw_status srw_parse_text_device(const char *h_text, size_t len, int weighted, i
       while (e < len && !srw_line_end(h_text[e])) e++;
       srw_edges *tmp = nullptr;
       std::string msg = "malformed line";
-      if (srw_edges_parse_buffer(h_text + c0 + sb, e - (c0 + sb), weighted, partitioned, &tmp) != SRW_OK) {
+      const bool empty = e == c0 + sb;           // the host parser sees an empty line only through its terminator
+      if (srw_edges_parse_buffer(empty ? "\n" : h_text + c0 + sb, empty ? 1 : e - (c0 + sb), weighted, partitioned, &tmp) != SRW_OK) {
         msg = srw_last_error();
         const size_t colon = msg.find(": ");
         if (msg.compare(0, 5, "line ") == 0 && colon != std::string::npos) msg = msg.substr(colon + 2);
