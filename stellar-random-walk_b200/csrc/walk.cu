@@ -747,6 +747,43 @@ __global__ void finalize_paths_kernel(int64_t n_walkers, int32_t stride, const i
   if ((threadIdx.x & 31) == 0 && steps) atomicAdd(stats, steps);
 }
 
+// The same pass over the matrix as ONE contiguous array of int2 (even stride: rows are 8-byte aligned and adjacent),
+// four independent 8-byte loads and eight id gathers in flight per thread instead of one dependent chain per lane.
+// row = e2 / half by a 64-bit multiply-high (magic = ceil(2^64 / half), exact for e2 * half < 2^64).
+__global__ void __launch_bounds__(256) finalize_paths_flat_kernel(int64_t n_pairs, uint32_t half, uint64_t magic, const int32_t *__restrict__ vids,
+                                                                  const int32_t *__restrict__ lens, int2 *paths, unsigned long long *stats) {
+  constexpr int U = 4;
+  unsigned long long steps = 0;
+  const int64_t base = (int64_t)blockIdx.x * (256 * U) + threadIdx.x;
+  int2 v[U];
+  int32_t len[U];
+  uint32_t c[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int64_t e = base + (int64_t)u * 256;
+    v[u] = make_int2(0, 0); len[u] = 0; c[u] = 0;
+    if (e < n_pairs) {
+      v[u] = paths[e];
+      const uint64_t r = __umul64hi((uint64_t)e, magic);
+      c[u] = (uint32_t)((uint64_t)e - r * half) * 2u;
+      len[u] = __ldg(lens + r);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int64_t e = base + (int64_t)u * 256;
+    if (e < n_pairs) {
+      int2 o;
+      o.x = (int32_t)c[u] < len[u] ? __ldg(vids + v[u].x) : -1;
+      o.y = (int32_t)c[u] + 1 < len[u] ? __ldg(vids + v[u].y) : -1;
+      paths[e] = o;
+      if (c[u] == 0) steps += (unsigned long long)(len[u] - 1);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, o);
+  if ((threadIdx.x & 31) == 0 && steps) atomicAdd(stats, steps);
+}
+
 // ---- KAT kernels: one thread, same device functions as the exact walk ----
 __global__ void kat_sample_kernel(int64_t n, const float *w, float u, int64_t *out) {
   *out = cdf_pick(n, u, [&](int64_t j) { return w[j]; });
@@ -924,7 +961,16 @@ srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLa
     const int64_t total = l.n_walkers * (int64_t)a.stride;
     int64_t blocks = (total + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    finalize_paths_kernel<<<(unsigned)blocks, 256, 0, l.stream>>>(l.n_walkers, a.stride, g->d_vids, l.d_lens, l.d_paths, d_stats);
+    const bool flat = (a.stride & 1) == 0 && (reinterpret_cast<uintptr_t>(l.d_paths) & 7) == 0 && !getenv("SRW_FINALIZE_ROWS");
+    if (flat && total > 0) {
+      const uint32_t half = (uint32_t)a.stride / 2;
+      const uint64_t magic = ~0ULL / half + 1;                  // ceil(2^64 / half) (half >= 1; half == 1: wraps to 0, handled below)
+      const int64_t n_pairs = total / 2;
+      if (half == 1) finalize_paths_kernel<<<(unsigned)blocks, 256, 0, l.stream>>>(l.n_walkers, a.stride, g->d_vids, l.d_lens, l.d_paths, d_stats);
+      else finalize_paths_flat_kernel<<<(unsigned)((n_pairs + 1023) / 1024), 256, 0, l.stream>>>(n_pairs, half, magic, g->d_vids, l.d_lens, reinterpret_cast<int2 *>(l.d_paths), d_stats);
+    } else {
+      finalize_paths_kernel<<<(unsigned)blocks, 256, 0, l.stream>>>(l.n_walkers, a.stride, g->d_vids, l.d_lens, l.d_paths, d_stats);
+    }
   }
   unsigned long long *h_stats = ev.h_stats;
   SRW_CUDA(cudaMemcpyAsync(h_stats, d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, l.stream));
