@@ -12,14 +12,15 @@ sys.path.insert(0, ROOT)
 
 VARIANTS = [
     ("v4", {"SRW_FOLD": "v4"}),
-    ("v5", {}),
+    ("v5", {"SRW_FOLD_VAR": "0"}),
     ("v5-64B", {"SRW_FOLD_VAR": "1"}),
-    ("v5-occ5", {"SRW_FOLD_OCC": "5"}),
-    ("v5-occ6", {"SRW_FOLD_OCC": "6"}),
+    ("v5-occ5", {"SRW_FOLD_VAR": "0", "SRW_FOLD_OCC": "5"}),
+    ("v5-occ6", {"SRW_FOLD_VAR": "0", "SRW_FOLD_OCC": "6"}),
     ("v5-64B-occ5", {"SRW_FOLD_VAR": "1", "SRW_FOLD_OCC": "5"}),
     ("v5-64B-occ6", {"SRW_FOLD_VAR": "1", "SRW_FOLD_OCC": "6"}),
     ("v4-again", {"SRW_FOLD": "v4"}),
-    ("v5-again", {}),
+    ("v5-again", {"SRW_FOLD_VAR": "0"}),
+    ("default", {}),
 ]
 
 

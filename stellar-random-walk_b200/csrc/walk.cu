@@ -889,7 +889,7 @@ srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLa
     // A/B (read per launch, so one process can time every variant on one graph): SRW_FOLD=v4 runs the
     // pre-convergence kernel; SRW_FOLD_VAR bit 0 = L2::64B loads in v5; SRW_FOLD_OCC = 5 | 6 blocks per SM
     const bool fold_v4 = getenv("SRW_FOLD") && !strcmp(getenv("SRW_FOLD"), "v4");
-    constexpr int kFoldVarDefault = 0;   // v5 load flavour used when SRW_FOLD_VAR is unset
+    constexpr int kFoldVarDefault = 1;   // v5 load flavour when SRW_FOLD_VAR is unset: L2::64B gathers (half the DRAM traffic at the same speed, profiles/)
     const int fold_var = getenv("SRW_FOLD_VAR") ? atoi(getenv("SRW_FOLD_VAR")) : kFoldVarDefault;
     if ((peer || fold) && !fold_v4) {
       PeerTable pt{};

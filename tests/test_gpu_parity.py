@@ -458,7 +458,7 @@ def test_fold_kernel_generations_agree(oracle, monkeypatch):
     res = {}
     for wl in (80, 13, 0):       # even and odd strides: both alignments of the staged path stores
         want_ids, want_offs, _ = twin.walk(walk_length=wl, num_walks=2, p=0.5, q=2.0, seed=9, fold=1)
-        for name, env in (("v4", {"SRW_FOLD": "v4"}), ("v5", {}), ("v5-64B", {"SRW_FOLD_VAR": "1"}), ("v5-occ5", {"SRW_FOLD_OCC": "5"}),
+        for name, env in (("v4", {"SRW_FOLD": "v4"}), ("default", {}), ("v5-plain", {"SRW_FOLD_VAR": "0"}), ("v5-64B", {"SRW_FOLD_VAR": "1"}), ("v5-occ5", {"SRW_FOLD_OCC": "5"}),
                           ("v5-occ6", {"SRW_FOLD_OCC": "6"}), ("v5-64B-occ6", {"SRW_FOLD_VAR": "1", "SRW_FOLD_OCC": "6"})):
             for k in ("SRW_FOLD", "SRW_FOLD_VAR", "SRW_FOLD_OCC"):
                 monkeypatch.delenv(k, raising=False)
