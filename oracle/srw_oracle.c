@@ -610,6 +610,8 @@ struct oa_graph {
   uint32_t *thr;      /* Vose bucket threshold (NULL when every weight is 1.0f) */
   uint32_t *alias;    /* row-relative alias slot */
   uint32_t *mult;     /* parallel-edge multiplicity of every entry */
+  double *wsum;       /* per row: sequential double sum of the weights (the W of the Vose build); weighted graphs */
+  double *wb;         /* per entry: double sum, in row order, of the weights of all parallel entries to the same neighbour */
   int has_alias;
   int directed;       /* set by the caller: folding is defined for undirected graphs only */
 };
@@ -629,7 +631,7 @@ static int64_t rank_of(const int32_t *vids, int64_t nv, int32_t v) {
 /* Vose alias table by the in-order "sweep" (two cursors, no work lists):
  *   scaled(k) = (double)w[k] * (double)n / W,  W = sequential double sum of the row.
  *   i walks the light items (scaled < 1) upward, j the heavy ones; r is heavy j's residual. */
-static void alias_row(int64_t n, const float *w, uint32_t *thr, uint32_t *alias) {
+static double alias_row(int64_t n, const float *w, uint32_t *thr, uint32_t *alias) {
   double W = 0.0;
   for (int64_t k = 0; k < n; ++k) { W = W + (double)w[k]; thr[k] = 0xFFFFFFFFu; alias[k] = (uint32_t)k; }
   const double dn = (double)n;
@@ -637,7 +639,7 @@ static void alias_row(int64_t n, const float *w, uint32_t *thr, uint32_t *alias)
   int64_t i = 0, j = 0;
   while (i < n && !(SCALED(i) < 1.0)) i++;
   while (j < n && (SCALED(j) < 1.0)) j++;
-  if (j >= n) return;
+  if (j >= n) return W;
   double r = SCALED(j);
   while (j < n) {
     if (!(r < 1.0)) {
@@ -659,6 +661,7 @@ static void alias_row(int64_t n, const float *w, uint32_t *thr, uint32_t *alias)
     }
   }
 #undef SCALED
+  return W;
 }
 
 oa_graph *oa_build(const og_graph *g) {
@@ -704,20 +707,32 @@ oa_graph *oa_build(const og_graph *g) {
   if (has) {
     a->thr = (uint32_t *)malloc((size_t)(nnz ? nnz : 1) * 4);
     a->alias = (uint32_t *)malloc((size_t)(nnz ? nnz : 1) * 4);
+    a->wsum = (double *)calloc((size_t)(a->nv ? a->nv : 1), 8);
+    a->wb = (double *)malloc((size_t)(nnz ? nnz : 1) * 8);
     for (int64_t v = 0; v < a->nv; ++v) {
       int64_t d = a->offsets[v + 1] - a->offsets[v];
-      if (d > 0) alias_row(d, a->w + a->offsets[v], a->thr + a->offsets[v], a->alias + a->offsets[v]);
+      if (d > 0) a->wsum[v] = alias_row(d, a->w + a->offsets[v], a->thr + a->offsets[v], a->alias + a->offsets[v]);
+      const int64_t lo = a->offsets[v], hi = a->offsets[v + 1];
+      for (int64_t i = lo; i < hi;) {                 /* bundle weight: the run of equal neighbours, summed in row order */
+        int64_t j = i;
+        double sum = 0.0;
+        while (j < hi && a->col[j] == a->col[i]) { sum = sum + (double)a->w[j]; j++; }
+        for (int64_t k = i; k < j; ++k) a->wb[k] = sum;
+        i = j;
+      }
     }
   }
   return a;
 }
 void oa_free(oa_graph *a) {
   if (!a) return;
-  free(a->vids); free(a->offsets); free(a->col); free(a->w); free(a->thr); free(a->alias); free(a->mult); free(a);
+  free(a->vids); free(a->offsets); free(a->col); free(a->w); free(a->thr); free(a->alias); free(a->mult); free(a->wsum); free(a->wb); free(a);
 }
 int64_t oa_num_vertices(const oa_graph *a) { return a->nv; }
 int oa_has_alias(const oa_graph *a) { return a->has_alias; }
 const uint32_t *oa_mult(const oa_graph *a) { return a->mult; }
+const double *oa_wsum(const oa_graph *a) { return a->wsum; }
+const double *oa_wbundle(const oa_graph *a) { return a->wb; }
 void oa_set_directed(oa_graph *a, int directed) { a->directed = directed; }
 void oa_view(const oa_graph *a, const int32_t **vids, const int64_t **offsets, const int32_t **col,
              const float **w, const uint32_t **thr, const uint32_t **alias) {
@@ -779,10 +794,11 @@ int64_t oracle_alias_walk(const oa_graph *a, const oracle_walk_cfg *cfg, int32_t
   oracle_alias_thresholds(cfg->p, cfg->q, &t_ret, &t_common, &t_far);
   double fold_a = 0.0, fold_mp = 1.0;
   int fold = 0;
-  if (cfg->fold && !a->has_alias && !a->directed) {
+  int wfold = 0;             /* weighted alias-fold: the return draw and the accept draw share r[2] (see below) */
+  if (cfg->fold && !a->directed) {
     uint64_t fc, ff;
     oracle_fold_thresholds(cfg->p, cfg->q, &fc, &ff, &fold_a, &fold_mp);
-    if (fold_a > 0.0) { fold = 1; t_common = fc; t_far = ff; t_ret = 4294967296ULL; }
+    if (fold_a > 0.0) { fold = 1; wfold = a->has_alias; t_common = fc; t_far = ff; t_ret = 4294967296ULL; }
   }
   int32_t *tmp = (int32_t *)malloc((size_t)(nv ? nv : 1) * (size_t)stride * 4);
   int32_t *lens = (int32_t *)malloc((size_t)(nv ? nv : 1) * 4);
@@ -808,6 +824,7 @@ int64_t oracle_alias_walk(const oa_graph *a, const oracle_walk_cfg *cfg, int32_t
         walker_rng(cfg->seed, walker, 0u, 0u, r);           /* first-order step: proposal accepted */
         int64_t kk = alias_pick(a, off, deg, r);
         uint32_t m_ret = a->mult[off + kk];                  /* parallel edges start<->first (undirected: symmetric) */
+        double w_ret = wfold ? a->wb[off + kk] : 0.0;        /* their total weight (weighted fold) */
         path[len++] = a->col[off + kk];
         st_steps++;
         while (len != stride) {
@@ -820,14 +837,38 @@ int64_t oracle_alias_walk(const oa_graph *a, const oracle_walk_cfg *cfg, int32_t
            * a*m / (Mp*deg + a*m) (always accepted), else a uniform entry under the envelope Mp */
           /* division-free form: return iff r1 * (Mp*deg + a*m) < a*m * 2^32 (IEEE double, one
            * rounding per operation; the kernel evaluates the same expression) */
-          double ret_lhs = 0.0, ret_rhs = 0.0;
-          if (fold) {
+          double ret_lhs = 0.0, ret_rhs = 0.0, wf_t2 = 0.0;
+          if (fold && !wfold) {
             const double t1 = fold_a * (double)m_ret, t2 = fold_mp * (double)deg;
             ret_lhs = t2 + t1;
             ret_rhs = t1 * 4294967296.0;
           }
+          if (wfold) {
+            /* weighted: mass of the return-excess component a*wb against the envelope Mp*W(curr).  ONE draw z = r[2]
+             * decides both: z*den < t1*2^32 -> return; else the proposal of class c is accepted iff
+             * z*den < t1*2^32 + t2*T_c  (z rescaled to the non-return part of [0,1); r[1] stays the Vose coin). */
+            const double t1 = fold_a * w_ret;
+            wf_t2 = fold_mp * a->wsum[curr];
+            ret_lhs = wf_t2 + t1;
+            ret_rhs = t1 * 4294967296.0;
+          }
           for (uint32_t trial = 0;; ++trial) {
             walker_rng(cfg->seed, walker, (uint32_t)(len - 1), trial, r);
+            if (wfold) {
+              const double zl = (double)r[2] * ret_lhs;
+              if (zl < ret_rhs) { x = prev; kk = -1; st_prop++; break; }
+              kk = alias_pick(a, off, deg, r);
+              x = a->col[off + kk];
+              st_prop++;
+              if (x == prev || deg == 1) break;                 /* mass Mp of Mp under the envelope: always accepted */
+              const double rc = ret_rhs + wf_t2 * (double)t_common, rf = ret_rhs + wf_t2 * (double)t_far;
+              const double rlo = rc < rf ? rc : rf, rhi = rc < rf ? rf : rc;
+              if (zl < rlo) break;
+              if (!(zl < rhi)) continue;
+              st_mem++; st_log += ceil_log2_p1(pdeg);
+              if (zl < (row_contains(a->col + poff, pdeg, x) ? rc : rf)) break;
+              continue;
+            }
             if (fold && (double)r[1] * ret_lhs < ret_rhs) { x = prev; kk = -1; st_prop++; break; }
             kk = alias_pick(a, off, deg, r);
             x = a->col[off + kk];
@@ -843,6 +884,7 @@ int64_t oracle_alias_walk(const oa_graph *a, const oracle_walk_cfg *cfg, int32_t
             }
             if ((uint64_t)r[2] < t) break;
           }
+          if (wfold && kk >= 0) w_ret = a->wb[off + kk];         /* a direct return keeps the bundle (symmetric) */
           if (fold) {
             if (kk >= 0) m_ret = a->mult[off + kk];
             else {                                            /* direct return: multiplicity of prev in N(curr) */

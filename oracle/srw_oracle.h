@@ -89,7 +89,9 @@ typedef struct oracle_walk_cfg {
   /* alias twin only: 1 = "alias-fold" (the product's SRW_SAMPLER_ALIAS_FOLD): on an undirected,
    * unweighted graph with 1/p > max(1, 1/q) the return edge's excess weight is sampled as its own
    * mixture component, so the rejection envelope is max(1, 1/q) instead of 1/p.  Ignored (classic
-   * rejection) when the graph or (p, q) do not qualify. */
+   * rejection) when the graph or (p, q) do not qualify.  On a WEIGHTED undirected graph the same folding applies with
+   * (multiplicity, degree) replaced by (bundle weight, row weight sum), and the accept draw r[2] doubles as the
+   * component draw (rescaled), because r[1] is the Vose coin. */
   int32_t fold;
 } oracle_walk_cfg;
 
@@ -128,6 +130,9 @@ void oracle_alias_thresholds(double p, double q, uint64_t *t_ret, uint64_t *t_co
 void oracle_fold_thresholds(double p, double q, uint64_t *t_common, uint64_t *t_far, double *a, double *mp);
 /* per-entry multiplicity (number of parallel edges to the same neighbour), sorted-row order */
 const uint32_t *oa_mult(const oa_graph *a);
+/* weighted graphs: per-row weight sum W (sequential double sum, the Vose build's) and per-entry bundle weight */
+const double *oa_wsum(const oa_graph *a);
+const double *oa_wbundle(const oa_graph *a);
 void oa_set_directed(oa_graph *a, int directed);   /* folding needs mult(prev->curr) == mult(curr->prev) */
 
 /* ---- CPU-baseline helpers (bench.py only): dense CSR (vid == rank), no GraphMap hash lookups and

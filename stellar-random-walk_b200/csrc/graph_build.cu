@@ -170,7 +170,7 @@ __device__ __forceinline__ double scaled_w(const float *__restrict__ w, int64_t 
   return __ddiv_rn(__dmul_rn((double)w[k], dn), W);
 }
 __global__ void k_alias_rows(int64_t nv, const int64_t *__restrict__ off, const int32_t *__restrict__ col,
-                             const float *__restrict__ w_all, AliasSlot *slot_all) {
+                             const float *__restrict__ w_all, AliasSlot *slot_all, RowMeta *meta) {
   for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nv; v += (int64_t)gridDim.x * blockDim.x) {
     const int64_t o = off[v], n = off[v + 1] - o;
     if (n <= 0) continue;
@@ -183,6 +183,7 @@ __global__ void k_alias_rows(int64_t nv, const int64_t *__restrict__ off, const 
       AliasSlot s; s.thr = 0xFFFFFFFFu; s.own = c[k]; s.alias_vertex = c[k]; s.alias_index = (uint32_t)k;
       slot[k] = s;
     }
+    if (meta) meta[v].w_sum = W;
     const double dn = (double)n;
     int64_t i = 0, j = 0;
     while (i < n && !(scaled_w(w, i, dn, W) < 1.0)) i++;
@@ -213,12 +214,39 @@ __global__ void k_alias_rows(int64_t nv, const int64_t *__restrict__ off, const 
   }
 }
 
+// Weighted alias-fold: bundle weight of every entry (double sum, in row order, over the run of equal neighbours) ...
+__global__ void k_bundle_weights(int64_t nnz, const uint32_t *__restrict__ row_of, const int32_t *__restrict__ col,
+                                 const int64_t *__restrict__ off, const float *__restrict__ w, double *wb) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t lo = off[row_of[i]], hi = off[row_of[i] + 1];
+    const int32_t x = col[i];
+    int64_t a = i, b = i;
+    while (a > lo && col[a - 1] == x) a--;
+    while (b + 1 < hi && col[b + 1] == x) b++;
+    double sum = 0.0;
+    for (int64_t t = a; t <= b; ++t) sum = __dadd_rn(sum, (double)w[t]);
+    wb[i] = sum;
+  }
+}
+// ... and the 32-byte slots that carry it for both outcomes of the Vose coin
+__global__ void k_slots_w(int64_t nnz, const uint32_t *__restrict__ row_of, const int64_t *__restrict__ off,
+                          const AliasSlot *__restrict__ slot, const double *__restrict__ wb, AliasSlotW *out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+    const AliasSlot s = slot[i];
+    AliasSlotW o;
+    o.thr = s.thr; o.own = s.own; o.alias_vertex = s.alias_vertex; o.alias_index = s.alias_index;
+    o.wb_own = wb[i];
+    o.wb_alias = wb[off[row_of[i]] + (int64_t)s.alias_index];
+    out[i] = o;
+  }
+}
+
 // ---- per-row neighbour hash sets + packed row descriptors ----
 __global__ void k_row_meta(int64_t rows, const int64_t *__restrict__ off, RowMeta *meta) {
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
     RowMeta m;
     m.off = off[r]; m.deg = (uint32_t)(off[r + 1] - off[r]);
-    m.hoff = srw_hash_first(m.off); m.nb = srw_hash_buckets(m.off, m.deg); m.pad0 = 0; m.pad1 = 0;
+    m.hoff = srw_hash_first(m.off); m.nb = srw_hash_buckets(m.off, m.deg); m.w_sum = (double)m.deg;
     meta[r] = m;
   }
 }
@@ -545,14 +573,28 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
       SRW_CUDA(ws.alloc((size_t)nnz * 4));
       k_gather_w<<<grid(nnz), kThreads>>>(nnz, v_in, gidx, d_w, wshift, ws.as<float>());
       SRW_CUDA(cudaMalloc(&g->d_slot, (size_t)nnz * sizeof(AliasSlot)));
-      k_alias_rows<<<grid_for(nrows, 64), 64>>>(nrows, g->d_off, g->d_col, ws.as<float>(), g->d_slot);
+      k_alias_rows<<<grid_for(nrows, 64), 64>>>(nrows, g->d_off, g->d_col, ws.as<float>(), g->d_slot, g->d_meta);
       SRW_CUDA(cudaDeviceSynchronize());
       g->has_alias = true;
+      // weighted alias-fold (undirected, unsharded): 32-byte slots with the bundle weights.  48 bytes per entry in all:
+      // HBM capacity is spent to keep a proposal at ONE memory request.
+      if (!directed && !sharded && g->d_meta && !getenv("SRW_NO_WFOLD")) {
+        DevBuf wb;
+        SRW_CUDA(wb.alloc((size_t)nnz * 8));
+        k_bundle_weights<<<grid(nnz), kThreads>>>(nnz, k_in, g->d_col, g->d_off, ws.as<float>(), wb.as<double>());
+        if (cudaMalloc(&g->d_slotw, (size_t)nnz * sizeof(AliasSlotW)) == cudaSuccess) {
+          k_slots_w<<<grid(nnz), kThreads>>>(nnz, k_in, g->d_off, g->d_slot, wb.as<double>(), g->d_slotw);
+          SRW_CUDA(cudaDeviceSynchronize());
+        } else {
+          cudaGetLastError();            // not enough HBM for the wide slots: the classic alias sampler still runs
+          g->d_slotw = nullptr;
+        }
+      }
     }
   }
   SRW_CUDA(cudaGetLastError());
   g->device_bytes = (int64_t)(words * 8 + (size_t)nv * 12 + (size_t)nnz * 4) + (g->d_col_app ? nnz * 8 : 0) +
-                    (g->d_slot ? nnz * 16 : 0) + (g->d_vpid ? nv * 4 : 0) + (g->d_meta ? nrows * 32 : 0) + (g->d_hash ? g->hash_buckets * 32 : 0) + (g->d_ent ? nnz * 16 : 0);
+                    (g->d_slot ? nnz * 16 : 0) + (g->d_slotw ? nnz * 32 : 0) + (g->d_vpid ? nv * 4 : 0) + (g->d_meta ? nrows * 32 : 0) + (g->d_hash ? g->hash_buckets * 32 : 0) + (g->d_ent ? nnz * 16 : 0);
   return SRW_OK;
 }
 

@@ -19,6 +19,18 @@ struct SRW_ALIGN(16) AliasSlot {
   uint32_t alias_index;   // row-relative index of the alias slot
 };
 
+// Vose slot of the WEIGHTED alias-fold sampler (undirected weighted graphs): the 16 bytes above plus, for whichever
+// neighbour the coin picks, the total weight of the parallel edges to it ("bundle weight", double sum in row order).  The
+// walker carries it to the next step, where it is the mass of the return edge (symmetric on an undirected graph).
+struct SRW_ALIGN(32) AliasSlotW {
+  uint32_t thr;
+  int32_t own;
+  int32_t alias_vertex;
+  uint32_t alias_index;
+  double wb_own;
+  double wb_alias;
+};
+
 // Row descriptor read once per walk step.  Rows with more than kHashMinDeg neighbours also own a hash
 // set of their neighbour ids (`nb` buckets of 8 slots starting at bucket `hoff`): the d(t,x)=1
 // membership test of node2vec becomes ~1 sector instead of a ~log2(deg) binary search.
@@ -27,7 +39,7 @@ struct SRW_ALIGN(32) RowMeta {
   int64_t hoff;    // first bucket in d_hash
   uint32_t deg;
   uint32_t nb;     // 0: no hash set (short row: binary search in d_col)
-  uint32_t pad0, pad1;
+  double w_sum;    // weighted graphs: sequential double sum of the row's weights (the W of the Vose build); else deg
 };
 // Hash-set placement is DERIVED from the row extent, so nothing but (off, deg) is needed to probe it:
 // row r owns buckets [off >> 2, (off + deg) >> 2) -- about deg/4 buckets of 8 slots (load <= ~0.5).

@@ -50,6 +50,7 @@ struct srw_graph {
   float *d_w_app = nullptr;       // [nnz]
   int32_t *d_col = nullptr;       // [nnz] neighbour ranks, ascending per row (membership + unweighted proposals)
   AliasSlot *d_slot = nullptr;    // [nnz] iff has_alias                              (SRW_BUILD_ALIAS)
+  AliasSlotW *d_slotw = nullptr;  // [nnz] weighted, undirected, unsharded graphs: slots + bundle weights (weighted alias-fold)
   int32_t *d_vpid = nullptr;      // [nv] GM:21 vertexPartitionMap (-1 = absent)
   struct RowMeta *d_meta = nullptr;  // [rows] packed row descriptor: one 32-byte load per step   (SRW_BUILD_ALIAS)
   int32_t *d_hash = nullptr;         // per-row neighbour hash sets, 8-slot (32-byte) buckets, -1 = empty

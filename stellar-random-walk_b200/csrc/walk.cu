@@ -886,6 +886,11 @@ srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLa
         f.a = 0.0; f.mp = 1.0; f.t_ret = a.t_ret; f.t_common = a.t_common; f.t_far = a.t_far;
       }
     }
+    // SRW_SAMPLER_ALIAS_FOLD on a weighted undirected graph: the same folding over bundle weights (walk_wfold_conv_kernel);
+    // the CPU twin applies the same rule
+    FoldArgs wf{};
+    const bool wfold = !peer && p->sampler == SRW_SAMPLER_ALIAS_FOLD && g->has_alias && !g->directed && g->d_slotw && g->d_meta &&
+                       g->d_hash && !use_v1 && !use_v2 && !use_v3 && srw_fold_args(p->p, p->q, true, &wf);
     // A/B (read per launch, so one process can time every variant on one graph): SRW_FOLD=v4 runs the
     // pre-convergence kernel; SRW_FOLD_VAR bit 0 = L2::64B loads in v5; SRW_FOLD_OCC = 5 | 6 blocks per SM
     const bool fold_v4 = getenv("SRW_FOLD") && !strcmp(getenv("SRW_FOLD"), "v4");
@@ -931,6 +936,12 @@ srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLa
       else if (occ == 6) walk_fold_kernel<false, false, 6><<<grid, 256, 0, l.stream>>>(a, f, pt);
       else if (occ == 8) walk_fold_kernel<false, false, 8><<<grid, 256, 0, l.stream>>>(a, f, pt);
       else walk_fold_kernel<false, false><<<grid, 256, 0, l.stream>>>(a, f, pt);
+    } else if (wfold) {
+      // v5, weighted alias-fold: bundle weights in 32-byte slots, row weight sums in the descriptors
+      const bool v64 = (fold_var & 1) != 0;
+      if (st) walk_wfold_conv_kernel<true, 0><<<grid, 256, 0, l.stream>>>(a, wf, g->d_meta, g->d_hash, g->d_slotw);
+      else if (v64) walk_wfold_conv_kernel<false, 1><<<grid, 256, 0, l.stream>>>(a, wf, g->d_meta, g->d_hash, g->d_slotw);
+      else walk_wfold_conv_kernel<false, 0><<<grid, 256, 0, l.stream>>>(a, wf, g->d_meta, g->d_hash, g->d_slotw);
     } else if (!use_v1 && !use_v2 && !use_v3 && g->d_meta && g->d_hash) {
       // v5: the classic alias sampler in the warp-convergent layout (walk_conv.cuh)
       const RowMeta *mt = g->d_meta;

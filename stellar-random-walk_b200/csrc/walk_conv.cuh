@@ -402,3 +402,175 @@ __global__ void __launch_bounds__(256, 4) walk_alias_conv_kernel(WalkArgs a, con
     atomicAdd(a.stats + 3, n_log);
   }
 }
+
+// ------------------------------------------------------------------------------------------
+// K6 (v5, WEIGHTED alias-fold: undirected weighted graphs with 1/p > max(1, 1/q)).  The folding of
+// walk_fold_conv_kernel with (multiplicity, degree) replaced by (bundle weight wb, row weight sum W):
+// a trial returns to prev with probability a*wb / (Mp*W + a*wb), else proposes from the Vose table under the
+// envelope Mp.  r.y is the Vose coin, so ONE draw z = r.z decides both: with t1 = a*wb, t2 = Mp*W,
+//     z*(t2 + t1) < t1*2^32                 -> return (no memory access; the walker already holds prev's row)
+//     z*(t2 + t1) < t1*2^32 + t2*T(class)   -> the proposal is accepted (z rescaled to the rest of [0, 1))
+// all in IEEE double, one rounding per operation (the CPU twin evaluates the same expressions).  One 32-byte
+// AliasSlotW gather yields the neighbour AND its bundle weight whichever way the coin falls; W rides in the
+// row descriptor.  Requests per step: 1 descriptor + ~1.9 slots + ~0.9 buckets instead of 1 + 3.7 + 1.8.
+// ------------------------------------------------------------------------------------------
+template <bool STATS, int VAR>
+__global__ void __launch_bounds__(256, 4) walk_wfold_conv_kernel(WalkArgs a, FoldArgs f, const RowMeta *__restrict__ meta,
+                                                                 const int32_t *__restrict__ hash, const AliasSlotW *__restrict__ slotw) {
+  __shared__ int32_t sbuf[kStage * 256];
+  const int tid = threadIdx.x;
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + tid;
+  const bool live = i < a.n_walkers;
+  const uint64_t walker = a.walker_first + (uint64_t)(live ? i : 0);
+  int32_t curr = (int32_t)(walker % (uint64_t)a.nv), prev = -1;
+  int32_t *path = a.paths + (live ? i : 0) * a.stride;
+  int32_t len = 0, staged = 0, flushed = 0;
+  const int head = (int)(((16u - (uint32_t)(reinterpret_cast<uintptr_t>(path) & 15u)) & 15u) >> 2);
+  int lim = head ? kStage - 4 + head : kStage;
+  auto flush = [&]() {
+    int32_t *dst = path + flushed;
+    if (staged == kStage && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+      for (int j = 0; j < kStage; j += 4)
+        *reinterpret_cast<int4 *>(dst + j) = make_int4(sbuf[j * 256 + tid], sbuf[(j + 1) * 256 + tid], sbuf[(j + 2) * 256 + tid], sbuf[(j + 3) * 256 + tid]);
+    } else {
+      int j = 0;
+      if ((reinterpret_cast<uintptr_t>(dst) & 4) && staged >= 1) { dst[0] = sbuf[tid]; j = 1; }
+      if ((reinterpret_cast<uintptr_t>(dst + j) & 8) && j + 1 < staged) {
+        *reinterpret_cast<int2 *>(dst + j) = make_int2(sbuf[j * 256 + tid], sbuf[(j + 1) * 256 + tid]);
+        j += 2;
+      }
+#pragma unroll 1
+      for (; j + 3 < staged; j += 4)
+        *reinterpret_cast<int4 *>(dst + j) = make_int4(sbuf[j * 256 + tid], sbuf[(j + 1) * 256 + tid], sbuf[(j + 2) * 256 + tid], sbuf[(j + 3) * 256 + tid]);
+#pragma unroll 1
+      for (; j + 1 < staged; j += 2) *reinterpret_cast<int2 *>(dst + j) = make_int2(sbuf[j * 256 + tid], sbuf[(j + 1) * 256 + tid]);
+#pragma unroll 1
+      for (; j < staged; ++j) dst[j] = sbuf[j * 256 + tid];
+    }
+    flushed += staged; staged = 0; lim = kStage;
+  };
+  uint32_t off = 0, poff = 0, k = 0;            // row offsets fit 32 bits: the ABI caps nnz below 2^32
+  uint32_t deg = 0, pdeg = 0, trial = 0, lo = 0, hi = 0, coin = 0, bkt = 0, pnb = 0;
+  int32_t x = 0;
+  double W = 0.0, pW = 0.0, wb = 0.0, xwb = 0.0, zl = 0.0;
+  unsigned long long n_prop = 0, n_mem = 0, n_log = 0;
+  int state = ST_DONE;
+  if (live) { sbuf[tid] = curr; staged = 1; len = 1; state = ST_EXTENT; }
+
+  while (__any_sync(0xffffffffu, state != ST_DONE)) {
+    int32_t newv = 0;
+    int moved = 0;             // 1 = accepted proposal (the new row's descriptor is needed), 2 = direct return
+    // ---- A: draw ----
+    if (state == ST_WAIT) {
+      const Philox4 r = walker_rng(a.seed_lo, a.seed_hi, walker, (uint32_t)(len - 1), trial);
+      trial++;
+      bool ret = false;
+      if (len > 1) {
+        const double t1 = __dmul_rn(f.a, wb), t2 = __dmul_rn(f.mp, W);
+        zl = __dmul_rn((double)r.z, __dadd_rn(t2, t1));
+        ret = zl < __dmul_rn(t1, 4294967296.0);
+      }
+      if (ret) {                                               // return-excess component: always accepted, no memory access
+        if (STATS) n_prop++;
+        newv = prev; moved = 2;
+        const int32_t c = curr; curr = prev; prev = c;
+        const uint32_t o = off; off = poff; poff = o;
+        const uint32_t d = deg; deg = pdeg; pdeg = d;
+        const double w = W; W = pW; pW = w;                    // wb unchanged: the same bundle of parallel edges
+      } else {
+        k = (uint32_t)__umul64hi(((uint64_t)r.x << 32) | (uint64_t)r.w, (uint64_t)deg);
+        coin = r.y;
+        state = ST_PROPOSE;
+      }
+    }
+    __syncwarp();
+    // ---- B: one memory access per lane ----
+    int4 q0 = make_int4(0, 0, 0, 0), q1 = make_int4(0, 0, 0, 0);
+    int32_t v = 0;
+    if (!moved) {
+      if (state == ST_EXTENT || state == ST_HASH || state == ST_PROPOSE) {
+        const int4 *P = state == ST_EXTENT ? reinterpret_cast<const int4 *>(meta + curr)
+                      : state == ST_HASH   ? reinterpret_cast<const int4 *>(hash + ((uint64_t)(poff >> 2) + bkt) * 8)
+                                           : reinterpret_cast<const int4 *>(slotw + ((uint64_t)off + k));
+        gather32<VAR>(P, q0, q1);
+      } else if (state == ST_SEARCH) {
+        v = __ldg(a.col + ((uint64_t)poff + ((lo + hi) >> 1)));
+      }
+    }
+    __syncwarp();
+    // ---- C: consume it ----
+    int verdict = 0;           // 1 = accept x, 2 = reject (next trial)
+    if (!moved) {
+      if (state == ST_EXTENT) {
+        off = (uint32_t)q0.x;
+        deg = (uint32_t)q1.x;
+        W = __hiloint2double(q1.w, q1.z);
+        trial = 0;
+        state = deg == 0 ? ST_DONE : ST_WAIT;                  // dead end (RW:59-62); cannot happen after the first vertex (undirected)
+      } else if (state == ST_PROPOSE) {
+        const bool own = coin < (uint32_t)q0.x;
+        x = own ? q0.y : q0.z;
+        xwb = own ? __hiloint2double(q1.y, q1.x) : __hiloint2double(q1.w, q1.z);
+        if (STATS && len > 1) n_prop++;
+        if (len == 1 || deg == 1 || x == prev) verdict = 1;    // first-order step (RW:57) / single choice / envelope mass Mp of Mp
+        else {
+          const double t1 = __dmul_rn(f.a, wb), t2 = __dmul_rn(f.mp, W), r0 = __dmul_rn(t1, 4294967296.0);
+          const double rc = __dadd_rn(r0, __dmul_rn(t2, (double)f.t_common)), rf = __dadd_rn(r0, __dmul_rn(t2, (double)f.t_far));
+          const double rlo = rc < rf ? rc : rf, rhi = rc < rf ? rf : rc;
+          if (zl < rlo) verdict = 1;
+          else if (!(zl < rhi)) verdict = 2;
+          else {
+            if (STATS) { n_mem++; n_log += ceil_log2_p1(pdeg); }
+            pnb = srw_hash_buckets((int64_t)poff, pdeg);
+            if (pnb) { bkt = __umulhi(srw_hash32((uint32_t)x), pnb); state = ST_HASH; }
+            else { lo = 0; hi = pdeg; state = ST_SEARCH; }
+          }
+        }
+      } else if (state == ST_HASH || state == ST_SEARCH) {
+        int member = -1;       // 1 = x in N(prev), 0 = absent, -1 = undecided (next probe)
+        if (state == ST_HASH) {
+          const bool found = q0.x == x || q0.y == x || q0.z == x || q0.w == x || q1.x == x || q1.y == x || q1.z == x || q1.w == x;
+          if (found) member = 1;
+          else if (q1.w == -1) member = 0;                     // bucket not full: x is absent
+          else bkt = bkt + 1 == pnb ? 0 : bkt + 1;             // full bucket: linear probing
+        } else {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (v == x) member = 1;
+          else {
+            if (v < x) lo = mid + 1; else hi = mid;
+            if (lo >= hi) member = 0;
+          }
+        }
+        if (member >= 0) {
+          const double t1 = __dmul_rn(f.a, wb), t2 = __dmul_rn(f.mp, W), r0 = __dmul_rn(t1, 4294967296.0);
+          const double rr = __dadd_rn(r0, __dmul_rn(t2, (double)(member ? f.t_common : f.t_far)));   // RS:38 / RS:34
+          verdict = zl < rr ? 1 : 2;
+        }
+      }
+    }
+    if (verdict == 1) {                                        // move along the proposal
+      newv = x; moved = 1;
+      prev = curr; poff = off; pdeg = deg; pW = W;
+      curr = x; wb = xwb;
+    } else if (verdict == 2) {
+      state = ST_WAIT;
+    }
+    if (moved) {                                               // RW:114, then RW:103
+      sbuf[staged * 256 + tid] = newv;
+      staged++; len++;
+      if (staged == lim) flush();
+      trial = 0;
+      state = (len == a.stride) ? ST_DONE : (moved == 1 ? ST_EXTENT : ST_WAIT);
+    }
+  }
+  if (live) {
+    flush();
+    a.lens[i] = len;
+  }
+  if (STATS) {
+    atomicAdd(a.stats + 1, n_prop);
+    atomicAdd(a.stats + 2, n_mem);
+    atomicAdd(a.stats + 3, n_log);
+  }
+}

@@ -40,3 +40,9 @@ static inline bool __any_sync(unsigned, bool pred) {
   return emu_linger-- > 0;
 }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
+static inline double __hiloint2double(int hi, int lo) {
+  const uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint64_t)(uint32_t)lo;
+  double d;
+  memcpy(&d, &u, 8);
+  return d;
+}

@@ -125,7 +125,7 @@ extern "C" int emu_alias_walk(int64_t nv, const int64_t *off, const int32_t *col
   for (int64_t r = 0; r < nv; ++r) {
     RowMeta m;
     m.off = off[r]; m.deg = (uint32_t)(off[r + 1] - off[r]);
-    m.hoff = srw_hash_first(m.off); m.nb = srw_hash_buckets(m.off, m.deg); m.pad0 = m.pad1 = 0;
+    m.hoff = srw_hash_first(m.off); m.nb = srw_hash_buckets(m.off, m.deg); m.w_sum = (double)m.deg;
     meta[(size_t)r] = m;
     for (int64_t e = off[r]; e < off[r + 1]; ++e) hash_insert(hash, m.off, m.deg, col[e]);
   }
@@ -160,6 +160,53 @@ extern "C" int emu_alias_walk(int64_t nv, const int64_t *off, const int32_t *col
         if (var & 1) walk_alias_conv_kernel<false, false, 1>(a, meta.data(), hash.data());
         else walk_alias_conv_kernel<false, true, 0>(a, meta.data(), hash.data());
       }
+    }
+  }
+  if (stats_out) memcpy(stats_out, st, sizeof(st));
+  return 0;
+}
+
+// The weighted alias-fold sampler (walk_wfold_conv_kernel): Vose tables, row weight sums and bundle weights as the
+// twin computes them (oa_view / oa_wsum / oa_wbundle), laid out as graph_build.cu does (RowMeta.w_sum, AliasSlotW).
+extern "C" int emu_wfold_walk(int64_t nv, const int64_t *off, const int32_t *col, const uint32_t *thr, const uint32_t *alias,
+                              const double *wsum, const double *wb, double p, double q, uint64_t seed, int32_t walk_length,
+                              uint64_t walker_first, int64_t n_walkers, int32_t *paths, int32_t *lens, int var, int extra,
+                              unsigned long long *stats_out) {
+  const int64_t nnz = off[nv];
+  std::vector<RowMeta> meta((size_t)nv);
+  std::vector<int32_t> hash((size_t)(((nnz >> 2) + 1) * 8), -1);
+  std::vector<AliasSlotW> slot((size_t)nnz);
+  for (int64_t r = 0; r < nv; ++r) {
+    RowMeta m;
+    m.off = off[r]; m.deg = (uint32_t)(off[r + 1] - off[r]);
+    m.hoff = srw_hash_first(m.off); m.nb = srw_hash_buckets(m.off, m.deg); m.w_sum = wsum[r];
+    meta[(size_t)r] = m;
+    for (int64_t e = off[r]; e < off[r + 1]; ++e) {
+      hash_insert(hash, m.off, m.deg, col[e]);
+      AliasSlotW s;
+      s.thr = thr[e]; s.own = col[e]; s.alias_index = alias[e]; s.alias_vertex = col[off[r] + alias[e]];
+      s.wb_own = wb[e]; s.wb_alias = wb[off[r] + alias[e]];
+      slot[(size_t)e] = s;
+    }
+  }
+  WalkArgs a{};
+  a.off = off; a.col = col; a.nv = nv; a.walker_first = walker_first; a.n_walkers = n_walkers;
+  a.stride = walk_length + 2; a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
+  a.paths = paths; a.lens = lens;
+  unsigned long long st[4] = {0, 0, 0, 0};
+  a.stats = st;
+  FoldArgs f{};
+  if (!srw_fold_args(p, q, true, &f)) return -2;
+  emu_extra_iters = extra;
+  blockDim.x = 256; blockDim.y = blockDim.z = 1;
+  const int64_t n_blocks = (n_walkers + 255) / 256;
+  for (int64_t b = 0; b < n_blocks; ++b) {
+    blockIdx.x = (unsigned)b;
+    for (unsigned t = 0; t < 256; ++t) {
+      threadIdx.x = t;
+      emu_linger = 0;
+      if (var & 1) walk_wfold_conv_kernel<false, 1>(a, f, meta.data(), hash.data(), slot.data());
+      else walk_wfold_conv_kernel<true, 0>(a, f, meta.data(), hash.data(), slot.data());
     }
   }
   if (stats_out) memcpy(stats_out, st, sizeof(st));

@@ -374,7 +374,8 @@ def test_fold_sampler_bit_equal(oracle, scale, ef, p, q, seed):
 def test_fold_sampler_fallbacks(oracle):
     s, d = synth.rmat_edges(9, 8, seed=42)
     w = synth.edge_weights(len(s), seed=43)
-    for kw, prm in ((dict(w=None, directed=True), (0.5, 2.0)), (dict(w=w, directed=False), (0.5, 2.0)), (dict(w=None, directed=False), (2.0, 0.5))):
+    for kw, prm in ((dict(w=None, directed=True), (0.5, 2.0)), (dict(w=w, directed=True), (0.5, 2.0)), (dict(w=w, directed=False), (2.0, 0.5)),
+                    (dict(w=None, directed=False), (2.0, 0.5))):
         g = srw.Graph.from_edges(s, d, kw["w"], directed=kw["directed"], flags=srw.BUILD_ALIAS)
         a = g.walk(srw.Params(walkLength=30, numWalks=2, p=prm[0], q=prm[1], seed=5, sampler="fold")).arrays()
         b = g.walk(srw.Params(walkLength=30, numWalks=2, p=prm[0], q=prm[1], seed=5, sampler="alias")).arrays()
@@ -467,3 +468,45 @@ def test_fold_kernel_generations_agree(oracle, monkeypatch):
             ids, offs = g.walk(srw.Params(walkLength=wl, numWalks=2, p=0.5, q=2.0, seed=9, sampler="fold")).arrays()
             res[(wl, name)] = bool(np.array_equal(ids, want_ids) and np.array_equal(offs, want_offs))
     assert all(res.values()), res
+
+
+# ---- SRW_SAMPLER_ALIAS_FOLD on WEIGHTED undirected graphs (walk_wfold_conv_kernel): device build (row weight sums, bundle
+# weights, 32-byte slots) + kernel == the CPU twin, bit for bit ----
+@pytest.mark.parametrize("scale,ef,p,q,seed", [(8, 8, 0.5, 2.0, 1), (10, 16, 0.25, 4.0, 2), (11, 4, 0.1, 0.5, 3), (9, 8, 0.5, 1.0, 4)])
+def test_weighted_fold_sampler_bit_equal(oracle, scale, ef, p, q, seed):
+    s, d = synth.rmat_edges(scale, ef, seed=42)
+    w = synth.edge_weights(len(s), seed=43)
+    twin = oracle.AliasGraph(oracle.Graph().load_edges(s, d, w))
+    g = srw.Graph.from_edges(s, d, w, flags=srw.BUILD_ALIAS)
+    for wl, rounds in ((60, 3), (7, 2)):
+        ids, offs, st = twin.walk(walk_length=wl, num_walks=rounds, p=p, q=q, seed=seed, fold=1)
+        got_ids, got_offs = g.walk(srw.Params(walkLength=wl, numWalks=rounds, p=p, q=q, seed=seed, sampler="fold")).arrays()
+        assert (got_offs == offs).all() and (got_ids == ids).all()
+    # ... and it is not the classic sampler's output
+    c_ids, _ = g.walk(srw.Params(walkLength=7, numWalks=2, p=p, q=q, seed=seed, sampler="alias")).arrays()
+    assert not np.array_equal(c_ids, got_ids)
+
+
+def test_weighted_fold_hubs_bundles_and_text_weights(oracle, tmp_path):
+    """Zipf hubs, parallel edges with different weights (bundle weight != any single weight), self-loops; then karate
+    with printed weights through the CLI (`--sampler fold --weighted true`)."""
+    zs, zd = synth.zipf_edges(2048, seed=7, cap=600)
+    w = synth.edge_weights(len(zs), seed=5)
+    es, ed = np.array([0, 0, 0, 5, 5, 9], np.int32), np.array([1, 1, 1, 5, 6, 9], np.int32)
+    ew = np.array([0.25, 1.5, 3.0, 2.0, 0.125, 7.0], np.float32)
+    s, d, w = np.concatenate([zs, es]), np.concatenate([zd, ed]), np.concatenate([w, ew])
+    twin = oracle.AliasGraph(oracle.Graph().load_edges(s, d, w))
+    g = srw.Graph.from_edges(s, d, w, flags=srw.BUILD_ALIAS)
+    ids, offs, _ = twin.walk(walk_length=25, num_walks=2, p=0.25, q=4.0, seed=21, fold=1)
+    got = g.walk(srw.Params(walkLength=25, numWalks=2, p=0.25, q=4.0, seed=21, sampler="fold")).arrays()
+    assert (got[1] == offs).all() and (got[0] == ids).all()
+    rows = [ln.split() for ln in open(KARATE).read().split("\n") if ln]
+    txt = "".join("%s %s %.2f\n" % (a, b, 0.5 + (i % 7) / 4.0) for i, (a, b) in enumerate(rows))
+    inp = tmp_path / "kw.txt"
+    inp.write_text(txt)
+    out = str(tmp_path / "o")
+    assert srw.Main.main(["--cmd", "randomwalk", "--input", str(inp), "--output", out, "--numWalks", "3", "--walkLength", "20", "--p", "0.5",
+                          "--q", "2.0", "--seed", "8", "--sampler", "fold"]) == 0
+    og = oracle.Graph().load_text(txt, weighted=True)
+    ids, offs, _ = oracle.AliasGraph(og).walk(walk_length=20, num_walks=3, p=0.5, q=2.0, seed=8, fold=1)
+    assert open(os.path.join(out, "path", "part-00000"), "rb").read() == oracle.format_paths(ids, offs)

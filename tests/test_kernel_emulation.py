@@ -35,6 +35,9 @@ def emu():
     lib.emu_alias_walk.restype = C.c_int
     lib.emu_alias_walk.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
                                    C.c_int32, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.emu_wfold_walk.restype = C.c_int
+    lib.emu_wfold_walk.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                                   C.c_uint64, C.c_int32, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     return lib
 
 
@@ -200,3 +203,60 @@ def test_emulated_alias_kernel_hubs(emu, oracle):
         want, _ = _twin_paths(oracle, tw, walk_length=25, num_walks=1, p=0.25, q=4.0, seed=21)
         got, _ = _emu_alias_walk(emu, oracle, tw, walk_length=25, p=0.25, q=4.0, seed=21)
         assert got == want
+
+
+# ---- the weighted alias-fold sampler (walk_wfold_conv_kernel) ----
+def _emu_wfold_walk(emu, oracle, tw, *, walk_length, p, q, seed, var=0, extra=2, rounds=1):
+    v = tw.view()
+    off = np.ascontiguousarray(v["offsets"], np.int64)
+    col = np.ascontiguousarray(v["col"], np.int32)
+    thr = np.ascontiguousarray(v["thr"], np.uint32)
+    al = np.ascontiguousarray(v["alias"], np.uint32)
+    nv, nnz = len(off) - 1, int(off[-1])
+    L = oracle.lib()
+    L.oa_wbundle.restype = C.POINTER(C.c_double)
+    L.oa_wsum.restype = C.POINTER(C.c_double)
+    wb = np.ctypeslib.as_array(L.oa_wbundle(tw.h), (nnz,)).copy()
+    ws = np.ctypeslib.as_array(L.oa_wsum(tw.h), (nv,)).copy()
+    n = nv * rounds
+    stride = walk_length + 2
+    paths = np.full((n, stride), -7, np.int32)
+    lens = np.zeros(n, np.int32)
+    st = np.zeros(4, np.uint64)
+    rc = emu.emu_wfold_walk(nv, off.ctypes.data, col.ctypes.data, thr.ctypes.data, al.ctypes.data, ws.ctypes.data, wb.ctypes.data,
+                            p, q, seed, walk_length, 0, n, paths.ctypes.data, lens.ctypes.data, var, extra, st.ctypes.data)
+    assert rc == 0
+    for i in range(n):
+        assert (paths[i, lens[i]:] == -7).all()
+    vids = v["vids"]
+    return [vids[paths[i, :lens[i]]].tolist() for i in range(n)], st
+
+
+@pytest.mark.parametrize("p,q", [(0.5, 2.0), (0.25, 4.0), (0.1, 0.5), (0.5, 1.0)])
+def test_emulated_weighted_fold_kernel_equals_twin(emu, oracle, p, q):
+    s, d = synth.rmat_edges(9, 8, seed=42)
+    w = synth.edge_weights(len(s), seed=43)
+    tw = oracle.AliasGraph(oracle.Graph().load_edges(s, d, w))
+    assert tw.has_alias
+    for wl in (30, 13):
+        want, wst = _twin_paths(oracle, tw, walk_length=wl, num_walks=2, p=p, q=q, seed=17, fold=1)
+        classic, cst = _twin_paths(oracle, tw, walk_length=wl, num_walks=2, p=p, q=q, seed=17, fold=0)
+        assert want != classic and wst.proposals < cst.proposals          # the fold really is a different, cheaper sampler
+        for var, extra in ((0, 2), (1, 0)):
+            got, st = _emu_wfold_walk(emu, oracle, tw, walk_length=wl, p=p, q=q, seed=17, var=var, extra=extra, rounds=2)
+            assert got == want
+            if var == 0:
+                assert int(st[1]) == wst.proposals and int(st[2]) == wst.member_tests
+
+
+def test_emulated_weighted_fold_kernel_hubs_and_bundles(emu, oracle):
+    """Zipf hubs plus parallel edges of different weights (bundle weight != any single weight) and self-loops."""
+    zs, zd = synth.zipf_edges(2048, seed=7, cap=600)
+    w = synth.edge_weights(len(zs), seed=5)
+    es = np.array([0, 0, 0, 5, 5, 9], np.int32)
+    ed = np.array([1, 1, 1, 5, 6, 9], np.int32)
+    ew = np.array([0.25, 1.5, 3.0, 2.0, 0.125, 7.0], np.float32)
+    tw = oracle.AliasGraph(oracle.Graph().load_edges(np.concatenate([zs, es]), np.concatenate([zd, ed]), np.concatenate([w, ew])))
+    want, _ = _twin_paths(oracle, tw, walk_length=25, num_walks=1, p=0.25, q=4.0, seed=21, fold=1)
+    got, _ = _emu_wfold_walk(emu, oracle, tw, walk_length=25, p=0.25, q=4.0, seed=21)
+    assert got == want

@@ -111,11 +111,13 @@ def test_rmat_generator_shape():
     assert w.dtype == np.float32 and w.min() >= 1.0 and w.max() < 2.0
 
 
+@pytest.mark.parametrize("weighted", [False, True])
 @pytest.mark.parametrize("p,q", [(0.5, 2.0), (0.25, 4.0), (0.1, 0.5)])
-def test_alias_fold_distribution(oracle, p, q):
+def test_alias_fold_distribution(oracle, p, q, weighted):
     """alias-fold (return edge folded out of the envelope) samples the same exact distribution;
-    karate has a parallel edge (9-33 twice), so the multiplicity path is exercised."""
-    g = oracle.Graph().load_file(KARATE)
+    karate has a parallel edge (9-33 twice), so the multiplicity / bundle-weight path is exercised.
+    Weighted: the bundle weight and the row weight sum take the place of multiplicity and degree."""
+    g = _weighted_karate(oracle) if weighted else oracle.Graph().load_file(KARATE)
     a = oracle.AliasGraph(g)
     ids, offs, st = a.walk(walk_length=40, num_walks=300, p=p, q=q, seed=12, fold=1)
     ids0, _, st0 = a.walk(walk_length=40, num_walks=300, p=p, q=q, seed=12, fold=0)
@@ -155,8 +157,28 @@ def test_alias_fold_falls_back_when_not_applicable(oracle):
     i1, _, _ = d.walk(walk_length=20, num_walks=2, p=0.5, q=2.0, seed=3, fold=1)
     i0, _, _ = d.walk(walk_length=20, num_walks=2, p=0.5, q=2.0, seed=3, fold=0)
     assert np.array_equal(i1, i0)
-    w = _weighted_karate(oracle)
-    aw = oracle.AliasGraph(w)
-    i1, _, _ = aw.walk(walk_length=20, num_walks=2, p=0.5, q=2.0, seed=3, fold=1)
-    i0, _, _ = aw.walk(walk_length=20, num_walks=2, p=0.5, q=2.0, seed=3, fold=0)
+    dw = oracle.AliasGraph(oracle.Graph().load_text(open(KARATE).read().replace("\n", " 1.5\n"), weighted=True, directed=True), directed=True)
+    i1, _, _ = dw.walk(walk_length=20, num_walks=2, p=0.5, q=2.0, seed=3, fold=1)
+    i0, _, _ = dw.walk(walk_length=20, num_walks=2, p=0.5, q=2.0, seed=3, fold=0)
     assert np.array_equal(i1, i0)
+
+
+def test_weighted_fold_bundle_weights_are_symmetric(oracle):
+    """The bundle weight read on prev's row must equal the one on curr's row (the kernel carries it across the step)."""
+    import ctypes as C
+    g = _weighted_karate(oracle)
+    a = oracle.AliasGraph(g)
+    v = a.view()
+    L = oracle.lib()
+    L.oa_wbundle.restype = C.POINTER(C.c_double)
+    L.oa_wsum.restype = C.POINTER(C.c_double)
+    nnz = int(v["offsets"][-1])
+    wb = np.ctypeslib.as_array(L.oa_wbundle(a.h), (nnz,))
+    ws = np.ctypeslib.as_array(L.oa_wsum(a.h), (a.nv,))
+    off, col = v["offsets"], v["col"]
+    for r in range(a.nv):
+        assert abs(ws[r] - v["w"][off[r]:off[r + 1]].astype(np.float64).sum()) < 1e-9
+        for e in range(off[r], off[r + 1]):
+            x = col[e]
+            k = off[x] + np.searchsorted(col[off[x]:off[x + 1]], r)
+            assert col[k] == r and wb[k] == wb[e]
