@@ -348,14 +348,14 @@ def run_b200(a):
     # ---- roofline of the dominant kernel ----
     # algorithmic bytes per sampled transition (DESIGN.md "bytes per step"): row extent 8 B +
     # T * (neighbour id 4 B [+ Vose slot 8 B when weighted]) + 4 B per binary-search probe + 4 B path write
-    per_prop = 4 + (8 if a.weighted else 0)
+    per_prop = 4 + (8 if a.weighted else 0) + (8 if (a.weighted and a.sampler == "fold") else 0)   # + bundle weight
     B = 8 + T_bar * per_prop + 4 * probes_per_step + 4
     B_survey = T_bar * (20 + 4 * (st.probes_log2 / max(1, st.proposals))) + 4      # SURVEY 8(d) formula, same measurements
     peak, peak_src = peaks()
     kernel_s = kernel_ms * 1e-3
     achieved = steps * B / kernel_s / 1e9
     traffic, l2_requests = None, None
-    kernel_name = "walk_fold_conv_kernel" if (a.sampler == "fold" and not a.weighted) else "walk_alias_conv_kernel"
+    kernel_name = ("walk_wfold_conv_kernel" if a.weighted else "walk_fold_conv_kernel") if a.sampler == "fold" else "walk_alias_conv_kernel"
     tj = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tj):
         try:

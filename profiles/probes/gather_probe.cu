@@ -58,6 +58,49 @@ __global__ void gather32(const uint4 *table, uint64_t n_sectors, int per_thread,
   if (acc == 0x12345678u) *sink = acc;
 }
 
+// W x 32 bytes from one random (W*32)-byte aligned address: 256-bit loads (LDG.E.256), optionally with the L2::64B hint.
+// Does a 64-byte (or 128-byte) gather cost one request slot or several?
+template <int W, bool L64>
+__global__ void gather_wide(const uint4 *table, uint64_t n_units, int per_thread, uint32_t *sink) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t acc = 0, s = mix(t + 1);
+  for (int k = 0; k < per_thread; k += 4) {
+    uint32_t a[4][W];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      s = mix(s + 0x9E3779B9u * (j + 1));
+      const uint64_t i = __umul64hi(((uint64_t)s << 32) | mix(s), n_units);
+      const uint4 *p = table + 2 * W * i;
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+        if (L64) asm volatile("ld.global.nc.L2::64B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7) : "l"(p + 2 * w));
+        else asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7) : "l"(p + 2 * w));
+        a[j][w] = r0 ^ r7;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int w = 0; w < W; ++w) acc += a[j][w];
+  }
+  if (acc == 0x12345678u) *sink = acc;
+}
+template <int W, bool L64>
+void run_wide(const uint32_t *table, uint64_t bytes, uint32_t *sink, const char *name) {
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  const int per_thread = 64, threads = 256, blocks = 148 * 8 * 4;
+  gather_wide<W, L64><<<blocks, threads>>>((const uint4 *)table, bytes / (32 * W), per_thread, sink);
+  cudaEventRecord(a);
+  gather_wide<W, L64><<<blocks, threads>>>((const uint4 *)table, bytes / (32 * W), per_thread, sink);
+  cudaEventRecord(b);
+  cudaEventSynchronize(b);
+  float ms;
+  cudaEventElapsedTime(&ms, a, b);
+  printf("%-34s %8.3f ms  %7.2f G gathers/s  err=%s\n", name, ms, (double)blocks * threads * per_thread / ms / 1e6, cudaGetErrorString(cudaGetLastError()));
+}
+
 template <int MODE>
 float run(const uint32_t *table, uint64_t n_words, uint32_t *sink, const char *name) {
   cudaEvent_t a, b;
@@ -108,5 +151,10 @@ int main(int argc, char **argv) {
     cudaEventElapsedTime(&ms, a, b);
     printf("%-34s %8.3f ms  %7.2f G gathers/s\n", "32B sector (2 x ldg.128)", ms, (double)blocks * threads * per_thread / ms / 1e6);
   }
+  run_wide<1, false>(table, bytes, sink, "32B (1 x ldg.256)");
+  run_wide<1, true>(table, bytes, sink, "32B (1 x ldg.256.L2::64B)");
+  run_wide<2, false>(table, bytes, sink, "64B aligned (2 x ldg.256)");
+  run_wide<2, true>(table, bytes, sink, "64B aligned (2 x ldg.256.L2::64B)");
+  run_wide<4, false>(table, bytes, sink, "128B line (4 x ldg.256)");
   return 0;
 }

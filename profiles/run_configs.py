@@ -72,6 +72,7 @@ n, s, d, w = rmat(24, True)
 g = srw.Graph.from_device_edges(n, s.data_ptr(), d.data_ptr(), w.data_ptr(), False, srw.BUILD_ALIAS)
 del s, d, w
 run("C3 rmat-24 weighted", g, "alias", 0.5, 2.0)
+run("C3 rmat-24 weighted", g, "fold", 0.5, 2.0)
 g.free()
 torch.cuda.empty_cache()
 hs, hd = synth.zipf_edges(1 << 22, cap=1000000, seed=7)
