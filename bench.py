@@ -382,9 +382,10 @@ def run_b200(a):
         try:
             srw.check(lib.srw_gather_ceiling(8 << 30, 1 << 28, C.byref(gs), C.byref(gg)))
             roofline["gather_ceiling_requests_per_s"] = gs.value
-            # memory requests the kernel cannot avoid, per step: one neighbour-entry gather per proposal, one hash bucket per
-            # membership test (rows shorter than 8 use a <= 3-probe search instead), 1/8 of a 32-byte sector for the path id
-            req = T_bar + st.member_tests / max(1, st.steps) + 0.125
+            # 32-byte sector requests the kernel cannot avoid, per step: one neighbour-entry / Vose-slot gather per proposal, one hash
+            # bucket per membership test (rows shorter than 8 use a <= 3-probe search instead), 1/8 of a sector for the path id, and
+            # (weighted / classic kernels, whose entries do not carry the neighbour's row extent) one row descriptor
+            req = T_bar + st.member_tests / max(1, st.steps) + 0.125 + (0.0 if kernel_name == "walk_fold_conv_kernel" else 1.0)   # + the row descriptor
             roofline["requests_per_step_model"] = req
             roofline["frac_of_gather_ceiling"] = (steps / kernel_s) * req / gs.value
         except Exception as ex:   # noqa: BLE001
