@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--sampler", default="fold", choices=["fold", "alias"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-exact", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--gen-seed", type=int, default=42)
     ap.add_argument("--seed", type=int, default=1)
@@ -468,6 +469,33 @@ def run_b200(a):
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %s" % ex}
 
     log("cpu baseline done")
+    # ---- the bit-parity sampler on the same workload (N=1, bounded sample; not part of `value`) ----
+    exact = None
+    if rank == 0 and world == 1 and not a.no_exact:
+        try:
+            n_ex = min(nv, 1 << 16)
+            g.free()
+            del paths, lens
+            torch.cuda.empty_cache()
+            s_, d_, w_ = gen_edges()
+            gx = srw.Graph.from_device_edges(n_edges, s_.data_ptr(), d_.data_ptr(), None if w_ is None else w_.data_ptr(), False, srw.BUILD_ALL)
+            del s_, d_, w_
+            px = torch.empty((n_ex, stride), dtype=torch.int32, device=dev)
+            lx = torch.empty(n_ex, dtype=torch.int32, device=dev)
+            cpx = srw.Params(walkLength=a.walk_length, numWalks=1, p=a.p, q=a.q, seed=a.seed, sampler="exact").to_c()
+            first = (nv // 3) if nv > 3 * n_ex else 0
+            srw.check(lib.srw_walk_device(gx.h, C.byref(cpx), first, min(n_ex, 4096), px.data_ptr(), lx.data_ptr(), stream.cuda_stream))   # warm-up
+            srw.check(lib.srw_walk_device(gx.h, C.byref(cpx), first, n_ex, px.data_ptr(), lx.data_ptr(), stream.cuda_stream))
+            wi = srw.last_walk_info()
+            exact = {"value": wi.steps / (wi.kernel_ms * 1e-3), "unit": UNIT, "walkers": n_ex, "steps": int(wi.steps), "kernel_ms": wi.kernel_ms,
+                     "kernel": "walk_exact_cert_kernel",
+                     "note": "SRW_SAMPLER_EXACT: RS:12-62 literally (float32 bias weights, in-order float64 CDF), bit-identical to the oracle "
+                             "(tests/test_gpu_parity.py); %d walkers of the same graph starting at vertex rank %d, kernel time only" % (n_ex, first)}
+            gx.free()
+            g = None
+        except Exception as ex:   # noqa: BLE001
+            exact = {"value": None, "error": str(ex)}
+        log("exact sampler sample done")
     sharded_line = None
     if world > 1 and a.mode == "auto":
         # also measure the vertex-range-sharded walk (BASELINE config C4) on the same ranks
@@ -495,6 +523,8 @@ def run_b200(a):
                            "walker all-to-all is measured beside it in `sharded_c4`" % (world, graph_bytes / 1e9),
                            "sampler": "alias-fold (SRW_SAMPLER_ALIAS_FOLD; classic alias rejection when the graph is weighted/directed)" if a.sampler == "fold" else "alias"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk}
+        if exact is not None:
+            line["exact_sampler"] = exact
         if sharded_line is not None:
             pg = sharded_line.get("peer_gather")
             tup = {k: sharded_line.get(k) for k in ("value", "unit", "steps", "ms_per_step", "config", "error") if k in sharded_line}
