@@ -163,7 +163,7 @@ class Params:
     partitioned: bool = False
     cmd: str = "node2vec"
     seed: int = 1
-    sampler: str = "alias"
+    sampler: str = "fold"
     gpus: int = 1
 
     _TASKS = ("node2vec", "randomwalk", "embedding")

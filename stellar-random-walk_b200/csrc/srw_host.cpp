@@ -42,7 +42,7 @@ extern "C" srw_status srw_params_default(srw_params *o) {
   o->walk_length = 80; o->num_walks = 10; o->p = 1.0; o->q = 1.0;                                      // Params:12-15
   o->weighted = 1; o->directed = 0;                                                                    // Params:16-17
   o->rdd_partitions = 200; o->single_output = 1; o->partitioned = 0; o->cmd = SRW_TASK_NODE2VEC;       // Params:20-23
-  o->seed = 1; o->sampler = SRW_SAMPLER_ALIAS; o->u_mode = SRW_U_PHILOX; o->u_const = 0.f; o->num_gpus = 1;
+  o->seed = 1; o->sampler = SRW_SAMPLER_ALIAS_FOLD; o->u_mode = SRW_U_PHILOX; o->u_const = 0.f; o->num_gpus = 1;
   return SRW_OK;
 }
 
@@ -68,7 +68,7 @@ extern "C" const char *srw_usage(void) {
          "  --dim <value>            Number of dimensions in word2vec: 128\n"
          "  --window <value>         Window size in word2vec: 10\n"
          "  --seed <value>           [b200] Philox seed: 1\n"
-         "  --sampler <value>        [b200] alias | fold | exact: alias\n"
+         "  --sampler <value>        [b200] fold | alias | exact: fold\n"
          "  --gpus <value>           [b200] number of GPUs: 1\n";
 }
 

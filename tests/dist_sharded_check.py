@@ -83,7 +83,7 @@ def full():
         ds, dd = torch.from_numpy(s).cuda(), torch.from_numpy(d).cuda()
         dw = torch.from_numpy(w).cuda() if weighted else None
         shard = sh.Shard(len(s), ds.data_ptr(), dd.data_ptr(), None if dw is None else dw.data_ptr(), rank, world)
-        prm = srw.Params(walkLength=30, numWalks=2, p=p, q=q, seed=23)
+        prm = srw.Params(walkLength=30, numWalks=2, p=p, q=q, seed=23, sampler="alias")
         out, stats = sh.run_sharded([shard], prm, 0, 2)
         twin = oracle_lib.AliasGraph(oracle_lib.Graph().load_edges(s, d, w))
         ids, offs, st = twin.walk(walk_length=30, num_walks=2, p=p, q=q, seed=23)

@@ -184,7 +184,7 @@ def test_alias_karate_text_output_matches_twin(oracle, tmp_path):
     assert lines[-1] == "" and len(lines) == 35 and all(len(ln.split("\t")) == 12 for ln in lines[:-1])
     assert os.path.exists(os.path.join(out, "path", "_SUCCESS"))
     twin = oracle.AliasGraph(oracle.Graph().load_file(KARATE))
-    ids, offs, _ = twin.walk(walk_length=10, num_walks=1, seed=5)
+    ids, offs, _ = twin.walk(walk_length=10, num_walks=1, seed=5, fold=1)
     assert sorted(lines[:-1]) == sorted(oracle.format_paths(ids, offs).decode().split("\n")[:-1])
     # a second run into the same directory fails like Hadoop's saveAsTextFile
     assert srw.Main.main(["--cmd", "randomwalk", "--input", KARATE, "--output", out]) != 0
@@ -296,7 +296,7 @@ def test_c3_weighted_rmat_layout_and_walk(oracle):
     tv, lay = twin.view(), g.layout()
     assert (lay["offsets"] == tv["offsets"]).all() and (lay["col"] == tv["col"]).all()
     assert (lay["thr"] == tv["thr"]).all() and (lay["alias"] == tv["alias"]).all()
-    ids, offs, st = twin.walk(walk_length=80, num_walks=1, p=0.5, q=2.0, seed=1)
+    ids, offs, st = twin.walk(walk_length=80, num_walks=1, p=0.5, q=2.0, seed=1, fold=1)
     got_ids, got_offs = g.walk(srw.Params(walkLength=80, numWalks=1, p=0.5, q=2.0, seed=1)).arrays()
     assert (got_offs == offs).all() and (got_ids == ids).all()
 
@@ -314,7 +314,7 @@ s, d = synth.rmat_edges(12, 16, seed=3)
 out = []
 for w in (None, synth.edge_weights(len(s), seed=4)):
     g = srw.Graph.from_edges(s, d, w)
-    ids, offs = g.walk(srw.Params(walkLength=60, numWalks=2, p=0.5, q=2.0, seed=9)).arrays()
+    ids, offs = g.walk(srw.Params(walkLength=60, numWalks=2, p=0.5, q=2.0, seed=9, sampler="alias")).arrays()
     out.append(hashlib.sha256(ids.tobytes() + offs.tobytes()).hexdigest())
 print(",".join(out))
 ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -343,7 +343,7 @@ def test_vcut_cli_partitioned_input(oracle, tmp_path):
     for f in files:
         lines += open(os.path.join(out, "path", f)).read().split("\n")[:-1]
     og = oracle.Graph().load_text(txt, weighted=True, partitioned=True)
-    ids, offs, _ = oracle.AliasGraph(og).walk(walk_length=15, num_walks=2, p=0.5, q=2.0, seed=8)
+    ids, offs, _ = oracle.AliasGraph(og).walk(walk_length=15, num_walks=2, p=0.5, q=2.0, seed=8, fold=1)
     assert sorted(lines) == sorted(oracle.format_paths(ids, offs).decode().split("\n")[:-1])
     # GraphMap.getPartition analogue
     rw = srw.VCutRandomWalk(srw.Params(input=str(inp), partitioned=True))

@@ -35,7 +35,7 @@ def test_sharded_equals_twin(oracle, world, weighted, directed, p, q):
     assert all(x.bounds == shards[0].bounds for x in shards)
     assert shards[0].bounds == sh.plan_bounds(tv["offsets"], world)
     assert sum(x.nnz_local for x in shards) == int(tv["offsets"][-1])
-    prm = srw.Params(walkLength=25, numWalks=3, p=p, q=q, seed=17)
+    prm = srw.Params(walkLength=25, numWalks=3, p=p, q=q, seed=17, sampler="alias")
     out, stats = sh.run_sharded(shards, prm, 0, 3, rec_cap=1 << 12 if world == 3 else 1 << 20)   # small cap: exercises parking
     ids, offs, st = twin.walk(walk_length=25, num_walks=3, p=p, q=q, seed=17)
     want = oracle.paths_as_lists(ids, offs)
@@ -60,7 +60,7 @@ def test_sharded_matches_single_gpu_kernel():
     s, d = synth.rmat_edges(12, 8, seed=7)
     ds, dd, _ = _device_edges(s, d, None)
     g = srw.Graph.from_device_edges(len(s), ds.data_ptr(), dd.data_ptr())
-    prm = srw.Params(walkLength=40, numWalks=2, p=0.5, q=2.0, seed=5)
+    prm = srw.Params(walkLength=40, numWalks=2, p=0.5, q=2.0, seed=5, sampler="alias")     # the tuple-exchange shards run the classic sampler
     ref_ids, ref_offs = g.walk(prm).arrays()
     shards = [sh.Shard(len(s), ds.data_ptr(), dd.data_ptr(), None, r, 4) for r in range(4)]
     out, _ = sh.run_sharded(shards, prm, 0, 2)
