@@ -12,6 +12,7 @@
 //
 // Both are HBM-streaming integer/byte work (no tensor cores): bounds and measurements in DESIGN.md section 4.
 #include <cuda_runtime.h>
+#include <dirent.h>
 #include <errno.h>
 #include <fcntl.h>
 #include <stdio.h>
@@ -596,7 +597,44 @@ extern "C" srw_status srw_edges_parse_buffer_device(const char *buf, size_t len,
 }
 
 // A1 + A2 from a file: mmap -> device parse -> CSR build; the edge arrays never exist on the host.
+// SparkContext.textFile accepts a directory (URW:23): every regular file in it, in name order, files whose name starts
+// with '_' or '.' skipped (Hadoop's hidden-file filter: _SUCCESS, .crc).  A file's last line needs no terminator.
+static srw_status load_directory(const srw_params *params, unsigned flags, srw_graph **out) {
+  std::vector<std::string> names;
+  DIR *dp = opendir(params->input);
+  if (!dp) { srw_set_error("Input path does not exist: %s", params->input); return SRW_ERR_IO; }
+  while (struct dirent *de = readdir(dp)) {
+    if (de->d_name[0] == '_' || de->d_name[0] == '.') continue;
+    const std::string path = std::string(params->input) + "/" + de->d_name;
+    struct stat st;
+    if (stat(path.c_str(), &st) == 0 && S_ISREG(st.st_mode)) names.push_back(path);
+  }
+  closedir(dp);
+  std::sort(names.begin(), names.end());
+  std::string text;
+  for (const std::string &path : names) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) { srw_set_error("cannot read %s: %s", path.c_str(), strerror(errno)); return SRW_ERR_IO; }
+    char chunk[1 << 16];
+    size_t r;
+    while ((r = fread(chunk, 1, sizeof(chunk), f)) > 0) text.append(chunk, r);
+    fclose(f);
+    if (!text.empty() && !srw_line_end(text.back())) text.push_back('\n');
+  }
+  int64_t n = 0;
+  int32_t *s = nullptr, *d = nullptr, *p = nullptr;
+  float *w = nullptr;
+  SRW_TRY(srw_parse_text_device(text.data(), text.size(), params->weighted, params->partitioned, &n, &s, &d, &w, &p));
+  srw_status rc = srw_build_graph_device(n, s, d, w, p, params->directed, flags, out);
+  cudaFree(s); cudaFree(d); cudaFree(w); cudaFree(p);
+  return rc;
+}
+
 srw_status srw_graph_load_device(const srw_params *params, unsigned flags, srw_graph **out) {
+  {
+    struct stat sd;
+    if (stat(params->input, &sd) == 0 && S_ISDIR(sd.st_mode)) return load_directory(params, flags, out);
+  }
   const int fd = open(params->input, O_RDONLY);
   if (fd < 0) { srw_set_error("Input path does not exist: %s", params->input); return SRW_ERR_IO; }
   struct stat stt;

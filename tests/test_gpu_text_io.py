@@ -91,6 +91,24 @@ def test_graph_load_uses_the_device_parser(oracle, tmp_path):
         assert g.neighbors(int(v)) == og.neighbors(int(v))
 
 
+def test_graph_load_accepts_a_directory_of_part_files(oracle, tmp_path):
+    """SparkContext.textFile on a directory (URW:23): part files in name order, _SUCCESS / hidden files skipped, a last
+    line without a newline still ends its file."""
+    rows = open(KARATE).read().split("\n")
+    rows = [r for r in rows if r]
+    d = tmp_path / "in"
+    d.mkdir()
+    (d / "part-00000").write_text("\n".join(rows[:30]))              # no trailing newline
+    (d / "part-00001").write_text("\n".join(rows[30:]) + "\n")
+    (d / "_SUCCESS").write_text("")
+    (d / ".part-00000.crc").write_text("garbage that must not be parsed")
+    g = srw.Graph.load(srw.Params(input=str(d)))
+    og = oracle.Graph().load_file(KARATE)
+    assert g.stats() == (og.num_vertices, og.num_edges)
+    for v in og.vertex_ids():
+        assert g.neighbors(int(v)) == og.neighbors(int(v))
+
+
 def _format_on_device(paths, lens):
     import torch
     n, stride = paths.shape
