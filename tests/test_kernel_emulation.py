@@ -260,3 +260,24 @@ def test_emulated_weighted_fold_kernel_hubs_and_bundles(emu, oracle):
     want, _ = _twin_paths(oracle, tw, walk_length=25, num_walks=1, p=0.25, q=4.0, seed=21, fold=1)
     got, _ = _emu_wfold_walk(emu, oracle, tw, walk_length=25, p=0.25, q=4.0, seed=21)
     assert got == want
+
+
+@pytest.mark.parametrize("walk_length", [0, 1, 2, 14, 15, 16, 17])
+def test_emulated_weighted_and_classic_kernels_short_walks(emu, oracle, walk_length):
+    """Stride boundaries of the staged stores and the first-order-only walk (walkLength 0) for the two kernels that share
+    the flush code with the fold kernel."""
+    s, d = synth.rmat_edges(8, 8, seed=42)
+    w = synth.edge_weights(len(s), seed=43)
+    tw = oracle.AliasGraph(oracle.Graph().load_edges(s, d, w))
+    want, _ = _twin_paths(oracle, tw, walk_length=walk_length, num_walks=2, p=0.5, q=2.0, seed=5, fold=1)
+    got, _ = _emu_wfold_walk(emu, oracle, tw, walk_length=walk_length, p=0.5, q=2.0, seed=5, rounds=2)
+    assert got == want
+    want, _ = _twin_paths(oracle, tw, walk_length=walk_length, num_walks=2, p=0.5, q=2.0, seed=5, fold=0)
+    got, _ = _emu_alias_walk(emu, oracle, tw, walk_length=walk_length, p=0.5, q=2.0, seed=5, rounds=2)
+    assert got == want
+    td = oracle.AliasGraph(oracle.Graph().load_edges(s, d, None, directed=True), directed=True)     # dead ends: ragged paths
+    want, _ = _twin_paths(oracle, td, walk_length=walk_length, num_walks=2, p=0.5, q=2.0, seed=5, fold=1)
+    got, _ = _emu_alias_walk(emu, oracle, td, walk_length=walk_length, p=0.5, q=2.0, seed=5, rounds=2)
+    assert got == want
+    if walk_length > 0:
+        assert len({len(x) for x in got}) > 1
