@@ -488,7 +488,7 @@ def run_b200(a):
             srw.check(lib.srw_walk_device(gx.h, C.byref(cpx), first, n_ex, px.data_ptr(), lx.data_ptr(), stream.cuda_stream))
             wi = srw.last_walk_info()
             exact = {"value": wi.steps / (wi.kernel_ms * 1e-3), "unit": UNIT, "walkers": n_ex, "steps": int(wi.steps), "kernel_ms": wi.kernel_ms,
-                     "kernel": "walk_exact_cert_kernel",
+                     "kernel": "walk_exact_cert2_kernel",
                      "note": "SRW_SAMPLER_EXACT: RS:12-62 literally (float32 bias weights, in-order float64 CDF), bit-identical to the oracle "
                              "(tests/test_gpu_parity.py); %d walkers of the same graph starting at vertex rank %d, kernel time only" % (n_ex, first)}
             gx.free()

@@ -1,7 +1,7 @@
 """Exact (bit-parity, RS:12-62) sampler throughput per kernel generation on one B200 (not a bench line).
     python profiles/run_exact.py > profiles/r1_exact.jsonl
 thread = one walker per thread; warp = one warp per walker, in-order float64 fold; cert = certified parallel
-CDF search with in-order replay of ambiguous steps.  The A/B switch SRW_EXACT is read once per process, so
+CDF search with in-order replay of ambiguous steps; cert2 = cert + common-neighbour list + two-level search on long rows.  The A/B switch SRW_EXACT is read once per process, so
 every mode runs in its own subprocess.  131072 walkers of round 0, walkLength 80."""
 import ctypes as C
 import importlib
@@ -34,15 +34,15 @@ def child(mode, scale, p, q, n_walkers):
     chk = int(paths.to(torch.int64).sum())
     print(json.dumps({"config": "rmat-%d" % scale, "sampler": "exact", "kernel": mode, "p": p, "q": q, "walkers": nw, "steps": wi.steps,
                       "kernel_ms": wi.kernel_ms, "steps_per_s_kernel": wi.steps / (wi.kernel_ms * 1e-3),
-                      "in_order_replays": wi.member_tests if mode == "cert" else None, "path_checksum": chk}), flush=True)
+                      "in_order_replays": wi.member_tests if mode.startswith("cert") else None, "path_checksum": chk}), flush=True)
 
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--child":
         child(sys.argv[2], int(sys.argv[3]), float(sys.argv[4]), float(sys.argv[5]), int(sys.argv[6]))
     else:
-        for scale, p, q, modes in ((18, 0.5, 2.0, ("thread", "warp", "cert")), (20, 0.5, 2.0, ("warp", "cert")), (20, 1.0, 1.0, ("cert",)),
-                                   (22, 0.5, 2.0, ("cert",))):
+        for scale, p, q, modes in ((18, 0.5, 2.0, ("thread", "warp", "cert", "cert2")), (20, 0.5, 2.0, ("warp", "cert", "cert2")),
+                                   (20, 1.0, 1.0, ("cert", "cert2")), (22, 0.5, 2.0, ("cert", "cert2")), (24, 0.5, 2.0, ("cert", "cert2"))):
             for mode in modes:
                 env = dict(os.environ, SRW_EXACT=mode)
                 subprocess.run([sys.executable, os.path.abspath(__file__), "--child", mode, str(scale), str(p), str(q), "131072"], env=env,

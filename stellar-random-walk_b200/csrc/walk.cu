@@ -27,16 +27,8 @@
 namespace {
 
 #include "walk_conv.cuh"   // WalkArgs, FoldArgs, PeerTable, the state enum and the convergent kernels (v5)
+#include "walk_exact.cuh"  // row_contains / hash_contains and K5, the exact (bit-parity) sampler kernels
 
-// x in sorted row [lo, lo+n)?
-__device__ __forceinline__ bool row_contains(const int32_t *__restrict__ col, int64_t lo, int64_t n, int32_t x) {
-  int64_t a = 0, b = n;
-  while (a < b) {
-    const int64_t m = (a + b) >> 1;
-    if (__ldg(col + lo + m) < x) a = m + 1; else b = m;
-  }
-  return a < n && __ldg(col + lo + a) == x;
-}
 
 
 // alias proposal from row [off, off+deg): slot index from 64 random bits, Vose coin from r.y
@@ -466,268 +458,6 @@ __global__ void __launch_bounds__(256, MINB) walk_fold_kernel(WalkArgs a, FoldAr
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// K5: exact sampler (also used by the KAT entry points)
-// ------------------------------------------------------------------------------------------
-// RS:12-25 over weights produced by `wf(i)`: two passes, float64 accumulation, left to right.
-template <class WF>
-__device__ __forceinline__ int64_t cdf_pick(int64_t n, float u, WF wf) {
-  double sum = 0.0;
-  for (int64_t i = 0; i < n; ++i) sum = __dadd_rn(sum, (double)wf(i));     // RS:14
-  double acc = 0.0;
-  for (int64_t i = 0; i < n; ++i) {
-    acc = __dadd_rn(acc, __ddiv_rn((double)wf(i), sum));                   // RS:19
-    if (acc >= (double)u) return i;                                        // RS:20
-  }
-  return 0;                                                                // RS:24 edges.head
-}
-
-// RS:33-41 for one neighbour
-__device__ __forceinline__ float biased_weight(float p, float q, int32_t prev, int32_t dst, float w, bool in_prev_row) {
-  float un = __fdiv_rn(w, q);
-  if (dst == prev) un = __fdiv_rn(w, p);
-  else if (in_prev_row) un = w;
-  return un;
-}
-
-__device__ __forceinline__ float draw_u(const WalkArgs &a, uint64_t walker, uint32_t step) {
-  if (a.u_mode == SRW_U_CONST) return a.u_const;
-  return u01_from_bits(walker_rng(a.seed_lo, a.seed_hi, walker, step, 0u).x);
-}
-
-__global__ void __launch_bounds__(128) walk_exact_kernel(WalkArgs a) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= a.n_walkers) return;
-  const uint64_t walker = a.walker_first + (uint64_t)i;
-  int32_t curr = (int32_t)(walker % (uint64_t)a.nv);
-  int32_t *path = a.paths + i * a.stride;
-  path[0] = curr;
-  int32_t len = 1;
-  int64_t off = a.off[curr], deg = a.off[curr + 1] - off;
-  if (deg > 0) {
-    const float *w0 = a.w_app + off;
-    int64_t k = cdf_pick(deg, draw_u(a, walker, 0u), [&](int64_t j) { return w0[j]; });   // RW:57
-    int32_t prev = curr;
-    int64_t poff = off, pdeg = deg;
-    curr = a.col_app[off + k];
-    path[len++] = curr;
-    while (len != a.stride) {
-      off = a.off[curr];
-      deg = a.off[curr + 1] - off;
-      if (deg <= 0) break;
-      const int32_t *cd = a.col_app + off;
-      const float *cw = a.w_app + off;
-      const float u = draw_u(a, walker, (uint32_t)(len - 1));
-      k = cdf_pick(deg, u, [&](int64_t j) {
-        const int32_t d = cd[j];
-        const bool need = (d != prev) && (a.p != 1.0f || a.q != 1.0f);
-        return biased_weight(a.p, a.q, prev, d, cw[j], need ? row_contains(a.col, poff, pdeg, d) : false);
-      });
-      prev = curr; poff = off; pdeg = deg;
-      curr = cd[k];
-      path[len++] = curr;
-    }
-  }
-  a.lens[i] = len;
-}
-
-// ------------------------------------------------------------------------------------------
-// K5 (v2): the exact sampler with one WARP per walker.  RS:27-44 is embarrassingly parallel over the
-// neighbours of curr (one membership test each), RS:14 / RS:19 are not: float64 addition does not
-// associate, so the sum and the running CDF stay strictly left-to-right.  Each lane therefore computes the
-// biased weight (and, in pass 2, the float64 quotient w'/sum) of one neighbour per 32-wide chunk -- a hash
-// probe in prev's neighbour set, or a binary search in its sorted row when no set was built -- and the 32
-// values are then folded in order through warp shuffles, every lane carrying the same accumulator.
-// Bit-identical to walk_exact_kernel and to the oracle; O(d_c/32) chunk rounds per pass instead of O(d_c).
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool hash_contains(const int32_t *__restrict__ hash, int64_t poff, uint32_t pnb, int32_t x) {
-  uint32_t b = __umulhi(srw_hash32((uint32_t)x), pnb);
-  for (;;) {
-    const int4 *q = reinterpret_cast<const int4 *>(hash + (srw_hash_first(poff) + (int64_t)b) * 8);
-    const int4 q0 = __ldg(q), q1 = __ldg(q + 1);
-    if (q0.x == x || q0.y == x || q0.z == x || q0.w == x || q1.x == x || q1.y == x || q1.z == x || q1.w == x) return true;
-    if (q1.w == -1) return false;
-    b = b + 1 == pnb ? 0 : b + 1;
-  }
-}
-
-__global__ void __launch_bounds__(256) walk_exact_warp_kernel(WalkArgs a, const int32_t *__restrict__ hash) {
-  const int lane = threadIdx.x & 31;
-  const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;     // one warp per walker
-  if (i >= a.n_walkers) return;
-  const uint64_t walker = a.walker_first + (uint64_t)i;
-  int32_t curr = (int32_t)(walker % (uint64_t)a.nv), prev = -1;
-  int32_t *path = a.paths + i * a.stride;
-  if (lane == 0) path[0] = curr;
-  int32_t len = 1;
-  int64_t poff = 0;
-  uint32_t pdeg = 0;
-  const bool biased = a.p != 1.0f || a.q != 1.0f;
-  while (len != a.stride) {                                                     // RW:103
-    const int64_t off = __ldg(a.off + curr);
-    const uint32_t deg = (uint32_t)(__ldg(a.off + curr + 1) - off);
-    if (deg == 0) break;                                                        // RW:59-62 / RW:115-119
-    const int32_t *cd = a.col_app + off;
-    const float *cw = a.w_app + off;
-    const float u = draw_u(a, walker, (uint32_t)(len - 1));
-    const bool second = len > 1;
-    const uint32_t pnb = (second && biased && hash) ? srw_hash_buckets(poff, pdeg) : 0u;
-    auto weight_of = [&](uint32_t j) -> float {                                 // RS:33-41 for neighbour j (first step: RS:12 plain weights)
-      const float w = __ldg(cw + j);
-      if (!second) return w;
-      const int32_t d = __ldg(cd + j);
-      bool in_prev = false;
-      if (biased && d != prev) in_prev = pnb ? hash_contains(hash, poff, pnb, d) : row_contains(a.col, poff, pdeg, d);
-      return biased_weight(a.p, a.q, prev, d, w, in_prev);
-    };
-    // pass 1 (RS:14): sum, strictly left to right
-    double sum = 0.0;
-    for (uint32_t base = 0; base < deg; base += 32) {
-      const uint32_t j = base + lane, n = min(32u, deg - base);
-      const float wv = j < deg ? weight_of(j) : 0.0f;
-      for (uint32_t l = 0; l < n; ++l) sum = __dadd_rn(sum, (double)__shfl_sync(0xffffffffu, wv, (int)l));
-    }
-    // pass 2 (RS:16-22): acc += w / sum; first index with acc >= u
-    double acc = 0.0;
-    int64_t pick = 0;                                                           // RS:24 edges.head
-    bool found = false;
-    for (uint32_t base = 0; base < deg && !found; base += 32) {
-      const uint32_t j = base + lane, n = min(32u, deg - base);
-      const double qv = j < deg ? __ddiv_rn((double)weight_of(j), sum) : 0.0;
-      for (uint32_t l = 0; l < n; ++l) {
-        acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, qv, (int)l));
-        if (acc >= (double)u) { pick = base + l; found = true; break; }
-      }
-    }
-    const int32_t nxt = __ldg(cd + pick);
-    if (lane == 0) path[len] = nxt;                                             // RW:114
-    len++;
-    prev = curr; poff = off; pdeg = deg;
-    curr = nxt;
-  }
-  if (lane == 0) a.lens[i] = len;
-}
-
-// ------------------------------------------------------------------------------------------
-// K5 (v3): the exact sampler with a CERTIFIED parallel inverse-CDF search.  Still bit-identical to RS:12-25,
-// but the two float64 chains of the reference (sum, then acc += w/sum) are not replayed element by element
-// unless they have to be.  For non-negative weights, ANY summation order of k terms is within
-// k * 2^-53 * (exact sum) of the exact sum (Higham, gamma_k), and fl(w/sum) is within 2^-53 relative of w/sum.
-// Hence, with S = a parallel (tree) sum of the row and P_k = a parallel prefix sum,
-//        | acc_k(reference, sequential) - P_k / S |  <=  (3k + 2) * 2^-53 * (1 + tiny)
-// and the reference's answer "first k with acc_k >= u" is decided by comparing P_k with (u -+ delta) * S,
-// delta = (4n + 64) * 2^-52, whenever no prefix falls inside the +-delta band around u.  The first prefix
-// certainly above the band is then the reference's pick -- every earlier one is certainly below.  If some
-// earlier prefix lands inside the band (probability ~ n * 2 * delta per step, < 2^-8 for a million-entry
-// row), or a weight is negative / non-finite, or the sum is not a positive finite number, the step is
-// replayed with the in-order chains of walk_exact_warp_kernel.  O(d_c / 32) warp scans per step instead of
-// d_c dependent float64 additions.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ double warp_scan_incl(double v, int lane) {
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const double t = __shfl_up_sync(0xffffffffu, v, o);
-    if (lane >= o) v = __dadd_rn(v, t);
-  }
-  return v;
-}
-
-__global__ void __launch_bounds__(256) walk_exact_cert_kernel(WalkArgs a, const int32_t *__restrict__ hash) {
-  const int lane = threadIdx.x & 31;
-  const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;     // one warp per walker
-  if (i >= a.n_walkers) return;
-  const uint64_t walker = a.walker_first + (uint64_t)i;
-  int32_t curr = (int32_t)(walker % (uint64_t)a.nv), prev = -1;
-  int32_t *path = a.paths + i * a.stride;
-  if (lane == 0) path[0] = curr;
-  int32_t len = 1;
-  int64_t poff = 0;
-  uint32_t pdeg = 0;
-  unsigned long long n_replay = 0;
-  const bool biased = a.p != 1.0f || a.q != 1.0f;
-  while (len != a.stride) {                                                     // RW:103
-    const int64_t off = __ldg(a.off + curr);
-    const uint32_t deg = (uint32_t)(__ldg(a.off + curr + 1) - off);
-    if (deg == 0) break;                                                        // RW:59-62 / RW:115-119
-    const int32_t *cd = a.col_app + off;
-    const float *cw = a.w_app + off;
-    const float u = draw_u(a, walker, (uint32_t)(len - 1));
-    const bool second = len > 1;
-    const uint32_t pnb = (second && biased && hash) ? srw_hash_buckets(poff, pdeg) : 0u;
-    auto weight_of = [&](uint32_t j) -> float {                                 // RS:33-41 for neighbour j (first step: RS:12 plain weights)
-      const float w = __ldg(cw + j);
-      if (!second) return w;
-      const int32_t d = __ldg(cd + j);
-      bool in_prev = false;
-      if (biased && d != prev) in_prev = pnb ? hash_contains(hash, poff, pnb, d) : row_contains(a.col, poff, pdeg, d);
-      return biased_weight(a.p, a.q, prev, d, w, in_prev);
-    };
-    int64_t pick = -1;
-    // ---- certified parallel search ----
-    {
-      double part = 0.0;
-      bool bad = false;
-      for (uint32_t j = lane; j < deg; j += 32) {
-        const float wv = weight_of(j);
-        bad |= !(wv >= 0.0f) || !(wv <= 3.0e38f);
-        part = __dadd_rn(part, (double)wv);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) part = __dadd_rn(part, __shfl_xor_sync(0xffffffffu, part, o));
-      bad = __any_sync(0xffffffffu, bad) || !(part > 0.0) || !(part <= 1.0e300);
-      if (!bad) {
-        const double delta = (4.0 * (double)deg + 64.0) * 2.220446049250313e-16;        // 2^-52
-        const double uu = (double)u;
-        const double t_hi = (uu + delta) * part * (1.0 + 1e-15), t_lo = (uu - delta) * part;   // t_lo < 0: every prefix is above it
-        double carry = 0.0;
-        for (uint32_t base = 0; base < deg; base += 32) {
-          const uint32_t j = base + lane;
-          const double wv = j < deg ? (double)weight_of(j) : 0.0;
-          const double P = __dadd_rn(carry, warp_scan_incl(wv, lane));
-          const unsigned valid = (deg - base >= 32u) ? 0xffffffffu : ((1u << (deg - base)) - 1u);
-          const unsigned hi = __ballot_sync(0xffffffffu, P >= t_hi) & valid;
-          const unsigned band = __ballot_sync(0xffffffffu, P > t_lo) & valid;     // includes the hi lanes
-          const unsigned below_first_hi = hi ? ((1u << (__ffs(hi) - 1)) - 1u) : 0xffffffffu;
-          if (band & ~hi & below_first_hi) break;                                  // a prefix inside the band: replay in order
-          if (hi) { pick = base + (__ffs(hi) - 1); break; }
-          carry = __shfl_sync(0xffffffffu, P, 31);
-          if (base + 32 >= deg) pick = 0;                                          // never reached u, certainly: RS:24 edges.head
-        }
-      }
-    }
-    if (pick < 0) {
-      // ---- in-order replay (RS:14, RS:16-22 literally) ----
-      n_replay++;
-      double sum = 0.0;
-      for (uint32_t base = 0; base < deg; base += 32) {
-        const uint32_t j = base + lane, n = min(32u, deg - base);
-        const float wv = j < deg ? weight_of(j) : 0.0f;
-        for (uint32_t l = 0; l < n; ++l) sum = __dadd_rn(sum, (double)__shfl_sync(0xffffffffu, wv, (int)l));
-      }
-      double acc = 0.0;
-      pick = 0;                                                                 // RS:24 edges.head
-      bool found = false;
-      for (uint32_t base = 0; base < deg && !found; base += 32) {
-        const uint32_t j = base + lane, n = min(32u, deg - base);
-        const double qv = j < deg ? __ddiv_rn((double)weight_of(j), sum) : 0.0;
-        for (uint32_t l = 0; l < n; ++l) {
-          acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, qv, (int)l));
-          if (acc >= (double)u) { pick = base + l; found = true; break; }
-        }
-      }
-    }
-    const int32_t nxt = __ldg(cd + pick);
-    if (lane == 0) path[len] = nxt;                                             // RW:114
-    len++;
-    prev = curr; poff = off; pdeg = deg;
-    curr = nxt;
-  }
-  if (lane == 0) {
-    a.lens[i] = len;
-    if (n_replay) atomicAdd(a.stats + 2, n_replay);                             // reported as member_tests: in-order replays
-  }
-}
-
 // ranks -> original vertex ids, and the step count
 __global__ void finalize_paths_kernel(int64_t n_walkers, int32_t stride, const int32_t *__restrict__ vids,
                                       const int32_t *__restrict__ lens, int32_t *paths, unsigned long long *stats) {
@@ -863,10 +593,11 @@ srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLa
   a.stats = d_stats;
   SRW_CUDA(cudaEventRecord(ev.a, l.stream));
   if (exact) {
-    static const char *ex = getenv("SRW_EXACT");                                // A/B switch: thread | warp | cert (default)
+    const char *ex = getenv("SRW_EXACT");                                       // A/B switch (read per launch): thread | warp | cert | cert2 (default)
     if (ex && !strcmp(ex, "thread")) walk_exact_kernel<<<(unsigned)((l.n_walkers + 127) / 128), 128, 0, l.stream>>>(a);
     else if (ex && !strcmp(ex, "warp")) walk_exact_warp_kernel<<<(unsigned)((l.n_walkers + 7) / 8), 256, 0, l.stream>>>(a, g->d_hash);
-    else walk_exact_cert_kernel<<<(unsigned)((l.n_walkers + 7) / 8), 256, 0, l.stream>>>(a, g->d_hash);
+    else if (ex && !strcmp(ex, "cert")) walk_exact_cert_kernel<<<(unsigned)((l.n_walkers + 7) / 8), 256, 0, l.stream>>>(a, g->d_hash);
+    else walk_exact_cert2_kernel<<<(unsigned)((l.n_walkers + 7) / 8), 256, 0, l.stream>>>(a, g->d_hash);
   } else {
     const unsigned grid = (unsigned)((l.n_walkers + 255) / 256);
     const bool st = t_collect_stats != 0;

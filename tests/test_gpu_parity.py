@@ -443,12 +443,12 @@ out.append(hashlib.sha256(ids.tobytes() + offs.tobytes()).hexdigest())
 print(",".join(out))
 ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     res = {}
-    for k in ("thread", "warp", "cert"):
+    for k in ("thread", "warp", "cert", "cert2"):
         env = dict(os.environ, SRW_EXACT=k)
         r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, env=env)
         assert r.returncode == 0, r.stderr[-2000:]
         res[k] = r.stdout.strip().splitlines()[-1]
-    assert res["thread"] == res["warp"] == res["cert"], res
+    assert res["thread"] == res["warp"] == res["cert"] == res["cert2"], res
 
 
 # ---- the alias-fold kernel generations and load flavours produce the same bits (switches are read per launch) ----
