@@ -2,13 +2,41 @@
 // (tests/emu/cuda_emu.h) over a CSR handed in by the test, after laying the rows out exactly as
 // graph_build.cu does (16-byte neighbour entries, derived-placement hash sets, optional vertex-range
 // shards for the PEER variant).  The test compares the paths with the CPU twin (oracle_alias_walk).
+// Two builds: the default one drives the kernel one lane at a time (cuda_emu.h: fast, a "warp" is one lane); with
+// -DSRW_EMU_WARP the same kernels run under the lockstep 32-lane warp emulator (warp_emu.h), where lanes of a warp finish
+// at different times and the __any_sync loop / dead-lane logic is exercised for real.
+#ifdef SRW_EMU_WARP
+#include "warp_emu.h"
+#else
 #include "cuda_emu.h"
+#endif
 
+#include <functional>
 #include <vector>
 
 #include "../../stellar-random-walk_b200/csrc/walk_conv.cuh"
 
 namespace {
+
+// runs `kernel` for every thread of a grid of 256-thread blocks covering n_walkers walkers
+void run_grid(int64_t n_walkers, int extra, const std::function<void()> &kernel) {
+  const int64_t n_blocks = (n_walkers + 255) / 256;
+#ifdef SRW_EMU_WARP
+  (void)extra;
+  emu_launch_warps(n_blocks * 8, kernel);
+#else
+  emu_extra_iters = extra;
+  blockDim.x = 256; blockDim.y = blockDim.z = 1;
+  for (int64_t b = 0; b < n_blocks; ++b) {
+    blockIdx.x = (unsigned)b;
+    for (unsigned t = 0; t < 256; ++t) {
+      threadIdx.x = t;
+      emu_linger = 0;
+      kernel();
+    }
+  }
+#endif
+}
 
 struct ShardRows {
   std::vector<int64_t> off;        // shard-local offsets, rows+1
@@ -83,30 +111,28 @@ extern "C" int emu_fold_walk(int64_t nv, const int64_t *off, const int32_t *col,
   pt.world = shards;
   for (int s = 0; s <= shards; ++s) pt.first[s] = bounds[s];
   for (int s = 0; s < shards; ++s) { pt.off[s] = sh[(size_t)s].off.data(); pt.ent[s] = sh[(size_t)s].ent.data(); pt.hash[s] = sh[(size_t)s].hash.data(); }
-  emu_extra_iters = extra;
-  blockDim.x = 256; blockDim.y = blockDim.z = 1;
-  const int64_t n_blocks = (n_walkers + 255) / 256;
   const bool peer = shards > 1;
-  for (int64_t b = 0; b < n_blocks; ++b) {
-    blockIdx.x = (unsigned)b;
-    for (int pass = peer ? 0 : 1; pass < 2; ++pass) {      // pass 0: every lane only publishes the shard tables (s_ent / s_hash)
-      WalkArgs aa = a;
-      if (pass == 0) aa.n_walkers = 0;
-      for (unsigned t = 0; t < 256; ++t) {
-        threadIdx.x = t;
-        emu_linger = 0;
-        if (peer) {
-          if (var & 1) walk_fold_conv_kernel<false, true, 1>(aa, f, pt);
-          else if (stats) walk_fold_conv_kernel<true, true, 0>(aa, f, pt);
-          else walk_fold_conv_kernel<false, true, 0>(aa, f, pt);
-        } else {
-          if (var & 1) walk_fold_conv_kernel<false, false, 1>(aa, f, pt);
-          else if (stats) walk_fold_conv_kernel<true, false, 0>(aa, f, pt);
-          else walk_fold_conv_kernel<false, false, 0>(aa, f, pt);
-        }
+  auto launch = [&](const WalkArgs &aa) {
+    run_grid(n_walkers, extra, [&] {
+      if (peer) {
+        if (var & 1) walk_fold_conv_kernel<false, true, 1>(aa, f, pt);
+        else if (stats) walk_fold_conv_kernel<true, true, 0>(aa, f, pt);
+        else walk_fold_conv_kernel<false, true, 0>(aa, f, pt);
+      } else {
+        if (var & 1) walk_fold_conv_kernel<false, false, 1>(aa, f, pt);
+        else if (stats) walk_fold_conv_kernel<true, false, 0>(aa, f, pt);
+        else walk_fold_conv_kernel<false, false, 0>(aa, f, pt);
       }
-    }
+    });
+  };
+#ifndef SRW_EMU_WARP
+  if (peer) {                 // one lane at a time: a first pass (of the SAME instantiation: `static` stands in for __shared__) in
+    WalkArgs a0 = a;          // which every lane only publishes the shard tables (s_ent / s_hash)
+    a0.n_walkers = 0;
+    launch(a0);
   }
+#endif
+  launch(a);
   if (stats_out) memcpy(stats_out, st, sizeof(st));
   return folded ? 1 : 0;
 }
@@ -145,23 +171,15 @@ extern "C" int emu_alias_walk(int64_t nv, const int64_t *off, const int32_t *col
   a.paths = paths; a.lens = lens;
   unsigned long long st[4] = {0, 0, 0, 0};
   a.stats = st;
-  emu_extra_iters = extra;
-  blockDim.x = 256; blockDim.y = blockDim.z = 1;
-  const int64_t n_blocks = (n_walkers + 255) / 256;
-  for (int64_t b = 0; b < n_blocks; ++b) {
-    blockIdx.x = (unsigned)b;
-    for (unsigned t = 0; t < 256; ++t) {
-      threadIdx.x = t;
-      emu_linger = 0;
-      if (thr) {
-        if (var & 1) walk_alias_conv_kernel<true, false, 1>(a, meta.data(), hash.data());
-        else walk_alias_conv_kernel<true, true, 0>(a, meta.data(), hash.data());
-      } else {
-        if (var & 1) walk_alias_conv_kernel<false, false, 1>(a, meta.data(), hash.data());
-        else walk_alias_conv_kernel<false, true, 0>(a, meta.data(), hash.data());
-      }
+  run_grid(n_walkers, extra, [&] {
+    if (thr) {
+      if (var & 1) walk_alias_conv_kernel<true, false, 1>(a, meta.data(), hash.data());
+      else walk_alias_conv_kernel<true, true, 0>(a, meta.data(), hash.data());
+    } else {
+      if (var & 1) walk_alias_conv_kernel<false, false, 1>(a, meta.data(), hash.data());
+      else walk_alias_conv_kernel<false, true, 0>(a, meta.data(), hash.data());
     }
-  }
+  });
   if (stats_out) memcpy(stats_out, st, sizeof(st));
   return 0;
 }
@@ -197,18 +215,10 @@ extern "C" int emu_wfold_walk(int64_t nv, const int64_t *off, const int32_t *col
   a.stats = st;
   FoldArgs f{};
   if (!srw_fold_args(p, q, true, &f)) return -2;
-  emu_extra_iters = extra;
-  blockDim.x = 256; blockDim.y = blockDim.z = 1;
-  const int64_t n_blocks = (n_walkers + 255) / 256;
-  for (int64_t b = 0; b < n_blocks; ++b) {
-    blockIdx.x = (unsigned)b;
-    for (unsigned t = 0; t < 256; ++t) {
-      threadIdx.x = t;
-      emu_linger = 0;
-      if (var & 1) walk_wfold_conv_kernel<false, 1>(a, f, meta.data(), hash.data(), slot.data());
-      else walk_wfold_conv_kernel<true, 0>(a, f, meta.data(), hash.data(), slot.data());
-    }
-  }
+  run_grid(n_walkers, extra, [&] {
+    if (var & 1) walk_wfold_conv_kernel<false, 1>(a, f, meta.data(), hash.data(), slot.data());
+    else walk_wfold_conv_kernel<true, 0>(a, f, meta.data(), hash.data(), slot.data());
+  });
   if (stats_out) memcpy(stats_out, st, sizeof(st));
   return 0;
 }

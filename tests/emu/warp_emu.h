@@ -58,7 +58,7 @@ static inline unsigned __ballot_sync(unsigned, bool p) {
 static inline bool __any_sync(unsigned m, bool p) { return __ballot_sync(m, p) != 0; }
 static inline bool __all_sync(unsigned m, bool p) { return __ballot_sync(m, p) == 0xffffffffu; }
 static inline void __syncwarp() { g_warp->bar.arrive_and_wait(); }
-static inline void __syncthreads() {}
+static inline void __syncthreads() { g_warp->bar.arrive_and_wait(); }   // warps of a block run one after another: a warp barrier orders what matters
 static inline int __ffs(unsigned x) { return x ? __builtin_ctz(x) + 1 : 0; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 

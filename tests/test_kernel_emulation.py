@@ -19,14 +19,19 @@ EMU_DIR = os.path.join(ROOT, "tests", "emu")
 EMU_SO = os.path.join(EMU_DIR, "libsrw_emu.so")
 
 
-@pytest.fixture(scope="module")
-def emu():
-    srcs = [os.path.join(EMU_DIR, "emu_walk.cpp"), os.path.join(EMU_DIR, "cuda_emu.h")]
+@pytest.fixture(scope="module", params=["lane", "warp"])
+def emu(request):
+    """lane: one lane at a time (cuda_emu.h).  warp: the lockstep 32-lane warp emulator (warp_emu.h), where the lanes of a
+    warp finish at different times -- the `__any_sync` loop and the inert-finished-lane logic run for real."""
+    warp = request.param == "warp"
+    so = os.path.join(EMU_DIR, "libsrw_emu_warp.so" if warp else "libsrw_emu.so")
+    srcs = [os.path.join(EMU_DIR, "emu_walk.cpp"), os.path.join(EMU_DIR, "warp_emu.h" if warp else "cuda_emu.h")]
     csrc = os.path.join(ROOT, "stellar-random-walk_b200", "csrc")
     srcs += [os.path.join(csrc, f) for f in ("walk_conv.cuh", "layout.h", "philox.cuh")]
-    if not os.path.exists(EMU_SO) or any(os.path.getmtime(s) > os.path.getmtime(EMU_SO) for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-Wno-unknown-pragmas", "-shared", "-fPIC",
-                               srcs[0], "-o", EMU_SO])
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        flags = ["-std=c++20", "-DSRW_EMU_WARP", "-pthread"] if warp else ["-std=c++17"]
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-Wno-unknown-pragmas", "-shared", "-fPIC"] + flags + [srcs[0], "-o", so])
+    EMU_SO = so
     lib = C.CDLL(EMU_SO)
     lib.emu_fold_walk.restype = C.c_int
     lib.emu_fold_walk.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_int,
