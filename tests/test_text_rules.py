@@ -12,8 +12,14 @@ import pytest
 from conftest import KARATE, ROOT, TESTGRAPH
 
 srw = importlib.import_module("stellar-random-walk_b200")
+bld = importlib.import_module("stellar-random-walk_b200.build")
 EMU_DIR = os.path.join(ROOT, "tests", "emu")
 EMU_SO = os.path.join(EMU_DIR, "libsrw_emu_text.so")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    bld.build()          # the serial host parser these tests compare against lives in libsrw.so (nvcc cross-compiles without a GPU)
 
 
 @pytest.fixture(scope="module")
