@@ -161,6 +161,17 @@ srw_status srw_walk(const srw_graph *g, const srw_params *params, srw_paths **ou
 srw_status srw_walk_device(const srw_graph *g, const srw_params *params, uint64_t walker_first, int64_t n_walkers,
                            int32_t *d_paths, int32_t *d_lens, void *stream);
 /* timing / counters of the calling thread's most recent srw_walk* call */
+/* srw_walk_device in two halves.  _async enqueues the walk kernel on `stream` and the rank -> id pass on the library's
+ * high-priority finalisation stream, and returns; `stream` is then free for the next round's walk (into ANOTHER path
+ * buffer), so the L2-bound finalisation of round r runs under the DRAM-request-bound walk of round r+1.  srw_walk_wait
+ * blocks until the ticket's round is complete (d_paths / d_lens valid), fills *info (may be NULL) and releases the ticket.
+ * Every ticket must be waited for exactly once; the buffers of a round must not be reused before its wait. */
+typedef struct srw_walk_ticket srw_walk_ticket;
+struct srw_walk_info;
+srw_status srw_walk_device_async(const srw_graph *g, const srw_params *params, uint64_t walker_first, int64_t n_walkers,
+                                 int32_t *d_paths, int32_t *d_lens, void *stream, srw_walk_ticket **ticket);
+srw_status srw_walk_wait(srw_walk_ticket *ticket, struct srw_walk_info *info);
+
 typedef struct srw_walk_info {
   double kernel_ms;        /* CUDA-event time of the walk kernel(s) alone */
   int64_t kernel_launches; /* number of kernels launched (walk + finalize) */

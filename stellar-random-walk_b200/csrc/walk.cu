@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <mutex>
 #include <vector>
 
 #include "philox.cuh"
@@ -536,7 +537,8 @@ thread_local int t_collect_stats = 0;
 // path (those take driver-wide locks and serialise against other tools using the driver).
 struct LaunchCtx {
   int device = -1;
-  cudaEvent_t a = nullptr, b = nullptr;
+  cudaEvent_t a = nullptr, b = nullptr, done = nullptr;
+  bool pending = false;                    // kernels enqueued, srw_walk_wait not yet called
   unsigned long long *d_stats = nullptr;   // [4]
   unsigned long long *h_stats = nullptr;   // pinned [4]
   srw_status init(int dev) {
@@ -544,6 +546,7 @@ struct LaunchCtx {
     release();
     SRW_CUDA(cudaEventCreate(&a));
     SRW_CUDA(cudaEventCreate(&b));
+    SRW_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
     SRW_CUDA(cudaMalloc(&d_stats, 4 * sizeof(unsigned long long)));
     SRW_CUDA(cudaMallocHost(&h_stats, 4 * sizeof(unsigned long long)));
     device = dev;
@@ -552,19 +555,23 @@ struct LaunchCtx {
   void release() {
     if (a) cudaEventDestroy(a);
     if (b) cudaEventDestroy(b);
+    if (done) cudaEventDestroy(done);
     if (d_stats) cudaFree(d_stats);
     if (h_stats) cudaFreeHost(h_stats);
-    a = b = nullptr; d_stats = h_stats = nullptr; device = -1;
+    a = b = done = nullptr; d_stats = h_stats = nullptr; device = -1; pending = false;
   }
 };
 thread_local LaunchCtx t_ctx;
 
 }  // namespace
 
-srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLaunch &l) {
+// Enqueues the walk kernel on l.stream and the rank -> id pass (+ the 32-byte statistics copy) on `fin`: the same stream
+// for the blocking call, the library's high-priority finalisation stream for the asynchronous one -- there the caller's
+// stream is free for the next round's walk as soon as this round's walk kernel has been launched.
+static srw_status walk_enqueue(const srw_graph *g, const srw_params *p, const WalkLaunch &l, LaunchCtx &ev, cudaStream_t fin, bool own_fin) {
   if (p->walk_length < 0 || l.n_walkers < 0) { srw_set_error("walkLength and the walker count must be >= 0"); return SRW_ERR_ARG; }
   if (!(p->p > 0.0) || !(p->q > 0.0)) { srw_set_error("p and q must be > 0"); return SRW_ERR_ARG; }
-  t_info = srw_walk_info{};
+  ev.pending = false;
   const bool peer = g->shard_world > 1;
   if (peer) {
     // one shard of several: only the peer-gather walk runs through this entry point (the tuple-exchange
@@ -586,8 +593,7 @@ srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLa
   srw_alias_thresholds(p->p, p->q, &a.t_ret, &a.t_common, &a.t_far);
   a.p = (float)p->p; a.q = (float)p->q; a.u_mode = p->u_mode; a.u_const = p->u_const;
   a.paths = l.d_paths; a.lens = l.d_lens;
-  SRW_TRY(t_ctx.init(g->device));
-  LaunchCtx &ev = t_ctx;
+  SRW_TRY(ev.init(g->device));
   unsigned long long *d_stats = ev.d_stats;
   SRW_CUDA(cudaMemsetAsync(d_stats, 0, 4 * sizeof(unsigned long long), l.stream));
   a.stats = d_stats;
@@ -699,6 +705,7 @@ srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLa
     else              { if (st) walk_alias_kernel<false, true><<<grid, 256, 0, l.stream>>>(a); else walk_alias_kernel<false, false><<<grid, 256, 0, l.stream>>>(a); }
   }
   SRW_CUDA(cudaEventRecord(ev.b, l.stream));
+  if (own_fin) SRW_CUDA(cudaStreamWaitEvent(fin, ev.b, 0));
   {
     const int64_t total = l.n_walkers * (int64_t)a.stride;
     int64_t blocks = (total + 255) / 256;
@@ -708,25 +715,97 @@ srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLa
       const uint32_t half = (uint32_t)a.stride / 2;
       const uint64_t magic = ~0ULL / half + 1;                  // ceil(2^64 / half) (half >= 1; half == 1: wraps to 0, handled below)
       const int64_t n_pairs = total / 2;
-      if (half == 1) finalize_paths_kernel<<<(unsigned)blocks, 256, 0, l.stream>>>(l.n_walkers, a.stride, g->d_vids, l.d_lens, l.d_paths, d_stats);
-      else finalize_paths_flat_kernel<<<(unsigned)((n_pairs + 1023) / 1024), 256, 0, l.stream>>>(n_pairs, half, magic, g->d_vids, l.d_lens, reinterpret_cast<int2 *>(l.d_paths), d_stats);
+      if (half == 1) finalize_paths_kernel<<<(unsigned)blocks, 256, 0, fin>>>(l.n_walkers, a.stride, g->d_vids, l.d_lens, l.d_paths, d_stats);
+      else finalize_paths_flat_kernel<<<(unsigned)((n_pairs + 1023) / 1024), 256, 0, fin>>>(n_pairs, half, magic, g->d_vids, l.d_lens, reinterpret_cast<int2 *>(l.d_paths), d_stats);
     } else {
-      finalize_paths_kernel<<<(unsigned)blocks, 256, 0, l.stream>>>(l.n_walkers, a.stride, g->d_vids, l.d_lens, l.d_paths, d_stats);
+      finalize_paths_kernel<<<(unsigned)blocks, 256, 0, fin>>>(l.n_walkers, a.stride, g->d_vids, l.d_lens, l.d_paths, d_stats);
     }
   }
-  unsigned long long *h_stats = ev.h_stats;
-  SRW_CUDA(cudaMemcpyAsync(h_stats, d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, l.stream));
-  SRW_CUDA(cudaStreamSynchronize(l.stream));
+  SRW_CUDA(cudaMemcpyAsync(ev.h_stats, d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, fin));
+  SRW_CUDA(cudaEventRecord(ev.done, fin));
   SRW_CUDA(cudaGetLastError());
-  float ms = 0.f;
-  SRW_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));
-  t_info.kernel_ms = ms;
-  t_info.kernel_launches = 2;
-  t_info.steps = (int64_t)h_stats[0];
-  t_info.proposals = (int64_t)h_stats[1];
-  t_info.member_tests = (int64_t)h_stats[2];
-  t_info.probes_log2 = (int64_t)h_stats[3];
+  ev.pending = true;
   return SRW_OK;
+}
+
+// Blocks until an enqueued walk has finished and reports it.
+static srw_status walk_finish(LaunchCtx &ev, srw_walk_info *out) {
+  srw_walk_info wi{};
+  if (ev.pending) {
+    SRW_CUDA(cudaEventSynchronize(ev.done));
+    SRW_CUDA(cudaGetLastError());
+    float ms = 0.f;
+    SRW_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));
+    wi.kernel_ms = ms;
+    wi.kernel_launches = 2;
+    wi.steps = (int64_t)ev.h_stats[0];
+    wi.proposals = (int64_t)ev.h_stats[1];
+    wi.member_tests = (int64_t)ev.h_stats[2];
+    wi.probes_log2 = (int64_t)ev.h_stats[3];
+    ev.pending = false;
+  }
+  if (out) *out = wi;
+  return SRW_OK;
+}
+
+srw_status srw_walk_launch(const srw_graph *g, const srw_params *p, const WalkLaunch &l) {
+  t_info = srw_walk_info{};
+  SRW_TRY(walk_enqueue(g, p, l, t_ctx, l.stream, false));
+  return walk_finish(t_ctx, &t_info);
+}
+
+// ---- asynchronous rounds: tickets from a small pool, one high-priority finalisation stream per device ----
+struct srw_walk_ticket {
+  LaunchCtx ctx;
+};
+namespace {
+std::mutex g_ticket_mu;
+std::vector<srw_walk_ticket *> g_ticket_pool;
+cudaStream_t g_fin_stream[64] = {};
+srw_status fin_stream_for(int dev, cudaStream_t *out) {
+  if (dev < 0 || dev >= 64) { srw_set_error("device index %d out of range", dev); return SRW_ERR_ARG; }
+  std::lock_guard<std::mutex> lk(g_ticket_mu);
+  if (!g_fin_stream[dev]) {
+    int lo = 0, hi = 0;
+    SRW_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    SRW_CUDA(cudaStreamCreateWithPriority(&g_fin_stream[dev], cudaStreamNonBlocking, hi));
+  }
+  *out = g_fin_stream[dev];
+  return SRW_OK;
+}
+}  // namespace
+
+extern "C" srw_status srw_walk_device_async(const srw_graph *g, const srw_params *params, uint64_t walker_first, int64_t n_walkers,
+                                            int32_t *d_paths, int32_t *d_lens, void *stream, srw_walk_ticket **ticket) {
+  SRW_TRY(srw_require_device());
+  if (!g || !params || !ticket || (n_walkers > 0 && (!d_paths || !d_lens))) { srw_set_error("srw_walk_device_async: bad argument"); return SRW_ERR_ARG; }
+  SRW_CUDA(cudaSetDevice(g->device));
+  cudaStream_t fin;
+  SRW_TRY(fin_stream_for(g->device, &fin));
+  srw_walk_ticket *t = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_ticket_mu);
+    for (size_t i = 0; i < g_ticket_pool.size(); ++i)
+      if (g_ticket_pool[i]->ctx.device == g->device || g_ticket_pool[i]->ctx.device < 0) { t = g_ticket_pool[i]; g_ticket_pool.erase(g_ticket_pool.begin() + (long)i); break; }
+  }
+  if (!t) t = new srw_walk_ticket();
+  WalkLaunch l{walker_first, n_walkers, d_paths, d_lens, (cudaStream_t)stream};
+  const srw_status st = walk_enqueue(g, params, l, t->ctx, fin, true);
+  if (st != SRW_OK) {
+    std::lock_guard<std::mutex> lk(g_ticket_mu);
+    g_ticket_pool.push_back(t);
+    return st;
+  }
+  *ticket = t;
+  return SRW_OK;
+}
+
+extern "C" srw_status srw_walk_wait(srw_walk_ticket *ticket, srw_walk_info *info) {
+  if (!ticket) return SRW_ERR_ARG;
+  const srw_status st = walk_finish(ticket->ctx, info);
+  std::lock_guard<std::mutex> lk(g_ticket_mu);
+  g_ticket_pool.push_back(ticket);
+  return st;
 }
 
 void srw_set_walk_info(double kernel_ms, int64_t launches, int64_t steps, int64_t proposals, int64_t member_tests, int64_t probes_log2) {

@@ -510,3 +510,49 @@ def test_weighted_fold_hubs_bundles_and_text_weights(oracle, tmp_path):
     og = oracle.Graph().load_text(txt, weighted=True)
     ids, offs, _ = oracle.AliasGraph(og).walk(walk_length=20, num_walks=3, p=0.5, q=2.0, seed=8, fold=1)
     assert open(os.path.join(out, "path", "part-00000"), "rb").read() == oracle.format_paths(ids, offs)
+
+
+# ---- srw_walk_device_async / srw_walk_wait: rounds enqueued back to back, finalisation on the library's stream ----
+def test_async_rounds_equal_blocking_rounds():
+    import ctypes as C
+    import torch
+    s, d = synth.rmat_edges(14, 16, seed=42)
+    g = srw.Graph.from_edges(s, d, None, flags=srw.BUILD_ALIAS)
+    nv = g.num_vertices
+    L = 80
+    lib = srw.lib()
+    cp = srw.Params(walkLength=L, numWalks=1, p=0.5, q=2.0, seed=6, sampler="fold").to_c()
+    want = []
+    p0 = torch.empty((nv, L + 2), dtype=torch.int32, device="cuda")
+    l0 = torch.empty(nv, dtype=torch.int32, device="cuda")
+    for r in range(5):
+        srw.check(lib.srw_walk_device(g.h, C.byref(cp), r * nv, nv, p0.data_ptr(), l0.data_ptr(), None))
+        want.append((p0.clone(), l0.clone(), srw.last_walk_info().steps))
+    bufs = [(torch.empty_like(p0), torch.empty_like(l0)) for _ in range(2)]
+    st = torch.cuda.Stream()
+    tickets, got = [None, None], []
+
+    def wait(b):
+        if tickets[b] is not None:
+            wi = srw.WalkInfo()
+            srw.check(lib.srw_walk_wait(tickets[b], C.byref(wi)))
+            tickets[b] = None
+            got.append((bufs[b][0].clone(), bufs[b][1].clone(), wi.steps, wi.kernel_ms))
+
+    for r in range(5):
+        b = r & 1
+        wait(b)
+        tk = C.c_void_p()
+        srw.check(lib.srw_walk_device_async(g.h, C.byref(cp), r * nv, nv, bufs[b][0].data_ptr(), bufs[b][1].data_ptr(), st.cuda_stream, C.byref(tk)))
+        tickets[b] = tk
+    wait(1)
+    wait(0)
+    assert len(got) == 5
+    for (wp, wl, ws), (gp, gl, gs, ms) in zip(want, got):
+        assert bool((wp == gp).all()) and bool((wl == gl).all()) and ws == gs and ms > 0
+    # an empty launch still hands out a ticket that can be waited for
+    tk = C.c_void_p()
+    srw.check(lib.srw_walk_device_async(g.h, C.byref(cp), 0, 0, None, None, None, C.byref(tk)))
+    wi = srw.WalkInfo()
+    srw.check(lib.srw_walk_wait(tk, C.byref(wi)))
+    assert wi.steps == 0
