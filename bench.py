@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--sampler", default="fold", choices=["fold", "alias"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-reps", type=int, default=2)
+    ap.add_argument("--async-rounds", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-exact", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
@@ -321,42 +322,48 @@ def run_b200(a):
     log("stats pass done: T=%.2f proposals/step; warm-up" % T_bar)
     for r in range(a.warmup):
         one_round(r)
-    # the timed rounds go through the asynchronous half of the ABI: the walk kernels run back to back on `stream`, the
-    # rank -> id pass of round r (L2-bound) runs on the library's finalisation stream under the walk of round r+1
-    # (DRAM-request-bound); two path buffers, a round's buffer is reused only after its ticket has been waited for
-    pbuf = [paths, torch.empty_like(paths)]
-    lbuf = [lens, torch.empty_like(lens)]
     barrier()
     log("timed region: %d rounds" % a.steps)
     clocks.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     kernel_ms, steps, launches = 0.0, 0, 0
-    tickets = [None, None]
+    if a.async_rounds:
+        # A/B: srw_walk_device_async -- the rank -> id pass of round r on the library's stream under the walk of round r+1.
+        # Measured (profiles/r1_bench_rmat26_v5_async_finalize.json): no gain, the two kernels compete for the same request slots.
+        pbuf = [paths, torch.empty_like(paths)]
+        lbuf = [lens, torch.empty_like(lens)]
+        tickets = [None, None]
 
-    def wait_ticket(b):
-        nonlocal kernel_ms, steps, launches
-        if tickets[b] is not None:
-            wi = srw.WalkInfo()
-            srw.check(lib.srw_walk_wait(tickets[b], C.byref(wi)))
-            tickets[b] = None
+        def wait_ticket(b):
+            nonlocal kernel_ms, steps, launches
+            if tickets[b] is not None:
+                wi = srw.WalkInfo()
+                srw.check(lib.srw_walk_wait(tickets[b], C.byref(wi)))
+                tickets[b] = None
+                kernel_ms += wi.kernel_ms
+                steps += wi.steps
+                launches += wi.kernel_launches
+
+        for k in range(a.steps):
+            b = k & 1
+            wait_ticket(b)
+            tk = C.c_void_p()
+            srw.check(lib.srw_walk_device_async(g.h, C.byref(cp), (a.warmup + k) * nv + lo, n_local, pbuf[b].data_ptr(), lbuf[b].data_ptr(),
+                                                stream.cuda_stream, C.byref(tk)))
+            tickets[b] = tk
+        wait_ticket(a.steps & 1)
+        wait_ticket((a.steps + 1) & 1)
+        del pbuf, lbuf
+    else:
+        for k in range(a.steps):
+            wi = one_round(a.warmup + k)
             kernel_ms += wi.kernel_ms
             steps += wi.steps
             launches += wi.kernel_launches
-
-    for k in range(a.steps):
-        b = k & 1
-        wait_ticket(b)
-        tk = C.c_void_p()
-        srw.check(lib.srw_walk_device_async(g.h, C.byref(cp), (a.warmup + k) * nv + lo, n_local, pbuf[b].data_ptr(), lbuf[b].data_ptr(),
-                                            stream.cuda_stream, C.byref(tk)))
-        tickets[b] = tk
-    wait_ticket(a.steps & 1)
-    wait_ticket((a.steps + 1) & 1)
-    e1.record(stream)          # every round (walk + finalisation) is complete: the waits above are host-side
+    e1.record(stream)
     barrier()
     clk = clocks.stop()
-    del pbuf, lbuf
     elapsed_ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([elapsed_ms, float(steps)], dtype=torch.float64, device=dev)
