@@ -154,3 +154,13 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert "workload" in d["config"] and "model" not in d["config"]
     r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_abi_header_is_plain_c():
+    """include/srw.h is the drop-in boundary: it must compile as C (no C++, no CUDA, no torch types) ..."""
+    hdr = os.path.join(ROOT, "include", "srw.h")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # ... and every entry point says which reference interface it replaces
+    src = open(hdr).read()
+    assert len(re.findall(r"(RW|RS|GM|URW|VRW|CP|Main|Params)(\.scala)?:\d+", src)) >= 30
