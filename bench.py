@@ -511,6 +511,23 @@ def run_b200(a):
                    "sample": r["sample"] + "; CSR = the device build copied to the host (sorted rows; timing only)"}
         except Exception as ex:   # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %s" % ex}
+        # the GPU kernel's OWN algorithm (alias-fold, oracle twin) on the same host cores and the same CSR
+        if cpu and cpu.get("value") and not a.weighted:
+            try:
+                L = oracle_lib.lib()
+                fn = L.oracle_fold_walk_csr_timed
+                fn.restype = C.c_int64
+                fn.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.POINTER(C.c_double),
+                               C.POINTER(C.c_int64), C.POINTER(C.c_uint64), C.c_void_p]
+                cfg = oracle_lib.make_cfg(walk_length=a.walk_length, num_walks=1, p=a.p, q=a.q, seed=a.seed, threads=0, fold=1)
+                el, dn, ck = C.c_double(), C.c_int64(), C.c_uint64()
+                stride_t = max(1, nv // (1 << 21))
+                st_t = fn(nv, lay_off.ctypes.data, lay_col.ctypes.data, C.addressof(cfg), stride_t, 0, 5.0, C.byref(el), C.byref(dn), C.byref(ck), None)
+                cpu["alias_fold_twin"] = {"value": st_t / max(el.value, 1e-9), "unit": UNIT, "cores": cpu["cores"], "walkers": int(dn.value),
+                                          "note": "the product's alias-fold sampler (oracle twin, not the reference algorithm) on the host cores: "
+                                                  "same CSR, binary-search membership, 5 s budget"}
+            except Exception as ex:   # noqa: BLE001
+                cpu["alias_fold_twin"] = {"value": None, "error": str(ex)}
 
     log("cpu baseline done")
     # ---- the bit-parity sampler on the same workload (N=1, bounded sample; not part of `value`) ----

@@ -1058,3 +1058,104 @@ int64_t oracle_walk_csr_timed(int64_t nv, const int64_t *offsets, const int32_t 
   if (checksum) *checksum = sum;
   return steps;
 }
+
+/* The product's alias-fold algorithm (NOT the reference's: see oracle_alias_walk, whose decisions this repeats) over a
+ * dense, neighbour-sorted, UNWEIGHTED CSR -- bench.py's "optimised CPU twin" figure: the same sampler
+ * the GPU kernel runs, on the host cores, membership by binary search, multiplicity by scanning the run of equal
+ * neighbours.  Walker v of round 0 for every sampled start vertex; stops at the time budget. */
+int64_t oracle_fold_walk_csr_timed(int64_t nv, const int64_t *offsets, const int32_t *col, const oracle_walk_cfg *cfg,
+                                   int64_t sample_stride, int64_t sample_phase, double budget_s, double *elapsed_s,
+                                   int64_t *walkers_done, uint64_t *checksum, int32_t *paths_out) {
+  const int32_t full = cfg->walk_length + 2;
+  uint64_t t_ret, t_common, t_far;
+  oracle_alias_thresholds(cfg->p, cfg->q, &t_ret, &t_common, &t_far);
+  double fold_a = 0.0, fold_mp = 1.0;
+  int fold = 0;
+  {
+    uint64_t fc, ff;
+    oracle_fold_thresholds(cfg->p, cfg->q, &fc, &ff, &fold_a, &fold_mp);
+    if (fold_a > 0.0) { fold = 1; t_common = fc; t_far = ff; t_ret = 4294967296ULL; }
+  }
+  if (sample_stride < 1) sample_stride = 1;
+  const int64_t n_samples = (nv - sample_phase + sample_stride - 1) / sample_stride;
+  int64_t steps = 0, done = 0;
+  uint64_t sum = 0;
+  const double t0 = now_s();
+#ifdef _OPENMP
+#pragma omp parallel num_threads(cfg->threads > 0 ? cfg->threads : omp_get_max_threads()) reduction(+ : steps, done, sum)
+#endif
+  {
+    int32_t *path = (int32_t *)malloc((size_t)full * sizeof(int32_t));
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 16)
+#endif
+    for (int64_t sidx = 0; sidx < n_samples; ++sidx) {
+      if (now_s() - t0 > budget_s) continue;
+      const int64_t v = sample_phase + sidx * sample_stride;
+      const uint64_t walker = (uint64_t)v;
+      int32_t len = 0;
+      path[len++] = (int32_t)v;
+      int64_t off = offsets[v], deg = offsets[v + 1] - off;
+      uint32_t r[4];
+      if (deg > 0) {
+        walker_rng(cfg->seed, walker, 0u, 0u, r);
+        int64_t kk = (int64_t)mulhi64(((uint64_t)r[0] << 32) | (uint64_t)r[3], (uint64_t)deg);
+        /* multiplicity of the chosen neighbour in this (sorted) row */
+#define RUN_LEN(o, d, k, out)                                                         \
+  do {                                                                                \
+    int64_t a_ = (k), b_ = (k);                                                       \
+    while (a_ > 0 && col[(o) + a_ - 1] == col[(o) + (k)]) a_--;                       \
+    while (b_ + 1 < (d) && col[(o) + b_ + 1] == col[(o) + (k)]) b_++;                 \
+    (out) = (uint32_t)(b_ - a_ + 1);                                                  \
+  } while (0)
+        uint32_t m_ret;
+        RUN_LEN(off, deg, kk, m_ret);
+        path[len++] = col[off + kk];
+        steps++;
+        while (len != full) {
+          const int32_t curr = path[len - 1], prev = path[len - 2];
+          off = offsets[curr]; deg = offsets[curr + 1] - off;
+          if (deg <= 0) break;
+          const int64_t poff = offsets[prev], pdeg = offsets[prev + 1] - poff;
+          int32_t x = -1;
+          double ret_lhs = 0.0, ret_rhs = 0.0;
+          if (fold) {
+            const double t1 = fold_a * (double)m_ret, t2 = fold_mp * (double)deg;
+            ret_lhs = t2 + t1;
+            ret_rhs = t1 * 4294967296.0;
+          }
+          for (uint32_t trial = 0;; ++trial) {
+            walker_rng(cfg->seed, walker, (uint32_t)(len - 1), trial, r);
+            if (fold && (double)r[1] * ret_lhs < ret_rhs) { x = prev; kk = -1; break; }
+            kk = (int64_t)mulhi64(((uint64_t)r[0] << 32) | (uint64_t)r[3], (uint64_t)deg);
+            x = col[off + kk];
+            uint64_t t;
+            if (x == prev) t = t_ret;
+            else if (t_common == t_far) t = t_far;
+            else {
+              const uint64_t lo = t_common < t_far ? t_common : t_far, hi = t_common < t_far ? t_far : t_common;
+              if ((uint64_t)r[2] < lo) break;                       /* accepted whatever the class */
+              if ((uint64_t)r[2] >= hi) continue;                   /* rejected whatever the class */
+              t = row_contains(col + poff, pdeg, x) ? t_common : t_far;
+            }
+            if ((uint64_t)r[2] < t) break;
+          }
+          if (fold && kk >= 0) RUN_LEN(off, deg, kk, m_ret);        /* a direct return keeps the bundle (symmetric) */
+          path[len++] = x;
+          steps++;
+        }
+#undef RUN_LEN
+      }
+      for (int32_t k = 0; k < len; ++k) sum += (uint64_t)(uint32_t)path[k] * (uint64_t)(k + 1);
+      if (paths_out) {
+        for (int32_t k = 0; k < full; ++k) paths_out[sidx * full + k] = k < len ? path[k] : -1;
+      }
+      done++;
+    }
+    free(path);
+  }
+  if (elapsed_s) *elapsed_s = now_s() - t0;
+  if (walkers_done) *walkers_done = done;
+  if (checksum) *checksum = sum;
+  return steps;
+}

@@ -150,6 +150,11 @@ void oracle_csr_build(int64_t n_ids, int64_t n_edges, const int32_t *src, const 
 int64_t oracle_walk_csr_timed(int64_t nv, const int64_t *offsets, const int32_t *col, const float *w,
                               const oracle_walk_cfg *cfg, int64_t sample_stride, int64_t sample_phase,
                               double budget_s, double *elapsed_s, int64_t *walkers_done, uint64_t *checksum);
+/* the product's alias-fold sampler (the decisions of oracle_alias_walk with fold = 1) over a dense, neighbour-sorted,
+ * unweighted CSR: bench.py's "optimised CPU twin" figure.  paths_out (optional): [n_samples][walk_length + 2], -1 padded. */
+int64_t oracle_fold_walk_csr_timed(int64_t nv, const int64_t *offsets, const int32_t *col, const oracle_walk_cfg *cfg,
+                                   int64_t sample_stride, int64_t sample_phase, double budget_s, double *elapsed_s,
+                                   int64_t *walkers_done, uint64_t *checksum, int32_t *paths_out);
 int oracle_max_threads(void);
 
 #ifdef __cplusplus

