@@ -304,6 +304,29 @@ __global__ void k_hash_insert(int64_t nnz, const uint32_t *__restrict__ row_of, 
   }
 }
 
+// id-space variant of the two kernels above: hash sets of ORIGINAL ids, entries relabelled in place
+__global__ void k_hash_insert_ids(int64_t nnz, const uint32_t *__restrict__ row_of, const int32_t *__restrict__ col,
+                                  const RowMeta *__restrict__ meta, const int32_t *__restrict__ vids, int32_t *hash) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+    const RowMeta m = meta[row_of[i]];
+    if (m.nb == 0) continue;
+    const int32_t x = vids[col[i]];
+    uint32_t b = __umulhi(srw_hash32((uint32_t)x), m.nb);
+    bool done = false;
+    while (!done) {
+      int32_t *bucket = hash + (m.hoff + b) * 8;
+      for (int s = 0; s < 8 && !done; ++s) {
+        const int32_t old = atomicCAS(bucket + s, -1, x);
+        if (old == -1 || old == x) done = true;
+      }
+      b = b + 1 == m.nb ? 0 : b + 1;
+    }
+  }
+}
+__global__ void k_ent_relabel(int64_t nnz, const int32_t *__restrict__ vids, NbrEntry *ent) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) ent[i].x = vids[ent[i].x];
+}
+
 struct CastU32ToI64 {
   __host__ __device__ int64_t operator()(uint32_t x) const { return (int64_t)x; }
 };
@@ -563,6 +586,22 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
       int h = 0;
       SRW_CUDA(cudaMemcpy(&h, ovf.p, 4, cudaMemcpyDeviceToHost));
       if (h) { cudaFree(g->d_ent); g->d_ent = nullptr; }    // absurd multiplicities: fold sampler unavailable
+      // ID SPACE (opt-in, SRW_FOLD_IDS=1): the fold kernel treats a neighbour as an opaque label -- it compares it with prev,
+      // hashes it and appends it to the path -- so the entries can carry ORIGINAL VERTEX IDS and the walk emits ids directly:
+      // the rank -> id pass over the path matrix (7 % of a round at RMAT-26) disappears.  Costs a second, id-labelled copy
+      // of the hash sets (the rank-labelled one serves the other kernels).  Ranks ascend with ids, so rows stay sorted.
+      if (g->d_ent && !sharded && g->id_min >= 0 /* -1 marks an empty hash slot */ && getenv("SRW_FOLD_IDS") && atoi(getenv("SRW_FOLD_IDS")) != 0) {
+        if (cudaMalloc(&g->d_hash_id, (size_t)g->hash_buckets * 32) == cudaSuccess) {
+          SRW_CUDA(cudaMemset(g->d_hash_id, 0xFF, (size_t)g->hash_buckets * 32));
+          k_hash_insert_ids<<<grid(nnz), kThreads>>>(nnz, k_in, g->d_col, g->d_meta, g->d_vids, g->d_hash_id);
+          k_ent_relabel<<<grid(nnz), kThreads>>>(nnz, g->d_vids, g->d_ent);
+          SRW_CUDA(cudaDeviceSynchronize());
+          g->ent_ids = true;
+        } else {
+          cudaGetLastError();
+          g->d_hash_id = nullptr;
+        }
+      }
     }
   }
 
@@ -594,7 +633,7 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
   }
   SRW_CUDA(cudaGetLastError());
   g->device_bytes = (int64_t)(words * 8 + (size_t)nv * 12 + (size_t)nnz * 4) + (g->d_col_app ? nnz * 8 : 0) +
-                    (g->d_slot ? nnz * 16 : 0) + (g->d_slotw ? nnz * 32 : 0) + (g->d_vpid ? nv * 4 : 0) + (g->d_meta ? nrows * 32 : 0) + (g->d_hash ? g->hash_buckets * 32 : 0) + (g->d_ent ? nnz * 16 : 0);
+                    (g->d_slot ? nnz * 16 : 0) + (g->d_slotw ? nnz * 32 : 0) + (g->d_vpid ? nv * 4 : 0) + (g->d_meta ? nrows * 32 : 0) + (g->d_hash ? g->hash_buckets * 32 : 0) + (g->d_hash_id ? g->hash_buckets * 32 : 0) + (g->d_ent ? nnz * 16 : 0);
   return SRW_OK;
 }
 

@@ -56,6 +56,8 @@ struct srw_graph {
   int32_t *d_hash = nullptr;         // per-row neighbour hash sets, 8-slot (32-byte) buckets, -1 = empty
   int64_t hash_buckets = 0;
   NbrEntry *d_ent = nullptr;         // [nnz] unweighted, unsharded graphs (fold sampler)
+  int32_t *d_hash_id = nullptr;      // id-space fold (SRW_FOLD_IDS): hash sets of original ids; d_ent[].x then holds ids too
+  bool ent_ids = false;
   int64_t device_bytes = 0;
   mutable std::vector<int32_t> h_vids;  // lazy host copies for the query entry points
   mutable std::vector<int64_t> h_off;

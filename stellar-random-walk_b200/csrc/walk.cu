@@ -515,6 +515,18 @@ __global__ void __launch_bounds__(256) finalize_paths_flat_kernel(int64_t n_pair
   if ((threadIdx.x & 31) == 0 && steps) atomicAdd(stats, steps);
 }
 
+// id-space walks need no translation: count the steps and pad the rows of walkers that stopped early (dead ends) with -1
+__global__ void count_steps_kernel(int64_t n_walkers, int32_t stride, const int32_t *__restrict__ lens, int32_t *paths, unsigned long long *stats) {
+  unsigned long long steps = 0;
+  for (int64_t wk = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; wk < n_walkers; wk += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t len = __ldg(lens + wk);
+    steps += (unsigned long long)(len - 1);
+    for (int32_t k = len; k < stride; ++k) paths[wk * stride + k] = -1;
+  }
+  for (int o = 16; o > 0; o >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, o);
+  if ((threadIdx.x & 31) == 0 && steps) atomicAdd(stats, steps);
+}
+
 // ---- KAT kernels: one thread, same device functions as the exact walk ----
 __global__ void kat_sample_kernel(int64_t n, const float *w, float u, int64_t *out) {
   *out = cdf_pick(n, u, [&](int64_t j) { return w[j]; });
@@ -598,6 +610,7 @@ static srw_status walk_enqueue(const srw_graph *g, const srw_params *p, const Wa
   SRW_CUDA(cudaMemsetAsync(d_stats, 0, 4 * sizeof(unsigned long long), l.stream));
   a.stats = d_stats;
   SRW_CUDA(cudaEventRecord(ev.a, l.stream));
+  bool ids = false;                      // the walk kernel wrote original ids (id-space fold): no translation below
   if (exact) {
     const char *ex = getenv("SRW_EXACT");                                       // A/B switch (read per launch): thread | warp | cert | cert2 (default)
     if (ex && !strcmp(ex, "thread")) walk_exact_kernel<<<(unsigned)((l.n_walkers + 127) / 128), 128, 0, l.stream>>>(a);
@@ -633,6 +646,8 @@ static srw_status walk_enqueue(const srw_graph *g, const srw_params *p, const Wa
     const bool fold_v4 = getenv("SRW_FOLD") && !strcmp(getenv("SRW_FOLD"), "v4");
     constexpr int kFoldVarDefault = 1;   // v5 load flavour when SRW_FOLD_VAR is unset: L2::64B gathers (half the DRAM traffic at the same speed, profiles/)
     const int fold_var = getenv("SRW_FOLD_VAR") ? atoi(getenv("SRW_FOLD_VAR")) : kFoldVarDefault;
+    ids = fold && !peer && !fold_v4 && g->ent_ids && g->d_hash_id;
+    if (g->ent_ids && !ids && !exact && !g->has_alias && g->d_ent && (fold || fold_v4)) { srw_set_error("this graph was built in id space (SRW_FOLD_IDS): only the v5 alias-fold kernel can walk its neighbour entries"); return SRW_ERR_UNSUPPORTED; }
     if ((peer || fold) && !fold_v4) {
       PeerTable pt{};
       if (peer) {
@@ -646,7 +661,13 @@ static srw_status walk_enqueue(const srw_graph *g, const srw_params *p, const Wa
         else if (v64) walk_fold_conv_kernel<false, true, 1><<<grid, 256, 0, l.stream>>>(a, f, pt);
         else walk_fold_conv_kernel<false, true, 0><<<grid, 256, 0, l.stream>>>(a, f, pt);
       } else {
-        if (st) walk_fold_conv_kernel<true, false, 0><<<grid, 256, 0, l.stream>>>(a, f, pt);
+        if (ids) {                        // id space: entries and hash sets carry original ids, the walk emits ids (no rank -> id pass)
+          f.hash = g->d_hash_id;
+          if (st) walk_fold_conv_kernel<true, false, 0, 4, true><<<grid, 256, 0, l.stream>>>(a, f, pt);
+          else if (v64) walk_fold_conv_kernel<false, false, 1, 4, true><<<grid, 256, 0, l.stream>>>(a, f, pt);
+          else walk_fold_conv_kernel<false, false, 0, 4, true><<<grid, 256, 0, l.stream>>>(a, f, pt);
+        }
+        else if (st) walk_fold_conv_kernel<true, false, 0><<<grid, 256, 0, l.stream>>>(a, f, pt);
         else if (v64 && occ == 5) walk_fold_conv_kernel<false, false, 1, 5><<<grid, 256, 0, l.stream>>>(a, f, pt);
         else if (v64 && occ == 6) walk_fold_conv_kernel<false, false, 1, 6><<<grid, 256, 0, l.stream>>>(a, f, pt);
         else if (v64) walk_fold_conv_kernel<false, false, 1><<<grid, 256, 0, l.stream>>>(a, f, pt);
@@ -711,7 +732,9 @@ static srw_status walk_enqueue(const srw_graph *g, const srw_params *p, const Wa
     int64_t blocks = (total + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
     const bool flat = (a.stride & 1) == 0 && (reinterpret_cast<uintptr_t>(l.d_paths) & 7) == 0 && !getenv("SRW_FINALIZE_ROWS");
-    if (flat && total > 0) {
+    if (ids) {
+      count_steps_kernel<<<(unsigned)std::min<int64_t>((l.n_walkers + 255) / 256, 148 * 8), 256, 0, fin>>>(l.n_walkers, a.stride, l.d_lens, l.d_paths, d_stats);
+    } else if (flat && total > 0) {
       const uint32_t half = (uint32_t)a.stride / 2;
       const uint64_t magic = ~0ULL / half + 1;                  // ceil(2^64 / half) (half >= 1; half == 1: wraps to 0, handled below)
       const int64_t n_pairs = total / 2;

@@ -107,7 +107,7 @@ __device__ __forceinline__ void gather32(const int4 *p, int4 &lo, int4 &hi) {   
 #endif
 }
 
-template <bool STATS, bool PEER, int VAR, int MINB = 4>
+template <bool STATS, bool PEER, int VAR, int MINB = 4, bool IDS = false>
 __global__ void __launch_bounds__(256, MINB) walk_fold_conv_kernel(WalkArgs a, FoldArgs f, const PeerTable pt) {
   __shared__ int32_t sbuf[kStage * 256];
   __shared__ const NbrEntry *s_ent[SRW_MAX_SHARDS];
@@ -159,7 +159,6 @@ __global__ void __launch_bounds__(256, MINB) walk_fold_conv_kernel(WalkArgs a, F
   const uint64_t t_hi = f.t_common < f.t_far ? f.t_far : f.t_common;
   int state = ST_DONE;
   if (live) {
-    sbuf[tid] = curr; staged = 1; len = 1;
     int64_t e0, e1;                                             // the start vertex's extent: the only row-offset load
     if (PEER) {
       while ((int)cown + 1 < pt.world && (int64_t)curr >= pt.first[cown + 1]) cown++;
@@ -169,6 +168,8 @@ __global__ void __launch_bounds__(256, MINB) walk_fold_conv_kernel(WalkArgs a, F
       e0 = __ldg(a.off + curr); e1 = __ldg(a.off + curr + 1);
     }
     off = (uint32_t)e0; deg = (uint32_t)(e1 - e0);
+    if (IDS) curr = __ldg(a.vids + curr);                       // id space: from here on a vertex is its original id (entries and hash sets carry ids)
+    sbuf[tid] = curr; staged = 1; len = 1;
     if (deg != 0 && len != a.stride) state = ST_WAIT;           // dead end (RW:59-62) / RW:103
   }
 

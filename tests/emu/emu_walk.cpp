@@ -63,6 +63,10 @@ void hash_insert(std::vector<int32_t> &hash, int64_t off, uint32_t deg, int32_t 
 // Lays the graph out for `shards` vertex ranges (bounds[shards+1], first rank of every range; shards == 1:
 // the unsharded layout) and walks n_walkers walkers.  var: VAR template value; extra: see cuda_emu.h.
 // fold != 0: alias-fold arguments from (p, q); fold == 0: classic thresholds through the same kernel.
+extern "C" int emu_fold_walk_ids(int64_t nv, const int64_t *off, const int32_t *col, const uint32_t *mult, const int32_t *vids,
+                                 double p, double q, uint64_t seed, int32_t walk_length, uint64_t walker_first, int64_t n_walkers,
+                                 int32_t *paths, int32_t *lens, int var, int extra);
+
 extern "C" int emu_fold_walk(int64_t nv, const int64_t *off, const int32_t *col, const uint32_t *mult, int shards,
                              const int64_t *bounds, double p, double q, int fold, uint64_t t_ret, uint64_t t_common,
                              uint64_t t_far, uint64_t seed, int32_t walk_length, uint64_t walker_first, int64_t n_walkers,
@@ -220,5 +224,38 @@ extern "C" int emu_wfold_walk(int64_t nv, const int64_t *off, const int32_t *col
     else walk_wfold_conv_kernel<true, 0>(a, f, meta.data(), hash.data(), slot.data());
   });
   if (stats_out) memcpy(stats_out, st, sizeof(st));
+  return 0;
+}
+
+
+// ID SPACE (graph_build.cu, SRW_FOLD_IDS): entries and hash sets carry ORIGINAL vertex ids, the kernel (IDS = true) emits ids.
+extern "C" int emu_fold_walk_ids(int64_t nv, const int64_t *off, const int32_t *col, const uint32_t *mult, const int32_t *vids,
+                                 double p, double q, uint64_t seed, int32_t walk_length, uint64_t walker_first, int64_t n_walkers,
+                                 int32_t *paths, int32_t *lens, int var, int extra) {
+  const int64_t nnz = off[nv];
+  std::vector<NbrEntry> ent((size_t)nnz);
+  std::vector<int32_t> hash((size_t)(((nnz >> 2) + 1) * 8), -1);
+  for (int64_t r = 0; r < nv; ++r)
+    for (int64_t e = off[r]; e < off[r + 1]; ++e) {
+      const int32_t x = col[e];
+      NbrEntry ne;
+      ne.x = vids[x]; ne.deg = (uint32_t)(off[x + 1] - off[x]); ne.off_lo = (uint32_t)off[x]; ne.off_hi_mult = mult[e] << 8;
+      ent[(size_t)e] = ne;
+      hash_insert(hash, off[r], (uint32_t)(off[r + 1] - off[r]), vids[x]);
+    }
+  WalkArgs a{};
+  a.off = off; a.vids = vids; a.nv = nv; a.walker_first = walker_first; a.n_walkers = n_walkers; a.stride = walk_length + 2;
+  a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
+  a.paths = paths; a.lens = lens;
+  unsigned long long st[4] = {0, 0, 0, 0};
+  a.stats = st;
+  FoldArgs f{};
+  if (!srw_fold_args(p, q, true, &f)) return -2;
+  f.ent = ent.data(); f.hash = hash.data();
+  PeerTable pt{};
+  run_grid(n_walkers, extra, [&] {
+    if (var & 1) walk_fold_conv_kernel<false, false, 1, 4, true>(a, f, pt);
+    else walk_fold_conv_kernel<false, false, 0, 4, true>(a, f, pt);
+  });
   return 0;
 }

@@ -556,3 +556,26 @@ def test_async_rounds_equal_blocking_rounds():
     wi = srw.WalkInfo()
     srw.check(lib.srw_walk_wait(tk, C.byref(wi)))
     assert wi.steps == 0
+
+
+# ---- id-space fold (opt-in, SRW_FOLD_IDS=1 at build time): the walk emits original ids, no rank -> id pass ----
+def test_fold_in_id_space(oracle, monkeypatch):
+    s, d = synth.rmat_edges(11, 8, seed=42)
+    s, d = (s * 7 + 3).astype(np.int32), (d * 7 + 3).astype(np.int32)          # rank != id everywhere
+    twin = oracle.AliasGraph(oracle.Graph().load_edges(s, d))
+    monkeypatch.setenv("SRW_FOLD_IDS", "1")
+    g = srw.Graph.from_edges(s, d, None, flags=srw.BUILD_ALL)
+    monkeypatch.delenv("SRW_FOLD_IDS")
+    for wl in (60, 7):
+        ids, offs, st = twin.walk(walk_length=wl, num_walks=2, p=0.5, q=2.0, seed=4, fold=1)
+        got = g.walk(srw.Params(walkLength=wl, numWalks=2, p=0.5, q=2.0, seed=4, sampler="fold"))
+        gi, go = got.arrays()
+        assert (go == offs).all() and (gi == ids).all() and got.steps() == st.steps
+    # the other samplers keep working on the same handle (they use the rank-labelled hash sets and columns)
+    ids, offs, _ = twin.walk(walk_length=20, num_walks=1, p=2.0, q=0.5, seed=4, fold=1)            # not foldable: classic kernel
+    gi, go = g.walk(srw.Params(walkLength=20, numWalks=1, p=2.0, q=0.5, seed=4, sampler="fold")).arrays()
+    assert (go == offs).all() and (gi == ids).all()
+    og = oracle.Graph().load_edges(s, d)
+    ids, offs = oracle.walk(og, walk_length=10, num_walks=1, p=0.5, q=2.0, seed=4)
+    gi, go = g.walk(srw.Params(walkLength=10, numWalks=1, p=0.5, q=2.0, seed=4, sampler="exact")).arrays()
+    assert (go == offs).all() and (gi == ids).all()

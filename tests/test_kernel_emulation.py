@@ -37,6 +37,9 @@ def emu(request):
     lib.emu_fold_walk.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_int,
                                   C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.emu_fold_walk_ids.restype = C.c_int
+    lib.emu_fold_walk_ids.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_uint64, C.c_int32,
+                                      C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     lib.emu_alias_walk.restype = C.c_int
     lib.emu_alias_walk.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
                                    C.c_int32, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -286,3 +289,26 @@ def test_emulated_weighted_and_classic_kernels_short_walks(emu, oracle, walk_len
     assert got == want
     if walk_length > 0:
         assert len({len(x) for x in got}) > 1
+
+
+# ---- id-space fold (SRW_FOLD_IDS): entries and hash sets carry original ids, the kernel emits ids ----
+@pytest.mark.parametrize("p,q", [(0.5, 2.0), (0.25, 4.0)])
+def test_emulated_fold_kernel_in_id_space(emu, oracle, p, q):
+    s, d = synth.rmat_edges(10, 8, seed=42)
+    s, d = (s * 7 + 3).astype(np.int32), (d * 7 + 3).astype(np.int32)          # sparse, non-dense ids: rank != id everywhere
+    tw = oracle.AliasGraph(oracle.Graph().load_edges(s, d))
+    v = tw.view()
+    assert not np.array_equal(v["vids"], np.arange(tw.nv))
+    off = np.ascontiguousarray(v["offsets"], np.int64)
+    col = np.ascontiguousarray(v["col"], np.int32)
+    vids = np.ascontiguousarray(v["vids"], np.int32)
+    mult = _mult(col, off)
+    for wl in (40, 13):
+        want, _ = _twin_paths(oracle, tw, walk_length=wl, num_walks=2, p=p, q=q, seed=9, fold=1)
+        n = 2 * tw.nv
+        paths = np.full((n, wl + 2), -7, np.int32)
+        lens = np.zeros(n, np.int32)
+        rc = emu.emu_fold_walk_ids(tw.nv, off.ctypes.data, col.ctypes.data, mult.ctypes.data, vids.ctypes.data, p, q, 9, wl, 0, n,
+                                   paths.ctypes.data, lens.ctypes.data, 0, 2)
+        assert rc == 0
+        assert [paths[i, :lens[i]].tolist() for i in range(n)] == want
