@@ -32,6 +32,7 @@ def main(scale):
     s = torch.empty(n, dtype=torch.int32, device="cuda")
     d = torch.empty(n, dtype=torch.int32, device="cuda")
     srw.check(lib.srw_synth_rmat_device(scale, 16, 42, 0, n, s.data_ptr(), d.data_ptr()))
+    os.environ["SRW_FOLD_IDS"] = "0"     # the v4 kernel walks rank-labelled entries: this A/B runs in rank space (id space: run_ids_ab.py)
     g = srw.Graph.from_device_edges(n, s.data_ptr(), d.data_ptr(), None, False, srw.BUILD_ALIAS)
     del s, d
     nv, nnz = g.stats()

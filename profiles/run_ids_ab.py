@@ -21,11 +21,8 @@ def main(scale):
     srw.check(lib.srw_synth_rmat_device(scale, 16, 42, 0, n, s.data_ptr(), d.data_ptr()))
     cp = srw.Params(walkLength=80, numWalks=1, p=0.5, q=2.0, seed=1, sampler="fold").to_c()
     chk = {}
-    for name, env in (("rank space + finalize", None), ("id space", "1")):
-        if env:
-            os.environ["SRW_FOLD_IDS"] = env
-        else:
-            os.environ.pop("SRW_FOLD_IDS", None)
+    for name, env in (("rank space + finalize", "0"), ("id space", "1")):
+        os.environ["SRW_FOLD_IDS"] = env
         g = srw.Graph.from_device_edges(n, s.data_ptr(), d.data_ptr(), None, False, srw.BUILD_ALIAS)
         nv, nnz = g.stats()
         paths = torch.empty((nv, 82), dtype=torch.int32, device="cuda")

@@ -454,7 +454,10 @@ print(",".join(out))
 # ---- the alias-fold kernel generations and load flavours produce the same bits (switches are read per launch) ----
 def test_fold_kernel_generations_agree(oracle, monkeypatch):
     s, d = synth.rmat_edges(13, 16, seed=3)
+    monkeypatch.setenv("SRW_FOLD_IDS", "0")        # v4 walks rank-labelled entries only: build this handle in rank space
     g = srw.Graph.from_edges(s, d, None, flags=srw.BUILD_ALIAS)
+    monkeypatch.delenv("SRW_FOLD_IDS")
+    g_ids = srw.Graph.from_edges(s, d, None, flags=srw.BUILD_ALIAS)       # the default: id space (v5 only)
     twin = oracle.AliasGraph(oracle.Graph().load_edges(s, d))
     res = {}
     for wl in (80, 13, 0):       # even and odd strides: both alignments of the staged path stores
@@ -467,6 +470,12 @@ def test_fold_kernel_generations_agree(oracle, monkeypatch):
                 monkeypatch.setenv(k, v)
             ids, offs = g.walk(srw.Params(walkLength=wl, numWalks=2, p=0.5, q=2.0, seed=9, sampler="fold")).arrays()
             res[(wl, name)] = bool(np.array_equal(ids, want_ids) and np.array_equal(offs, want_offs))
+            if name != "v4":
+                ids, offs = g_ids.walk(srw.Params(walkLength=wl, numWalks=2, p=0.5, q=2.0, seed=9, sampler="fold")).arrays()
+                res[(wl, name + "/id-space")] = bool(np.array_equal(ids, want_ids) and np.array_equal(offs, want_offs))
+            else:
+                with pytest.raises(srw.SrwError):          # the id-space handle refuses the rank-space kernel instead of mixing labels
+                    g_ids.walk(srw.Params(walkLength=wl, numWalks=2, p=0.5, q=2.0, seed=9, sampler="fold"))
     assert all(res.values()), res
 
 
@@ -558,14 +567,12 @@ def test_async_rounds_equal_blocking_rounds():
     assert wi.steps == 0
 
 
-# ---- id-space fold (opt-in, SRW_FOLD_IDS=1 at build time): the walk emits original ids, no rank -> id pass ----
+# ---- id-space fold (the default; SRW_FOLD_IDS=0 at build time opts out): the walk emits original ids, no rank -> id pass ----
 def test_fold_in_id_space(oracle, monkeypatch):
     s, d = synth.rmat_edges(11, 8, seed=42)
     s, d = (s * 7 + 3).astype(np.int32), (d * 7 + 3).astype(np.int32)          # rank != id everywhere
     twin = oracle.AliasGraph(oracle.Graph().load_edges(s, d))
-    monkeypatch.setenv("SRW_FOLD_IDS", "1")
-    g = srw.Graph.from_edges(s, d, None, flags=srw.BUILD_ALL)
-    monkeypatch.delenv("SRW_FOLD_IDS")
+    g = srw.Graph.from_edges(s, d, None, flags=srw.BUILD_ALL)          # id space is the default
     for wl in (60, 7):
         ids, offs, st = twin.walk(walk_length=wl, num_walks=2, p=0.5, q=2.0, seed=4, fold=1)
         got = g.walk(srw.Params(walkLength=wl, numWalks=2, p=0.5, q=2.0, seed=4, sampler="fold"))
