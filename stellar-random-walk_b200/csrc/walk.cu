@@ -647,7 +647,7 @@ static srw_status walk_enqueue(const srw_graph *g, const srw_params *p, const Wa
     constexpr int kFoldVarDefault = 1;   // v5 load flavour when SRW_FOLD_VAR is unset: L2::64B gathers (half the DRAM traffic at the same speed, profiles/)
     const int fold_var = getenv("SRW_FOLD_VAR") ? atoi(getenv("SRW_FOLD_VAR")) : kFoldVarDefault;
     ids = fold && !peer && !fold_v4 && g->ent_ids && g->d_hash_id;
-    if (g->ent_ids && fold && !peer && !ids) {      // SRW_FOLD=v4 on an id-space handle srw_set_error("this graph was built in id space (SRW_FOLD_IDS): only the v5 alias-fold kernel can walk its neighbour entries"); return SRW_ERR_UNSUPPORTED; }
+    if (g->ent_ids && fold && !peer && !ids) { /* SRW_FOLD=v4 on an id-space handle */ srw_set_error("this graph was built in id space (SRW_FOLD_IDS): only the v5 alias-fold kernel can walk its neighbour entries"); return SRW_ERR_UNSUPPORTED; }
     if ((peer || fold) && !fold_v4) {
       PeerTable pt{};
       if (peer) {
