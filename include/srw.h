@@ -111,6 +111,7 @@ srw_status srw_edges_parse_buffer_device(const char *buf, size_t len, int weight
 #define SRW_BUILD_EXACT 1u   /* keep the file-appearance-order rows (needed by SRW_SAMPLER_EXACT) */
 #define SRW_BUILD_ALIAS 2u   /* build neighbour-sorted rows + Vose slots (needed by SRW_SAMPLER_ALIAS) */
 #define SRW_BUILD_ALL 3u
+#define SRW_BUILD_MIGRATE 4u /* sharded builds: also the replicated edge filter the migrating-walker exchange needs (srw_mig_*) */
 srw_status srw_graph_from_edges(int64_t n, const int32_t *h_src, const int32_t *h_dst, const float *h_w /*NULL=1.0f*/,
                                 const int32_t *h_pid /*NULL*/, int directed, unsigned flags, srw_graph **out);
 srw_status srw_graph_from_device_edges(int64_t n, const int32_t *d_src, const int32_t *d_dst, const float *d_w,

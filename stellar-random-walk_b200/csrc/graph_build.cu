@@ -123,6 +123,16 @@ __global__ void k_entries_range(int64_t n, const int32_t *__restrict__ src, cons
     if (k1) { ent_row[p1] = rd - row_first; ent_col[p1] = rs; ent_gidx[p1] = (uint32_t)(2 * e + 1); }
   }
 }
+// SRW_BUILD_MIGRATE: every undirected input edge {rank(src), rank(dst)} sets kMigBloomK bits of one 64-bit word
+__global__ void k_bloom_insert(int64_t n, const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
+                               const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ wordrank, int32_t id_min,
+                               unsigned long long *bloom, uint64_t n_words) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t word, mask;
+    srw_bloom_probe(rank_of(bitmap, wordrank, id_min, src[e]), rank_of(bitmap, wordrank, id_min, dst[e]), n_words, &word, &mask);
+    atomicOr(bloom + word, (unsigned long long)mask);
+  }
+}
 __global__ void k_rebase_off(int64_t rows, const int64_t *__restrict__ goff, int64_t row_first, int64_t *off) {
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r <= rows; r += (int64_t)gridDim.x * blockDim.x)
     off[r] = goff[row_first + r] - goff[row_first];
@@ -512,6 +522,17 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
   }
   const uint32_t *gidx = sharded ? ent_gidx.as<uint32_t>() : nullptr;
   deg.alloc(0);
+  if ((flags & SRW_BUILD_MIGRATE) && !directed && n > 0) {
+    // replicated on every shard: 16 bits per input edge by default (1 byte per adjacency entry; false positives ~0.4 %)
+    const char *eb = getenv("SRW_BLOOM_BITS");
+    const int64_t bits = eb && atoi(eb) > 0 ? atoi(eb) : 16;
+    g->bloom_words = (uint64_t)((n * bits + 63) / 64);
+    if (g->bloom_words < 64) g->bloom_words = 64;
+    SRW_CUDA(cudaMalloc(&g->d_bloom, g->bloom_words * 8));
+    SRW_CUDA(cudaMemset(g->d_bloom, 0, g->bloom_words * 8));
+    k_bloom_insert<<<grid(n), kThreads>>>(n, d_src, d_dst, g->d_bitmap, g->d_wordrank, mn, g->d_bloom, g->bloom_words);
+    SRW_CUDA(cudaDeviceSynchronize());
+  }
 
   if (d_pid) {  // GM:21,31
     DevBuf last;
@@ -633,7 +654,7 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
   }
   SRW_CUDA(cudaGetLastError());
   g->device_bytes = (int64_t)(words * 8 + (size_t)nv * 12 + (size_t)nnz * 4) + (g->d_col_app ? nnz * 8 : 0) +
-                    (g->d_slot ? nnz * 16 : 0) + (g->d_slotw ? nnz * 32 : 0) + (g->d_vpid ? nv * 4 : 0) + (g->d_meta ? nrows * 32 : 0) + (g->d_hash ? g->hash_buckets * 32 : 0) + (g->d_hash_id ? g->hash_buckets * 32 : 0) + (g->d_ent ? nnz * 16 : 0);
+                    (g->d_slot ? nnz * 16 : 0) + (g->d_slotw ? nnz * 32 : 0) + (g->d_vpid ? nv * 4 : 0) + (g->d_meta ? nrows * 32 : 0) + (g->d_hash ? g->hash_buckets * 32 : 0) + (g->d_hash_id ? g->hash_buckets * 32 : 0) + (g->d_ent ? nnz * 16 : 0) + (int64_t)g->bloom_words * 8;
   return SRW_OK;
 }
 

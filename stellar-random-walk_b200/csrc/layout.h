@@ -63,3 +63,27 @@ SRW_LAYOUT_HD uint32_t srw_hash32(uint32_t x) {
 }
 
 #define SRW_MAX_SHARDS 16
+
+// The replicated edge filter of the migrating sharded walk (migrate.cuh): one 64-bit Bloom word per probe, kMigBloomK bits
+// per undirected edge {a, b} of vertex ranks.
+constexpr int kMigBloomK = 5;
+SRW_LAYOUT_HD uint64_t srw_mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+// word index and bit mask of the pair (order-free)
+SRW_LAYOUT_HD void srw_bloom_probe(int32_t a, int32_t b, uint64_t n_words, uint64_t *word, uint64_t *mask) {
+  const uint32_t lo = (uint32_t)(a < b ? a : b), hi = (uint32_t)(a < b ? b : a);
+  const uint64_t h = srw_mix64(((uint64_t)hi << 32) | lo);
+#ifdef __CUDA_ARCH__
+  *word = __umul64hi(h, n_words);
+#else
+  *word = (uint64_t)(((unsigned __int128)h * n_words) >> 64);
+#endif
+  uint64_t g = srw_mix64(h), m = 0;
+  for (int j = 0; j < kMigBloomK; ++j) { m |= 1ull << (g & 63u); g >>= 6; }
+  *mask = m;
+}
+

@@ -159,7 +159,7 @@ extern "C" void srw_graph_free(srw_graph *g) {
   if (!g) return;
   cudaFree(g->d_bitmap); cudaFree(g->d_wordrank); cudaFree(g->d_vids);
   cudaFree(g->d_col_app); cudaFree(g->d_w_app); cudaFree(g->d_col); cudaFree(g->d_slot); cudaFree(g->d_slotw); cudaFree(g->d_vpid);
-  cudaFree(g->d_meta); cudaFree(g->d_hash_id);
+  cudaFree(g->d_meta); cudaFree(g->d_hash_id); cudaFree(g->d_bloom);
   if (!g->rows_external) { cudaFree(g->d_off); cudaFree(g->d_hash); cudaFree(g->d_ent); }
   for (int r = 0; r < SRW_MAX_SHARDS; ++r)
     if (g->peer_ipc[r]) {

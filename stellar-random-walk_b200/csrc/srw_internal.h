@@ -58,6 +58,8 @@ struct srw_graph {
   NbrEntry *d_ent = nullptr;         // [nnz] unweighted, unsharded graphs (fold sampler)
   int32_t *d_hash_id = nullptr;      // id-space fold (SRW_FOLD_IDS): hash sets of original ids; d_ent[].x then holds ids too
   bool ent_ids = false;
+  unsigned long long *d_bloom = nullptr;   // SRW_BUILD_MIGRATE: replicated edge filter of the migrating sharded walk (migrate.cuh), 64-bit words
+  uint64_t bloom_words = 0;
   int64_t device_bytes = 0;
   mutable std::vector<int32_t> h_vids;  // lazy host copies for the query entry points
   mutable std::vector<int64_t> h_off;
