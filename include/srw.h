@@ -73,7 +73,7 @@ typedef struct srw_params {
   int32_t cmd;             /* cmd = node2vec */
   /* ---- additive ---- */
   uint64_t seed;           /* --seed (default 1): the reference has no seed at all */
-  int32_t sampler;         /* --sampler alias|fold|exact (default alias) */
+  int32_t sampler;         /* --sampler alias|fold|exact (default fold = SRW_SAMPLER_ALIAS_FOLD; runs as alias where folding does not apply) */
   int32_t u_mode;          /* SRW_U_PHILOX; SRW_U_CONST for the reference's constant-u tests */
   float u_const;
   int32_t num_gpus;        /* --gpus (default 1) */
@@ -128,7 +128,9 @@ srw_status srw_graph_partition(const srw_graph *g, int32_t vid, int32_t *pid, in
 /* ascending vertex ids (this build's emission order) */
 srw_status srw_graph_vertex_ids(const srw_graph *g, int32_t *h_out, int64_t cap);
 /* device layout for inspection/tests: row offsets [nv+1], sorted neighbour ranks [nnz], and when
- * has_alias the Vose slots {thr, own, alias_vertex, alias_index} [nnz]; any pointer may be NULL */
+ * has_alias the Vose slots {thr, own, alias_vertex, alias_index} [nnz]; any pointer may be NULL.  On a vertex-range shard
+ * the arrays are the shard's own: row_last - row_first + 1 offsets relative to its first entry, nnz_local entries; and
+ * srw_graph_neighbors answers -1 ("not on this shard", GM:118) for a vertex another shard owns. */
 srw_status srw_graph_layout(const srw_graph *g, int64_t *h_offsets, int32_t *h_col_sorted, uint32_t *h_slots4,
                             int *has_alias);
 int64_t srw_graph_device_bytes(const srw_graph *g);
@@ -257,6 +259,38 @@ srw_status srw_shard_rows_info(const srw_graph *g, int64_t *rows, int64_t *nnz, 
 srw_status srw_shard_rows_relocate(srw_graph *g, void *d_block, int64_t block_bytes);   /* block must outlive g */
 srw_status srw_shard_attach_block(srw_graph *g, int peer_rank, const void *d_block, int64_t rows, int64_t nnz,
                                   int64_t hash_buckets);
+
+/* ---- A10, migrating walkers with the exchange fused into the step kernel (csrc/migrate.cuh) -- what `bench.py --gpus N`
+ * and srw_walk with num_gpus > 1 run.  Replaces RW:91-162 (super-step loop), RW:186-192 (shuffle), URW:103-112 (routing key =
+ * current vertex).  A walker lives on owner(curr); one kernel per super-step advances every resident walker and stores each
+ * departing walker as a 32-byte tuple straight into the destination GPU's inbox (peer memory), path entries straight into the
+ * walker's home GPU's path rows.  The d(t,x)=1 test (RS:38) is answered by a replicated edge filter and verified exactly at
+ * owner(x) (t in N(x)); ~1 hop per step.  Undirected, unweighted shards built with SRW_BUILD_ALIAS | SRW_BUILD_MIGRATE;
+ * samplers alias | fold; output bit-identical to the unsharded walk for any number of shards.
+ *
+ * The caller owns the peer-visible block of every rank (srw_mig_block_bytes bytes, the same on every rank: symmetric memory
+ * between processes, plain device memory with peer access inside one process) and the barrier between super-steps:
+ *     srw_mig_begin(m, round_first, n_rounds);  barrier;
+ *     for (s = 0; ; ++s) { srw_mig_superstep(m, s, d_sent); all-reduce(d_sent) (= barrier); if (sum == 0) break; }   (RW:162)
+ *     srw_mig_finish(m, ...)
+ * A super-step with nothing to do is harmless, so the termination test need not be read back every iteration. ---- */
+typedef struct srw_mig srw_mig;
+srw_status srw_mig_block_bytes(const srw_graph *g, const srw_params *params, int64_t n_rounds, int64_t seg_cap /*0 = default*/, int64_t *bytes);
+/* d_block_peers[world]: every rank's block as addressable from this device (entry `rank` is ignored: d_block_self) */
+srw_status srw_mig_create(const srw_graph *g, const srw_params *params, int64_t n_rounds, int64_t seg_cap, void *d_block_self,
+                          void *const *d_block_peers, srw_mig **out);
+srw_status srw_mig_collect_stats(srw_mig *m, int enable);    /* instrumented kernel: proposals / tests / exact tests */
+srw_status srw_mig_begin(srw_mig *m, int64_t round_first, int64_t n_rounds /* <= the n_rounds of srw_mig_create */, void *stream);
+srw_status srw_mig_superstep(srw_mig *m, int64_t s, unsigned long long *d_sent /*device, may be NULL*/, void *stream);
+/* [0] inbox slots this rank filled in the last super-step, [1] steps, [2] proposals, [3] membership tests (filter probes),
+ * [4] exact tests, [5] tuples spilled (region full), [6] error flags (nonzero => SRW_ERR_CUDA), [7] reserved; synchronises */
+srw_status srw_mig_counters(srw_mig *m, int64_t *h_out8, void *stream);
+/* ranks -> vertex ids over this rank's home rows.  *d_paths: [home_rows * n_rounds][walk_length + 2] inside the block (valid
+ * until the next srw_mig_begin); row (round - round_first) * home_rows + v / world belongs to the walker that started at
+ * vertex rank v = rank + (row % home_rows) * world.  d_lens_out (device, n_rows int32, may be NULL) receives the lengths. */
+srw_status srw_mig_finish(srw_mig *m, int32_t **d_paths, int32_t *d_lens_out, int64_t *n_rows, int64_t *steps, void *stream);
+srw_status srw_mig_info(const srw_mig *m, int64_t *seg_cap, int64_t *spill_cap, int64_t *home_rows, int64_t *block_bytes);
+void srw_mig_free(srw_mig *m);
 
 /* ---- synthetic inputs for the benchmark; device-resident, not on the walk path ---- */
 srw_status srw_synth_rmat_device(int scale, int edge_factor, uint64_t seed, int64_t first, int64_t count,

@@ -611,7 +611,7 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
       // hashes it and appends it to the path -- so the entries can carry ORIGINAL VERTEX IDS and the walk emits ids directly:
       // the rank -> id pass over the path matrix disappears (measured at RMAT-26, profiles/r1_fold_ids_ab.jsonl: 186.8 -> 174.2 ms per round).  Costs a second, id-labelled copy
       // of the hash sets (the rank-labelled one serves the other kernels).  Ranks ascend with ids, so rows stay sorted.
-      if (g->d_ent && !sharded && g->id_min >= 0 /* -1 marks an empty hash slot */ && !(getenv("SRW_FOLD_IDS") && atoi(getenv("SRW_FOLD_IDS")) == 0)) {
+      if (g->d_ent && !sharded && !(flags & SRW_BUILD_MIGRATE) /* the migrating walk routes by rank */ && g->id_min >= 0 /* -1 marks an empty hash slot */ && !(getenv("SRW_FOLD_IDS") && atoi(getenv("SRW_FOLD_IDS")) == 0)) {
         if (cudaMalloc(&g->d_hash_id, (size_t)g->hash_buckets * 32) == cudaSuccess) {
           SRW_CUDA(cudaMemset(g->d_hash_id, 0xFF, (size_t)g->hash_buckets * 32));
           k_hash_insert_ids<<<grid(nnz), kThreads>>>(nnz, k_in, g->d_col, g->d_meta, g->d_vids, g->d_hash_id);

@@ -60,7 +60,7 @@ struct srw_mig {
   const srw_graph *g = nullptr;
   srw_params prm;
   int world = 1, rank = 0;
-  int64_t n_rounds = 0, seg_cap = 0, spill_cap = 0, home_rows = 0, home_rows_max = 0, round_first = 0;
+  int64_t n_rounds = 0 /* capacity */, n_active = 0 /* rounds of the current batch */, seg_cap = 0, spill_cap = 0, home_rows = 0, home_rows_max = 0, round_first = 0;
   int32_t stride = 0;
   MigLayout L;
   char *block = nullptr;
@@ -94,7 +94,7 @@ int64_t default_seg_cap(const srw_graph *g, int64_t n_rounds, unsigned grid) {
 unsigned mig_grid() {
   const char *e = getenv("SRW_MIG_BLOCKS");
   if (e && atoi(e) > 0) return (unsigned)atoi(e);
-  return 148 * 4;
+  return 148 * 3;     // persistent: one wave at the 3 blocks per SM the kernel's registers allow
 }
 }  // namespace
 
@@ -171,19 +171,20 @@ extern "C" srw_status srw_mig_collect_stats(srw_mig *m, int enable) {
 
 // Start a batch: rounds [round_first, round_first + n_rounds).  Counters zeroed, both inbox count vectors zeroed, home rows = [v].
 // Every rank must have finished srw_mig_begin (barrier) before any rank runs super-step 0: peers write into this block.
-extern "C" srw_status srw_mig_begin(srw_mig *m, int64_t round_first, void *stream_) {
+extern "C" srw_status srw_mig_begin(srw_mig *m, int64_t round_first, int64_t n_rounds, void *stream_) {
   SRW_TRY(srw_require_device());
-  if (!m) return SRW_ERR_ARG;
+  if (!m || n_rounds < 1 || n_rounds > m->n_rounds) { srw_set_error("srw_mig_begin: the context holds batches of 1..%lld rounds", m ? (long long)m->n_rounds : 0LL); return SRW_ERR_ARG; }
+  m->n_active = n_rounds;
   cudaStream_t stream = (cudaStream_t)stream_;
   SRW_CUDA(cudaSetDevice(m->g->device));
   m->round_first = round_first;
   SRW_CUDA(cudaMemsetAsync(m->d_scratch, 0, kScratchWords * 8, stream));
   SRW_CUDA(cudaMemsetAsync(m->block + m->L.o_cnt, 0, 2 * kMigMaxDest * 8, stream));
-  const int64_t total = m->home_rows * m->n_rounds;
+  const int64_t total = m->home_rows * m->n_active;
   if (total > 0) {
     int64_t b = (total + 255) / 256;
     if (b > 148 * 16) b = 148 * 16;
-    mig_init_paths_kernel<<<(unsigned)b, 256, 0, stream>>>(m->home_rows, m->n_rounds, m->stride, m->rank, m->world,
+    mig_init_paths_kernel<<<(unsigned)b, 256, 0, stream>>>(m->home_rows, m->n_active, m->stride, m->rank, m->world,
                                                            (int32_t *)(m->block + m->L.o_paths), m->d_lens);
   }
   SRW_CUDA(cudaGetLastError());
@@ -203,7 +204,8 @@ extern "C" srw_status srw_mig_superstep(srw_mig *m, int64_t s, unsigned long lon
   a.in_base = (const int4 *)(m->block + m->L.o_base[cur]);
   a.in_ext = (const int4 *)(m->block + m->L.o_ext[cur]);
   a.in_cnt = (const unsigned long long *)(m->block + m->L.o_cnt) + cur * kMigMaxDest;
-  a.n_seed = s == 0 ? (m->g->row_last - m->g->row_first) * m->n_rounds : 0;
+  a.n_rounds = m->n_active;
+  a.n_seed = s == 0 ? (m->g->row_last - m->g->row_first) * m->n_active : 0;
   for (int d = 0; d <= m->world; ++d) {
     char *blk = d == m->world ? m->block : m->peers[d];
     const int64_t first = d == m->world ? (int64_t)m->world * m->seg_cap : (int64_t)m->rank * m->seg_cap;
@@ -235,11 +237,11 @@ extern "C" srw_status srw_mig_counters(srw_mig *m, int64_t *h_out8, void *stream
 // End of a batch (after the super-step in which no rank sent anything): ranks -> vertex ids over this rank's home rows.
 // *d_paths is [home_rows * n_rounds][walk_length + 2] inside the block (valid until the next srw_mig_begin), row
 // (round - round_first) * home_rows + v / world for the walker that started at vertex rank v = rank + (row % home_rows) * world.
-extern "C" srw_status srw_mig_finish(srw_mig *m, int32_t **d_paths, int32_t **d_lens, int64_t *n_rows, int64_t *steps, void *stream_) {
+extern "C" srw_status srw_mig_finish(srw_mig *m, int32_t **d_paths, int32_t *d_lens_out, int64_t *n_rows, int64_t *steps, void *stream_) {
   if (!m) return SRW_ERR_ARG;
   cudaStream_t stream = (cudaStream_t)stream_;
   SRW_CUDA(cudaSetDevice(m->g->device));
-  const int64_t rows = m->home_rows * m->n_rounds;
+  const int64_t rows = m->home_rows * m->n_active;
   int32_t *paths = (int32_t *)(m->block + m->L.o_paths);
   unsigned long long *d_steps = m->base.stats + 7;
   SRW_CUDA(cudaMemsetAsync(d_steps, 0, 8, stream));
@@ -253,7 +255,7 @@ extern "C" srw_status srw_mig_finish(srw_mig *m, int32_t **d_paths, int32_t **d_
   SRW_CUDA(cudaStreamSynchronize(stream));
   SRW_CUDA(cudaGetLastError());
   if (d_paths) *d_paths = paths;
-  if (d_lens) *d_lens = m->d_lens;
+  if (d_lens_out && rows > 0) SRW_CUDA(cudaMemcpy(d_lens_out, m->d_lens, (size_t)rows * 4, cudaMemcpyDeviceToDevice));
   if (n_rows) *n_rows = rows;
   if (steps) *steps = (int64_t)h;
   return SRW_OK;

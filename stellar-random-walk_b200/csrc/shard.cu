@@ -318,7 +318,9 @@ constexpr int kCounters = 2 + 4 * SRW_MAX_SHARDS;
 
 srw_status fill_args(const srw_graph *g, const srw_params *p, int64_t round_first, int64_t n_rounds, ShardArgs *a) {
   if (!g || !p) { srw_set_error("shard call: null graph or params"); return SRW_ERR_ARG; }
-  if (p->sampler != SRW_SAMPLER_ALIAS) { srw_set_error("the sharded walk implements --sampler alias only"); return SRW_ERR_UNSUPPORTED; }
+  // SRW_SAMPLER_ALIAS_FOLD (the default of srw_params_default) runs as the classic alias sampler here, as it does wherever
+  // folding does not apply: the same distribution, the classic thresholds (the migrating walk, migrate.cu, implements the fold)
+  if (p->sampler == SRW_SAMPLER_EXACT) { srw_set_error("the sharded walk implements --sampler alias (fold runs as alias), not exact"); return SRW_ERR_UNSUPPORTED; }
   if (p->walk_length < 0 || p->walk_length > 65000) { srw_set_error("sharded walk: walkLength must be in [0, 65000]"); return SRW_ERR_ARG; }
   if (!(p->p > 0.0) || !(p->q > 0.0)) { srw_set_error("p and q must be > 0"); return SRW_ERR_ARG; }
   SRW_CUDA(cudaSetDevice(g->device));

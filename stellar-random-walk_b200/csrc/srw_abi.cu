@@ -103,8 +103,14 @@ extern "C" srw_status srw_graph_stats(const srw_graph *g, int64_t *nv, int64_t *
 extern "C" srw_status srw_graph_neighbors(const srw_graph *g, int32_t vid, int32_t *h_dst, float *h_w, int64_t cap, int64_t *n) {
   if (!g || !n) return SRW_ERR_ARG;
   SRW_TRY(host_vids(g));
-  const int64_t r = host_rank(g, vid);
+  int64_t r = host_rank(g, vid);
   if (r < 0) { *n = -1; return SRW_OK; }                       // GM:118 case None => null
+  if (g->shard_world > 1) {
+    // a vertex-range shard holds rows [row_first, row_last) only and indexes them locally: a vertex owned by another
+    // shard is "not on this shard" -- the reference's null (GM:118, the RW:121-129 case)
+    if (r < g->row_first || r >= g->row_last) { *n = -1; return SRW_OK; }
+    r -= g->row_first;
+  }
   int64_t ext[2];
   SRW_CUDA(cudaMemcpy(ext, g->d_off + r, 16, cudaMemcpyDeviceToHost));
   const int64_t deg = ext[1] - ext[0];
@@ -147,7 +153,9 @@ extern "C" srw_status srw_graph_vertex_ids(const srw_graph *g, int32_t *h_out, i
 extern "C" srw_status srw_graph_layout(const srw_graph *g, int64_t *h_off, int32_t *h_col, uint32_t *h_slots4, int *has_alias) {
   if (!g) return SRW_ERR_ARG;
   if (has_alias) *has_alias = g->has_alias ? 1 : 0;
-  if (h_off) SRW_CUDA(cudaMemcpy(h_off, g->d_off, (size_t)(g->nv + 1) * 8, cudaMemcpyDeviceToHost));
+  // on a vertex-range shard the arrays are shard-local: row_last - row_first + 1 offsets (relative to the shard's first entry)
+  const int64_t n_rows = g->shard_world > 1 ? g->row_last - g->row_first : g->nv;
+  if (h_off) SRW_CUDA(cudaMemcpy(h_off, g->d_off, (size_t)(n_rows + 1) * 8, cudaMemcpyDeviceToHost));
   if (h_col && g->nnz) SRW_CUDA(cudaMemcpy(h_col, g->d_col, (size_t)g->nnz * 4, cudaMemcpyDeviceToHost));
   if (h_slots4 && g->has_alias) SRW_CUDA(cudaMemcpy(h_slots4, g->d_slot, (size_t)g->nnz * 16, cudaMemcpyDeviceToHost));
   return SRW_OK;

@@ -17,6 +17,8 @@ import torch
 
 from . import BUILD_ALIAS, check, lib
 
+BUILD_MIGRATE = 4   # srw.h SRW_BUILD_MIGRATE: the replicated edge filter of the migrating walk
+
 MSG_BYTES = 32
 REC_BYTES = 16
 
@@ -38,6 +40,16 @@ def _bind():
     L.srw_shard_rows_info.argtypes = [vp, i64p, i64p, i64p, i64p]
     L.srw_shard_rows_relocate.argtypes = [vp, vp, C.c_int64]
     L.srw_shard_attach_block.argtypes = [vp, C.c_int, vp, C.c_int64, C.c_int64, C.c_int64]
+    L.srw_mig_block_bytes.argtypes = [vp, vp, C.c_int64, C.c_int64, i64p]
+    L.srw_mig_create.argtypes = [vp, vp, C.c_int64, C.c_int64, vp, C.POINTER(vp), C.POINTER(vp)]
+    L.srw_mig_collect_stats.argtypes = [vp, C.c_int]
+    L.srw_mig_begin.argtypes = [vp, C.c_int64, C.c_int64, vp]
+    L.srw_mig_superstep.argtypes = [vp, C.c_int64, vp, vp]
+    L.srw_mig_counters.argtypes = [vp, i64p, vp]
+    L.srw_mig_finish.argtypes = [vp, C.POINTER(vp), vp, i64p, i64p, vp]
+    L.srw_mig_info.argtypes = [vp, i64p, i64p, i64p, i64p]
+    L.srw_mig_free.argtypes = [vp]
+    L.srw_mig_free.restype = None
     assert L.srw_walker_msg_bytes() == MSG_BYTES and L.srw_path_rec_bytes() == REC_BYTES
     L._shard_bound = True
     return L
@@ -67,10 +79,11 @@ def owner_of(bounds, v):
 class Shard:
     """One rank's rows of the graph plus its walker pools (device buffers owned here)."""
 
-    def __init__(self, n_edges, d_src, d_dst, d_w, rank, world, directed=False, device=None):
+    def __init__(self, n_edges, d_src, d_dst, d_w, rank, world, directed=False, device=None, migrate=False):
         L = _bind()
         self.h = C.c_void_p()
-        check(L.srw_graph_from_device_edges_sharded(n_edges, d_src, d_dst, d_w, int(directed), BUILD_ALIAS, rank, world, C.byref(self.h)))
+        flags = BUILD_ALIAS | (BUILD_MIGRATE if migrate else 0)
+        check(L.srw_graph_from_device_edges_sharded(n_edges, d_src, d_dst, d_w, int(directed), flags, rank, world, C.byref(self.h)))
         r, w = C.c_int(), C.c_int()
         rf, rl, nl = C.c_int64(), C.c_int64(), C.c_int64()
         b = (C.c_int64 * (world + 1))()
@@ -351,3 +364,114 @@ class ShardedWalker:
 def run_sharded(shards, params, round_first=0, n_rounds=1, exchange=None, rec_cap=1 << 22, stream=None, inbox_cap=None):
     """One-shot convenience wrapper around ShardedWalker."""
     return ShardedWalker(shards, params, n_rounds, exchange, rec_cap, inbox_cap, stream).run(round_first)
+
+
+class MigrateWalker:
+    """The migrating-walker sharded walk (csrc/migrate.cuh): ONE kernel per super-step and rank advances the resident walkers
+    and stores every departing walker straight into the destination GPU's inbox over NVLink; the only collective is the
+    all-reduce of the tuple count between super-steps (barrier + the RW:162 termination test).  Two deployments:
+      * one shard per process (torchrun): blocks are torch symmetric-memory allocations, all-reduce over NCCL;
+      * every shard in this process on one device (tests): blocks are plain tensors, shards run one after another.
+    Shards must be built with migrate=True."""
+
+    def __init__(self, shards, params, n_rounds=1, group=None, seg_cap=0, stats=False, check_every=4):
+        self.L = _bind()
+        self.shards = shards
+        self.params = params
+        self.n_rounds = n_rounds
+        self.world = shards[0].world
+        self.local = len(shards) == self.world
+        self.group = group
+        self.check_every = max(1, check_every)
+        self.stride = params.walkLength + 2
+        self.cp = params.to_c()
+        L, cp = self.L, self.cp
+        nb = C.c_int64()
+        check(L.srw_mig_block_bytes(shards[0].h, C.byref(cp), n_rounds, seg_cap, C.byref(nb)))
+        self.block_bytes = nb.value
+        self.blocks, self.ctx, self._symm = [], [], None
+        if self.local:
+            for s in shards:
+                self.blocks.append(torch.empty(nb.value, dtype=torch.uint8, device=s.device))
+            ptrs = [b.data_ptr() for b in self.blocks]
+        else:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm
+            assert len(shards) == 1
+            blk = symm.empty(nb.value, dtype=torch.uint8, device=shards[0].device)
+            self._symm = symm.rendezvous(blk, group if group is not None else dist.group.WORLD)
+            self.blocks.append(blk)
+            ptrs = list(self._symm.buffer_ptrs)
+        for i, s in enumerate(shards):
+            arr = (C.c_void_p * self.world)(*[C.c_void_p(p) for p in ptrs])
+            h = C.c_void_p()
+            check(L.srw_mig_create(s.h, C.byref(cp), n_rounds, seg_cap, self.blocks[i].data_ptr(), arr, C.byref(h)))
+            if stats:
+                check(L.srw_mig_collect_stats(h, 1))
+            self.ctx.append(h)
+        dev = shards[0].device
+        self.sent = torch.zeros(len(shards), dtype=torch.int64, device=dev)
+        self.hist = torch.zeros(1 << 16, dtype=torch.int64, device=dev)
+        self.lens = [torch.empty(max(1, s.home_rows * n_rounds), dtype=torch.int32, device=s.device) for s in shards]
+
+    def free(self):
+        for h in self.ctx:
+            self.L.srw_mig_free(h)
+        self.ctx = []
+        self.blocks, self._symm = [], None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def run(self, round_first=0, n_rounds=None, max_super_steps=1 << 16):
+        """Walks rounds [round_first, round_first + n_rounds).  Returns per local shard (paths [home_rows * n_rounds,
+        walkLength + 2] int32 vertex ids -- a view into the shard's block, valid until the next run -- and lens), and a stats
+        dict: super-steps, this process's steps / proposals / filter probes / exact tests / spills."""
+        L, st = self.L, torch.cuda.current_stream().cuda_stream
+        dist = None
+        if not self.local:
+            import torch.distributed as dist
+        n_rounds = self.n_rounds if n_rounds is None else n_rounds
+        for h in self.ctx:
+            check(L.srw_mig_begin(h, round_first, n_rounds, st))
+        if dist is not None:
+            # peers store into this block from super-step 0 on: every rank must have (re)initialised its block first
+            self.sent.zero_()
+            dist.all_reduce(self.sent, group=self.group)
+        s = 0
+        while True:
+            for i, h in enumerate(self.ctx):
+                check(L.srw_mig_superstep(h, s, self.sent.data_ptr() + 8 * i, st))
+            if dist is not None:
+                dist.all_reduce(self.sent, group=self.group)       # the barrier between super-steps; sum == 0 <=> RW:162
+                self.hist[s] = self.sent[0]
+            else:
+                self.hist[s] = self.sent.sum()
+            s += 1
+            if s % self.check_every == 0 or s >= max_super_steps:
+                h_hist = self.hist[s - self.check_every if s >= self.check_every else 0:s].tolist()
+                if 0 in h_hist or s >= max_super_steps:
+                    break
+        h_all = self.hist[:s].tolist()
+        super_steps = h_all.index(0) + 1 if 0 in h_all else s
+        stats = {"super_steps": super_steps, "super_steps_launched": s, "tuples_sent_all_ranks": int(sum(h_all)), "steps": 0, "proposals": 0,
+                 "filter_probes": 0, "exact_tests": 0, "spills": 0}
+        out = []
+        for i, (sh, h) in enumerate(zip(self.shards, self.ctx)):
+            c8 = (C.c_int64 * 8)()
+            check(L.srw_mig_counters(h, c8, st))
+            p, n, steps = C.c_void_p(), C.c_int64(), C.c_int64()
+            check(L.srw_mig_finish(h, C.byref(p), self.lens[i].data_ptr(), C.byref(n), C.byref(steps), st))
+            off = p.value - self.blocks[i].data_ptr()
+            paths = self.blocks[i][off:off + n.value * self.stride * 4].view(torch.int32).view(n.value, self.stride)
+            out.append((paths, self.lens[i][:n.value]))
+            assert n.value == sh.home_rows * n_rounds
+            stats["steps"] += steps.value
+            for k, j in (("proposals", 2), ("filter_probes", 3), ("exact_tests", 4), ("spills", 5)):
+                stats[k] += c8[j]
+        if 0 not in h_all:
+            raise RuntimeError("migrating walk did not terminate within %d super-steps" % s)
+        return out, stats

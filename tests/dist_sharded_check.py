@@ -117,6 +117,28 @@ def full():
                 dist.all_reduce(t)
                 ok = ok and int(t.item()) == st.steps
             dist.barrier()
+            # migrating walkers (csrc/migrate.cuh): the step kernel stores the tuples into the peer's inbox, NCCL all-reduce as barrier
+            mshard = sh.Shard(len(s), ds.data_ptr(), dd.data_ptr(), None, rank, world, migrate=True)
+            for sampler, fold, seg_cap in (("fold", 1, 0), ("alias", 0, 0), ("fold", 1, 256)):
+                ids, offs, st = twin.walk(walk_length=30, num_walks=2, p=p, q=q, seed=23, fold=fold)
+                want = oracle_lib.paths_as_lists(ids, offs)
+                mw = sh.MigrateWalker([mshard], srw.Params(walkLength=30, numWalks=2, p=p, q=q, seed=23, sampler=sampler), 2, seg_cap=seg_cap)
+                for rep in range(2):                       # a context is reusable: second batch into the same block
+                    mout, mstats = mw.run(0)
+                    P, Ln = mout[0][0].cpu().numpy(), mout[0][1].cpu().numpy()
+                    for rnd in range(2):
+                        for k, v in enumerate(mshard.home_vertices()):
+                            row = rnd * mshard.home_rows + k
+                            if P[row, :Ln[row]].tolist() != want[rnd * twin.nv + v]:
+                                ok = False
+                    t = torch.tensor([mstats["steps"], mstats["spills"]], dtype=torch.int64, device="cuda")
+                    dist.all_reduce(t)
+                    ok = ok and int(t[0].item()) == st.steps
+                    if seg_cap:
+                        ok = ok and int(t[1].item()) > 0
+                mw.free()
+                dist.barrier()
+            mshard.free()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

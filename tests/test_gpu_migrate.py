@@ -1,0 +1,121 @@
+"""SURVEY 8(e) gate for the migrating-walker sharded walk (csrc/migrate.cuh, srw_mig_*): the emitted paths are exactly the
+CPU twin's / the single-GPU kernel's for any number of shards.  All W shards live on one device here (peer pointers are plain
+pointers, shards run one after another inside a super-step); the same kernel over real NVLink peer memory with the NCCL
+all-reduce barrier runs in test_two_ranks_nccl (self-launched torchrun, needs 2 GPUs) and in bench.py --gpus N."""
+import importlib
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+srw = importlib.import_module("stellar-random-walk_b200")
+synth = importlib.import_module("stellar-random-walk_b200.synth")
+
+
+def _shards(s, d, world):
+    import torch
+    sh = importlib.import_module("stellar-random-walk_b200.sharded")
+    ds, dd = torch.from_numpy(s).cuda(), torch.from_numpy(d).cuda()
+    return sh, [sh.Shard(len(s), ds.data_ptr(), dd.data_ptr(), None, r, world, migrate=True) for r in range(world)]
+
+
+def _assemble(shards, out, nv, rounds, stride):
+    rows = np.full((rounds * nv, stride), -1, np.int32)
+    for x, (paths, lens) in zip(shards, out):
+        P = paths.cpu().numpy()
+        assert (lens.cpu().numpy() == stride).all()
+        for rnd in range(rounds):
+            rows[rnd * nv + x.rank:(rnd + 1) * nv:x.world] = P[rnd * x.home_rows:(rnd + 1) * x.home_rows]
+    return rows
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("sampler,p,q", [("fold", 0.5, 2.0), ("fold", 0.25, 4.0), ("alias", 0.5, 2.0), ("fold", 2.0, 0.5), ("alias", 1.0, 1.0)])
+def test_migrate_equals_twin(oracle, world, sampler, p, q):
+    sh, shards = _shards(*synth.rmat_edges(10, 8, seed=42), world)
+    s, d = synth.rmat_edges(10, 8, seed=42)
+    twin = oracle.AliasGraph(oracle.Graph().load_edges(s, d, None))
+    ids, offs, st = twin.walk(walk_length=30, num_walks=3, p=p, q=q, seed=9, fold=1 if sampler == "fold" else 0)
+    mw = sh.MigrateWalker(shards, srw.Params(walkLength=30, numWalks=3, p=p, q=q, seed=9, sampler=sampler), 3, stats=True)
+    out, stats = mw.run(0)
+    rows = _assemble(shards, out, twin.nv, 3, 32)
+    assert (np.diff(offs) == 32).all()
+    assert (rows.reshape(-1) == ids).all()
+    assert stats["steps"] == st.steps
+    if world > 1:
+        assert stats["tuples_sent_all_ranks"] > 0
+    mw.free()
+
+
+@pytest.mark.parametrize("world,seg_cap,bloom_bits", [(4, 128, 16), (8, 64, 16), (4, 0, 1), (8, 64, 2)])
+def test_migrate_spill_and_weak_filter(oracle, monkeypatch, world, seg_cap, bloom_bits):
+    """Regions of a few chunks (tuples spill locally and are forwarded a super-step later) and a 1-2 bit/edge filter (most
+    tests go to the exact check at owner(x): PENDING tuples, bounces).  Same paths."""
+    monkeypatch.setenv("SRW_BLOOM_BITS", str(bloom_bits))
+    monkeypatch.setenv("SRW_MIG_BLOCKS", "8")
+    s, d = synth.rmat_edges(11, 8, seed=5)
+    sh, shards = _shards(s, d, world)
+    twin = oracle.AliasGraph(oracle.Graph().load_edges(s, d, None))
+    ids, offs, st = twin.walk(walk_length=40, num_walks=2, p=0.5, q=2.0, seed=21, fold=1)
+    mw = sh.MigrateWalker(shards, srw.Params(walkLength=40, numWalks=2, p=0.5, q=2.0, seed=21, sampler="fold"), 2, seg_cap=seg_cap, stats=True)
+    for rep in range(2):                                   # the context is reusable
+        out, stats = mw.run(0)
+        rows = _assemble(shards, out, twin.nv, 2, 42)
+        assert (rows.reshape(-1) == ids).all()
+        assert stats["steps"] == st.steps
+        if seg_cap:
+            assert stats["spills"] > 0
+        if bloom_bits <= 2:
+            assert stats["exact_tests"] > stats["filter_probes"] // 4
+    mw.free()
+
+
+def test_migrate_matches_single_gpu_kernel_and_batches():
+    """RMAT-14, 4 shards, rounds walked as two batches (round_first 0 and 2) == srw_walk_device on the unsharded graph."""
+    import torch
+    s, d = synth.rmat_edges(14, 8, seed=7)
+    sh, shards = _shards(s, d, 4)
+    ds, dd = torch.from_numpy(s).cuda(), torch.from_numpy(d).cuda()
+    g = srw.Graph.from_device_edges(len(s), ds.data_ptr(), dd.data_ptr(), None, False, srw.BUILD_ALIAS)
+    prm = srw.Params(walkLength=80, numWalks=4, p=0.5, q=2.0, seed=5, sampler="fold")
+    ref_ids, ref_offs = g.walk(prm).arrays()
+    nv = g.num_vertices
+    mw = sh.MigrateWalker(shards, prm, 2)
+    got = []
+    for first in (0, 2):
+        out, stats = mw.run(first)
+        got.append(_assemble(shards, out, nv, 2, 82).copy())
+        assert stats["steps"] == 2 * nv * 81
+        # ~1 hop per step: every accepted step to a vertex another shard owns, plus the rare exact-test round trips
+        assert stats["tuples_sent_all_ranks"] < 1.3 * stats["steps"]
+    assert (np.concatenate(got).reshape(-1) == ref_ids).all()
+    mw.free()
+
+
+def test_migrate_refuses_what_it_cannot_do():
+    import torch
+    sh = importlib.import_module("stellar-random-walk_b200.sharded")
+    s, d = synth.rmat_edges(8, 4, seed=1)
+    ds, dd = torch.from_numpy(s).cuda(), torch.from_numpy(d).cuda()
+    plain = [sh.Shard(len(s), ds.data_ptr(), dd.data_ptr(), None, r, 2) for r in range(2)]           # no edge filter
+    with pytest.raises(srw.SrwError):
+        sh.MigrateWalker(plain, srw.Params(walkLength=10, numWalks=1), 1)
+    directed = [sh.Shard(len(s), ds.data_ptr(), dd.data_ptr(), None, r, 2, directed=True, migrate=True) for r in range(2)]
+    with pytest.raises(srw.SrwError):
+        sh.MigrateWalker(directed, srw.Params(walkLength=10, numWalks=1), 1)
+
+
+def test_two_ranks_nccl():
+    """tests/dist_sharded_check.py under torchrun with one rank per GPU: the NCCL tuple exchange, peer-gather over symmetric
+    memory and the migrating walk over real peer memory, each against the CPU twin.  Needs two GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (the driver's multi-GPU tier runs it)")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29571", os.path.join(ROOT, "tests", "dist_sharded_check.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "SHARDED_DIST_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
