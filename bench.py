@@ -45,7 +45,12 @@ def parse_args():
     ap.add_argument("--p", type=float, default=0.5)
     ap.add_argument("--q", type=float, default=2.0)
     ap.add_argument("--weighted", type=int, default=0)
-    ap.add_argument("--mode", default="auto", choices=["auto", "sharded", "peer", "replicated"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "sharded", "peer", "replicated"],
+                    help="N > 1: auto = the vertex-range-sharded walk with migrating walkers (value) + the replicated-graph leg beside it "
+                         "(parity check + extra key); sharded / peer = round 1's NCCL tuple exchange / peer-gather legs; replicated = replicas only")
+    ap.add_argument("--batch-rounds", type=int, default=5, help="N > 1: rounds walked as one batch of the sharded walk")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-host-abi", action="store_true")
     ap.add_argument("--sampler", default="fold", choices=["fold", "alias"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-reps", type=int, default=2)
@@ -79,6 +84,15 @@ def log(msg):
 def workload_name(a):
     return "rmat-%d ef%d undirected %s p=%g q=%g walkLength=%d (one round = one walker per present vertex)" % (
         a.scale, a.edge_factor, "weighted" if a.weighted else "unweighted", a.p, a.q, a.walk_length)
+
+
+def host_threads():
+    """Every core this process may run on.  torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arms pass this
+    count to the oracle explicitly instead of inheriting that."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
 
 
 def mem_available_gb():
@@ -169,17 +183,17 @@ def cpu_walk_sample(oracle_lib, offsets, col, w, a, budget_s, phase=0):
     """Times the literal reference algorithm on a strided walker sample of the CSR."""
     L = oracle_lib.lib()
     nv = len(offsets) - 1
-    cfg = oracle_lib.make_cfg(walk_length=a.walk_length, num_walks=1, p=a.p, q=a.q, seed=a.seed, threads=0)
+    cfg = oracle_lib.make_cfg(walk_length=a.walk_length, num_walks=1, p=a.p, q=a.q, seed=a.seed, threads=host_threads())
     elapsed, done, chk = C.c_double(), C.c_int64(), C.c_uint64()
     fn = L.oracle_walk_csr_timed
     fn.restype = C.c_int64
     fn.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_double,
                    C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_uint64)]
     L.oracle_max_threads.restype = C.c_int
-    stride = max(1, nv // 4096)           # ~4096 sampled start vertices spread over the id range
+    stride = max(1, nv // 4096)           # ~4096 sampled start vertices spread over the vertex ranks (as many as the budget allows are walked)
     steps = fn(nv, offsets.ctypes.data, col.ctypes.data, None if w is None else w.ctypes.data, C.addressof(cfg), stride, phase % stride,
                budget_s, C.byref(elapsed), C.byref(done), C.byref(chk))
-    cores = int(L.oracle_max_threads())
+    cores = host_threads()
     return {"steps": int(steps), "elapsed_s": elapsed.value, "walkers": int(done.value), "cores": cores,
             "value": steps / max(elapsed.value, 1e-9),
             "sample": "C port of RandomSample/RandomWalk (oracle/), not Spark: %d strided start vertices of %d, %.0f s budget, "
@@ -212,22 +226,35 @@ def run_reference(a):
     L.oracle_csr_build.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.oracle_csr_build(n_ids, n_edges, src.ctypes.data, dst.ctypes.data, offsets.ctypes.data, col.ctypes.data, 0)
     del src, dst
+    # the walkers of a round are the vertices PRESENT in the edge list (RW:23, URW:81-87): compact the nominal id space to
+    # ranks, as the GPU arm does, so that the strided sample below strides over real start vertices
+    deg = np.diff(offsets)
+    present = deg > 0
+    rank_of = np.cumsum(present, dtype=np.int64) - 1
+    nv_present = int(present.sum())
+    offsets = np.ascontiguousarray(np.concatenate([offsets[:-1][present], offsets[-1:]]))
+    for lo in range(0, len(col), 1 << 27):
+        col[lo:lo + (1 << 27)] = rank_of[col[lo:lo + (1 << 27)]]
+    del deg, present, rank_of
     build_s = time.time() - t0
-    log("reference arm: CPU build %.1f s; walking" % build_s)
+    log("reference arm: CPU build %.1f s (%d present vertices); walking on %d threads" % (build_s, nv_present, host_threads()))
     # each step: a bounded sample, sized so that steps+warmup end within a few minutes
     per_step = max(2.0, min(a.cpu_budget, 150.0 / max(1, a.steps + a.warmup)))
     for k in range(a.warmup):
         cpu_walk_sample(oracle_lib, offsets, col, None, a, per_step, phase=k)
-    tot_steps, tot_s, res = 0, 0.0, None
+    tot_steps, tot_s, tot_walkers, res = 0, 0.0, 0, None
     for k in range(a.steps):
         res = cpu_walk_sample(oracle_lib, offsets, col, None, a, per_step, phase=a.warmup + k)
         tot_steps += res["steps"]
         tot_s += res["elapsed_s"]
+        tot_walkers += res["walkers"]
     v = tot_steps / max(tot_s, 1e-9)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * tot_s / max(1, a.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 weights / f64 cdf (reference arithmetic)", "data": "synthetic",
-            "config": {"workload": workload_name(a), "cpu_graph_build_s": round(build_s, 1)},
+            "config": {"workload": workload_name(a), "vertices_present": nv_present, "adjacency_entries": int(offsets[-1]), "walkers_per_step": nv_present,
+                       "cpu_graph_build_s": round(build_s, 1), "sampled_walkers_per_step": tot_walkers / max(1, a.steps),
+                       "note": "a bounded sample of the round per step: the reference algorithm is O(deg(curr) * deg(prev)) per transition"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": res["sample"]},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)

@@ -184,6 +184,9 @@ typedef struct srw_walk_info {
   int64_t probes_log2;     /* sum over membership tests of ceil(log2(deg(prev)+1)) */
 } srw_walk_info;
 srw_status srw_last_walk_info(srw_walk_info *out);
+/* name of the walk kernel (with its template arguments) this thread's last srw_walk* call launched, e.g.
+ * "walk_fold_conv_kernel<0,0,1,4,1>": lets a profile be matched to the launch it describes */
+const char *srw_last_walk_kernel(void);
 /* make the next srw_walk_device of this thread also count proposals/member tests (slower kernel) */
 srw_status srw_walk_collect_stats(int enable);
 
@@ -296,9 +299,6 @@ void srw_mig_free(srw_mig *m);
 srw_status srw_synth_rmat_device(int scale, int edge_factor, uint64_t seed, int64_t first, int64_t count,
                                  int32_t *d_src, int32_t *d_dst);
 srw_status srw_synth_weights_device(uint64_t seed, int64_t first, int64_t count, float *d_w);
-/* random 32-byte-sector gather micro-benchmark over a table of table_bytes: returns achieved
- * sectors/s and the GB/s of sector traffic (the "random-gather roofline" of the north star) */
-srw_status srw_gather_ceiling(int64_t table_bytes, int64_t gathers, double *sectors_per_s, double *gb_per_s);
 
 #ifdef __cplusplus
 }

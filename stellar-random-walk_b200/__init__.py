@@ -37,7 +37,7 @@ ABI_SYMBOLS = [
     "srw_graphmap_free", "srw_sample", "srw_second_order_weights", "srw_second_order_sample", "srw_philox4x32_10",
     "srw_walk", "srw_walk_device", "srw_last_walk_info", "srw_walk_collect_stats", "srw_paths_view", "srw_paths_counts",
     "srw_save", "srw_paths_format", "srw_paths_free", "srw_main", "srw_synth_rmat_device", "srw_synth_weights_device",
-    "srw_gather_ceiling", "srw_edges_parse_buffer_device", "srw_paths_format_device", "srw_walk_save", "srw_walk_device_async", "srw_walk_wait",
+    "srw_last_walk_kernel", "srw_edges_parse_buffer_device", "srw_paths_format_device", "srw_walk_save", "srw_walk_device_async", "srw_walk_wait",
     "srw_graph_from_device_edges_sharded", "srw_graph_shard_info", "srw_walker_msg_bytes", "srw_path_rec_bytes",
     "srw_shard_seed", "srw_shard_step", "srw_shard_apply", "srw_shard_finalize",
     "srw_shard_ipc_bytes", "srw_shard_ipc_export", "srw_shard_ipc_attach", "srw_shard_attach_local",
@@ -129,7 +129,6 @@ def lib():
     L.srw_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
     L.srw_synth_rmat_device.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_int64, vp, vp]
     L.srw_synth_weights_device.argtypes = [C.c_uint64, C.c_int64, C.c_int64, vp]
-    L.srw_gather_ceiling.argtypes = [C.c_int64, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = L
     return L
 

@@ -287,7 +287,7 @@ extern "C" int srw_main(int argc, const char *const *argv) {
 }
 
 // ------------------------------------------------------------------------------------------
-// synthetic inputs + gather ceiling (benchmark utilities)
+// synthetic inputs (benchmark utilities)
 // ------------------------------------------------------------------------------------------
 namespace {
 constexpr uint32_t kRmatTag = 0x524D4154u, kWeightTag = 0x57454947u;
@@ -318,25 +318,6 @@ __global__ void k_weights(uint32_t seed, int64_t first, int64_t count, float *w)
     w[i] = __fadd_rn(1.0f, __fdiv_rn((float)(r.x % 1000u), 1000.0f));
   }
 }
-// every thread chases `per_thread` independent random 32-byte sectors (4 in flight)
-__global__ void k_gather(const uint4 *__restrict__ table, uint64_t n_sectors2, int per_thread, uint32_t *sink) {
-  const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  uint32_t acc = 0;
-  for (int k = 0; k < per_thread; k += 8) {
-    const Philox4 r = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)k, 0x47415448u, 7u, 0u);
-    const Philox4 s = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)k, 0x47415449u, 7u, 0u);
-    const uint32_t w[8] = {r.x, r.y, r.z, r.w, s.x, s.y, s.z, s.w};
-    uint32_t v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {   // 8 independent 32-byte sectors in flight per thread
-      const uint64_t i = __umul64hi(((uint64_t)w[j] << 32) | w[(j + 1) & 7], n_sectors2);
-      v[j] = __ldg(reinterpret_cast<const uint32_t *>(table + 2 * i));
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc += v[j];
-  }
-  if (acc == 0x12345678u) *sink = acc;
-}
 }  // namespace
 
 extern "C" srw_status srw_synth_rmat_device(int scale, int edge_factor, uint64_t seed, int64_t first, int64_t count,
@@ -356,34 +337,5 @@ extern "C" srw_status srw_synth_weights_device(uint64_t seed, int64_t first, int
   if (count == 0) return SRW_OK;
   k_weights<<<148 * 8, 256>>>((uint32_t)seed, first, count, d_w);
   SRW_CUDA(cudaDeviceSynchronize());
-  return SRW_OK;
-}
-extern "C" srw_status srw_gather_ceiling(int64_t table_bytes, int64_t gathers, double *sectors_per_s, double *gb_per_s) {
-  SRW_TRY(srw_require_device());
-  if (table_bytes < 64 || gathers < 1) return SRW_ERR_ARG;
-  Dev<uint4> table; Dev<uint32_t> sink;
-  SRW_CUDA(cudaMalloc(&table.p, (size_t)table_bytes));
-  SRW_CUDA(cudaMemset(table.p, 1, (size_t)table_bytes));
-  SRW_CUDA(cudaMalloc(&sink.p, 4));
-  const int per_thread = 64;
-  const int64_t threads = (gathers + per_thread - 1) / per_thread;
-  const unsigned grid = (unsigned)((threads + 255) / 256);
-  cudaEvent_t a, b;
-  SRW_CUDA(cudaEventCreate(&a)); SRW_CUDA(cudaEventCreate(&b));
-  k_gather<<<grid, 256>>>(table.p, (uint64_t)table_bytes / 32, per_thread, sink.p);   // warm-up
-  float best = 1e30f;
-  for (int it = 0; it < 3; ++it) {
-    SRW_CUDA(cudaEventRecord(a));
-    k_gather<<<grid, 256>>>(table.p, (uint64_t)table_bytes / 32, per_thread, sink.p);
-    SRW_CUDA(cudaEventRecord(b));
-    SRW_CUDA(cudaEventSynchronize(b));
-    float ms = 0;
-    SRW_CUDA(cudaEventElapsedTime(&ms, a, b));
-    if (ms < best) best = ms;
-  }
-  cudaEventDestroy(a); cudaEventDestroy(b);
-  const double n = (double)grid * 256.0 * per_thread;
-  if (sectors_per_s) *sectors_per_s = n / (best * 1e-3);
-  if (gb_per_s) *gb_per_s = n * 32.0 / (best * 1e-3) / 1e9;
   return SRW_OK;
 }

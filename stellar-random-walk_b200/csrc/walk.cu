@@ -32,433 +32,6 @@ namespace {
 
 
 
-// alias proposal from row [off, off+deg): slot index from 64 random bits, Vose coin from r.y
-template <bool HAS_ALIAS>
-__device__ __forceinline__ int32_t propose(const WalkArgs &a, int64_t off, int64_t deg, const Philox4 &r) {
-  const uint64_t R = ((uint64_t)r.x << 32) | (uint64_t)r.w;
-  const int64_t k = (int64_t)__umul64hi(R, (uint64_t)deg);
-  if (HAS_ALIAS) {
-    const int4 raw = __ldg(reinterpret_cast<const int4 *>(a.slot + off + k));
-    return (r.y < (uint32_t)raw.x) ? raw.y : raw.z;
-  } else {
-    return __ldg(a.col + off + k);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// K6: alias sampler
-// ------------------------------------------------------------------------------------------
-template <bool HAS_ALIAS, bool STATS>
-__global__ void __launch_bounds__(256) walk_alias_kernel(WalkArgs a) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= a.n_walkers) return;
-  const uint64_t walker = a.walker_first + (uint64_t)i;
-  int32_t curr = (int32_t)(walker % (uint64_t)a.nv);
-  int32_t *path = a.paths + i * a.stride;
-  path[0] = curr;
-  int32_t len = 1;
-  int64_t off = __ldg(a.off + curr), deg = __ldg(a.off + curr + 1) - off;
-  unsigned long long n_prop = 0, n_mem = 0, n_log = 0;
-  if (deg > 0) {
-    // RW:51-66 first step: first-order draw, the proposal is the sample
-    Philox4 r = walker_rng(a.seed_lo, a.seed_hi, walker, 0u, 0u);
-    int32_t prev = curr;
-    int64_t poff = off, pdeg = deg;
-    curr = propose<HAS_ALIAS>(a, off, deg, r);
-    path[len++] = curr;
-    const uint64_t t_lo = a.t_common < a.t_far ? a.t_common : a.t_far;
-    const uint64_t t_hi = a.t_common < a.t_far ? a.t_far : a.t_common;
-    while (len != a.stride) {                                  // RW:103
-      off = __ldg(a.off + curr);
-      deg = __ldg(a.off + curr + 1) - off;
-      if (deg <= 0) break;                                     // RW:115-119 dead end
-      int32_t x;
-      if (deg == 1) {
-        x = __ldg(a.col + off);                                // single choice: any trial count accepts it
-        if (STATS) n_prop++;
-      } else {
-        for (uint32_t trial = 0;; ++trial) {
-          r = walker_rng(a.seed_lo, a.seed_hi, walker, (uint32_t)(len - 1), trial);
-          x = propose<HAS_ALIAS>(a, off, deg, r);
-          if (STATS) n_prop++;
-          const uint64_t y = r.z;
-          uint64_t t;
-          if (x == prev) t = a.t_ret;                          // RS:36  w/p
-          else if (y < t_lo) break;                            // below both bounds: accept without a test
-          else if (y >= t_hi) continue;                        // above both bounds: reject without a test
-          else {
-            if (STATS) { n_mem++; n_log += ceil_log2_p1(pdeg); }
-            t = row_contains(a.col, poff, pdeg, x) ? a.t_common : a.t_far;   // RS:38 w  |  RS:34 w/q
-          }
-          if (y < t) break;
-        }
-      }
-      prev = curr; poff = off; pdeg = deg;
-      curr = x;
-      path[len++] = x;                                         // RW:114
-    }
-  }
-  a.lens[i] = len;
-  if (STATS) {
-    atomicAdd(a.stats + 1, n_prop);
-    atomicAdd(a.stats + 2, n_mem);
-    atomicAdd(a.stats + 3, n_log);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// K6 (v2): the same sampler as a per-lane state machine.  The v1 loop nest above leaves ~5 of 32
-// lanes active (ncu: smsp__thread_inst_executed_per_inst_executed = 4.8) because rejection loops and
-// binary searches of different lengths serialise inside a warp.  Here every lane performs exactly ONE
-// dependent memory access per iteration of a single convergent loop -- a row-extent load, a proposal
-// gather or a binary-search probe, whichever its walker needs next -- so a warp keeps 32 independent
-// gathers in flight.  Decisions are the same pure functions of (seed; walker, step, trial): the
-// output is bit-identical to v1 and to the CPU twin.
-// ------------------------------------------------------------------------------------------
-
-template <bool HAS_ALIAS, bool STATS>
-__global__ void __launch_bounds__(256) walk_alias_sm_kernel(WalkArgs a) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= a.n_walkers) return;
-  const uint64_t walker = a.walker_first + (uint64_t)i;
-  int32_t curr = (int32_t)(walker % (uint64_t)a.nv), prev = -1;
-  int32_t *path = a.paths + i * a.stride;
-  path[0] = curr;
-  int32_t len = 1;
-  int64_t off = 0, poff = 0;
-  uint32_t deg = 0, pdeg = 0, trial = 0, lo = 0, hi = 0, y = 0;
-  int32_t x = 0;
-  uint64_t k = 0;              // proposal slot of the pending trial
-  uint32_t coin = 0;           // Vose coin of the pending trial
-  int state = ST_EXTENT;
-  unsigned long long n_prop = 0, n_mem = 0, n_log = 0;
-  const uint64_t t_lo = a.t_common < a.t_far ? a.t_common : a.t_far;
-  const uint64_t t_hi = a.t_common < a.t_far ? a.t_far : a.t_common;
-
-  while (state != ST_DONE) {
-    // ---- one memory access per lane ----
-    int64_t e0 = 0, e1 = 0;
-    int32_t v = 0, v_alias = 0;
-    uint32_t thr = 0xFFFFFFFFu;
-    if (state == ST_EXTENT) {
-      e0 = __ldg(a.off + curr);
-      e1 = __ldg(a.off + curr + 1);
-    } else if (state == ST_PROPOSE) {
-      if (HAS_ALIAS) {
-        const int4 raw = __ldg(reinterpret_cast<const int4 *>(a.slot + off + (int64_t)k));
-        thr = (uint32_t)raw.x; v = raw.y; v_alias = raw.z;
-      } else {
-        v = __ldg(a.col + off + (int64_t)k);
-      }
-    } else {
-      v = __ldg(a.col + poff + (int64_t)((lo + hi) >> 1));
-    }
-    // ---- consume it ----
-    int verdict = 0;           // 0 = nothing yet, 1 = accept x, 2 = reject (next trial)
-    if (state == ST_EXTENT) {
-      off = e0;
-      deg = (uint32_t)(e1 - e0);
-      if (deg == 0) { state = ST_DONE; continue; }              // RW:59-62 / RW:115-119 dead end
-      trial = 0;
-      verdict = 2;                                             // draw trial 0
-    } else if (state == ST_PROPOSE) {
-      x = (HAS_ALIAS && !(coin < thr)) ? v_alias : v;
-      if (STATS && len > 1) n_prop++;
-      if (len == 1 || deg == 1) verdict = 1;                   // first-order step (RW:57) / single choice
-      else if (x == prev) verdict = ((uint64_t)y < a.t_ret) ? 1 : 2;    // RS:36  w/p
-      else if ((uint64_t)y < t_lo) verdict = 1;                // below both bounds: accept without a test
-      else if ((uint64_t)y >= t_hi) verdict = 2;               // above both bounds: reject without a test
-      else {
-        if (STATS) { n_mem++; n_log += ceil_log2_p1(pdeg); }
-        lo = 0; hi = pdeg;
-        state = ST_SEARCH;
-      }
-    } else {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (v == x) verdict = ((uint64_t)y < a.t_common) ? 1 : 2;          // RS:38  x in N(prev): w
-      else {
-        if (v < x) lo = mid + 1; else hi = mid;
-        if (lo >= hi) verdict = ((uint64_t)y < a.t_far) ? 1 : 2;         // RS:34  not a neighbour: w/q
-      }
-    }
-    if (verdict == 1) {
-      path[len++] = x;                                         // RW:114
-      prev = curr; poff = off; pdeg = deg;
-      curr = x;
-      state = (len == a.stride) ? ST_DONE : ST_EXTENT;         // RW:103
-    } else if (verdict == 2) {
-      const Philox4 r = walker_rng(a.seed_lo, a.seed_hi, walker, (uint32_t)(len - 1), trial);
-      trial++;
-      k = __umul64hi(((uint64_t)r.x << 32) | (uint64_t)r.w, (uint64_t)deg);
-      coin = r.y;
-      y = r.z;
-      state = ST_PROPOSE;
-    }
-  }
-  a.lens[i] = len;
-  if (STATS) {
-    atomicAdd(a.stats + 1, n_prop);
-    atomicAdd(a.stats + 2, n_mem);
-    atomicAdd(a.stats + 3, n_log);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// K6 (v3): v2's state machine over packed row descriptors and per-row neighbour hash sets.
-// ncu on v2 (RMAT-24): 865 B of DRAM traffic per step, about half of it the ~10-probe binary search
-// for "is x a neighbour of prev" (RS:38).  Here that test is one 32-byte bucket probe (rows longer
-// than kHashMinDeg), and the row extent is one aligned 32-byte RowMeta load.  Same decisions, same bits.
-// ------------------------------------------------------------------------------------------
-
-template <bool HAS_ALIAS, bool STATS>
-__global__ void __launch_bounds__(256) walk_alias_hash_kernel(WalkArgs a, const RowMeta *__restrict__ meta,
-                                                              const int32_t *__restrict__ hash) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= a.n_walkers) return;
-  const uint64_t walker = a.walker_first + (uint64_t)i;
-  int32_t curr = (int32_t)(walker % (uint64_t)a.nv), prev = -1;
-  int32_t *path = a.paths + i * a.stride;
-  path[0] = curr;
-  int32_t len = 1;
-  int64_t off = 0, hoff = 0, poff = 0, phoff = 0;
-  uint32_t deg = 0, nb = 0, pdeg = 0, pnb = 0, trial = 0, lo = 0, hi = 0, y = 0, coin = 0, bkt = 0;
-  int32_t x = 0;
-  uint64_t k = 0;
-  int state = ST_EXTENT;
-  unsigned long long n_prop = 0, n_mem = 0, n_log = 0;
-  const uint64_t t_lo = a.t_common < a.t_far ? a.t_common : a.t_far;
-  const uint64_t t_hi = a.t_common < a.t_far ? a.t_far : a.t_common;
-
-  while (state != ST_DONE) {
-    // ---- one memory access per lane ----
-    int4 q0 = make_int4(0, 0, 0, 0), q1 = make_int4(0, 0, 0, 0);
-    int32_t v = 0;
-    if (state == ST_EXTENT) {
-      const int4 *m = reinterpret_cast<const int4 *>(meta + curr);
-      q0 = __ldg(m); q1 = __ldg(m + 1);
-    } else if (state == ST_PROPOSE) {
-      if (HAS_ALIAS) q0 = __ldg(reinterpret_cast<const int4 *>(a.slot + off + (int64_t)k));
-      else v = __ldg(a.col + off + (int64_t)k);
-    } else if (state == ST_HASH) {
-      const int4 *b = reinterpret_cast<const int4 *>(hash + (phoff + (int64_t)bkt) * 8);
-      q0 = __ldg(b); q1 = __ldg(b + 1);
-    } else {
-      v = __ldg(a.col + poff + (int64_t)((lo + hi) >> 1));
-    }
-    // ---- consume it ----
-    int verdict = 0;           // 1 = accept x, 2 = reject (next trial)
-    if (state == ST_EXTENT) {
-      off = ((int64_t)(uint32_t)q0.x) | ((int64_t)q0.y << 32);
-      hoff = ((int64_t)(uint32_t)q0.z) | ((int64_t)q0.w << 32);
-      deg = (uint32_t)q1.x; nb = (uint32_t)q1.y;
-      if (deg == 0) { state = ST_DONE; continue; }              // dead end (RW:59-62, RW:115-119)
-      trial = 0;
-      verdict = 2;
-    } else if (state == ST_PROPOSE) {
-      if (HAS_ALIAS) x = (coin < (uint32_t)q0.x) ? q0.y : q0.z; else x = v;
-      if (STATS && len > 1) n_prop++;
-      if (len == 1 || deg == 1) verdict = 1;                   // first-order step (RW:57) / single choice
-      else if (x == prev) verdict = ((uint64_t)y < a.t_ret) ? 1 : 2;    // RS:36  w/p
-      else if ((uint64_t)y < t_lo) verdict = 1;
-      else if ((uint64_t)y >= t_hi) verdict = 2;
-      else {
-        if (STATS) { n_mem++; n_log += ceil_log2_p1(pdeg); }
-        if (pnb) { bkt = __umulhi(srw_hash32((uint32_t)x), pnb); state = ST_HASH; }
-        else { lo = 0; hi = pdeg; state = ST_SEARCH; }
-      }
-    } else if (state == ST_HASH) {
-      const bool found = q0.x == x || q0.y == x || q0.z == x || q0.w == x || q1.x == x || q1.y == x || q1.z == x || q1.w == x;
-      if (found) verdict = ((uint64_t)y < a.t_common) ? 1 : 2;           // RS:38  x in N(prev): w
-      else if (q1.w == -1) verdict = ((uint64_t)y < a.t_far) ? 1 : 2;    // bucket not full: x is absent (RS:34 w/q)
-      else bkt = bkt + 1 == pnb ? 0 : bkt + 1;                           // full bucket: linear probing
-    } else {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (v == x) verdict = ((uint64_t)y < a.t_common) ? 1 : 2;
-      else {
-        if (v < x) lo = mid + 1; else hi = mid;
-        if (lo >= hi) verdict = ((uint64_t)y < a.t_far) ? 1 : 2;
-      }
-    }
-    if (verdict == 1) {
-      path[len++] = x;                                         // RW:114
-      prev = curr; poff = off; pdeg = deg; phoff = hoff; pnb = nb;
-      curr = x;
-      state = (len == a.stride) ? ST_DONE : ST_EXTENT;         // RW:103
-    } else if (verdict == 2) {
-      const Philox4 r = walker_rng(a.seed_lo, a.seed_hi, walker, (uint32_t)(len - 1), trial);
-      trial++;
-      k = __umul64hi(((uint64_t)r.x << 32) | (uint64_t)r.w, (uint64_t)deg);
-      coin = r.y;
-      y = r.z;
-      state = ST_PROPOSE;
-    }
-  }
-  a.lens[i] = len;
-  if (STATS) {
-    atomicAdd(a.stats + 1, n_prop);
-    atomicAdd(a.stats + 2, n_mem);
-    atomicAdd(a.stats + 3, n_log);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// K6 (v4, SRW_SAMPLER_ALIAS_FOLD): fewer memory requests per step.  ncu on v3 (RMAT-26): the kernel runs
-// at the memory system's random-request ceiling (~46 G requests/s, profiles/README.md) with 6.1 requests
-// per step: 3.7 proposals, 1 row descriptor, ~1 hash probe, 1 path write.  v4 removes most of them:
-//   * fold: for 1/p > max(1, 1/q) the return edge's excess weight (1/p - Mp) * mult is its own mixture
-//     component, picked with probability a*m / (Mp*deg + a*m) and always accepted; everything else is
-//     rejection under the envelope Mp = max(1, 1/q) instead of 1/p  (3.7 -> ~1.8 proposals per step);
-//   * the 16-byte neighbour entry carries deg/off/multiplicity of the neighbour: no row-descriptor load;
-//   * the hash set of prev is addressed from (poff, pdeg) alone;
-//   * path ids are staged in shared memory and flushed as 8-byte stores, 16 ids at a time.
-// Defined for undirected, unweighted graphs (multiplicity of prev in N(curr) == multiplicity of the edge
-// just taken); otherwise the launch falls back to v3.  CPU twin: oracle_alias_walk with cfg.fold = 1.
-// ------------------------------------------------------------------------------------------
-template <bool STATS, bool PEER, int MINB = 4>
-__global__ void __launch_bounds__(256, MINB) walk_fold_kernel(WalkArgs a, FoldArgs f, const PeerTable pt) {
-  __shared__ int32_t sbuf[kStage * 256];
-  __shared__ const NbrEntry *s_ent[SRW_MAX_SHARDS];
-  __shared__ const int32_t *s_hash[SRW_MAX_SHARDS];
-  const int tid = threadIdx.x;
-  if (PEER) {
-    if (tid < SRW_MAX_SHARDS) { s_ent[tid] = pt.ent[tid]; s_hash[tid] = pt.hash[tid]; }
-    __syncthreads();
-  }
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + tid;
-  if (i >= a.n_walkers) return;
-  const uint64_t walker = a.walker_first + (uint64_t)i;
-  int32_t curr = (int32_t)(walker % (uint64_t)a.nv), prev = -1;
-  int32_t *path = a.paths + i * a.stride;
-  const bool vec2 = ((a.stride & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.paths) & 7) == 0);
-  int32_t len = 0, staged = 0, flushed = 0;
-  auto flush = [&]() {
-    int32_t *dst = path + flushed;
-    int j = 0;
-    if (vec2) for (; j + 1 < staged; j += 2) *reinterpret_cast<int2 *>(dst + j) = make_int2(sbuf[j * 256 + tid], sbuf[(j + 1) * 256 + tid]);
-    for (; j < staged; ++j) dst[j] = sbuf[j * 256 + tid];
-    flushed += staged; staged = 0;
-  };
-  auto push = [&](int32_t v) {
-    sbuf[staged * 256 + tid] = v;
-    staged++; len++;
-    if (staged == kStage) flush();
-  };
-  push(curr);
-  int64_t off = 0, poff = 0, xoff = 0;
-  uint32_t deg = 0, pdeg = 0, m = 1, xdeg = 0, xm = 1, trial = 0, lo = 0, hi = 0, y = 0, bkt = 0, pnb = 0;
-  uint32_t cown = 0, pown = 0, xown = 0;   // PEER: shards that hold the rows of curr / prev / x
-  int32_t x = 0;
-  uint64_t k = 0;
-  double ret_lhs = 0.0, ret_rhs = 0.0;
-  int state = ST_EXTENT;      // only for the start vertex
-  unsigned long long n_prop = 0, n_mem = 0, n_log = 0;
-  const uint64_t t_lo = f.t_common < f.t_far ? f.t_common : f.t_far;
-  const uint64_t t_hi = f.t_common < f.t_far ? f.t_far : f.t_common;
-
-  while (state != ST_DONE) {
-    // ---- one memory access per lane ----
-    int4 q0 = make_int4(0, 0, 0, 0), q1 = make_int4(0, 0, 0, 0);
-    int64_t e0 = 0, e1 = 0;
-    int32_t v = 0;
-    if (state == ST_EXTENT) {
-      if (PEER) {
-        while ((int)cown + 1 < pt.world && (int64_t)curr >= pt.first[cown + 1]) cown++;
-        const int64_t *o = pt.off[cown] + ((int64_t)curr - pt.first[cown]);
-        e0 = __ldg(o); e1 = __ldg(o + 1);
-      } else {
-        e0 = __ldg(a.off + curr); e1 = __ldg(a.off + curr + 1);
-      }
-    } else if (state == ST_PROPOSE) {
-      q0 = __ldg(reinterpret_cast<const int4 *>((PEER ? s_ent[cown] : f.ent) + off + (int64_t)k));
-    } else if (state == ST_HASH) {
-      const int4 *b = reinterpret_cast<const int4 *>((PEER ? s_hash[pown] : f.hash) + (srw_hash_first(poff) + (int64_t)bkt) * 8);
-      q0 = __ldg(b); q1 = __ldg(b + 1);
-    } else {
-      v = __ldg(&(PEER ? s_ent[pown] : f.ent)[poff + (int64_t)((lo + hi) >> 1)].x);
-    }
-    // ---- consume it ----
-    int verdict = 0;           // 1 = accept entry x, 2 = reject (next trial), 3 = new step: draw trial 0, 4 = direct return
-    if (state == ST_EXTENT) {
-      off = e0; deg = (uint32_t)(e1 - e0);
-      if (deg == 0) { state = ST_DONE; continue; }              // dead end (RW:59-62)
-      verdict = 3;
-    } else if (state == ST_PROPOSE) {
-      x = q0.x; xdeg = (uint32_t)q0.y;
-      xoff = (int64_t)(uint32_t)q0.z;
-      xown = (uint32_t)q0.w & 0xFFu;
-      xm = (uint32_t)q0.w >> 8;
-      if (STATS && len > 1) n_prop++;
-      if (len == 1 || deg == 1) verdict = 1;                   // first-order step (RW:57) / single choice
-      else if (x == prev) verdict = ((uint64_t)y < f.t_ret) ? 1 : 2;   // RS:36; folded: mass Mp of Mp, t_ret = 2^32
-      else if ((uint64_t)y < t_lo) verdict = 1;
-      else if ((uint64_t)y >= t_hi) verdict = 2;
-      else {
-        if (STATS) { n_mem++; n_log += ceil_log2_p1(pdeg); }
-        pnb = srw_hash_buckets(poff, pdeg);
-        if (pnb) { bkt = __umulhi(srw_hash32((uint32_t)x), pnb); state = ST_HASH; }
-        else { lo = 0; hi = pdeg; state = ST_SEARCH; }
-      }
-    } else if (state == ST_HASH) {
-      const bool found = q0.x == x || q0.y == x || q0.z == x || q0.w == x || q1.x == x || q1.y == x || q1.z == x || q1.w == x;
-      if (found) verdict = ((uint64_t)y < f.t_common) ? 1 : 2;           // RS:38
-      else if (q1.w == -1) verdict = ((uint64_t)y < f.t_far) ? 1 : 2;    // RS:34
-      else bkt = bkt + 1 == pnb ? 0 : bkt + 1;
-    } else {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (v == x) verdict = ((uint64_t)y < f.t_common) ? 1 : 2;
-      else {
-        if (v < x) lo = mid + 1; else hi = mid;
-        if (lo >= hi) verdict = ((uint64_t)y < f.t_far) ? 1 : 2;
-      }
-    }
-    bool draw = false;
-    if (verdict == 1) {                                        // move along entry (x, xoff, xdeg, xm)
-      push(x);                                                 // RW:114
-      prev = curr; poff = off; pdeg = deg; pown = cown;
-      curr = x; off = xoff; deg = xdeg; m = xm; cown = xown;
-      verdict = 3;
-    }
-    if (verdict == 3) {                                        // a new step starts at curr
-      if (len == a.stride || deg == 0) { state = ST_DONE; continue; }   // RW:103 / RW:115-119
-      trial = 0;
-      draw = true;
-    } else if (verdict == 2) {
-      trial++;
-      draw = true;
-    }
-    while (draw) {
-      if (trial == 0 && len > 1) {                             // per step: P(return-excess component) = a*m / (Mp*deg + a*m)
-        const double t1 = __dmul_rn(f.a, (double)m), t2 = __dmul_rn(f.mp, (double)deg);
-        ret_lhs = __dadd_rn(t2, t1);
-        ret_rhs = __dmul_rn(t1, 4294967296.0);
-      }
-      const Philox4 r = walker_rng(a.seed_lo, a.seed_hi, walker, (uint32_t)(len - 1), trial);
-      if (len > 1 && __dmul_rn((double)r.y, ret_lhs) < ret_rhs) {   // return-excess component: always accepted, no memory access
-        if (STATS) n_prop++;
-        push(prev);
-        const int32_t c = curr; curr = prev; prev = c;
-        const int64_t o = off; off = poff; poff = o;
-        const uint32_t d = deg; deg = pdeg; pdeg = d;          // m unchanged: the same bundle of parallel edges
-        const uint32_t w = cown; cown = pown; pown = w;
-        if (len == a.stride) { state = ST_DONE; break; }
-        trial = 0;
-        continue;                                              // draw trial 0 of the next step
-      }
-      k = __umul64hi(((uint64_t)r.x << 32) | (uint64_t)r.w, (uint64_t)deg);
-      y = r.z;
-      state = ST_PROPOSE;
-      draw = false;
-    }
-  }
-  flush();
-  a.lens[i] = len;
-  if (STATS) {
-    atomicAdd(a.stats + 1, n_prop);
-    atomicAdd(a.stats + 2, n_mem);
-    atomicAdd(a.stats + 3, n_log);
-  }
-}
-
 // ranks -> original vertex ids, and the step count
 __global__ void finalize_paths_kernel(int64_t n_walkers, int32_t stride, const int32_t *__restrict__ vids,
                                       const int32_t *__restrict__ lens, int32_t *paths, unsigned long long *stats) {
@@ -544,6 +117,7 @@ __global__ void kat_philox_kernel(const uint32_t *ctr, const uint32_t *key, uint
 
 thread_local srw_walk_info t_info = {};
 thread_local int t_collect_stats = 0;
+thread_local const char *t_kernel = "";   // the walk kernel (with its template arguments) of this thread's last launch
 
 // Per-thread launch context, created once: no cudaMalloc / cudaFree / event creation on the call
 // path (those take driver-wide locks and serialise against other tools using the driver).
@@ -611,21 +185,16 @@ static srw_status walk_enqueue(const srw_graph *g, const srw_params *p, const Wa
   a.stats = d_stats;
   SRW_CUDA(cudaEventRecord(ev.a, l.stream));
   bool ids = false;                      // the walk kernel wrote original ids (id-space fold): no translation below
+  // ONE kernel per sampler (+ its instrumented variant).  Gathers carry L2::64B (VAR = 1): a missing 16/32-byte gather fills 64
+  // instead of 128 bytes at the same request rate (profiles/README.md).  Earlier kernel generations live in profiles/museum/.
   if (exact) {
-    const char *ex = getenv("SRW_EXACT");                                       // A/B switch (read per launch): thread | warp | cert | cert2 (default)
-    if (ex && !strcmp(ex, "thread")) walk_exact_kernel<<<(unsigned)((l.n_walkers + 127) / 128), 128, 0, l.stream>>>(a);
-    else if (ex && !strcmp(ex, "warp")) walk_exact_warp_kernel<<<(unsigned)((l.n_walkers + 7) / 8), 256, 0, l.stream>>>(a, g->d_hash);
-    else if (ex && !strcmp(ex, "cert")) walk_exact_cert_kernel<<<(unsigned)((l.n_walkers + 7) / 8), 256, 0, l.stream>>>(a, g->d_hash);
-    else walk_exact_cert2_kernel<<<(unsigned)((l.n_walkers + 7) / 8), 256, 0, l.stream>>>(a, g->d_hash);
+    t_kernel = "walk_exact_cert2_kernel";
+    walk_exact_cert2_kernel<<<(unsigned)((l.n_walkers + 7) / 8), 256, 0, l.stream>>>(a, g->d_hash);
   } else {
     const unsigned grid = (unsigned)((l.n_walkers + 255) / 256);
     const bool st = t_collect_stats != 0;
-    static const bool use_v1 = getenv("SRW_KERNEL") && !strcmp(getenv("SRW_KERNEL"), "v1");   // A/B switches
-    static const bool use_v2 = getenv("SRW_KERNEL") && !strcmp(getenv("SRW_KERNEL"), "v2");
-    static const bool use_v3 = getenv("SRW_KERNEL") && !strcmp(getenv("SRW_KERNEL"), "v3");
-    // SRW_SAMPLER_ALIAS_FOLD: undirected + unweighted + 1/p > max(1, 1/q), else the classic sampler
-    // (the CPU twin applies the same rule, oracle_alias_walk)
-    const int occ = getenv("SRW_FOLD_OCC") ? atoi(getenv("SRW_FOLD_OCC")) : 0;   // A/B (read per launch): resident blocks per SM the fold kernel is compiled for
+    // SRW_SAMPLER_ALIAS_FOLD: undirected + 1/p > max(1, 1/q), else the classic sampler (the CPU twin applies the same rule,
+    // oracle_alias_walk); unweighted graphs fold over multiplicities (walk_fold_conv_kernel), weighted ones over bundle weights
     FoldArgs f{};
     bool fold = false;
     if ((peer || p->sampler == SRW_SAMPLER_ALIAS_FOLD) && (peer || (g->d_ent && g->d_hash)) && !g->directed && !g->has_alias) {
@@ -636,94 +205,54 @@ static srw_status walk_enqueue(const srw_graph *g, const srw_params *p, const Wa
         f.a = 0.0; f.mp = 1.0; f.t_ret = a.t_ret; f.t_common = a.t_common; f.t_far = a.t_far;
       }
     }
-    // SRW_SAMPLER_ALIAS_FOLD on a weighted undirected graph: the same folding over bundle weights (walk_wfold_conv_kernel);
-    // the CPU twin applies the same rule
     FoldArgs wf{};
     const bool wfold = !peer && p->sampler == SRW_SAMPLER_ALIAS_FOLD && g->has_alias && !g->directed && g->d_slotw && g->d_meta &&
-                       g->d_hash && !use_v1 && !use_v2 && !use_v3 && srw_fold_args(p->p, p->q, true, &wf);
-    // A/B (read per launch, so one process can time every variant on one graph): SRW_FOLD=v4 runs the
-    // pre-convergence kernel; SRW_FOLD_VAR bit 0 = L2::64B loads in v5; SRW_FOLD_OCC = 5 | 6 blocks per SM
-    const bool fold_v4 = getenv("SRW_FOLD") && !strcmp(getenv("SRW_FOLD"), "v4");
-    constexpr int kFoldVarDefault = 1;   // v5 load flavour when SRW_FOLD_VAR is unset: L2::64B gathers (half the DRAM traffic at the same speed, profiles/)
-    const int fold_var = getenv("SRW_FOLD_VAR") ? atoi(getenv("SRW_FOLD_VAR")) : kFoldVarDefault;
-    ids = fold && !peer && !fold_v4 && g->ent_ids && g->d_hash_id;
-    if (g->ent_ids && fold && !peer && !ids) { /* SRW_FOLD=v4 on an id-space handle */ srw_set_error("this graph was built in id space (SRW_FOLD_IDS): only the v5 alias-fold kernel can walk its neighbour entries"); return SRW_ERR_UNSUPPORTED; }
-    if ((peer || fold) && !fold_v4) {
+                       g->d_hash && srw_fold_args(p->p, p->q, true, &wf);
+    ids = fold && !peer && g->ent_ids && g->d_hash_id;
+    if (g->ent_ids && !ids && !g->has_alias && g->d_ent) {
+      // the neighbour entries of this handle carry original ids: only the id-space fold kernel may read them, and the classic
+      // kernel below does not (it reads d_col / d_hash, which stay in rank space)
+      fold = false;
+    }
+    if (peer || fold) {
       PeerTable pt{};
       if (peer) {
         pt.world = g->shard_world;
         for (int r = 0; r <= g->shard_world; ++r) pt.first[r] = g->bounds[(size_t)r];
         for (int r = 0; r < g->shard_world; ++r) { pt.off[r] = g->peer_off[r]; pt.ent[r] = g->peer_ent[r]; pt.hash[r] = g->peer_hash[r]; }
-      }
-      const bool v64 = (fold_var & 1) != 0;
-      if (peer) {
+        t_kernel = st ? "walk_fold_conv_kernel<1,1,0,4,0>" : "walk_fold_conv_kernel<0,1,1,4,0>";
         if (st) walk_fold_conv_kernel<true, true, 0><<<grid, 256, 0, l.stream>>>(a, f, pt);
-        else if (v64) walk_fold_conv_kernel<false, true, 1><<<grid, 256, 0, l.stream>>>(a, f, pt);
-        else walk_fold_conv_kernel<false, true, 0><<<grid, 256, 0, l.stream>>>(a, f, pt);
+        else walk_fold_conv_kernel<false, true, 1><<<grid, 256, 0, l.stream>>>(a, f, pt);
+      } else if (ids) {                   // id space: entries and hash sets carry original ids, the walk emits ids (no rank -> id pass)
+        f.hash = g->d_hash_id;
+        t_kernel = st ? "walk_fold_conv_kernel<1,0,0,4,1>" : "walk_fold_conv_kernel<0,0,1,4,1>";
+        if (st) walk_fold_conv_kernel<true, false, 0, 4, true><<<grid, 256, 0, l.stream>>>(a, f, pt);
+        else walk_fold_conv_kernel<false, false, 1, 4, true><<<grid, 256, 0, l.stream>>>(a, f, pt);
       } else {
-        if (ids) {                        // id space: entries and hash sets carry original ids, the walk emits ids (no rank -> id pass)
-          f.hash = g->d_hash_id;
-          if (st) walk_fold_conv_kernel<true, false, 0, 4, true><<<grid, 256, 0, l.stream>>>(a, f, pt);
-          else if (v64) walk_fold_conv_kernel<false, false, 1, 4, true><<<grid, 256, 0, l.stream>>>(a, f, pt);
-          else walk_fold_conv_kernel<false, false, 0, 4, true><<<grid, 256, 0, l.stream>>>(a, f, pt);
-        }
-        else if (st) walk_fold_conv_kernel<true, false, 0><<<grid, 256, 0, l.stream>>>(a, f, pt);
-        else if (v64 && occ == 5) walk_fold_conv_kernel<false, false, 1, 5><<<grid, 256, 0, l.stream>>>(a, f, pt);
-        else if (v64 && occ == 6) walk_fold_conv_kernel<false, false, 1, 6><<<grid, 256, 0, l.stream>>>(a, f, pt);
-        else if (v64) walk_fold_conv_kernel<false, false, 1><<<grid, 256, 0, l.stream>>>(a, f, pt);
-        else if (occ == 5) walk_fold_conv_kernel<false, false, 0, 5><<<grid, 256, 0, l.stream>>>(a, f, pt);
-        else if (occ == 6) walk_fold_conv_kernel<false, false, 0, 6><<<grid, 256, 0, l.stream>>>(a, f, pt);
-        else walk_fold_conv_kernel<false, false, 0><<<grid, 256, 0, l.stream>>>(a, f, pt);
+        t_kernel = st ? "walk_fold_conv_kernel<1,0,0,4,0>" : "walk_fold_conv_kernel<0,0,1,4,0>";
+        if (st) walk_fold_conv_kernel<true, false, 0><<<grid, 256, 0, l.stream>>>(a, f, pt);
+        else walk_fold_conv_kernel<false, false, 1><<<grid, 256, 0, l.stream>>>(a, f, pt);
       }
-    } else if (peer) {
-      PeerTable pt{};
-      pt.world = g->shard_world;
-      for (int r = 0; r <= g->shard_world; ++r) pt.first[r] = g->bounds[(size_t)r];
-      for (int r = 0; r < g->shard_world; ++r) { pt.off[r] = g->peer_off[r]; pt.ent[r] = g->peer_ent[r]; pt.hash[r] = g->peer_hash[r]; }
-      if (st) walk_fold_kernel<true, true><<<grid, 256, 0, l.stream>>>(a, f, pt);
-      else if (occ == 2) walk_fold_kernel<false, true, 2><<<grid, 256, 0, l.stream>>>(a, f, pt);
-      else if (occ == 5) walk_fold_kernel<false, true, 5><<<grid, 256, 0, l.stream>>>(a, f, pt);
-      else if (occ == 6) walk_fold_kernel<false, true, 6><<<grid, 256, 0, l.stream>>>(a, f, pt);
-      else if (occ == 8) walk_fold_kernel<false, true, 8><<<grid, 256, 0, l.stream>>>(a, f, pt);
-      else walk_fold_kernel<false, true><<<grid, 256, 0, l.stream>>>(a, f, pt);
-    } else if (fold) {
-      const PeerTable pt{};
-      if (st) walk_fold_kernel<true, false><<<grid, 256, 0, l.stream>>>(a, f, pt);
-      else if (occ == 2) walk_fold_kernel<false, false, 2><<<grid, 256, 0, l.stream>>>(a, f, pt);
-      else if (occ == 5) walk_fold_kernel<false, false, 5><<<grid, 256, 0, l.stream>>>(a, f, pt);
-      else if (occ == 6) walk_fold_kernel<false, false, 6><<<grid, 256, 0, l.stream>>>(a, f, pt);
-      else if (occ == 8) walk_fold_kernel<false, false, 8><<<grid, 256, 0, l.stream>>>(a, f, pt);
-      else walk_fold_kernel<false, false><<<grid, 256, 0, l.stream>>>(a, f, pt);
     } else if (wfold) {
-      // v5, weighted alias-fold: bundle weights in 32-byte slots, row weight sums in the descriptors
-      const bool v64 = (fold_var & 1) != 0;
+      // weighted alias-fold: bundle weights in 32-byte slots, row weight sums in the descriptors
+      t_kernel = st ? "walk_wfold_conv_kernel<1,0>" : "walk_wfold_conv_kernel<0,1>";
       if (st) walk_wfold_conv_kernel<true, 0><<<grid, 256, 0, l.stream>>>(a, wf, g->d_meta, g->d_hash, g->d_slotw);
-      else if (v64) walk_wfold_conv_kernel<false, 1><<<grid, 256, 0, l.stream>>>(a, wf, g->d_meta, g->d_hash, g->d_slotw);
-      else walk_wfold_conv_kernel<false, 0><<<grid, 256, 0, l.stream>>>(a, wf, g->d_meta, g->d_hash, g->d_slotw);
-    } else if (!use_v1 && !use_v2 && !use_v3 && g->d_meta && g->d_hash) {
-      // v5: the classic alias sampler in the warp-convergent layout (walk_conv.cuh)
+      else walk_wfold_conv_kernel<false, 1><<<grid, 256, 0, l.stream>>>(a, wf, g->d_meta, g->d_hash, g->d_slotw);
+    } else {
+      // the classic alias sampler (weighted or directed graphs, or (p, q) where folding does not apply)
+      if (!g->d_meta || !g->d_hash) { srw_set_error("graph was built without SRW_BUILD_ALIAS"); return SRW_ERR_ARG; }
       const RowMeta *mt = g->d_meta;
       const int32_t *hs = g->d_hash;
-      const bool v64 = (fold_var & 1) != 0;
       if (g->has_alias) {
+        t_kernel = st ? "walk_alias_conv_kernel<1,1,0>" : "walk_alias_conv_kernel<1,0,1>";
         if (st) walk_alias_conv_kernel<true, true, 0><<<grid, 256, 0, l.stream>>>(a, mt, hs);
-        else if (v64) walk_alias_conv_kernel<true, false, 1><<<grid, 256, 0, l.stream>>>(a, mt, hs);
-        else walk_alias_conv_kernel<true, false, 0><<<grid, 256, 0, l.stream>>>(a, mt, hs);
+        else walk_alias_conv_kernel<true, false, 1><<<grid, 256, 0, l.stream>>>(a, mt, hs);
       } else {
+        t_kernel = st ? "walk_alias_conv_kernel<0,1,0>" : "walk_alias_conv_kernel<0,0,1>";
         if (st) walk_alias_conv_kernel<false, true, 0><<<grid, 256, 0, l.stream>>>(a, mt, hs);
-        else if (v64) walk_alias_conv_kernel<false, false, 1><<<grid, 256, 0, l.stream>>>(a, mt, hs);
-        else walk_alias_conv_kernel<false, false, 0><<<grid, 256, 0, l.stream>>>(a, mt, hs);
+        else walk_alias_conv_kernel<false, false, 1><<<grid, 256, 0, l.stream>>>(a, mt, hs);
       }
-    } else if (!use_v1 && !use_v2 && g->d_meta) {
-      const RowMeta *mt = g->d_meta;
-      const int32_t *hs = g->d_hash;
-      if (g->has_alias) { if (st) walk_alias_hash_kernel<true, true><<<grid, 256, 0, l.stream>>>(a, mt, hs); else walk_alias_hash_kernel<true, false><<<grid, 256, 0, l.stream>>>(a, mt, hs); }
-      else              { if (st) walk_alias_hash_kernel<false, true><<<grid, 256, 0, l.stream>>>(a, mt, hs); else walk_alias_hash_kernel<false, false><<<grid, 256, 0, l.stream>>>(a, mt, hs); }
-    } else if (!use_v1) {
-      if (g->has_alias) { if (st) walk_alias_sm_kernel<true, true><<<grid, 256, 0, l.stream>>>(a); else walk_alias_sm_kernel<true, false><<<grid, 256, 0, l.stream>>>(a); }
-      else              { if (st) walk_alias_sm_kernel<false, true><<<grid, 256, 0, l.stream>>>(a); else walk_alias_sm_kernel<false, false><<<grid, 256, 0, l.stream>>>(a); }
-    } else if (g->has_alias) { if (st) walk_alias_kernel<true, true><<<grid, 256, 0, l.stream>>>(a); else walk_alias_kernel<true, false><<<grid, 256, 0, l.stream>>>(a); }
-    else              { if (st) walk_alias_kernel<false, true><<<grid, 256, 0, l.stream>>>(a); else walk_alias_kernel<false, false><<<grid, 256, 0, l.stream>>>(a); }
+    }
   }
   SRW_CUDA(cudaEventRecord(ev.b, l.stream));
   if (own_fin) SRW_CUDA(cudaStreamWaitEvent(fin, ev.b, 0));
@@ -731,7 +260,7 @@ static srw_status walk_enqueue(const srw_graph *g, const srw_params *p, const Wa
     const int64_t total = l.n_walkers * (int64_t)a.stride;
     int64_t blocks = (total + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    const bool flat = (a.stride & 1) == 0 && (reinterpret_cast<uintptr_t>(l.d_paths) & 7) == 0 && !getenv("SRW_FINALIZE_ROWS");
+    const bool flat = (a.stride & 1) == 0 && (reinterpret_cast<uintptr_t>(l.d_paths) & 7) == 0;
     if (ids) {
       count_steps_kernel<<<(unsigned)std::min<int64_t>((l.n_walkers + 255) / 256, 148 * 8), 256, 0, fin>>>(l.n_walkers, a.stride, l.d_lens, l.d_paths, d_stats);
     } else if (flat && total > 0) {
@@ -841,6 +370,8 @@ extern "C" srw_status srw_last_walk_info(srw_walk_info *out) {
   *out = t_info;
   return SRW_OK;
 }
+extern "C" const char *srw_last_walk_kernel(void) { return t_kernel; }
+
 extern "C" srw_status srw_walk_collect_stats(int enable) {
   t_collect_stats = enable;
   return SRW_OK;

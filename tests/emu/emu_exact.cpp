@@ -6,6 +6,7 @@
 #include "../../include/srw.h"
 #include "../../stellar-random-walk_b200/csrc/walk_conv.cuh"   // WalkArgs
 #include "../../stellar-random-walk_b200/csrc/walk_exact.cuh"
+#include "../../profiles/museum/exact_generations.cuh"   // kernels 0 and 1 below: superseded generations, kept as a cross-check
 
 namespace {
 void hash_insert(std::vector<int32_t> &hash, int64_t off, uint32_t deg, int32_t x) {

@@ -301,30 +301,50 @@ def test_c3_weighted_rmat_layout_and_walk(oracle):
     assert (got_offs == offs).all() and (got_ids == ids).all()
 
 
-# ---- every alias kernel generation produces the same bits (A/B switch SRW_KERNEL) ----
-def test_kernel_generations_agree(tmp_path):
-    import subprocess, sys, json
-    script = tmp_path / "run.py"
-    script.write_text('''
-import importlib, sys, hashlib
-sys.path.insert(0, %r)
-srw = importlib.import_module("stellar-random-walk_b200")
-synth = importlib.import_module("stellar-random-walk_b200.synth")
-s, d = synth.rmat_edges(12, 16, seed=3)
-out = []
-for w in (None, synth.edge_weights(len(s), seed=4)):
-    g = srw.Graph.from_edges(s, d, w)
-    ids, offs = g.walk(srw.Params(walkLength=60, numWalks=2, p=0.5, q=2.0, seed=9, sampler="alias")).arrays()
-    out.append(hashlib.sha256(ids.tobytes() + offs.tobytes()).hexdigest())
-print(",".join(out))
-''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    res = {}
-    for k in ("v1", "v2", "v3", "v5"):
-        env = dict(os.environ, SRW_KERNEL=k)
-        r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, env=env)
-        assert r.returncode == 0, r.stderr[-2000:]
-        res[k] = r.stdout.strip().splitlines()[-1]
-    assert res["v1"] == res["v2"] == res["v3"] == res["v5"], res
+# ---- the superseded kernel generations (profiles/museum/, a TEST-ONLY library) produce the bits of the product kernels ----
+def _museum():
+    """profiles/museum/libsrw_museum.so, built on demand with nvcc (present on the GPU box: same image)."""
+    import ctypes as C, subprocess
+    mdir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "museum")
+    so = os.path.join(mdir, "libsrw_museum.so")
+    srcs = [os.path.join(mdir, f) for f in ("walk_museum.cu", "alias_generations.cuh", "exact_generations.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(x) > os.path.getmtime(so) for x in srcs):
+        subprocess.check_call(["bash", os.path.join(mdir, "build.sh")])
+    srw.lib()
+    L = C.CDLL(so)
+    L.srw_museum_walk.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p]
+    L.srw_museum_walk.restype = C.c_int
+    return L
+
+
+def _museum_walk(L, g, prm, variant, n_walkers):
+    """paths as vertex ids (the museum kernels emit ranks), lens"""
+    import ctypes as C, torch
+    stride = prm.walkLength + 2
+    paths = torch.full((n_walkers, stride), -1, dtype=torch.int32, device="cuda")
+    lens = torch.zeros(n_walkers, dtype=torch.int32, device="cuda")
+    cp = prm.to_c()
+    rc = L.srw_museum_walk(g.h, C.byref(cp), variant.encode(), 0, n_walkers, paths.data_ptr(), lens.data_ptr())
+    assert rc == 0, (variant, rc)
+    vids = np.asarray(g.vertex_ids())
+    P, Ln = paths.cpu().numpy(), lens.cpu().numpy()
+    return [vids[P[i, :Ln[i]]].tolist() for i in range(n_walkers)]
+
+
+def _product_paths(g, prm):
+    ids, offs = g.walk(prm).arrays()
+    return [ids[offs[i]:offs[i + 1]].tolist() for i in range(len(offs) - 1)]
+
+
+def test_kernel_generations_agree():
+    L = _museum()
+    s, d = synth.rmat_edges(12, 16, seed=3)
+    for w in (None, synth.edge_weights(len(s), seed=4)):
+        g = srw.Graph.from_edges(s, d, w)
+        prm = srw.Params(walkLength=60, numWalks=2, p=0.5, q=2.0, seed=9, sampler="alias")
+        want = _product_paths(g, prm)
+        for v in ("alias_v1", "alias_v2", "alias_v3"):
+            assert _museum_walk(L, g, prm, v, len(want)) == want, v
 
 
 # ---- VCut input format through the native Main (--partitioned true, 3rd column = partition id) ----
@@ -420,63 +440,42 @@ def test_exact_cert_adversarial_weights(oracle, kind):
         assert (got[1] == offs).all() and (got[0] == ids).all(), (kind, p, q)
 
 
-def test_exact_kernel_generations_agree(tmp_path):
-    """thread (one walker per thread), warp (in-order fold through shuffles) and cert (certified parallel
-    search) produce the same bits on a weighted hub graph."""
-    import subprocess, sys
-    script = tmp_path / "run.py"
-    script.write_text('''
-import importlib, sys, hashlib
-sys.path.insert(0, %r)
-srw = importlib.import_module("stellar-random-walk_b200")
-synth = importlib.import_module("stellar-random-walk_b200.synth")
-out = []
-s, d = synth.rmat_edges(12, 16, seed=3)
-for w in (None, synth.edge_weights(len(s), seed=4)):
-    g = srw.Graph.from_edges(s, d, w)
-    ids, offs = g.walk(srw.Params(walkLength=20, numWalks=1, p=0.5, q=2.0, seed=9, sampler="exact")).arrays()
-    out.append(hashlib.sha256(ids.tobytes() + offs.tobytes()).hexdigest())
-s, d = synth.zipf_edges(4096, cap=3000, seed=7)
-g = srw.Graph.from_edges(s, d)
-ids, offs = g.walk(srw.Params(walkLength=20, numWalks=1, p=0.25, q=4.0, seed=2, sampler="exact")).arrays()
-out.append(hashlib.sha256(ids.tobytes() + offs.tobytes()).hexdigest())
-print(",".join(out))
-''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    res = {}
-    for k in ("thread", "warp", "cert", "cert2"):
-        env = dict(os.environ, SRW_EXACT=k)
-        r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, env=env)
-        assert r.returncode == 0, r.stderr[-2000:]
-        res[k] = r.stdout.strip().splitlines()[-1]
-    assert res["thread"] == res["warp"] == res["cert"] == res["cert2"], res
+def test_exact_kernel_generations_agree():
+    """thread (one walker per thread), warp (in-order fold through shuffles) and cert (first certified parallel search), kept in
+    profiles/museum/, produce the bits of the product's walk_exact_cert2_kernel on weighted and hub graphs."""
+    L = _museum()
+    cases = []
+    s, d = synth.rmat_edges(12, 16, seed=3)
+    for w in (None, synth.edge_weights(len(s), seed=4)):
+        cases.append((srw.Graph.from_edges(s, d, w), srw.Params(walkLength=20, numWalks=1, p=0.5, q=2.0, seed=9, sampler="exact")))
+    s, d = synth.zipf_edges(4096, cap=3000, seed=7)
+    cases.append((srw.Graph.from_edges(s, d), srw.Params(walkLength=20, numWalks=1, p=0.25, q=4.0, seed=2, sampler="exact")))
+    for g, prm in cases:
+        want = _product_paths(g, prm)
+        for v in ("exact_thread", "exact_warp", "exact_cert"):
+            assert _museum_walk(L, g, prm, v, len(want)) == want, v
 
 
-# ---- the alias-fold kernel generations and load flavours produce the same bits (switches are read per launch) ----
+# ---- the alias-fold kernel in rank space and in id space, and its pre-convergence generation (museum), produce the twin's bits ----
 def test_fold_kernel_generations_agree(oracle, monkeypatch):
+    L = _museum()
     s, d = synth.rmat_edges(13, 16, seed=3)
     monkeypatch.setenv("SRW_FOLD_IDS", "0")        # v4 walks rank-labelled entries only: build this handle in rank space
     g = srw.Graph.from_edges(s, d, None, flags=srw.BUILD_ALIAS)
     monkeypatch.delenv("SRW_FOLD_IDS")
-    g_ids = srw.Graph.from_edges(s, d, None, flags=srw.BUILD_ALIAS)       # the default: id space (v5 only)
+    g_ids = srw.Graph.from_edges(s, d, None, flags=srw.BUILD_ALIAS)       # the default: id space
     twin = oracle.AliasGraph(oracle.Graph().load_edges(s, d))
-    res = {}
     for wl in (80, 13, 0):       # even and odd strides: both alignments of the staged path stores
+        prm = srw.Params(walkLength=wl, numWalks=2, p=0.5, q=2.0, seed=9, sampler="fold")
         want_ids, want_offs, _ = twin.walk(walk_length=wl, num_walks=2, p=0.5, q=2.0, seed=9, fold=1)
-        for name, env in (("v4", {"SRW_FOLD": "v4"}), ("default", {}), ("v5-plain", {"SRW_FOLD_VAR": "0"}), ("v5-64B", {"SRW_FOLD_VAR": "1"}), ("v5-occ5", {"SRW_FOLD_OCC": "5"}),
-                          ("v5-occ6", {"SRW_FOLD_OCC": "6"}), ("v5-64B-occ6", {"SRW_FOLD_VAR": "1", "SRW_FOLD_OCC": "6"})):
-            for k in ("SRW_FOLD", "SRW_FOLD_VAR", "SRW_FOLD_OCC"):
-                monkeypatch.delenv(k, raising=False)
-            for k, v in env.items():
-                monkeypatch.setenv(k, v)
-            ids, offs = g.walk(srw.Params(walkLength=wl, numWalks=2, p=0.5, q=2.0, seed=9, sampler="fold")).arrays()
-            res[(wl, name)] = bool(np.array_equal(ids, want_ids) and np.array_equal(offs, want_offs))
-            if name != "v4":
-                ids, offs = g_ids.walk(srw.Params(walkLength=wl, numWalks=2, p=0.5, q=2.0, seed=9, sampler="fold")).arrays()
-                res[(wl, name + "/id-space")] = bool(np.array_equal(ids, want_ids) and np.array_equal(offs, want_offs))
-            else:
-                with pytest.raises(srw.SrwError):          # the id-space handle refuses the rank-space kernel instead of mixing labels
-                    g_ids.walk(srw.Params(walkLength=wl, numWalks=2, p=0.5, q=2.0, seed=9, sampler="fold"))
-    assert all(res.values()), res
+        want = oracle.paths_as_lists(want_ids, want_offs)
+        for name, h in (("rank-space", g), ("id-space", g_ids)):
+            ids, offs = h.walk(prm).arrays()
+            assert np.array_equal(ids, want_ids) and np.array_equal(offs, want_offs), (wl, name)
+        assert _museum_walk(L, g, prm, "fold_v4", len(want)) == want, wl
+        import ctypes as C
+        cp = prm.to_c()
+        assert L.srw_museum_walk(g_ids.h, C.byref(cp), b"fold_v4", 0, 1, None, None) != 0   # refuses id-labelled entries
 
 
 # ---- SRW_SAMPLER_ALIAS_FOLD on WEIGHTED undirected graphs (walk_wfold_conv_kernel): device build (row weight sums, bundle
