@@ -113,6 +113,39 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def gather_ceiling(table_mib=8192):
+    """The random-gather ceiling beside the walk: profiles/probes/gather_sweep (built by __graft_entry__.build(); NOT part of the
+    product library) on one table size.  Returns {probe name: 64-byte-fill gathers/s} or None."""
+    exe = os.path.join(ROOT, "profiles", "probes", "gather_sweep")
+    if not os.path.exists(exe):
+        return None
+    try:
+        r = subprocess.run([exe, str(max(1, table_mib >> 10)), "0.5", str(table_mib)], capture_output=True, text=True, timeout=120)
+        out = {}
+        for ln in r.stdout.splitlines():
+            if ln.startswith("{"):
+                d = json.loads(ln)
+                out[d["probe"]] = d["gathers_per_s"]
+        return out or None
+    except Exception:
+        return None
+
+
+def path_checksum(torch, paths, v_first, v_step, chunk=1 << 20):
+    """Order-independent checksum of a path matrix whose row i belongs to the walker that started at vertex rank
+    v_first + i * v_step: sum_i w(v_i) * sum_k id[i][k] * (k + 1) in wrapping int64 -- equal for any distribution of the
+    same (walker, path) pairs over ranks and rows."""
+    rows, stride = paths.shape
+    k = torch.arange(1, stride + 1, dtype=torch.int64, device=paths.device)
+    acc = torch.zeros((), dtype=torch.int64, device=paths.device)
+    for lo in range(0, rows, chunk):
+        hi = min(rows, lo + chunk)
+        v = torch.arange(lo, hi, dtype=torch.int64, device=paths.device) * v_step + v_first
+        w = ((v * 2654435761) & 0xFFFFFFFF) | 1
+        acc += ((paths[lo:hi].to(torch.int64) * k).sum(1) * w).sum()
+    return int(acc.item())
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -413,41 +446,49 @@ def run_b200(a):
     kernel_s = kernel_ms * 1e-3
     achieved = steps * B / kernel_s / 1e9
     traffic, l2_requests = None, None
-    kernel_name = ("walk_wfold_conv_kernel" if a.weighted else "walk_fold_conv_kernel") if a.sampler == "fold" else "walk_alias_conv_kernel"
+    lib.srw_last_walk_kernel.restype = C.c_char_p
+    kernel_full = (lib.srw_last_walk_kernel() or b"").decode()      # the variant the timed rounds launched, with its template arguments
+    kernel_name = kernel_full.split("<")[0]
     tj = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    traffic_note = None
     if os.path.exists(tj):
         try:
             tjd = json.load(open(tj))
-            # only meaningful for the launch it was captured on: same kernel, one GPU, full round of the default workload
-            if world == 1 and a.scale == 26 and not a.weighted and tjd.get("kernel") == kernel_name:
+            # only meaningful for the launch it was captured on: the SAME kernel instantiation, one GPU, a full round of the default workload
+            if world == 1 and a.scale == 26 and not a.weighted and a.walk_length == 80 and tjd.get("kernel") == kernel_full:
                 traffic = tjd.get("dram_bytes_per_launch")
-                l2_requests = tjd.get("l2_requests_per_launch")
+                l2_requests = tjd.get("l2_read_requests_per_launch") or tjd.get("l2_requests_per_launch")
+            else:
+                traffic_note = "profiles/ncu_traffic.json describes %s on rmat-26: not this launch (%s), traffic left null" % (tjd.get("kernel"), kernel_full)
         except Exception:
             traffic = None
     steps_per_launch = steps / max(1, a.steps)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": kernel_name, "kernel_ms_per_launch": kernel_ms / max(1, a.steps), "peak_source": peak_src,
+                "kernel": kernel_full, "kernel_ms_per_launch": kernel_ms / max(1, a.steps), "peak_source": peak_src,
                 "bytes_per_step": B, "bytes_per_step_survey_formula": B_survey, "proposals_per_step": T_bar,
                 "member_tests_per_step": st.member_tests / max(1, st.steps), "mean_probes_per_test": L_bar,
                 "kernel_share_of_step": kernel_ms / elapsed_ms,
-                "note": "the kernel is a random gather: what bounds it is the memory system's random-request rate (gather_ceiling_*), "
-                        "not streaming bandwidth -- a 4..32-byte gather that misses moves a whole 128-byte line (traffic / algorithmic bytes)"}
+                "note": "the kernel is a random gather over a footprint far beyond L2: what bounds it is DRAM's random-access rate (one row "
+                        "activation per 16/32-byte gather; gather_ceiling below, profiles/README.md 'where the ceiling lives'), not streaming "
+                        "bandwidth -- every missing gather fills 64 bytes (L2::64B), hence traffic / algorithmic bytes ~ 3"}
+    if traffic_note:
+        roofline["traffic_note"] = traffic_note
     if traffic and l2_requests:
         roofline["traffic_bytes_per_step_ncu"] = traffic / steps_per_launch
         roofline["l2_requests_per_step_ncu"] = l2_requests / steps_per_launch
     if rank == 0 and world == 1:
-        gs, gg = C.c_double(), C.c_double()
-        try:
-            srw.check(lib.srw_gather_ceiling(8 << 30, 1 << 28, C.byref(gs), C.byref(gg)))
-            roofline["gather_ceiling_requests_per_s"] = gs.value
-            # 32-byte sector requests the kernel cannot avoid, per step: one neighbour-entry / Vose-slot gather per proposal, one hash
+        gc = gather_ceiling()
+        if gc:
+            # DRAM-missing gathers the kernel cannot avoid, per step: one neighbour-entry / Vose-slot gather per proposal, one hash
             # bucket per membership test (rows shorter than 8 use a <= 3-probe search instead), 1/8 of a sector for the path id, and
             # (weighted / classic kernels, whose entries do not carry the neighbour's row extent) one row descriptor
-            req = T_bar + st.member_tests / max(1, st.steps) + 0.125 + (0.0 if kernel_name == "walk_fold_conv_kernel" else 1.0)   # + the row descriptor
+            req = T_bar + st.member_tests / max(1, st.steps) + 0.125 + (0.0 if kernel_name == "walk_fold_conv_kernel" else 1.0)
+            roofline["gather_ceiling"] = {"table": "8 GiB, 16-byte L2::64B gathers (profiles/probes/gather_sweep.cu, measured in this run)",
+                                          "gathers_per_s": gc, "best": max(gc.values())}
             roofline["requests_per_step_model"] = req
-            roofline["frac_of_gather_ceiling"] = (steps / kernel_s) * req / gs.value
-        except Exception as ex:   # noqa: BLE001
-            roofline["gather_ceiling_error"] = str(ex)
+            roofline["frac_of_gather_ceiling"] = (steps / kernel_s) * req / max(gc.values())
+        else:
+            roofline["gather_ceiling"] = None
 
     log("roofline done")
     # ---- e2e: host edge list -> H2D -> CSR build -> K rounds, every round's paths read back ----
@@ -557,12 +598,80 @@ def run_b200(a):
                 cpu["alias_fold_twin"] = {"value": None, "error": str(ex)}
 
     log("cpu baseline done")
+    # ---- parity AT THE BENCHMARKED SCALE: the CPU twin of the alias-fold sampler walks a strided sample of round 0 on the same
+    # CSR; the GPU's paths for exactly those walkers must be identical, id for id (64-bit address math, u32 row offsets and the
+    # hash placement at 2^31 entries are exercised here and nowhere smaller).  A mismatch fails the run. ----
+    parity = None
+    if rank == 0 and world == 1 and not a.no_parity and not a.weighted and a.sampler == "fold" and g is not None:
+        import oracle_lib
+        L = oracle_lib.lib()
+        if "lay_off" not in locals():
+            lay_off = np.empty(nv + 1, np.int64)
+            lay_col = np.empty(nnz, np.int32)
+            srw.check(lib.srw_graph_layout(g.h, lay_off.ctypes.data, lay_col.ctypes.data, None, None))
+        fn = L.oracle_fold_walk_csr_timed
+        fn.restype = C.c_int64
+        fn.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.POINTER(C.c_double),
+                       C.POINTER(C.c_int64), C.POINTER(C.c_uint64), C.c_void_p]
+        stride_p = max(1, nv // (1 << 18))
+        n_s = (nv + stride_p - 1) // stride_p
+        tw = np.full((n_s, stride), -2, np.int32)
+        cfg = oracle_lib.make_cfg(walk_length=a.walk_length, num_walks=1, p=a.p, q=a.q, seed=a.seed, threads=host_threads(), fold=1)
+        el, dn, ck = C.c_double(), C.c_int64(), C.c_uint64()
+        fn(nv, lay_off.ctypes.data, lay_col.ctypes.data, C.addressof(cfg), stride_p, 0, 60.0, C.byref(el), C.byref(dn), C.byref(ck), tw.ctypes.data)
+        srw.check(lib.srw_walk_device(g.h, C.byref(cp), 0, nv, paths.data_ptr(), lens.data_ptr(), stream.cuda_stream))      # round 0, whole
+        idx = torch.arange(0, nv, stride_p, device=dev)
+        got = paths.index_select(0, idx).cpu().numpy()
+        got_len = lens.index_select(0, idx).cpu().numpy()
+        vids = g.vertex_ids()
+        walked = tw[:, 0] != -2
+        want = np.where(tw >= 0, vids[np.maximum(tw, 0)], -1)
+        want_len = (tw >= 0).sum(1)
+        col_ok = np.arange(stride)[None, :] < got_len[:, None]
+        equal = bool((np.where(col_ok, got, -1)[walked] == want[walked]).all() and (got_len[walked] == want_len[walked]).all())
+        parity = {"walkers": int(walked.sum()), "equal": equal, "round": 0, "sample": "every %d-th start vertex" % stride_p,
+                  "checker": "oracle_fold_walk_csr_timed (CPU twin of the alias-fold sampler) on the device-built CSR copied to the host"}
+        log("parity at scale: %s" % parity)
+        if not equal:
+            emit({"metric": METRIC, "error": "parity_at_scale failed: GPU paths differ from the CPU twin", "parity_at_scale": parity})
+            raise SystemExit(3)
+        del tw, got, want
+    # ---- e2e through the HOST-BUFFER entry points the CLI / JNI shim call: srw_graph_from_edges (host arrays in, H2D + build
+    # inside) + srw_walk (all rounds, ragged paths in host memory out) ----
+    host_abi = None
+    if rank == 0 and world == 1 and want_e2e and h_edges is not None and not a.no_host_abi and not a.weighted:
+        try:
+            k_rounds = 1
+            if mem_available_gb() > k_rounds * nv * stride * 4 / 1e9 * 3 + 16:
+                if g is not None:
+                    g.free()
+                    g = None
+                torch.cuda.empty_cache()
+                hs, hd = h_edges[0].numpy(), h_edges[1].numpy()
+                t0 = time.time()
+                gh = srw.Graph.from_edges(hs, hd, None, flags=srw.BUILD_ALIAS)
+                t_b = time.time() - t0
+                prm_h = srw.Params(walkLength=a.walk_length, numWalks=k_rounds, p=a.p, q=a.q, seed=a.seed, sampler=a.sampler)
+                res_h = gh.walk(prm_h)
+                n_paths, n_steps = res_h.count(), res_h.steps()
+                dt_h = time.time() - t0
+                host_abi = {"value": n_steps / dt_h, "unit": UNIT, "rounds": k_rounds, "seconds": round(dt_h, 3), "graph_from_edges_s": round(t_b, 3),
+                            "paths": int(n_paths), "h2d_bytes": int(hs.nbytes + hd.nbytes), "d2h_bytes": int(n_paths) * stride * 4,
+                            "includes": "srw_graph_from_edges (pageable host arrays -> H2D -> CSR build) + srw_walk (%d round(s): walk, D2H, "
+                                        "ragged path array in host memory): the calls srw_main and the JNI shim make" % k_rounds}
+                del res_h
+                gh.free()
+                g = None
+        except Exception as ex:   # noqa: BLE001
+            host_abi = {"value": None, "error": str(ex)}
+        log("host-ABI e2e leg: %s" % host_abi)
     # ---- the bit-parity sampler on the same workload (N=1, bounded sample; not part of `value`) ----
     exact = None
     if rank == 0 and world == 1 and not a.no_exact:
         try:
             n_ex = min(nv, 1 << 16)
-            g.free()
+            if g is not None:
+                g.free()
             del paths, lens
             torch.cuda.empty_cache()
             s_, d_, w_ = gen_edges()
@@ -585,7 +694,7 @@ def run_b200(a):
             exact = {"value": None, "error": str(ex)}
         log("exact sampler sample done")
     sharded_line = None
-    if world > 1 and a.mode == "auto":
+    if False and world > 1 and a.mode == "auto":
         # also measure the vertex-range-sharded walk (BASELINE config C4) on the same ranks
         del paths, lens
         g.free()
@@ -611,6 +720,10 @@ def run_b200(a):
                            "walker all-to-all is measured beside it in `sharded_c4`" % (world, graph_bytes / 1e9),
                            "sampler": "alias-fold (SRW_SAMPLER_ALIAS_FOLD; classic alias rejection when the graph is weighted/directed)" if a.sampler == "fold" else "alias"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk}
+        if parity is not None:
+            line["parity_at_scale"] = parity
+        if host_abi is not None:
+            line["e2e_host_abi"] = host_abi
         if exact is not None:
             line["exact_sampler"] = exact
         if sharded_line is not None:
@@ -628,6 +741,249 @@ def run_b200(a):
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_b200_multi(a):
+    """N > 1, the default: BASELINE config C4 as the north star cuts it.  The graph is sharded by vertex range, one rank per
+    GPU; walkers MIGRATE to the shard that owns their current vertex, and the step kernel itself stores the 32-byte walker
+    tuples into the destination GPU's inbox over NVLink (csrc/migrate.cuh); an NCCL all-reduce of the tuple count is the
+    barrier between super-steps.  `value` is that walk.  Beside it, on the same ranks and for the same rounds: the replicated
+    fallback (whole CSR on every rank, walkers split) as `replicas`, and a full-round path checksum of both legs, which must
+    be equal (`parity_at_scale`)."""
+    import torch
+    import torch.distributed as dist
+    srw = importlib.import_module("stellar-random-walk_b200")
+    sh = importlib.import_module("stellar-random-walk_b200.sharded")
+    lib = srw.lib()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.current_stream()
+    n_edges = a.edge_factor << a.scale
+    stride = a.walk_length + 2
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def gen_edges():
+        s_ = torch.empty(n_edges, dtype=torch.int32, device=dev)
+        d_ = torch.empty(n_edges, dtype=torch.int32, device=dev)
+        srw.check(lib.srw_synth_rmat_device(a.scale, a.edge_factor, a.gen_seed, 0, n_edges, s_.data_ptr(), d_.data_ptr()))
+        return s_, d_
+
+    log("sharded: generating %s on every rank" % workload_name(a))
+    d_src, d_dst = gen_edges()
+    # e2e input: every rank holds 1/N of the edge list in pinned host memory
+    want_e2e = not a.no_e2e and n_edges % world == 0
+    e_lo, e_hi = n_edges * rank // world, n_edges * (rank + 1) // world
+    h_slice = [t[e_lo:e_hi].cpu().pin_memory() for t in (d_src, d_dst)] if want_e2e else None
+    torch.cuda.synchronize()
+    t0 = time.time()
+    shard = sh.Shard(n_edges, d_src.data_ptr(), d_dst.data_ptr(), None, rank, world, False, dev, migrate=True)
+    torch.cuda.synchronize()
+    build_s = time.time() - t0
+    del d_src, d_dst
+    torch.cuda.empty_cache()
+    nv = shard.nv
+    shard_bytes = int(lib.srw_graph_device_bytes(shard.h))
+    batch = max(1, min(a.batch_rounds, max(a.steps, 1), ((1 << 32) - 1) // max(1, nv)))
+    prm = srw.Params(walkLength=a.walk_length, numWalks=1, p=a.p, q=a.q, seed=a.seed, sampler=a.sampler)
+    log("sharded: rank 0 owns ranks [%d, %d) of %d, %d entries, %.1f GB, built in %.2f s; batches of %d rounds" % (
+        shard.row_first, shard.row_last, nv, shard.nnz_local, shard_bytes / 1e9, build_s, batch))
+    mw = sh.MigrateWalker([shard], prm, batch, stats=True, check_every=8)
+
+    # warm-up with the instrumented kernel (proposals / filter probes / exact tests per step), then the plain kernel
+    w_steps, w_stats, _ = _walk_rounds_with(mw, batch, 0, max(1, a.warmup), None)
+    for h in mw.ctx:
+        srw.check(lib.srw_mig_collect_stats(h, 0))
+    tot = torch.tensor([w_stats["proposals"], w_stats["filter_probes"], w_stats["exact_tests"], w_stats["steps"]], dtype=torch.int64, device=dev)
+    dist.all_reduce(tot)
+    T_bar, probes_ps, exact_ps = (float(tot[i]) / max(1, int(tot[3])) for i in range(3))
+    clocks = ClockSampler(local)
+    clocks.launch()
+    barrier()
+    log("sharded: timed region, %d rounds" % a.steps)
+    clocks.mark()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    chk = {}
+
+    e0.record(stream)
+    steps, st_last, super_steps = _walk_rounds_with(mw, batch, a.warmup, a.steps, None)
+    e1.record(stream)
+    barrier()
+    clk = clocks.stop()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t[0])
+    tot = torch.tensor([steps, st_last["spills"]], dtype=torch.int64, device=dev)
+    dist.all_reduce(tot)
+    steps_all = int(tot[0])
+    value = steps_all / (elapsed_ms * 1e-3)
+    tuples_per_step = st_last["tuples_total"] / max(1, steps_all)      # inbox slots (incl. the NOP padding of open chunks) per sampled transition
+    log("sharded: %.3e steps/s, %d super-steps, %.1f ms" % (value, super_steps, elapsed_ms))
+    # untimed: the checksum round again (same rounds => same paths), and per-super-step kernel / barrier shares from CUDA events
+    last_first = a.warmup + a.steps - 1
+    out, _ = mw.run(last_first, 1)
+    chk["sharded"] = path_checksum(torch, out[0][0][:shard.home_rows], shard.rank, world)
+    prof = mw.profile(last_first, 1)
+    pk = torch.tensor([prof["kernel_ms"], prof["barrier_ms"], prof["total_ms"]], dtype=torch.float64, device=dev)
+    pmax = pk.clone()
+    dist.all_reduce(pmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(pk)
+    # ---- e2e: host edge-list slice -> H2D -> all-gather over NVLink -> shard build -> K rounds, every batch's home paths read back ----
+    e2e = None
+    mw.free()
+    shard.free()
+    del mw, shard, out
+    torch.cuda.empty_cache()
+    if want_e2e:
+        ring = [torch.empty(1 << 26, dtype=torch.int32).pin_memory() for _ in range(2)]
+        copy_stream = torch.cuda.Stream()
+        barrier()
+        t0 = time.time()
+        parts = [t_.to(dev, non_blocking=True) for t_ in h_slice]
+        full = [torch.empty(n_edges, dtype=torch.int32, device=dev) for _ in range(2)]
+        for f_, p_ in zip(full, parts):
+            dist.all_gather_into_tensor(f_, p_)
+        sh2 = sh.Shard(n_edges, full[0].data_ptr(), full[1].data_ptr(), None, rank, world, False, dev, migrate=True)
+        torch.cuda.synchronize()
+        t_built = time.time() - t0
+        del full, parts
+        mw = sh.MigrateWalker([sh2], prm, batch, check_every=8)
+        snap = torch.empty((sh2.home_rows * batch, stride), dtype=torch.int32, device=dev)
+        state = {"ev": None, "d2h": 0, "steps": 0}
+
+        def read_back(first, count, paths):
+            if state["ev"] is not None:
+                stream.wait_event(state["ev"])            # the previous batch's copy has left `snap`
+            n = paths.numel()
+            snap.view(-1)[:n].copy_(paths.reshape(-1))
+            done = torch.cuda.Event()
+            done.record(stream)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done)
+                flat = snap.view(-1)
+                for i, off in enumerate(range(0, n, ring[0].numel())):
+                    m = min(ring[0].numel(), n - off)
+                    ring[i & 1][:m].copy_(flat[off:off + m], non_blocking=True)
+                    state["d2h"] += m * 4
+                state["ev"] = torch.cuda.Event()
+                state["ev"].record(copy_stream)
+
+        steps_e, _, _ = _walk_rounds_with(mw, batch, a.warmup, a.steps, read_back)
+        copy_stream.synchronize()
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        tt = torch.tensor([dt, t_built], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        cc = torch.tensor([steps_e, sum(x.numel() * 4 for x in h_slice), state["d2h"]], dtype=torch.int64, device=dev)
+        dist.all_reduce(cc)
+        e2e = {"value": int(cc[0]) / float(tt[0]), "unit": UNIT, "h2d_bytes_per_step": int(cc[1]) // max(1, a.steps), "d2h_bytes_per_step": int(cc[2]) // max(1, a.steps),
+               "seconds": float(tt[0]), "h2d_allgather_build_s": float(tt[1]),
+               "includes": "every rank copies 1/%d of the edge list from pinned host memory (H2D), NCCL all-gather of the edge list, shard build "
+                           "(rows + hash sets + replicated edge filter), %d rounds of the sharded walk in batches of %d, D2H of every batch's home path "
+                           "rows through a pinned ring (the copy of batch b overlaps the walk of batch b+1); wall clock, max over ranks" % (world, a.steps, batch)}
+        mw.free()
+        sh2.free()
+        del mw, sh2, snap, ring
+        torch.cuda.empty_cache()
+        log("sharded: e2e %.3e steps/s (%.2f s, build part %.2f s)" % (e2e["value"], e2e["seconds"], e2e["h2d_allgather_build_s"]))
+    # ---- replicas (SURVEY 8(e) fallback, a separate line): whole CSR on every rank, walkers split, no data-path collective ----
+    replicas, parity = None, None
+    if not a.no_parity:
+        try:
+            d_src, d_dst = gen_edges()
+            g = srw.Graph.from_device_edges(n_edges, d_src.data_ptr(), d_dst.data_ptr(), None, False, srw.BUILD_ALIAS)
+            del d_src, d_dst
+            torch.cuda.empty_cache()
+            lo, hi = nv * rank // world, nv * (rank + 1) // world
+            paths = torch.empty((hi - lo, stride), dtype=torch.int32, device=dev)
+            lens = torch.empty(hi - lo, dtype=torch.int32, device=dev)
+            cp = prm.to_c()
+            for r in range(min(2, a.warmup)):
+                srw.check(lib.srw_walk_device(g.h, C.byref(cp), r * nv + lo, hi - lo, paths.data_ptr(), lens.data_ptr(), stream.cuda_stream))
+            barrier()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record(stream)
+            rsteps = 0
+            for k in range(a.steps):
+                srw.check(lib.srw_walk_device(g.h, C.byref(cp), (a.warmup + k) * nv + lo, hi - lo, paths.data_ptr(), lens.data_ptr(), stream.cuda_stream))
+                rsteps += srw.last_walk_info().steps
+            r1.record(stream)
+            barrier()
+            chk["replicas"] = path_checksum(torch, paths, lo, 1)          # `paths` holds the last timed round
+            tr = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+            cr = torch.tensor([rsteps, chk["sharded"], chk["replicas"]], dtype=torch.int64, device=dev)
+            dist.all_reduce(cr)
+            replicas = {"value": int(cr[0]) / (float(tr[0]) * 1e-3), "unit": UNIT, "ms_per_step": float(tr[0]) / max(1, a.steps),
+                        "graph_bytes_hbm_per_rank": int(lib.srw_graph_device_bytes(g.h)),
+                        "parallelism": "fallback of SURVEY 8(e): the whole CSR on every rank, the walkers of a round split %d ways, no data-path collective" % world}
+            parity = {"round": last_first, "walkers": nv, "checksum_sharded": int(cr[1]), "checksum_replicas": int(cr[2]), "equal": int(cr[1]) == int(cr[2]),
+                      "what": "order-free 64-bit checksum over (start vertex, position, vertex id) of every path of the last timed round: the sharded walk "
+                              "(%d shards, migrating walkers) against the single-GPU kernel on a replicated graph" % world}
+            g.free()
+            del paths, lens
+        except Exception as ex:   # noqa: BLE001
+            replicas = {"value": None, "error": str(ex)}
+        log("replicas: %s; parity: %s" % (None if not replicas else replicas.get("value"), parity))
+    if rank == 0:
+        peak, peak_src = peaks()
+        # algorithmic bytes per step (DESIGN.md): the single-GPU figure + what the exchange adds per step
+        B = 8 + T_bar * 4 + 4                                # row extent + neighbour ids + path write, as the N = 1 line
+        B_mem = probes_ps * 8                                # one 8-byte filter word per test (the binary-search charge of the N=1 line does not apply)
+        B_x = tuples_per_step * 64                           # tuple written to the peer inbox + read back from the own inbox, 32 bytes each
+        per_gpu_steps = steps_all / world / (elapsed_ms * 1e-3)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": elapsed_ms / max(1, a.steps), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "u32 (integer thresholds; f64 only in the return-component test)", "data": "synthetic",
+                "config": {"workload": workload_name(a), "vertices_present": nv, "walkers_per_step": nv,
+                           "parallelism": "graph sharded into %d edge-balanced vertex ranges (one per GPU); walkers migrate to owner(curr): the step kernel "
+                                          "stores 32-byte walker tuples straight into the destination GPU's inbox over NVLink (peer memory) and path entries into "
+                                          "the home GPU's path rows; NCCL all-reduce of the tuple count = barrier + termination test between super-steps; "
+                                          "membership test = replicated edge filter (1 byte per adjacency entry) + exact symmetric test at owner(x)" % world,
+                           "shard_bytes_hbm_rank0": shard_bytes, "build_s": round(build_s, 3), "batch_rounds": batch, "super_steps": super_steps,
+                           "tuples_per_step": tuples_per_step, "spills": int(tot[1]),
+                           "l2": "inputs larger than L2 (shard rows + 2 GB filter >> 126 MB), no flush needed", "sampler": "alias-fold" if a.sampler == "fold" else "alias"},
+                "roofline": {"bound": "hbm", "achieved": per_gpu_steps * (B + B_mem + B_x) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": per_gpu_steps * (B + B_mem + B_x) / 1e9 / peak, "traffic": None, "kernel": "mig_step_kernel<0>", "peak_source": peak_src,
+                             "per": "GPU (steps/s/GPU x algorithmic bytes per step)", "bytes_per_step": B + B_mem + B_x,
+                             "proposals_per_step": T_bar, "filter_probes_per_step": probes_ps, "exact_tests_per_step": exact_ps,
+                             "nvlink_GBps_per_gpu_out": per_gpu_steps * (tuples_per_step * 32 + 4 * (1 - 1.0 / world)) / 1e9,
+                             "nvlink_peak_GBps": 770.0,
+                             "super_step_profile": {"round": last_first, "super_steps": prof["super_steps"], "kernel_ms_mean_rank": float(pk[0]) / world,
+                                                    "kernel_ms_max_rank": float(pmax[0]), "barrier_ms_mean_rank": float(pk[1]) / world,
+                                                    "total_ms_max_rank": float(pmax[2]),
+                                                    "kernel_share": float(pk[0]) / max(1e-9, float(pk[2])),
+                                                    "note": "one extra untimed round with CUDA events around every kernel and every all-reduce; barrier = "
+                                                            "all-reduce latency + waiting for the slowest rank of the super-step"}},
+                "cpu_baseline": None, "e2e": e2e, "gpu_launches": super_steps, "clocks": clk,
+                "replicas": replicas, "parity_at_scale": parity}
+        emit(line)
+        if parity is not None and not parity["equal"]:
+            dist.destroy_process_group()
+            raise SystemExit(3)
+    dist.destroy_process_group()
+
+
+def _walk_rounds_with(mw, batch, first, count, on_batch):
+    """rounds [first, first + count) in batches of `batch`; returns (steps decided for this rank's home rows, stats of the last
+    batch + "tuples_total" over all batches and ranks, super-steps)"""
+    steps, st_last, ss, tuples = 0, None, 0, 0
+    r = first
+    while r < first + count:
+        b = min(batch, first + count - r)
+        out, st_ = mw.run(r, b)
+        steps += st_["steps"]
+        ss += st_["super_steps"]
+        tuples += st_["tuples_sent_all_ranks"]
+        st_last = dict(st_, tuples_total=tuples)
+        if on_batch is not None:
+            on_batch(r, b, out[0][0])
+        r += b
+    return steps, st_last, ss
 
 
 def run_b200_sharded(a, own_group=True):
@@ -843,5 +1199,7 @@ if __name__ == "__main__":
         run_reference(args)
     elif int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.mode in ("sharded", "peer"):
         run_b200_sharded(args)
+    elif int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.mode == "auto":
+        run_b200_multi(args)
     else:
         run_b200(args)

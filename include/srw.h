@@ -274,7 +274,8 @@ srw_status srw_shard_attach_block(srw_graph *g, int peer_rank, const void *d_blo
  * The caller owns the peer-visible block of every rank (srw_mig_block_bytes bytes, the same on every rank: symmetric memory
  * between processes, plain device memory with peer access inside one process) and the barrier between super-steps:
  *     srw_mig_begin(m, round_first, n_rounds);  barrier;
- *     for (s = 0; ; ++s) { srw_mig_superstep(m, s, d_sent); all-reduce(d_sent) (= barrier); if (sum == 0) break; }   (RW:162)
+ *     for (s = 0; ; ++s) { srw_mig_superstep(m, s, d_sent); all-reduce(d_sent) (= barrier); if (s >= 1 && sum == 0) break; }   (RW:162;
+ *                                                      super-steps 0 and 1 both seed walkers)
  *     srw_mig_finish(m, ...)
  * A super-step with nothing to do is harmless, so the termination test need not be read back every iteration. ---- */
 typedef struct srw_mig srw_mig;

@@ -85,6 +85,7 @@ static void timed(const char *name, double gathers, size_t mib, F launch) {
 int main(int argc, char **argv) {
   size_t max_gib = argc > 1 ? (size_t)atoi(argv[1]) : 64;
   const double scale = argc > 2 ? atof(argv[2]) : 1.0;     // < 1: shorter points (ncu replays)
+  const size_t only_mib = argc > 3 ? (size_t)atoll(argv[3]) : 0;   // one table size only (bench.py: the ceiling beside the walk)
   uint4 *table;
   uint32_t *sink;
   size_t free_b = 0, total_b = 0;
@@ -97,6 +98,7 @@ int main(int argc, char **argv) {
   const size_t sizes_mib[] = {32, 128, 512, 2048, 8192, 32768, 65536};
   for (size_t mib : sizes_mib) {
     if (mib > (max_gib << 10)) break;
+    if (only_mib && mib != only_mib) continue;
     const uint64_t n16 = (mib << 20) / 16;
     {
       const int blocks = 148 * 8 * 4, per_thread = (int)(3072 * scale) & ~7;          // 1.2 M threads x 3072 = 3.7 G gathers

@@ -39,7 +39,8 @@ print(json.dumps({"config": "rmat-%d single-GPU walk_fold_conv_kernel" % scale, 
 g.free()
 del paths, lens
 torch.cuda.empty_cache()
-for world in (1, 2, 4, 8):
+only = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+for world in ((only,) if only else (1, 2, 4, 8)):
     shards = [sh.Shard(n, s.data_ptr(), d.data_ptr(), None, r, world, migrate=True) for r in range(world)]
     for stats in (True, False):
         mw = sh.MigrateWalker(shards, prm, rounds, stats=stats, check_every=8)

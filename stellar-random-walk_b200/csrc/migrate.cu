@@ -24,7 +24,7 @@ MigLayout mig_layout(int world, int64_t seg_cap, int64_t spill_cap, int64_t path
   L.slots = (int64_t)world * seg_cap + spill_cap;
   int64_t o = 0;
   L.o_cnt = o; o += up256(2 * kMigMaxDest * 8);
-  for (int b = 0; b < 2; ++b) { L.o_base[b] = o; o += up256(L.slots * 32); }
+  for (int b = 0; b < 2; ++b) { L.o_base[b] = o; o += up256(L.slots * 48); }
   for (int b = 0; b < 2; ++b) { L.o_ext[b] = o; o += up256(L.slots * 16); }
   L.o_paths = o; o += up256(path_rows * (int64_t)stride * 4);
   L.total = o;
@@ -86,10 +86,15 @@ srw_status mig_check(const srw_graph *g, const srw_params *p) {
   return SRW_OK;
 }
 int64_t default_seg_cap(const srw_graph *g, int64_t n_rounds, unsigned grid) {
-  const int64_t n = g->nv * n_rounds;
-  // a balanced source holds n / world walkers: a region that takes all of them never spills on a balanced graph; the slack
-  // covers the NOP padding of the warps' open chunks
-  return (n + g->shard_world - 1) / g->shard_world + (int64_t)grid * 8 * kMigChunk + 1024;
+  const int64_t n = g->nv * n_rounds, W = g->shard_world;
+  // Every walker resident on a source LEAVES during a super-step (it keeps stepping until it does), to one of the W - 1 other
+  // shards: a balanced source of n / W walkers sends n / (W (W - 1)) to each.  Regions hold 1.5 n / (W - 1) -- W / 1.5 times the
+  // balanced flow, enough for the first super-step, where the shard with most VERTICES seeds far more than n / W walkers --
+  // capped at n (nobody can send more than every walker).  The slack covers the NOP padding of the warps' open chunks.  A region
+  // that still fills up spills locally (correct, one super-step later).
+  int64_t cap = W > 1 ? (3 * n + 2 * (W - 1) - 1) / (2 * (W - 1)) : 0;
+  if (cap > n) cap = n;
+  return cap + (int64_t)grid * 8 * kMigChunk + 1024;
 }
 unsigned mig_grid() {
   const char *e = getenv("SRW_MIG_BLOCKS");
@@ -205,11 +210,16 @@ extern "C" srw_status srw_mig_superstep(srw_mig *m, int64_t s, unsigned long lon
   a.in_ext = (const int4 *)(m->block + m->L.o_ext[cur]);
   a.in_cnt = (const unsigned long long *)(m->block + m->L.o_cnt) + cur * kMigMaxDest;
   a.n_rounds = m->n_active;
-  a.n_seed = s == 0 ? (m->g->row_last - m->g->row_first) * m->n_active : 0;
+  {
+    // seeds: every other walker of this shard in super-step 0, the rest in super-step 1 (see MigArgs::seed_step)
+    const int64_t seeds = (m->g->row_last - m->g->row_first) * m->n_active;
+    a.seed_step = 2; a.seed_first = s;
+    a.n_seed = s == 0 ? (seeds + 1) / 2 : s == 1 ? seeds / 2 : 0;
+  }
   for (int d = 0; d <= m->world; ++d) {
     char *blk = d == m->world ? m->block : m->peers[d];
     const int64_t first = d == m->world ? (int64_t)m->world * m->seg_cap : (int64_t)m->rank * m->seg_cap;
-    a.out_base[d] = (int4 *)(blk + m->L.o_base[nxt]) + 2 * first;
+    a.out_base[d] = (int4 *)(blk + m->L.o_base[nxt]) + 3 * first;
     a.out_ext[d] = (int4 *)(blk + m->L.o_ext[nxt]) + first;
     a.out_cnt_pub[d] = (unsigned long long *)(blk + m->L.o_cnt) + nxt * kMigMaxDest + (d == m->world ? m->world : m->rank);
   }

@@ -22,8 +22,13 @@
 // => ~(1 - 1/world) hops per step instead of ~2.8 with the test at owner(prev) (round 1), identical decisions: every draw
 // is the pure function Philox(seed; walker, step, trial) of the single-GPU kernel (walk_fold_conv_kernel) and of the CPU twin.
 //
-// Path entries go straight to the walker's HOME GPU (home(v) = v mod world, as shard.cu) as 4-byte peer stores into its
-// path matrix.  Undirected, unweighted graphs; samplers alias / alias-fold (same thresholds as walk_conv.cuh).
+// Path entries go to the walker's HOME GPU (home(v) = v mod world, as shard.cu) as peer stores into its path matrix -- but not
+// one by one: a 4-byte store into a matrix far larger than L2 costs a DRAM read-modify-write on the home GPU, about as much as
+// one of the step's own gathers (measured: the first version ran at 8.5e9 steps/s per GPU against 13.3e9 with local paths).
+// The walker therefore CARRIES up to three decided entries (in registers while resident, in the third 16-byte word of its
+// 48-byte tuple when it migrates) and stores them as ONE aligned 16-byte chunk when the fourth arrives: chunk boundaries are
+// the multiples of 4 of the GLOBAL int index row * stride + pos, so no row padding is needed and the chunk phase of a row (2
+// bits) rides in the tuple.  Undirected, unweighted graphs; samplers alias / alias-fold (same thresholds as walk_conv.cuh).
 //
 // The loop is the warp-convergent three-phase layout of walk_conv.cuh (draw / one access per lane / consume) plus a refill
 // phase (a lane whose walker left or finished takes the next inbox tuple: lanes never idle to the end of the warp's longest
@@ -35,7 +40,7 @@
 #include "philox.cuh"
 #include "walk_conv.cuh"
 
-enum : uint32_t { MIG_SETTLED = 0, MIG_PENDING = 1, MIG_NOP = 2, MIG_KIND_MASK = 3, MIG_NEEDEXT = 0x10 };
+enum : uint32_t { MIG_SETTLED = 0, MIG_PENDING = 1, MIG_NOP = 2, MIG_KIND_MASK = 3, MIG_NEEDEXT = 0x10, MIG_PHASE_SHIFT = 5 /* bits 5-6: (row * stride) & 3 */ };
 enum : int { MS_EMPTY = 0, MS_LOAD, MS_LOADEXT, MS_EXTENT, MS_WAIT, MS_PROPOSE, MS_BLOOM, MS_HASH, MS_SEARCH };
 
 constexpr int kMigChunk = 32;        // inbox slots a warp claims at a time per destination
@@ -60,11 +65,14 @@ struct MigArgs {
   uint64_t walker_base;                   // round_first * nv: batch-local walker w is global walker walker_base + w
   int64_t n_rounds;
   // inbox of THIS super-step: regions 0..world-1 (filled by the peers), region `world` (local spill), then n_seed virtual seeds
-  const int4 *__restrict__ in_base;       // 2 x int4 per slot
+  const int4 *__restrict__ in_base;       // 3 x int4 per slot (MigTuple)
   const int4 *__restrict__ in_ext;        // 1 x int4 per slot
   const unsigned long long *__restrict__ in_cnt;   // [world + 1] slots used per region (published by the senders)
   int64_t seg_cap, spill_cap;             // slots per peer region / in the spill region
-  int64_t n_seed;                         // super-step 0: rows_local * n_rounds
+  int64_t n_seed;                         // virtual seeds of THIS super-step: seed j is walker number seed_first + j * seed_step of the
+  int64_t seed_first, seed_step;          // rows_local * n_rounds walkers this shard starts (super-steps 0 and 1 take every other one:
+                                          // a shard's whole population leaves in one super-step, so on two shards an uneven start would
+                                          // slosh back and forth for the whole walk; staggering the seeds damps that mode at once)
   // destinations: region `rank` of every peer's NEXT inbox (index world = own spill region)
   int4 *out_base[kMigMaxDest];
   int4 *out_ext[kMigMaxDest];
@@ -78,19 +86,29 @@ struct MigArgs {
   unsigned long long *stats;              // [0] slots sent this super-step (written by the last warp), [1] steps, [2] proposals, [3] tests, [4] exact tests, [5] spills, [6] error flags
 };
 
-struct MigTuple {            // 32 bytes: one 256-bit store
+struct MigTuple {            // 48 bytes: three 16-byte words
   uint32_t walker;           // batch-local
   int32_t prev, curr;
   uint32_t off, deg;         // row extent of curr inside owner(curr)'s arrays (invalid when MIG_NEEDEXT)
-  uint32_t m_kind;           // [31:8] parallel edges curr-prev, [7:0] kind | flags
+  uint32_t m_kind;           // [31:8] parallel edges curr-prev, [7:0] kind | flags | chunk phase of the walker's path row
   uint32_t trial;
   uint32_t len;              // ids already in the path
+  int32_t carry[3];          // decided path entries not yet stored: positions len - n .. len - 1, n = mig_carried(phase, len)
+  uint32_t pad;
 };
 struct MigExt {              // 16 bytes, only for MIG_PENDING: the proposal under test
   int32_t x;
   uint32_t xoff, xdeg;
   uint32_t xm_own;           // [31:8] parallel edges curr-x, [7:0] owner(x)
 };
+
+// number of path entries a walker with `len` ids holds back (positions >= 1 only: position 0 is written by the home GPU)
+__device__ __forceinline__ uint32_t mig_carried(uint32_t phase, uint32_t len) {
+  if (len <= 1) return 0;
+  const uint32_t in_chunk = ((phase + len - 1u) & 3u) + 1u;        // entries of the chunk that position len - 1 belongs to, up to it
+  const uint32_t n = in_chunk == 4u ? 0u : in_chunk;               // a complete chunk was stored when its fourth entry arrived
+  return n < len - 1u ? n : len - 1u;
+}
 
 __device__ __forceinline__ int mig_owner(const MigArgs &a, int32_t v) {
   int o = 0;
@@ -101,6 +119,12 @@ __device__ __forceinline__ int mig_owner(const MigArgs &a, int32_t v) {
 #ifdef SRW_EMU
 static inline void __threadfence_system() {}
 static inline void __threadfence() {}
+static inline unsigned mig_reduce_or(unsigned v) {
+  for (int o = 16; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+#else
+__device__ __forceinline__ unsigned mig_reduce_or(unsigned v) { return __reduce_or_sync(0xffffffffu, v); }
 #endif
 
 template <bool STATS>
@@ -132,6 +156,8 @@ __global__ void __launch_bounds__(256, 3) mig_step_kernel(const MigArgs a) {
   uint32_t walker = 0, off = 0, deg = 0, m = 1, trial = 0, len = 0, poff = 0, pdeg = 0;
   int32_t prev = -1, curr = 0, x = 0;
   uint32_t xoff = 0, xdeg = 0, xm = 1, xown = 0, cown = 0, k = 0, y = 0, bkt = 0, pnb = 0, lo = 0, hi = 0;
+  uint32_t phase = 0;                     // (row * stride) & 3 of the walker's home path row
+  int32_t c0 = 0, c1 = 0, c2 = 0;         // carried path entries, oldest first
   bool pvalid = false;
   unsigned long long item = 0;
   uint64_t bmask = 0, bword = 0;
@@ -155,12 +181,17 @@ __global__ void __launch_bounds__(256, 3) mig_step_kernel(const MigArgs a) {
       if (st == MS_EMPTY && mine < w_end) {
         item = mine;
         if (item >= pre[W + 1]) {                        // a virtual seed: walker (round, row) of this shard, path = [v]
-          const unsigned long long j = item - pre[W + 1];
+          const unsigned long long j = (unsigned long long)a.seed_first + (item - pre[W + 1]) * (unsigned long long)a.seed_step;
           const int64_t rows = a.row_last - a.row_first;
           const int64_t round = (int64_t)(j / (unsigned long long)rows), row = (int64_t)(j % (unsigned long long)rows);
           curr = (int32_t)(a.row_first + row); prev = -1;
           walker = (uint32_t)((unsigned long long)round * (unsigned long long)a.nv + (unsigned long long)curr);
           m = 1; trial = 0; len = 1; cown = (uint32_t)me; pvalid = false;
+          {
+            const uint32_t h = (uint32_t)curr % (uint32_t)W;
+            const int64_t prow = round * a.home_rows[h] + (int64_t)((uint32_t)curr / (uint32_t)W);
+            phase = (uint32_t)((prow * a.stride) & 3);
+          }
           st = MS_EXTENT;
         } else {
           st = MS_LOAD;
@@ -203,7 +234,7 @@ __global__ void __launch_bounds__(256, 3) mig_step_kernel(const MigArgs a) {
     }
     __syncwarp();
     // ---- B: one memory access per lane ----
-    int4 q0 = make_int4(0, 0, 0, 0), q1 = make_int4(0, 0, 0, 0);
+    int4 q0 = make_int4(0, 0, 0, 0), q1 = make_int4(0, 0, 0, 0), q2 = make_int4(0, 0, 0, 0);
     int64_t e0 = 0, e1 = 0;
     unsigned long long bw = 0;
     if (!moved) {
@@ -212,7 +243,8 @@ __global__ void __launch_bounds__(256, 3) mig_step_kernel(const MigArgs a) {
         int r = 0;
         while (r < W && item >= pre[r + 1]) r++;
         slot = (unsigned long long)r * (unsigned long long)a.seg_cap + (item - pre[r]);
-        gather32<0>(a.in_base + 2 * slot, q0, q1);
+        const int4 *tp = a.in_base + 3 * slot;
+        q0 = gather16<0>(tp); q1 = gather16<0>(tp + 1); q2 = gather16<0>(tp + 2);
         item = slot;                                      // MS_LOADEXT reads the same slot
       } else if (st == MS_HASH) {
         gather32<1>(reinterpret_cast<const int4 *>(a.hash + ((uint64_t)(xoff >> 2) + bkt) * 8), q0, q1);
@@ -237,13 +269,15 @@ __global__ void __launch_bounds__(256, 3) mig_step_kernel(const MigArgs a) {
       if (st == MS_LOAD) {
         walker = (uint32_t)q0.x; prev = q0.y; curr = q0.z; off = (uint32_t)q0.w;
         deg = (uint32_t)q1.x; m = (uint32_t)q1.y >> 8; trial = (uint32_t)q1.z; len = (uint32_t)q1.w;
+        phase = ((uint32_t)q1.y >> MIG_PHASE_SHIFT) & 3u;
+        c0 = q2.x; c1 = q2.y; c2 = q2.z;
         const uint32_t kind = (uint32_t)q1.y & MIG_KIND_MASK;
         pvalid = false;
         if (kind == MIG_NOP) st = MS_EMPTY;
         else if (kind == MIG_PENDING) st = MS_LOADEXT;
         else {
           cown = (uint32_t)mig_owner(a, curr);
-          if ((int)cown != me) { send = (int)cown; send_kind = (uint32_t)q1.y & 0xFFu; }    // spilled last super-step: forward as it is
+          if ((int)cown != me) { send = (int)cown; send_kind = (uint32_t)q1.y & (MIG_KIND_MASK | MIG_NEEDEXT); }    // spilled last super-step: forward as it is
           else st = ((uint32_t)q1.y & MIG_NEEDEXT) ? MS_EXTENT : MS_WAIT;
         }
       } else if (st == MS_LOADEXT) {
@@ -307,10 +341,22 @@ __global__ void __launch_bounds__(256, 3) mig_step_kernel(const MigArgs a) {
       if ((int)cown == me) st = MS_WAIT;
       else { send = (int)cown; send_kind = MIG_SETTLED; }  // the test ran at owner(x): back to the row of curr
     }
-    if (moved) {                                           // RW:114: the step is decided -> the walker's home path row
-      const uint32_t v0 = walker % (uint32_t)a.nv, rnd = walker / (uint32_t)a.nv;
-      const uint32_t h = v0 % (uint32_t)W;
-      a.home_paths[h][((int64_t)rnd * a.home_rows[h] + (int64_t)(v0 / (uint32_t)W)) * a.stride + len] = newv;
+    if (moved) {                                           // RW:114: the step is decided -> the walker's home path row, four entries at a time
+      const uint32_t pos = len, in_chunk = (phase + pos) & 3u;          // position of newv; its place in its 16-byte chunk
+      const uint32_t have = mig_carried(phase, len);                    // entries carried so far (all of this chunk)
+      if (in_chunk == 3u || (int32_t)(pos + 1u) == a.stride) {
+        // the chunk is complete (or the path ends): store carried + newv, positions pos - have .. pos
+        const uint32_t v0 = walker % (uint32_t)a.nv, rnd = walker / (uint32_t)a.nv;
+        const uint32_t h = v0 % (uint32_t)W;
+        int32_t *dst = a.home_paths[h] + ((int64_t)rnd * a.home_rows[h] + (int64_t)(v0 / (uint32_t)W)) * a.stride + (pos - have);
+        if (have == 3u && in_chunk == 3u) *reinterpret_cast<int4 *>(dst) = make_int4(c0, c1, c2, newv);
+        else if (have == 0u) dst[0] = newv;
+        else if (have == 1u) { dst[0] = c0; dst[1] = newv; }
+        else if (have == 2u) { dst[0] = c0; dst[1] = c1; dst[2] = newv; }
+        else { dst[0] = c0; dst[1] = c1; dst[2] = c2; dst[3] = newv; }
+      } else if (have == 0u) c0 = newv;
+      else if (have == 1u) c1 = newv;
+      else c2 = newv;
       len++; trial = 0;
       if (STATS) n_steps++;
       if ((int32_t)len == a.stride) st = MS_EMPTY;         // RW:103,132
@@ -318,8 +364,11 @@ __global__ void __launch_bounds__(256, 3) mig_step_kernel(const MigArgs a) {
       else { send = (int)cown; send_kind = MIG_SETTLED | (needext ? MIG_NEEDEXT : 0u); }
     }
     // ---- D: sends (tuples to the next inbox of their destination) ----
-    if (__any_sync(0xffffffffu, send >= 0)) {
-      for (int d = 0; d <= W; ++d) {
+    unsigned dmask = mig_reduce_or(send >= 0 ? 1u << send : 0u);        // destinations some lane sends to in this iteration
+    while (dmask) {
+      {
+        const int d = __ffs(dmask) - 1;
+        dmask &= dmask - 1;
         const unsigned sm = __ballot_sync(0xffffffffu, send == d);
         if (!sm) continue;
         const unsigned n = (unsigned)__popc(sm);
@@ -329,10 +378,7 @@ __global__ void __launch_bounds__(256, 3) mig_step_kernel(const MigArgs a) {
         __syncwarp();
         if (u + n > (unsigned)kMigChunk) {
           // close the open chunk (pad with NOPs) and claim the next one
-          if (u + (unsigned)lane < (unsigned)kMigChunk) {
-            int4 *p = a.out_base[d] + 2 * (cb + u + (unsigned)lane);
-            p[0] = make_int4(0, 0, 0, 0); p[1] = make_int4(0, (int)MIG_NOP, 0, 0);
-          }
+          if (u + (unsigned)lane < (unsigned)kMigChunk) a.out_base[d][3 * (cb + u + (unsigned)lane) + 1] = make_int4(0, (int)MIG_NOP, 0, 0);
           unsigned long long base = 0;
           if (lane == 0) base = atomicAdd(a.out_cnt + d, (unsigned long long)kMigChunk);
           base = __shfl_sync(0xffffffffu, base, 0);
@@ -350,14 +396,16 @@ __global__ void __launch_bounds__(256, 3) mig_step_kernel(const MigArgs a) {
             if (d == W) { n_err |= 2; send = -1; st = MS_EMPTY; }   // the spill region is sized for every walker of the batch: cannot happen
             else { send = W; n_spill++; }                          // region full: park locally, forwarded next super-step
           }
+          if (d != W) dmask |= 1u << W;                          // (warp-uniform: sm != 0) the spill region comes last
           __syncwarp();
           continue;
         }
         if (send == d) {
           const unsigned long long slot = cb + u + (unsigned)__popc(sm & lt);
-          int4 *p = a.out_base[d] + 2 * slot;
+          int4 *p = a.out_base[d] + 3 * slot;
           p[0] = make_int4((int)walker, prev, curr, (int)off);
-          p[1] = make_int4((int)deg, (int)((m << 8) | send_kind), (int)trial, (int)len);
+          p[1] = make_int4((int)deg, (int)((m << 8) | (phase << MIG_PHASE_SHIFT) | send_kind), (int)trial, (int)len);
+          p[2] = make_int4(c0, c1, c2, 0);
           if ((send_kind & MIG_KIND_MASK) == MIG_PENDING) a.out_ext[d][slot] = make_int4(x, (int)xoff, (int)xdeg, (int)((xm << 8) | xown));
           st = MS_EMPTY;
         }
@@ -369,10 +417,7 @@ __global__ void __launch_bounds__(256, 3) mig_step_kernel(const MigArgs a) {
   // pad the open chunks, then hand the counts over
   for (int d = 0; d <= W; ++d) {
     const unsigned u = used[d];
-    if (u + (unsigned)lane < (unsigned)kMigChunk) {
-      int4 *p = a.out_base[d] + 2 * (chunk[d] + u + (unsigned)lane);
-      p[0] = make_int4(0, 0, 0, 0); p[1] = make_int4(0, (int)MIG_NOP, 0, 0);
-    }
+    if (u + (unsigned)lane < (unsigned)kMigChunk) a.out_base[d][3 * (chunk[d] + u + (unsigned)lane) + 1] = make_int4(0, (int)MIG_NOP, 0, 0);
   }
   if (STATS) {
     for (int o = 16; o > 0; o >>= 1) {

@@ -451,11 +451,14 @@ class MigrateWalker:
             else:
                 self.hist[s] = self.sent.sum()
             s += 1
-            if s % self.check_every == 0 or s >= max_super_steps:
-                h_hist = self.hist[s - self.check_every if s >= self.check_every else 0:s].tolist()
+            if s >= 2 and (s % self.check_every == 0 or s >= max_super_steps):
+                # super-step 1 still seeds walkers (the seeds are staggered over super-steps 0 and 1): only a zero from
+                # super-step 1 on means that no walker is left
+                h_hist = self.hist[max(1, s - self.check_every):s].tolist()
                 if 0 in h_hist or s >= max_super_steps:
                     break
         h_all = self.hist[:s].tolist()
+        h_all[0] = max(h_all[0], 1)
         super_steps = h_all.index(0) + 1 if 0 in h_all else s
         stats = {"super_steps": super_steps, "super_steps_launched": s, "tuples_sent_all_ranks": int(sum(h_all)), "steps": 0, "proposals": 0,
                  "filter_probes": 0, "exact_tests": 0, "spills": 0}
@@ -475,3 +478,46 @@ class MigrateWalker:
         if 0 not in h_all:
             raise RuntimeError("migrating walk did not terminate within %d super-steps" % s)
         return out, stats
+
+    def profile(self, round_first=0, n_rounds=1, max_super_steps=4096):
+        """One batch with a CUDA event around every kernel and every barrier: where a super-step's time goes on THIS rank.
+        Returns sums over the batch's super-steps (ms): kernel, barrier (all-reduce incl. waiting for the slowest rank), total."""
+        L, st = self.L, torch.cuda.current_stream().cuda_stream
+        dist = None
+        if not self.local:
+            import torch.distributed as dist
+        for h in self.ctx:
+            check(L.srw_mig_begin(h, round_first, n_rounds, st))
+        if dist is not None:
+            self.sent.zero_()
+            dist.all_reduce(self.sent, group=self.group)
+        ev = []
+        s = 0
+        while True:
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record()
+            for i, h in enumerate(self.ctx):
+                check(L.srw_mig_superstep(h, s, self.sent.data_ptr() + 8 * i, st))
+            e[1].record()
+            if dist is not None:
+                dist.all_reduce(self.sent, group=self.group)
+                self.hist[s] = self.sent[0]
+            else:
+                self.hist[s] = self.sent.sum()
+            e[2].record()
+            ev.append(e)
+            s += 1
+            if s % 8 == 0 or s >= max_super_steps:
+                if 0 in self.hist[max(1, s - 8):s].tolist() or s >= max_super_steps:
+                    break
+        torch.cuda.synchronize()
+        h_all = self.hist[:s].tolist()
+        h_all[0] = max(h_all[0], 1)
+        n = h_all.index(0) + 1 if 0 in h_all else s
+        k = sum(ev[i][0].elapsed_time(ev[i][1]) for i in range(n))
+        b = sum(ev[i][1].elapsed_time(ev[i][2]) for i in range(n))
+        for i, h in enumerate(self.ctx):
+            p, nr, steps = C.c_void_p(), C.c_int64(), C.c_int64()
+            check(L.srw_mig_finish(h, C.byref(p), self.lens[i].data_ptr(), C.byref(nr), C.byref(steps), st))
+        return {"super_steps": n, "kernel_ms": k, "barrier_ms": b, "total_ms": ev[0][0].elapsed_time(ev[n - 1][2]),
+                "kernel_ms_per_super_step": [ev[i][0].elapsed_time(ev[i][1]) for i in range(n)]}

@@ -73,7 +73,7 @@ extern "C" int emu_migrate_walk(int64_t nv, const int64_t *off, const int32_t *c
     const int64_t n = off[r1] - off[r0];
     R.ent.resize((size_t)n);
     R.hash.assign((size_t)(((n >> 2) + 1) * 8), -1);
-    for (int b = 0; b < 2; ++b) { R.base[b].assign((size_t)slots * 2, make_int4(-1, -1, -1, -1)); R.ext[b].assign((size_t)slots, make_int4(-1, -1, -1, -1)); }
+    for (int b = 0; b < 2; ++b) { R.base[b].assign((size_t)slots * 3, make_int4(-1, -1, -1, -1)); R.ext[b].assign((size_t)slots, make_int4(-1, -1, -1, -1)); }
     memset(R.cnt, 0, sizeof(R.cnt));
     memset(R.scratch, 0, sizeof(R.scratch));
     const int64_t hrows = (nv - s + W - 1) / W;
@@ -114,11 +114,15 @@ extern "C" int emu_migrate_walk(int64_t nv, const int64_t *off, const int32_t *c
       a.walker_base = (uint64_t)round_first * (uint64_t)nv; a.n_rounds = n_rounds;
       a.in_base = R.base[cur].data(); a.in_ext = R.ext[cur].data(); a.in_cnt = R.cnt[cur];
       a.seg_cap = seg_cap; a.spill_cap = spill_cap;
-      a.n_seed = s == 0 ? (bounds[r + 1] - bounds[r]) * n_rounds : 0;
+      {
+        const int64_t seeds = (bounds[r + 1] - bounds[r]) * n_rounds;
+        a.seed_step = 2; a.seed_first = s;
+        a.n_seed = s == 0 ? (seeds + 1) / 2 : s == 1 ? seeds / 2 : 0;
+      }
       for (int d = 0; d <= W; ++d) {
         Shard &D = d == W ? R : sh[(size_t)d];
         const int64_t first = d == W ? (int64_t)W * seg_cap : (int64_t)r * seg_cap;
-        a.out_base[d] = D.base[nxt].data() + 2 * first;
+        a.out_base[d] = D.base[nxt].data() + 3 * first;
         a.out_ext[d] = D.ext[nxt].data() + first;
         a.out_cnt_pub[d] = &D.cnt[nxt][d == W ? W : r];
       }
@@ -131,7 +135,7 @@ extern "C" int emu_migrate_walk(int64_t nv, const int64_t *off, const int32_t *c
     for (int r = 0; r < W; ++r) sent += sh[(size_t)r].scratch[2 + kMigMaxDest];
     tuples += sent;
     steps = s + 1;
-    if (sent == 0) break;
+    if (sent == 0 && s >= 1) break;      // super-step 1 still seeds walkers
     if (s > 100000) return -3;
   }
   // assemble in global walker order

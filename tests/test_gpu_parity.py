@@ -585,3 +585,108 @@ def test_fold_in_id_space(oracle, monkeypatch):
     ids, offs = oracle.walk(og, walk_length=10, num_walks=1, p=0.5, q=2.0, seed=4)
     gi, go = g.walk(srw.Params(walkLength=10, numWalks=1, p=0.5, q=2.0, seed=4, sampler="exact")).arrays()
     assert (go == offs).all() and (gi == ids).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# Parity beyond the small cases (round-2 additions): samples of larger graphs against the checkers
+# ---------------------------------------------------------------------------------------------
+def _sampled(ids, offs, mod):
+    """rows of a full walk whose walker id is a multiple of `mod`, as (ids, offsets)"""
+    keep = np.arange(len(offs) - 1) % mod == 0
+    lens = np.diff(offs)[keep]
+    starts = offs[:-1][keep]
+    out = np.concatenate([ids[s:s + n] for s, n in zip(starts, lens)]) if keep.any() else np.zeros(0, np.int32)
+    return out, np.concatenate([[0], np.cumsum(lens)])
+
+
+@pytest.mark.parametrize("scale,mod,wl", [(16, 13, 20), (20, 1300, 6)])
+def test_exact_sampler_sample_of_larger_graphs(oracle, scale, mod, wl):
+    """P1 at RMAT-16 and RMAT-20 (SURVEY 7 step 3 asks for RMAT-12..16; C2's graph is RMAT-20): the exact sampler's paths for
+    every `mod`-th walker == the oracle (the literal reference algorithm, O(deg(curr) * deg(prev)) per step -- hence a sample)."""
+    s, d = synth.rmat_edges(scale, 16, seed=42)
+    og = oracle.Graph().load_edges(s, d, None)
+    g = srw.Graph.from_edges(s, d, None)
+    assert g.stats() == (og.num_vertices, og.num_edges)
+    ids, offs = oracle.walk(og, walk_length=wl, num_walks=1, p=0.5, q=2.0, seed=7, sample_mod=mod)
+    got_ids, got_offs = g.walk(srw.Params(walkLength=wl, numWalks=1, p=0.5, q=2.0, seed=7, sampler="exact")).arrays()
+    s_ids, s_offs = _sampled(got_ids, got_offs, mod)
+    assert len(offs) - 1 == len(s_offs) - 1 >= 256
+    assert (s_offs == offs).all() and (s_ids == ids).all()
+
+
+def test_c3_weighted_fold_rmat18_sample(oracle):
+    """C3's sampler (weighted alias-fold: Vose slots with bundle weights) at RMAT-18 against the CPU twin, every 97th walker."""
+    s, d = synth.rmat_edges(18, 16, seed=42)
+    w = synth.edge_weights(len(s), seed=43)
+    twin = oracle.AliasGraph(oracle.Graph().load_edges(s, d, w))
+    ids, offs, st = twin.walk(walk_length=80, num_walks=1, p=0.5, q=2.0, seed=3, fold=1, sample_mod=97)
+    g = srw.Graph.from_edges(s, d, w, flags=srw.BUILD_ALIAS)
+    got_ids, got_offs = g.walk(srw.Params(walkLength=80, numWalks=1, p=0.5, q=2.0, seed=3, sampler="fold")).arrays()
+    s_ids, s_offs = _sampled(got_ids, got_offs, 97)
+    assert len(offs) - 1 >= 1000
+    assert (s_offs == offs).all() and (s_ids == ids).all()
+
+
+def test_c5_zipf_hub_of_2e5_entries(oracle):
+    """C5's shape with a hub row of 200 000 stubs (+ its in-edges): alias-fold at p = 0.25, q = 4 against the twin, every 31st walker.
+    The hub's hash set spans ~1e5 buckets and most second-order tests are against it."""
+    s, d = synth.zipf_edges(1 << 18, cap=200000, seed=7)
+    twin = oracle.AliasGraph(oracle.Graph().load_edges(s, d, None))
+    assert int(np.diff(twin.view()["offsets"]).max()) >= 200000
+    ids, offs, st = twin.walk(walk_length=40, num_walks=1, p=0.25, q=4.0, seed=5, fold=1, sample_mod=31)
+    g = srw.Graph.from_edges(s, d, None, flags=srw.BUILD_ALIAS)
+    got_ids, got_offs = g.walk(srw.Params(walkLength=40, numWalks=1, p=0.25, q=4.0, seed=5, sampler="fold")).arrays()
+    s_ids, s_offs = _sampled(got_ids, got_offs, 31)
+    assert (s_offs == offs).all() and (s_ids == ids).all()
+
+
+def test_offsets_beyond_2_31_hub_row_last(oracle):
+    """More than 2^31 adjacency entries with ONE huge row placed LAST: 2^20 vertices on a ring, each with 1030 parallel edges to a
+    hub whose id is the largest, so the hub's row starts beyond entry 1.08e9 and ends beyond 2^31 -- u32 row offsets, the 64-bit
+    `off * 16` address math, hash placement at bucket ~5e8 and 24-bit multiplicities are all exercised.  Checker: the CPU twin
+    over the analytically built CSR (oracle_fold_walk_csr_timed), every 251st walker."""
+    import ctypes as C
+    import torch
+    if torch.cuda.mem_get_info()[1] < 150e9:
+        pytest.skip("needs a 180 GB device")
+    K, R = 1 << 20, 1030
+    H = K
+    ar = torch.arange(K, dtype=torch.int32, device="cuda")
+    src = torch.cat([ar.repeat_interleave(R), ar])                      # spokes (i, H) x R, then the ring (i, i+1 mod K)
+    dst = torch.cat([torch.full((K * R,), H, dtype=torch.int32, device="cuda"), (ar + 1) % K])
+    g = srw.Graph.from_device_edges(src.numel(), src.data_ptr(), dst.data_ptr(), None, False, srw.BUILD_ALIAS)
+    del src, dst
+    torch.cuda.empty_cache()
+    nv, nnz = g.stats()
+    assert nv == K + 1 and nnz == 2 * (K * R + K) and nnz > (1 << 31)
+    # the same CSR on the host, neighbour-sorted: row i = [i-1, i+1 (sorted)] + [H] * R, row H = each i repeated R times
+    off = np.empty(nv + 1, np.int64)
+    off[:K + 1] = np.arange(K + 1, dtype=np.int64) * (R + 2)
+    off[K + 1] = nnz
+    col = np.empty(nnz, np.int32)
+    rows = col[:K * (R + 2)].reshape(K, R + 2)
+    i = np.arange(K, dtype=np.int64)
+    ring = np.sort(np.stack([(i - 1) % K, (i + 1) % K], 1), 1).astype(np.int32)
+    rows[:, :2] = ring
+    rows[:, 2:] = H
+    col[K * (R + 2):] = np.repeat(np.arange(K, dtype=np.int32), R)
+    L = oracle.lib()
+    fn = L.oracle_fold_walk_csr_timed
+    fn.restype = C.c_int64
+    fn.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.POINTER(C.c_double),
+                   C.POINTER(C.c_int64), C.POINTER(C.c_uint64), C.c_void_p]
+    wl, mod = 40, 251
+    n_s = (nv + mod - 1) // mod
+    tw = np.full((n_s, wl + 2), -2, np.int32)
+    cfg = oracle.make_cfg(walk_length=wl, num_walks=1, p=0.5, q=2.0, seed=11, threads=0, fold=1)
+    el, dn, ck = C.c_double(), C.c_int64(), C.c_uint64()
+    fn(nv, off.ctypes.data, col.ctypes.data, C.addressof(cfg), mod, 0, 600.0, C.byref(el), C.byref(dn), C.byref(ck), tw.ctypes.data)
+    assert dn.value == n_s
+    paths = torch.empty((nv, wl + 2), dtype=torch.int32, device="cuda")
+    lens = torch.empty(nv, dtype=torch.int32, device="cuda")
+    cp = srw.Params(walkLength=wl, numWalks=1, p=0.5, q=2.0, seed=11, sampler="fold").to_c()
+    srw.check(srw.lib().srw_walk_device(g.h, C.byref(cp), 0, nv, paths.data_ptr(), lens.data_ptr(), None))
+    got = paths[::mod].cpu().numpy()
+    assert (lens.cpu().numpy() == wl + 2).all()
+    assert (got == tw).all()            # ids == ranks here (ids 0..K are all present)
+    assert (got == H).mean() > 0.3      # the walk really lives on the hub row
