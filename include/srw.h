@@ -116,6 +116,11 @@ srw_status srw_graph_from_edges(int64_t n, const int32_t *h_src, const int32_t *
                                 const int32_t *h_pid /*NULL*/, int directed, unsigned flags, srw_graph **out);
 srw_status srw_graph_from_device_edges(int64_t n, const int32_t *d_src, const int32_t *d_dst, const float *d_w,
                                        const int32_t *d_pid, int directed, unsigned flags, srw_graph **out);
+/* One process, several GPUs (`--gpus N`, srw_params::num_gpus): one edge-balanced vertex-range shard per device inside ONE handle.
+ * srw_walk / srw_walk_save / srw_walk_device (whole rounds, result on device 0) then run the migrating-walker walk (srw_mig_*
+ * below) over peer memory; srw_graph_stats / _neighbors / _vertex_ids answer for the whole graph.  Undirected, unweighted.
+ * srw_graph_load builds the same when params->num_gpus > 1. */
+srw_status srw_graph_from_edges_multi(int64_t n, const int32_t *h_src, const int32_t *h_dst, int directed, int num_gpus, srw_graph **out);
 /* loadGraph(): URW:17-88 / VRW:13-98 chosen by params->partitioned (Main:54-57) */
 srw_status srw_graph_load(const srw_params *params, unsigned flags, srw_graph **out);
 /* RW:23-24 nVertices / nEdges (= adjacency entries) */
@@ -287,7 +292,7 @@ srw_status srw_mig_collect_stats(srw_mig *m, int enable);    /* instrumented ker
 srw_status srw_mig_begin(srw_mig *m, int64_t round_first, int64_t n_rounds /* <= the n_rounds of srw_mig_create */, void *stream);
 srw_status srw_mig_superstep(srw_mig *m, int64_t s, unsigned long long *d_sent /*device, may be NULL*/, void *stream);
 /* [0] inbox slots this rank filled in the last super-step, [1] steps, [2] proposals, [3] membership tests (filter probes),
- * [4] exact tests, [5] tuples spilled (region full), [6] error flags (nonzero => SRW_ERR_CUDA), [7] reserved; synchronises */
+ * [4] exact tests, [5] tuples spilled (region full), [6] error flags (nonzero => SRW_ERR_CUDA), [7] exact tests that found the edge (instrumented); synchronises */
 srw_status srw_mig_counters(srw_mig *m, int64_t *h_out8, void *stream);
 /* ranks -> vertex ids over this rank's home rows.  *d_paths: [home_rows * n_rounds][walk_length + 2] inside the block (valid
  * until the next srw_mig_begin); row (round - round_first) * home_rows + v / world belongs to the walker that started at

@@ -43,7 +43,7 @@ ABI_SYMBOLS = [
     "srw_shard_ipc_bytes", "srw_shard_ipc_export", "srw_shard_ipc_attach", "srw_shard_attach_local",
     "srw_shard_rows_info", "srw_shard_rows_relocate", "srw_shard_attach_block",
     "srw_mig_block_bytes", "srw_mig_create", "srw_mig_collect_stats", "srw_mig_begin", "srw_mig_superstep", "srw_mig_counters",
-    "srw_mig_finish", "srw_mig_info", "srw_mig_free",
+    "srw_mig_finish", "srw_mig_info", "srw_mig_free", "srw_graph_from_edges_multi",
 ]
 
 

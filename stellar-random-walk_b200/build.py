@@ -17,7 +17,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-ccbin", "/usr/bin/g++",
          "--expt-relaxed-constexpr", "--extended-lambda", "-Xptxas", "-v"]
-SOURCES = ["srw_host.cpp", "graph_build.cu", "walk.cu", "srw_abi.cu", "shard.cu", "migrate.cu", "text_io.cu"]
+SOURCES = ["srw_host.cpp", "graph_build.cu", "walk.cu", "srw_abi.cu", "shard.cu", "migrate.cu", "multi.cu", "text_io.cu"]
 HEADERS = ["srw_internal.h", "philox.cuh", "layout.h", "walk_conv.cuh", "migrate.cuh", "walk_exact.cuh", "text_io.cuh", os.path.join("..", "..", "include", "srw.h")]
 
 

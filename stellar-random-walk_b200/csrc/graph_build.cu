@@ -126,9 +126,10 @@ __global__ void k_entries_range(int64_t n, const int32_t *__restrict__ src, cons
 // SRW_BUILD_MIGRATE: every undirected input edge {rank(src), rank(dst)} sets kMigBloomK bits of one 64-bit word
 __global__ void k_bloom_insert(int64_t n, const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
                                const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ wordrank, int32_t id_min,
-                               unsigned long long *bloom, uint64_t n_words) {
+                               unsigned long long *bloom, uint32_t n_words) {
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-    uint64_t word, mask;
+    uint32_t word;
+    uint64_t mask;
     srw_bloom_probe(rank_of(bitmap, wordrank, id_min, src[e]), rank_of(bitmap, wordrank, id_min, dst[e]), n_words, &word, &mask);
     atomicOr(bloom + word, (unsigned long long)mask);
   }
@@ -528,9 +529,10 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
     const int64_t bits = eb && atoi(eb) > 0 ? atoi(eb) : 16;
     g->bloom_words = (uint64_t)((n * bits + 63) / 64);
     if (g->bloom_words < 64) g->bloom_words = 64;
+    if (g->bloom_words > 0xFFFFFFFFull) g->bloom_words = 0xFFFFFFFFull;     // the probe indexes words with 32 bits (32 GB of filter)
     SRW_CUDA(cudaMalloc(&g->d_bloom, g->bloom_words * 8));
     SRW_CUDA(cudaMemset(g->d_bloom, 0, g->bloom_words * 8));
-    k_bloom_insert<<<grid(n), kThreads>>>(n, d_src, d_dst, g->d_bitmap, g->d_wordrank, mn, g->d_bloom, g->bloom_words);
+    k_bloom_insert<<<grid(n), kThreads>>>(n, d_src, d_dst, g->d_bitmap, g->d_wordrank, mn, g->d_bloom, (uint32_t)g->bloom_words);
     SRW_CUDA(cudaDeviceSynchronize());
   }
 

@@ -73,7 +73,7 @@ struct srw_mig {
 };
 
 namespace {
-constexpr int kScratchWords = 2 + kMigMaxDest + 8;
+constexpr int kScratchWords = 2 + kMigMaxDest + 8 + 1;   // cursor, done, out_cnt[], stats[8], finish scratch
 
 srw_status mig_check(const srw_graph *g, const srw_params *p) {
   if (!g || !p) { srw_set_error("srw_mig: null graph or params"); return SRW_ERR_ARG; }
@@ -130,6 +130,12 @@ extern "C" srw_status srw_mig_create(const srw_graph *g, const srw_params *p, in
   m->home_rows = (g->nv - m->rank + m->world - 1) / m->world;
   m->home_rows_max = (g->nv + m->world - 1) / m->world;
   m->L = mig_layout(m->world, m->seg_cap, m->spill_cap, m->home_rows_max * n_rounds, m->stride);
+  if (m->L.slots >= ((int64_t)1 << 32) || m->home_rows_max * n_rounds > (int64_t)kMigRowMask) {
+    srw_set_error("srw_mig_create: a batch of %lld rounds needs %lld inbox slots / %lld path rows per rank; the tuple format holds 2^32 / 2^28: use smaller batches",
+                  (long long)n_rounds, (long long)m->L.slots, (long long)(m->home_rows_max * n_rounds));
+    delete m;
+    return SRW_ERR_ARG;
+  }
   m->block = (char *)d_block_self;
   for (int r = 0; r < m->world; ++r) m->peers[r] = r == m->rank ? m->block : (char *)d_block_peers[r];
   for (int r = 0; r < m->world; ++r)
@@ -143,7 +149,7 @@ extern "C" srw_status srw_mig_create(const srw_graph *g, const srw_params *p, in
   SRW_CUDA(cudaMemset(m->block + m->L.o_cnt, 0, 2 * kMigMaxDest * 8));
   MigArgs &a = m->base;
   memset(&a, 0, sizeof(a));
-  a.off = g->d_off; a.ent = g->d_ent; a.hash = g->d_hash; a.bloom = (const unsigned long long *)g->d_bloom; a.bloom_words = g->bloom_words;
+  a.off = g->d_off; a.ent = g->d_ent; a.hash = g->d_hash; a.bloom = (const unsigned long long *)g->d_bloom; a.bloom_words = (uint32_t)g->bloom_words;
   a.nv = g->nv; a.row_first = g->row_first; a.row_last = g->row_last; a.world = m->world; a.rank = m->rank;
   for (int r = 0; r <= m->world; ++r) a.bounds[r] = g->bounds[(size_t)r];
   FoldArgs f;
@@ -231,7 +237,7 @@ extern "C" srw_status srw_mig_superstep(srw_mig *m, int64_t s, unsigned long lon
 }
 
 // counters of the batch so far (synchronises the stream): [0] slots sent in the last super-step, [1] steps, [2] proposals,
-// [3] membership tests, [4] exact (hash-set) tests, [5] spills, [6] error flags, [7] reserved
+// [3] membership tests, [4] exact (hash-set) tests, [5] spills, [6] error flags, [7] exact tests that found the edge
 extern "C" srw_status srw_mig_counters(srw_mig *m, int64_t *h_out8, void *stream_) {
   if (!m || !h_out8) return SRW_ERR_ARG;
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -253,7 +259,7 @@ extern "C" srw_status srw_mig_finish(srw_mig *m, int32_t **d_paths, int32_t *d_l
   SRW_CUDA(cudaSetDevice(m->g->device));
   const int64_t rows = m->home_rows * m->n_active;
   int32_t *paths = (int32_t *)(m->block + m->L.o_paths);
-  unsigned long long *d_steps = m->base.stats + 7;
+  unsigned long long *d_steps = m->base.stats + 8;
   SRW_CUDA(cudaMemsetAsync(d_steps, 0, 8, stream));
   if (rows > 0) {
     int64_t b = (rows * 32 + 255) / 256;

@@ -102,6 +102,15 @@ extern "C" srw_status srw_graph_stats(const srw_graph *g, int64_t *nv, int64_t *
 
 extern "C" srw_status srw_graph_neighbors(const srw_graph *g, int32_t vid, int32_t *h_dst, float *h_w, int64_t cap, int64_t *n) {
   if (!g || !n) return SRW_ERR_ARG;
+  if (!g->shards.empty()) {                       // container: the shard that owns the vertex answers (everyone else says -1)
+    for (srw_graph *sh : g->shards) {
+      SRW_CUDA(cudaSetDevice(sh->device));
+      SRW_TRY(srw_graph_neighbors(sh, vid, h_dst, h_w, cap, n));
+      if (*n >= 0) break;
+    }
+    cudaSetDevice(0);
+    return SRW_OK;
+  }
   SRW_TRY(host_vids(g));
   int64_t r = host_rank(g, vid);
   if (r < 0) { *n = -1; return SRW_OK; }                       // GM:118 case None => null
@@ -145,6 +154,7 @@ extern "C" srw_status srw_graph_partition(const srw_graph *g, int32_t vid, int32
 
 extern "C" srw_status srw_graph_vertex_ids(const srw_graph *g, int32_t *h_out, int64_t cap) {
   if (!g || (cap > 0 && !h_out)) return SRW_ERR_ARG;
+  if (!g->shards.empty()) { SRW_CUDA(cudaSetDevice(0)); return srw_graph_vertex_ids(g->shards[0], h_out, cap); }   // replicated on every shard
   const int64_t m = std::min(cap, g->nv);
   if (m > 0) SRW_CUDA(cudaMemcpy(h_out, g->d_vids, (size_t)m * 4, cudaMemcpyDeviceToHost));
   return SRW_OK;
@@ -152,6 +162,7 @@ extern "C" srw_status srw_graph_vertex_ids(const srw_graph *g, int32_t *h_out, i
 
 extern "C" srw_status srw_graph_layout(const srw_graph *g, int64_t *h_off, int32_t *h_col, uint32_t *h_slots4, int *has_alias) {
   if (!g) return SRW_ERR_ARG;
+  if (!g->shards.empty()) { srw_set_error("srw_graph_layout: a multi-GPU graph has one layout per shard"); return SRW_ERR_UNSUPPORTED; }
   if (has_alias) *has_alias = g->has_alias ? 1 : 0;
   // on a vertex-range shard the arrays are shard-local: row_last - row_first + 1 offsets (relative to the shard's first entry)
   const int64_t n_rows = g->shard_world > 1 ? g->row_last - g->row_first : g->nv;
@@ -165,6 +176,13 @@ extern "C" int64_t srw_graph_device_bytes(const srw_graph *g) { return g ? g->de
 
 extern "C" void srw_graph_free(srw_graph *g) {
   if (!g) return;
+  if (!g->shards.empty() || g->multi) {           // multi-GPU container
+    srw_multi_free(g->multi);
+    for (srw_graph *sh : g->shards) { if (sh) { cudaSetDevice(sh->device); srw_graph_free(sh); } }
+    cudaSetDevice(0);
+    delete g;
+    return;
+  }
   cudaFree(g->d_bitmap); cudaFree(g->d_wordrank); cudaFree(g->d_vids);
   cudaFree(g->d_col_app); cudaFree(g->d_w_app); cudaFree(g->d_col); cudaFree(g->d_slot); cudaFree(g->d_slotw); cudaFree(g->d_vpid);
   cudaFree(g->d_meta); cudaFree(g->d_hash_id); cudaFree(g->d_bloom);
@@ -187,6 +205,15 @@ extern "C" srw_status srw_walk_device(const srw_graph *g, const srw_params *para
                                       int32_t *d_paths, int32_t *d_lens, void *stream) {
   SRW_TRY(srw_require_device());
   if (!g || !params || (n_walkers > 0 && (!d_paths || !d_lens))) { srw_set_error("srw_walk_device: bad argument"); return SRW_ERR_ARG; }
+  if (!g->shards.empty()) {
+    // multi-GPU container: whole rounds only (the sharded walk seeds one walker per vertex and round), delivered on device 0
+    if (g->nv == 0 || walker_first % (uint64_t)g->nv != 0 || n_walkers % g->nv != 0) { srw_set_error("srw_walk_device on a multi-GPU graph walks whole rounds: walker_first and n_walkers must be multiples of nVertices"); return SRW_ERR_ARG; }
+    if (n_walkers == 0) return SRW_OK;
+    srw_walk_info wi;
+    SRW_TRY(srw_multi_walk_rounds(g, params, (int64_t)(walker_first / (uint64_t)g->nv), n_walkers / g->nv, d_paths, d_lens, &wi));
+    srw_set_walk_info(wi.kernel_ms, wi.kernel_launches, wi.steps, 0, 0, 0);
+    return SRW_OK;
+  }
   WalkLaunch l{walker_first, n_walkers, d_paths, d_lens, (cudaStream_t)stream};
   return srw_walk_launch(g, params, l);
 }
@@ -197,7 +224,8 @@ extern "C" srw_status srw_walk(const srw_graph *g, const srw_params *params, srw
   SRW_TRY(srw_require_device());
   if (!g || !params || !out) { srw_set_error("srw_walk: bad argument"); return SRW_ERR_ARG; }
   if (params->num_walks < 0) { srw_set_error("numWalks must be >= 0"); return SRW_ERR_ARG; }
-  if (params->num_gpus > 1) { srw_set_error("srw_walk is single-GPU; the sharded walk is driven per rank (see shard API)"); return SRW_ERR_UNSUPPORTED; }
+  const bool multi = !g->shards.empty();
+  if (params->num_gpus > 1 && !multi) { srw_set_error("--gpus %d: the graph was loaded on one GPU (load it with the same --gpus)", params->num_gpus); return SRW_ERR_ARG; }
   SRW_CUDA(cudaSetDevice(g->device));
   const int32_t stride = params->walk_length + 2;
   const int64_t total = (int64_t)params->num_walks * g->nv;
@@ -209,6 +237,11 @@ extern "C" srw_status srw_walk(const srw_graph *g, const srw_params *params, srw
   int64_t batch = (int64_t)(free_b / 2) / ((int64_t)stride * 4 + 4);
   if (batch > total) batch = total;
   if (batch < 1) batch = 1;
+  if (multi && g->nv > 0) {
+    // whole rounds per batch; device 0 also holds its shard and its exchange block (~400 bytes per walker of the batch)
+    int64_t rounds = std::max<int64_t>(1, std::min<int64_t>({(int64_t)params->num_walks, ((int64_t)1 << 25) / g->nv, (int64_t)(free_b / 3) / (g->nv * ((int64_t)stride * 4 + 420))}));
+    batch = rounds * g->nv;
+  }
   Dev<int32_t> d_paths, d_lens;
   SRW_CUDA(cudaMalloc(&d_paths.p, (size_t)batch * stride * 4));
   SRW_CUDA(cudaMalloc(&d_lens.p, (size_t)batch * 4));
@@ -217,8 +250,7 @@ extern "C" srw_status srw_walk(const srw_graph *g, const srw_params *params, srw
   int64_t launches = 0, steps = 0, props = 0, mem = 0, logs = 0;
   for (int64_t first = 0; first < total; first += batch) {
     const int64_t n = std::min(batch, total - first);
-    WalkLaunch l{(uint64_t)first, n, d_paths.p, d_lens.p, nullptr};
-    srw_status s = srw_walk_launch(g, params, l);
+    srw_status s = srw_walk_device(g, params, (uint64_t)first, n, d_paths.p, d_lens.p, nullptr);
     if (s != SRW_OK) { delete P; return s; }
     srw_walk_info wi;
     srw_last_walk_info(&wi);

@@ -78,7 +78,17 @@ struct srw_graph {
   bool peer_attached[SRW_MAX_SHARDS] = {};
   bool peer_ipc[SRW_MAX_SHARDS] = {};   // mapping opened with cudaIpcOpenMemHandle (closed on free)
   bool rows_external = false;           // d_off / d_ent / d_hash live in a caller-owned block (srw_shard_rows_relocate)
+  // multi-GPU container (multi.cu, `--gpus N` in one process): shards[r] is the vertex-range shard on device r; the container
+  // itself holds no device arrays.  `multi` caches the exchange blocks / contexts of the last walk.
+  std::vector<srw_graph *> shards;
+  struct MultiWalk *multi = nullptr;
 };
+void srw_multi_free(struct MultiWalk *w);
+srw_status srw_build_graph_device_multi(int64_t n, const int32_t *d_src, const int32_t *d_dst, const float *d_w, int directed,
+                                        int num_gpus, srw_graph **out);
+// rounds [round_first, round_first + n_rounds) over a container graph, delivered on device 0 in walker order
+srw_status srw_multi_walk_rounds(const srw_graph *g, const srw_params *p, int64_t round_first, int64_t n_rounds, int32_t *d_paths0,
+                                 int32_t *d_lens0, srw_walk_info *info);
 
 srw_status srw_build_graph_device_sharded(int64_t n, const int32_t *d_src, const int32_t *d_dst, const float *d_w, int directed,
                                           unsigned flags, int rank, int world, srw_graph **out);

@@ -212,7 +212,8 @@ extern "C" srw_status srw_walk_save(const srw_graph *g, const srw_params *params
   SRW_TRY(srw_require_device());
   if (!g || !params || !params->output[0]) { srw_set_error("srw_walk_save: no graph / output path"); return SRW_ERR_ARG; }
   if (params->num_walks < 0) { srw_set_error("numWalks must be >= 0"); return SRW_ERR_ARG; }
-  if (params->num_gpus > 1) { srw_set_error("srw_walk_save is single-GPU; the sharded walk is driven per rank (see shard API)"); return SRW_ERR_UNSUPPORTED; }
+  const bool multi = !g->shards.empty();
+  if (params->num_gpus > 1 && !multi) { srw_set_error("--gpus %d: the graph was loaded on one GPU (load it with the same --gpus)", params->num_gpus); return SRW_ERR_ARG; }
   const std::string dir = std::string(params->output) + "/path";          // Property.pathSuffix
   struct stat stt;
   if (stat(dir.c_str(), &stt) == 0) {   // Hadoop saveAsTextFile refuses an existing directory
@@ -231,6 +232,8 @@ extern "C" srw_status srw_walk_save(const srw_graph *g, const srw_params *params
   SRW_CUDA(cudaMemGetInfo(&free_b, &total_b));
   int64_t batch = std::min<int64_t>({total, (int64_t)1 << 24, (int64_t)(free_b / 3) / ((int64_t)stride * 4 + 4)});
   if (batch < 1) batch = 1;
+  if (multi && g->nv > 0)   // the sharded walk runs whole rounds (device 0 also holds its shard and ~420 bytes of exchange block per walker)
+    batch = g->nv * std::max<int64_t>(1, std::min<int64_t>({(int64_t)params->num_walks, ((int64_t)1 << 25) / g->nv, (int64_t)(free_b / 3) / (g->nv * ((int64_t)stride * 4 + 420))}));
   // text chunk: worst case 12 bytes per id; two device and two pinned host buffers
   const int64_t chunk_bytes = getenv("SRW_SAVE_CHUNK_BYTES") ? atoll(getenv("SRW_SAVE_CHUNK_BYTES")) : ((int64_t)256 << 20);
   int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(batch, chunk_bytes / ((int64_t)stride * 12)));
@@ -286,9 +289,9 @@ extern "C" srw_status srw_walk_save(const srw_graph *g, const srw_params *params
   srw_status rc = SRW_OK;
   for (int64_t first = 0; first < total && rc == SRW_OK && io_ok; first += batch) {
     const int64_t nb = std::min(batch, total - first);
-    WalkLaunch l{(uint64_t)first, nb, d_paths.as<int32_t>(), d_lens.as<int32_t>(), st};
-    rc = srw_walk_launch(g, params, l);
+    rc = srw_walk_device(g, params, (uint64_t)first, nb, d_paths.as<int32_t>(), d_lens.as<int32_t>(), st);
     if (rc != SRW_OK) break;
+    if (multi) SRW_CUDA(cudaSetDevice(g->device));
     srw_walk_info wi;
     srw_last_walk_info(&wi);
     kernel_ms += wi.kernel_ms; launches += wi.kernel_launches; steps += wi.steps;
@@ -599,6 +602,13 @@ extern "C" srw_status srw_edges_parse_buffer_device(const char *buf, size_t len,
 // A1 + A2 from a file: mmap -> device parse -> CSR build; the edge arrays never exist on the host.
 // SparkContext.textFile accepts a directory (URW:23): every regular file in it, in name order, files whose name starts
 // with '_' or '.' skipped (Hadoop's hidden-file filter: _SUCCESS, .crc).  A file's last line needs no terminator.
+// Main:54-57: Params decide which walker runs -- one GPU, or (--gpus N) one vertex-range shard per GPU of this process
+static srw_status build_for(const srw_params *params, int64_t n, const int32_t *s, const int32_t *d, const float *w, const int32_t *p,
+                            unsigned flags, srw_graph **out) {
+  if (params->num_gpus > 1) return srw_build_graph_device_multi(n, s, d, w, params->directed, params->num_gpus, out);
+  return srw_build_graph_device(n, s, d, w, p, params->directed, flags, out);
+}
+
 static srw_status load_directory(const srw_params *params, unsigned flags, srw_graph **out) {
   std::vector<std::string> names;
   DIR *dp = opendir(params->input);
@@ -625,7 +635,7 @@ static srw_status load_directory(const srw_params *params, unsigned flags, srw_g
   int32_t *s = nullptr, *d = nullptr, *p = nullptr;
   float *w = nullptr;
   SRW_TRY(srw_parse_text_device(text.data(), text.size(), params->weighted, params->partitioned, &n, &s, &d, &w, &p));
-  srw_status rc = srw_build_graph_device(n, s, d, w, p, params->directed, flags, out);
+  srw_status rc = build_for(params, n, s, d, w, p, flags, out);
   cudaFree(s); cudaFree(d); cudaFree(w); cudaFree(p);
   return rc;
 }
@@ -664,7 +674,7 @@ srw_status srw_graph_load_device(const srw_params *params, unsigned flags, srw_g
   srw_status rc = srw_parse_text_device(text, map ? len : small.size(), params->weighted, params->partitioned, &n, &s, &d, &w, &p);
   if (map) munmap(map, len);
   if (rc != SRW_OK) return rc;
-  rc = srw_build_graph_device(n, s, d, w, p, params->directed, flags, out);
+  rc = build_for(params, n, s, d, w, p, flags, out);
   cudaFree(s); cudaFree(d); cudaFree(w); cudaFree(p);
   return rc;
 }

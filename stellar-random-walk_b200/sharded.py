@@ -461,7 +461,7 @@ class MigrateWalker:
         h_all[0] = max(h_all[0], 1)
         super_steps = h_all.index(0) + 1 if 0 in h_all else s
         stats = {"super_steps": super_steps, "super_steps_launched": s, "tuples_sent_all_ranks": int(sum(h_all)), "steps": 0, "proposals": 0,
-                 "filter_probes": 0, "exact_tests": 0, "spills": 0}
+                 "filter_probes": 0, "exact_tests": 0, "exact_hits": 0, "spills": 0}
         out = []
         for i, (sh, h) in enumerate(zip(self.shards, self.ctx)):
             c8 = (C.c_int64 * 8)()
@@ -473,7 +473,7 @@ class MigrateWalker:
             out.append((paths, self.lens[i][:n.value]))
             assert n.value == sh.home_rows * n_rounds
             stats["steps"] += steps.value
-            for k, j in (("proposals", 2), ("filter_probes", 3), ("exact_tests", 4), ("spills", 5)):
+            for k, j in (("proposals", 2), ("filter_probes", 3), ("exact_tests", 4), ("spills", 5), ("exact_hits", 7)):
                 stats[k] += c8[j]
         if 0 not in h_all:
             raise RuntimeError("migrating walk did not terminate within %d super-steps" % s)

@@ -20,7 +20,7 @@ struct Shard {
   std::vector<int4> base[2], ext[2];
   unsigned long long cnt[2][kMigMaxDest];
   std::vector<int32_t> paths;
-  unsigned long long scratch[2 + kMigMaxDest + 8];
+  unsigned long long scratch[2 + kMigMaxDest + 9];
 };
 
 void hash_insert(std::vector<int32_t> &hash, int64_t off, uint32_t deg, int32_t x) {
@@ -50,12 +50,13 @@ extern "C" int emu_migrate_walk(int64_t nv, const int64_t *off, const int32_t *c
   const int64_t nnz = off[nv];
   auto owner_of = [&](int64_t v) { int o = 0; while (o + 1 < W && v >= bounds[o + 1]) o++; return o; };
   // the replicated filter
-  uint64_t bloom_words = (uint64_t)((nnz / 2 * bloom_bits + 63) / 64);
+  uint32_t bloom_words = (uint32_t)((nnz / 2 * bloom_bits + 63) / 64);
   if (bloom_words < 4) bloom_words = 4;
   std::vector<unsigned long long> bloom((size_t)bloom_words, 0ull);
   for (int64_t r = 0; r < nv; ++r)
     for (int64_t e = off[r]; e < off[r + 1]; ++e) {
-      uint64_t word, mask;
+      uint32_t word;
+      uint64_t mask;
       srw_bloom_probe((int32_t)r, col[e], bloom_words, &word, &mask);
       bloom[(size_t)word] |= mask;
     }

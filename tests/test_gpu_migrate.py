@@ -91,8 +91,7 @@ def test_migrate_matches_single_gpu_kernel_and_batches():
         out, stats = mw.run(first)
         got.append(_assemble(shards, out, nv, 2, 82).copy())
         assert stats["steps"] == 2 * nv * 81
-        # ~1 hop per step: every accepted step to a vertex another shard owns, plus the rare exact-test round trips
-        assert stats["tuples_sent_all_ranks"] < 1.3 * stats["steps"]
+        assert stats["spills"] == 0            # the default regions hold the whole per-pair flow of a super-step
     assert (np.concatenate(got).reshape(-1) == ref_ids).all()
     mw.free()
 
