@@ -99,7 +99,7 @@ int64_t default_seg_cap(const srw_graph *g, int64_t n_rounds, unsigned grid) {
 unsigned mig_grid() {
   const char *e = getenv("SRW_MIG_BLOCKS");
   if (e && atoi(e) > 0) return (unsigned)atoi(e);
-  return 148 * 3;     // persistent: one wave at the 3 blocks per SM the kernel's registers allow
+  return 148 * 4;     // persistent: one wave at the 4 blocks per SM the kernel is compiled for
 }
 }  // namespace
 

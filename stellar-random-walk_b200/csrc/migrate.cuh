@@ -134,8 +134,8 @@ __device__ __forceinline__ unsigned mig_reduce_or(unsigned v) { return __reduce_
 __device__ __forceinline__ unsigned mig_atomic_add32(unsigned long long *p, unsigned v) { return atomicAdd(reinterpret_cast<unsigned *>(p), v); }
 #endif
 
-template <bool STATS>
-__global__ void __launch_bounds__(256, 3) mig_step_kernel(const MigArgs a) {
+template <bool STATS, int MINB = 4>
+__global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
   // per-warp send state: open chunk (first slot, slots used) per destination region; prefix of the inbox regions (+ seeds)
   __shared__ unsigned int s_chunk[8][kMigMaxDest];
   __shared__ unsigned int s_used[8][kMigMaxDest];
@@ -161,12 +161,12 @@ __global__ void __launch_bounds__(256, 3) mig_step_kernel(const MigArgs a) {
   const uint32_t stride = (uint32_t)a.stride;
 
   // lane state: one walker
-  uint32_t walker = 0, off = 0, deg = 0, m = 1, trial = 0, len = 0, poff = 0, pdeg = 0;
+  uint32_t walker = 0, off = 0, deg = 0, m = 1, trial = 0, len = 0;
   int32_t prev = -1, curr = 0, x = 0;
   uint32_t xoff = 0, xdeg = 0, xm = 1, xown = 0, cown = 0, pown = 0, k = 0, y = 0, bkt = 0, pnb = 0, lo = 0, hi = 0;
-  uint32_t hrow = 0, phase = 0;           // home shard | path row; (row * stride) & 3
+  uint32_t hrow = 0;                      // home shard | path row
   int32_t c0 = 0, c1 = 0, c2 = 0;         // carried path entries, oldest first
-  bool pvalid = false, fwd = false;
+  bool fwd = false;
   uint32_t item = 0;
   int st = MS_EMPTY;
   uint32_t w_next = 0, w_end = 0, w_seg = 0;
@@ -197,11 +197,10 @@ __global__ void __launch_bounds__(256, 3) mig_step_kernel(const MigArgs a) {
           const int64_t round = (int64_t)(j / (unsigned long long)rows), row = (int64_t)(j % (unsigned long long)rows);
           curr = (int32_t)(a.row_first + row); prev = -1;
           walker = (uint32_t)((unsigned long long)round * (unsigned long long)a.nv + (unsigned long long)curr);
-          m = 1; trial = 0; len = 1; cown = (uint32_t)me; pown = 0; pvalid = false;
+          m = 1; trial = 0; len = 1; cown = (uint32_t)me; pown = 0;
           const uint32_t h = (uint32_t)curr % (uint32_t)W;
           const uint32_t prow = (uint32_t)(round * a.home_rows[h]) + (uint32_t)curr / (uint32_t)W;
           hrow = (h << 28) | prow;
-          phase = (prow * stride) & 3u;
           st = MS_EXTENT;
         } else {
           uint32_t r = w_seg;
@@ -237,10 +236,8 @@ __global__ void __launch_bounds__(256, 3) mig_step_kernel(const MigArgs a) {
         deg = (uint32_t)q1.x; m = (uint32_t)q1.y >> MIG_M_SHIFT; trial = (uint32_t)q1.z; len = (uint32_t)q1.w;
         pown = ((uint32_t)q1.y >> MIG_POWN_SHIFT) & 15u;
         c0 = q2.x; c1 = q2.y; c2 = q2.z; hrow = (uint32_t)q2.w;
-        phase = ((hrow & kMigRowMask) * stride) & 3u;
         const uint32_t kind = (uint32_t)q1.y & MIG_KIND_MASK;
         fwd = ((uint32_t)q1.y & MIG_FWD) != 0;
-        pvalid = false;
         cown = (uint32_t)me;
         if (kind == MIG_NOP) st = MS_EMPTY;
         else if (kind == MIG_PENDING) pend = true;
@@ -285,10 +282,9 @@ __global__ void __launch_bounds__(256, 3) mig_step_kernel(const MigArgs a) {
         if (STATS) n_prop++;
         newv = prev; moved = true;
         const int32_t c = curr; curr = prev; prev = c;
-        const uint32_t o = off, d = deg, w = cown;
-        if (pvalid) { off = poff; deg = pdeg; } else needext = true;
-        poff = o; pdeg = d; pvalid = true;               // m unchanged: the same bundle of parallel edges
-        cown = pown; pown = w;
+        const uint32_t w = cown;
+        needext = true;                                  // the row extent of prev is re-read at its owner (returns are rare: ~1/deg)
+        cown = pown; pown = w;                           // m unchanged: the same bundle of parallel edges
       } else {
         k = (uint32_t)__umul64hi(((uint64_t)r.x << 32) | (uint64_t)r.w, (uint64_t)deg);
         y = r.z;
@@ -354,7 +350,7 @@ __global__ void __launch_bounds__(256, 3) mig_step_kernel(const MigArgs a) {
     if (verdict == 1) {                                    // move along entry (x, xoff, xdeg, xm, xown)
       newv = x; moved = true;
       if (cown == 0xFFu) cown = (uint32_t)mig_owner(a, curr);
-      prev = curr; poff = off; pdeg = deg; pvalid = true; pown = cown;
+      prev = curr; pown = cown;
       curr = x; off = xoff; deg = xdeg; m = xm; cown = xown;
     } else if (verdict == 2) {
       trial++;
@@ -363,6 +359,7 @@ __global__ void __launch_bounds__(256, 3) mig_step_kernel(const MigArgs a) {
       else { send = (int)cown; send_kind = MIG_SETTLED; }  // the test ran at owner(x): back to the row of curr
     }
     if (moved) {                                           // RW:114: the step is decided -> the walker's home path row, four entries at a time
+      const uint32_t phase = ((hrow & kMigRowMask) * stride) & 3u;
       const uint32_t pos = len, in_chunk = (phase + pos) & 3u;          // position of newv; its place in its 16-byte chunk
       const uint32_t have = mig_carried(phase, len);                    // entries carried so far (all of this chunk)
       if (in_chunk == 3u || pos + 1u == stride) {
