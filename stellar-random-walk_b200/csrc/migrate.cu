@@ -94,7 +94,7 @@ int64_t default_seg_cap(const srw_graph *g, int64_t n_rounds, unsigned grid) {
   // that still fills up spills locally (correct, one super-step later).
   int64_t cap = W > 1 ? (3 * n + 2 * (W - 1) - 1) / (2 * (W - 1)) : 0;
   if (cap > n) cap = n;
-  return cap + (int64_t)grid * 8 * kMigChunk + 1024;
+  return (cap + (int64_t)grid * 8 * kMigChunk + 1024 + 31) & ~(int64_t)31;      // whole 32-slot blocks (mig_word)
 }
 unsigned mig_grid() {
   const char *e = getenv("SRW_MIG_BLOCKS");
@@ -108,7 +108,8 @@ extern "C" srw_status srw_mig_block_bytes(const srw_graph *g, const srw_params *
   if (n_rounds < 1 || !bytes) { srw_set_error("srw_mig_block_bytes: bad argument"); return SRW_ERR_ARG; }
   const unsigned grid = mig_grid();
   if (seg_cap <= 0) seg_cap = default_seg_cap(g, n_rounds, grid);
-  const int64_t spill = g->nv * n_rounds + (int64_t)grid * 8 * kMigChunk + 1024;
+  seg_cap = (seg_cap + 31) & ~(int64_t)31;
+  const int64_t spill = (g->nv * n_rounds + (int64_t)grid * 8 * kMigChunk + 1024 + 31) & ~(int64_t)31;
   const int64_t hmax = (g->nv + g->shard_world - 1) / g->shard_world;
   *bytes = mig_layout(g->shard_world, seg_cap, spill, hmax * n_rounds, p->walk_length + 2).total;
   return SRW_OK;
@@ -124,8 +125,8 @@ extern "C" srw_status srw_mig_create(const srw_graph *g, const srw_params *p, in
   srw_mig *m = new srw_mig();
   m->g = g; m->prm = *p; m->world = g->shard_world; m->rank = g->shard_rank; m->n_rounds = n_rounds;
   m->grid = mig_grid();
-  m->seg_cap = seg_cap > 0 ? seg_cap : default_seg_cap(g, n_rounds, m->grid);
-  m->spill_cap = g->nv * n_rounds + (int64_t)m->grid * 8 * kMigChunk + 1024;
+  m->seg_cap = ((seg_cap > 0 ? seg_cap : default_seg_cap(g, n_rounds, m->grid)) + 31) & ~(int64_t)31;
+  m->spill_cap = (g->nv * n_rounds + (int64_t)m->grid * 8 * kMigChunk + 1024 + 31) & ~(int64_t)31;
   m->stride = p->walk_length + 2;
   m->home_rows = (g->nv - m->rank + m->world - 1) / m->world;
   m->home_rows_max = (g->nv + m->world - 1) / m->world;

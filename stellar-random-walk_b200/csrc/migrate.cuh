@@ -115,6 +115,12 @@ __device__ __forceinline__ uint32_t mig_carried(uint32_t phase, uint32_t len) {
   return n < len - 1u ? n : len - 1u;
 }
 
+// Inbox slots are grouped in blocks of 32 (= the chunks senders claim); inside a block the three 16-byte words of the 32 tuples
+// are stored word by word (word k of slot j at block * 96 + k * 32 + j, in int4 units).  Lanes that send together hold
+// consecutive slots, so each of their three store instructions writes ONE contiguous run of 16-byte words -- NVLink carries
+// a few large write packets instead of a 16-byte packet per lane and word -- and lanes that refill together read the same way.
+__device__ __forceinline__ uint64_t mig_word(uint32_t slot, uint32_t k) { return (uint64_t)(slot >> 5) * 96u + k * 32u + (slot & 31u); }
+
 __device__ __forceinline__ int mig_owner(const MigArgs &a, int32_t v) {
   int o = 0;
   while (o + 1 < a.world && (int64_t)v >= a.bounds[o + 1]) o++;
@@ -230,8 +236,7 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
     if (__any_sync(0xffffffffu, st == MS_LOAD)) {
       bool pend = false;
       if (st == MS_LOAD) {
-        const int4 *tp = a.in_base + 3ull * item;
-        const int4 q0 = gather16<0>(tp), q1 = gather16<0>(tp + 1), q2 = gather16<0>(tp + 2);
+        const int4 q0 = gather16<0>(a.in_base + mig_word(item, 0)), q1 = gather16<0>(a.in_base + mig_word(item, 1)), q2 = gather16<0>(a.in_base + mig_word(item, 2));
         walker = (uint32_t)q0.x; prev = q0.y; curr = q0.z; off = (uint32_t)q0.w;
         deg = (uint32_t)q1.x; m = (uint32_t)q1.y >> MIG_M_SHIFT; trial = (uint32_t)q1.z; len = (uint32_t)q1.w;
         pown = ((uint32_t)q1.y >> MIG_POWN_SHIFT) & 15u;
@@ -334,7 +339,12 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
     // ---- B2 / C2: the filter word ----
     if (__any_sync(0xffffffffu, need_test)) {
       if (need_test) {
-        const unsigned long long bw = __ldg(a.bloom + bword);
+        unsigned long long bw;
+#ifdef SRW_EMU
+        bw = a.bloom[bword];
+#else
+        asm("ld.global.nc.L2::64B.u64 %0, [%1];" : "=l"(bw) : "l"(a.bloom + bword));     // a missing probe fills 64 bytes, not a 128-byte line
+#endif
         if ((bw & bmask) != bmask) member = 0;                             // definitely not adjacent
         else if ((int)xown != me) { send = (int)xown; send_kind = MIG_PENDING; }   // verify where the walker would go anyway
         else {                                                             // exact test in x's row, here, from the next pass on
@@ -392,7 +402,7 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
       __syncwarp();
       if (u + n > (unsigned)kMigChunk) {
         // close the open chunk (pad with NOPs) and claim the next one
-        if (u + (unsigned)lane < (unsigned)kMigChunk) a.out_base[d][3ull * (cb + u + (unsigned)lane) + 1] = make_int4(0, (int)MIG_NOP, 0, 0);
+        if (u + (unsigned)lane < (unsigned)kMigChunk) a.out_base[d][mig_word(cb + u + (unsigned)lane, 1)] = make_int4(0, (int)MIG_NOP, 0, 0);
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(a.out_cnt + d, (unsigned long long)kMigChunk);
         base = __shfl_sync(0xffffffffu, base, 0);
@@ -416,11 +426,11 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
       }
       if (send == d) {
         const unsigned int slot = cb + u + (unsigned)__popc(sm & lt);
-        int4 *p = a.out_base[d] + 3ull * slot;
+        int4 *p = a.out_base[d];
         const uint32_t flags = send_kind | (d == W ? (uint32_t)MIG_FWD : 0u);     // parked in the spill region: routed again next super-step
-        p[0] = make_int4((int)walker, prev, curr, (int)off);
-        p[1] = make_int4((int)deg, (int)((m << MIG_M_SHIFT) | ((pown & 15u) << MIG_POWN_SHIFT) | flags), (int)trial, (int)len);
-        p[2] = make_int4(c0, c1, c2, (int)hrow);
+        p[mig_word(slot, 0)] = make_int4((int)walker, prev, curr, (int)off);
+        p[mig_word(slot, 1)] = make_int4((int)deg, (int)((m << MIG_M_SHIFT) | ((pown & 15u) << MIG_POWN_SHIFT) | flags), (int)trial, (int)len);
+        p[mig_word(slot, 2)] = make_int4(c0, c1, c2, (int)hrow);
         if ((send_kind & MIG_KIND_MASK) == MIG_PENDING) a.out_ext[d][slot] = make_int4(x, (int)xoff, (int)xdeg, (int)((xm << 8) | xown));
         st = MS_EMPTY;
       }
@@ -431,7 +441,7 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
   // pad the open chunks, then hand the counts over
   for (int d = 0; d <= W; ++d) {
     const unsigned u = used[d];
-    if (u + (unsigned)lane < (unsigned)kMigChunk) a.out_base[d][3ull * (chunk[d] + u + (unsigned)lane) + 1] = make_int4(0, (int)MIG_NOP, 0, 0);
+    if (u + (unsigned)lane < (unsigned)kMigChunk) a.out_base[d][mig_word(chunk[d] + u + (unsigned)lane, 1)] = make_int4(0, (int)MIG_NOP, 0, 0);
   }
   if (STATS) {
     for (int o = 16; o > 0; o >>= 1) {

@@ -60,8 +60,9 @@ extern "C" int emu_migrate_walk(int64_t nv, const int64_t *off, const int32_t *c
       srw_bloom_probe((int32_t)r, col[e], bloom_words, &word, &mask);
       bloom[(size_t)word] |= mask;
     }
-  const int64_t spill_cap = nv * n_rounds + (int64_t)grid_blocks * 8 * kMigChunk + 64;
+  const int64_t spill_cap = (nv * n_rounds + (int64_t)grid_blocks * 8 * kMigChunk + 64 + 31) & ~(int64_t)31;
   if (seg_cap <= 0) seg_cap = (nv * n_rounds + W - 1) / W + (int64_t)grid_blocks * 8 * kMigChunk + 64;
+  seg_cap = (seg_cap + 31) & ~(int64_t)31;       // whole 32-slot blocks (mig_word)
   const int64_t slots = (int64_t)W * seg_cap + spill_cap;
   std::vector<Shard> sh((size_t)W);
   std::vector<int64_t> base((size_t)W);
