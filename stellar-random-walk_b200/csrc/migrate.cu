@@ -164,6 +164,7 @@ extern "C" srw_status srw_mig_create(const srw_graph *g, const srw_params *p, in
     a.home_paths[h] = (int32_t *)(m->peers[h] + m->L.o_paths);
     a.home_rows[h] = (g->nv - h + m->world - 1) / m->world;
   }
+  a.debug = getenv("SRW_MIG_DEBUG") ? atoi(getenv("SRW_MIG_DEBUG")) : 0;     // timing experiments only: the paths are wrong with it
   a.cursor = m->d_scratch; a.done_warps = m->d_scratch + 1; a.out_cnt = m->d_scratch + 2; a.stats = m->d_scratch + 2 + kMigMaxDest;
   *out = m;
   return SRW_OK;

@@ -87,6 +87,7 @@ struct MigArgs {
   unsigned long long *cursor;             // inbox work cursor (low 32 bits used)
   unsigned long long *out_cnt;            // [world + 1] slots claimed per destination region
   unsigned long long *done_warps;
+  int debug;                              // measurement switches (SRW_MIG_DEBUG): 1 = drop the path stores, 2 = path stores go to the local GPU
   unsigned long long *stats;              // [0] slots sent this super-step (written by the last warp), [1] steps, [2] proposals, [3] tests, [4] exact tests, [5] spills, [6] error flags, [7] exact tests that found the edge
 };
 
@@ -103,7 +104,7 @@ struct MigTuple {            // 48 bytes: three 16-byte words
 struct MigExt {              // 16 bytes, only for MIG_PENDING: the proposal under test
   int32_t x;
   uint32_t xoff, xdeg;
-  uint32_t xm_own;           // [31:8] parallel edges curr-x, [7:0] owner(x)
+  uint32_t xm_own;           // [31:8] parallel edges curr-x, [7:4] owner(curr), [3:0] owner(x)
 };
 
 // number of path entries a walker with `len` ids holds back (positions >= 1 only: position 0 is written by the home GPU);
@@ -253,8 +254,8 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
       if (__any_sync(0xffffffffu, pend)) {
         if (pend) {                                                        // a proposal under test arrives: t in N(x)? in x's own row
           const int4 q0 = gather16<0>(a.in_ext + item);
-          x = q0.x; xoff = (uint32_t)q0.y; xdeg = (uint32_t)q0.z; xm = (uint32_t)q0.w >> 8; xown = (uint32_t)q0.w & 0xFFu;
-          cown = 0xFFu;                                                    // owner(curr): only the verdict needs it (found then)
+          x = q0.x; xoff = (uint32_t)q0.y; xdeg = (uint32_t)q0.z; xm = (uint32_t)q0.w >> 8; xown = (uint32_t)q0.w & 15u;
+          cown = ((uint32_t)q0.w >> 4) & 15u;                              // owner(curr): where a rejected walker goes back to
           if (fwd && (int)xown != me) { send = (int)xown; send_kind = MIG_PENDING; }        // spilled: forward
           else {
             if (STATS) n_exact++;
@@ -359,12 +360,10 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
     if (member >= 0) verdict = (member ? acc_member : acc_non) ? 1 : 2;
     if (verdict == 1) {                                    // move along entry (x, xoff, xdeg, xm, xown)
       newv = x; moved = true;
-      if (cown == 0xFFu) cown = (uint32_t)mig_owner(a, curr);
       prev = curr; pown = cown;
       curr = x; off = xoff; deg = xdeg; m = xm; cown = xown;
     } else if (verdict == 2) {
       trial++;
-      if (cown == 0xFFu) cown = (uint32_t)mig_owner(a, curr);
       if ((int)cown == me) st = MS_TRIAL;
       else { send = (int)cown; send_kind = MIG_SETTLED; }  // the test ran at owner(x): back to the row of curr
     }
@@ -374,8 +373,9 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
       const uint32_t have = mig_carried(phase, len);                    // entries carried so far (all of this chunk)
       if (in_chunk == 3u || pos + 1u == stride) {
         // the chunk is complete (or the path ends): store carried + newv, positions pos - have .. pos
-        int32_t *dst = a.home_paths[hrow >> 28] + ((uint64_t)(hrow & kMigRowMask) * stride + (pos - have));
-        if (have == 3u && in_chunk == 3u) *reinterpret_cast<int4 *>(dst) = make_int4(c0, c1, c2, newv);
+        int32_t *dst = a.home_paths[a.debug == 2 ? (uint32_t)me : hrow >> 28] + ((uint64_t)(hrow & kMigRowMask) * stride + (pos - have));
+        if (a.debug == 1) {
+        } else if (have == 3u && in_chunk == 3u) *reinterpret_cast<int4 *>(dst) = make_int4(c0, c1, c2, newv);
         else if (have == 0u) dst[0] = newv;
         else if (have == 1u) { dst[0] = c0; dst[1] = newv; }
         else if (have == 2u) { dst[0] = c0; dst[1] = c1; dst[2] = newv; }
@@ -390,57 +390,53 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
       else { send = (int)cown; send_kind = MIG_SETTLED | (needext ? MIG_NEEDEXT : 0u); }
     }
     // ---- D: sends (tuples to the next inbox of their destination) ----
-    unsigned dmask = mig_reduce_or(send >= 0 ? 1u << send : 0u);        // destinations some lane sends to in this iteration
-    while (dmask) {
-      const int d = __ffs(dmask) - 1;
-      dmask &= dmask - 1;
-      const unsigned sm = __ballot_sync(0xffffffffu, send == d);
-      const unsigned n = (unsigned)__popc(sm);
-      unsigned u = used[d];
-      unsigned int cb = chunk[d];
-      bool full = false;
+    // A slot is claimed with ONE shared-memory atomic per sending lane on the warp's open chunk of that destination; only when a
+    // chunk fills up (once per 32 tuples and destination) does the warp claim the next one from the region's counter.  A chunk is
+    // full to the last slot before the next one is opened, so NOP padding exists only at the end of the kernel.
+    if (__any_sync(0xffffffffu, send >= 0)) {
+      unsigned pos = 0, cb = 0;
+      if (send >= 0) { pos = atomicAdd(&used[send], 1u); cb = chunk[send]; }      // the chunk this position belongs to (while pos < 32)
       __syncwarp();
-      if (u + n > (unsigned)kMigChunk) {
-        // close the open chunk (pad with NOPs) and claim the next one
-        if (u + (unsigned)lane < (unsigned)kMigChunk) a.out_base[d][mig_word(cb + u + (unsigned)lane, 1)] = make_int4(0, (int)MIG_NOP, 0, 0);
+      unsigned ovf = __ballot_sync(0xffffffffu, send >= 0 && pos >= (unsigned)kMigChunk);
+      while (ovf) {
+        const int d = __shfl_sync(0xffffffffu, send, __ffs(ovf) - 1);
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(a.out_cnt + d, (unsigned long long)kMigChunk);
         base = __shfl_sync(0xffffffffu, base, 0);
         const unsigned long long cap = d == W ? (unsigned long long)a.spill_cap : (unsigned long long)a.seg_cap;
-        if (base + kMigChunk > cap) {
-          full = true;
-          if (lane == 0) { used[d] = kMigChunk; atomicAdd(a.out_cnt + d, (unsigned long long)(0ull - (unsigned long long)kMigChunk)); }
+        const bool mine = send == d && pos >= (unsigned)kMigChunk;
+        if (base + kMigChunk > cap) {                                  // region full
+          if (lane == 0) atomicAdd(a.out_cnt + d, (unsigned long long)(0ull - (unsigned long long)kMigChunk));
+          if (mine) {
+            if (d == W) { n_err |= 2; send = -1; st = MS_EMPTY; }     // the spill region is sized for every walker of the batch: cannot happen
+            else { send = W; n_spill++; }                            // park locally: routed again next super-step
+          }
+          __syncwarp();
+          if (send == W && mine) { pos = atomicAdd(&used[W], 1u); cb = chunk[W]; }
         } else {
-          cb = (unsigned int)base; u = 0;
-          if (lane == 0) chunk[d] = cb;
+          if (lane == 0) { chunk[d] = (unsigned int)base; used[d] = 0; }
+          __syncwarp();
+          if (mine) { pos = atomicAdd(&used[d], 1u); cb = (unsigned int)base; }
         }
-      }
-      if (full) {
-        if (send == d) {
-          if (d == W) { n_err |= 2; send = -1; st = MS_EMPTY; }   // the spill region is sized for every walker of the batch: cannot happen
-          else { send = W; n_spill++; }                          // region full: park locally, forwarded next super-step
-        }
-        if (d != W) dmask |= 1u << W;                            // (warp-uniform) the spill region comes last
         __syncwarp();
-        continue;
+        ovf = __ballot_sync(0xffffffffu, send >= 0 && pos >= (unsigned)kMigChunk);
       }
-      if (send == d) {
-        const unsigned int slot = cb + u + (unsigned)__popc(sm & lt);
-        int4 *p = a.out_base[d];
-        const uint32_t flags = send_kind | (d == W ? (uint32_t)MIG_FWD : 0u);     // parked in the spill region: routed again next super-step
+      if (send >= 0) {
+        const unsigned int slot = cb + pos;
+        int4 *p = a.out_base[send];
+        const uint32_t flags = send_kind | (send == W ? (uint32_t)MIG_FWD : 0u);     // parked in the spill region: routed again next super-step
         p[mig_word(slot, 0)] = make_int4((int)walker, prev, curr, (int)off);
         p[mig_word(slot, 1)] = make_int4((int)deg, (int)((m << MIG_M_SHIFT) | ((pown & 15u) << MIG_POWN_SHIFT) | flags), (int)trial, (int)len);
         p[mig_word(slot, 2)] = make_int4(c0, c1, c2, (int)hrow);
-        if ((send_kind & MIG_KIND_MASK) == MIG_PENDING) a.out_ext[d][slot] = make_int4(x, (int)xoff, (int)xdeg, (int)((xm << 8) | xown));
+        if ((send_kind & MIG_KIND_MASK) == MIG_PENDING) a.out_ext[send][slot] = make_int4(x, (int)xoff, (int)xdeg, (int)((xm << 8) | ((cown & 15u) << 4) | (xown & 15u)));
         st = MS_EMPTY;
       }
-      if (lane == 0) used[d] = u + n;
       __syncwarp();
     }
   }
   // pad the open chunks, then hand the counts over
   for (int d = 0; d <= W; ++d) {
-    const unsigned u = used[d];
+    const unsigned u = used[d];          // <= kMigChunk here: an overflowing claim is resolved in the iteration it happens
     if (u + (unsigned)lane < (unsigned)kMigChunk) a.out_base[d][mig_word(chunk[d] + u + (unsigned)lane, 1)] = make_int4(0, (int)MIG_NOP, 0, 0);
   }
   if (STATS) {
