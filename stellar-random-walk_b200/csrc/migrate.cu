@@ -17,7 +17,7 @@ inline int64_t up256(int64_t x) { return (x + 255) & ~(int64_t)255; }
 
 struct MigLayout {
   int64_t slots;        // per inbox buffer: world * seg_cap + spill_cap
-  int64_t o_cnt, o_base[2], o_ext[2], o_paths, total;
+  int64_t o_cnt, o_base[2], o_paths, total;
 };
 MigLayout mig_layout(int world, int64_t seg_cap, int64_t spill_cap, int64_t path_rows, int32_t stride) {
   MigLayout L;
@@ -25,7 +25,6 @@ MigLayout mig_layout(int world, int64_t seg_cap, int64_t spill_cap, int64_t path
   int64_t o = 0;
   L.o_cnt = o; o += up256(2 * kMigMaxDest * 8);
   for (int b = 0; b < 2; ++b) { L.o_base[b] = o; o += up256(L.slots * 48); }
-  for (int b = 0; b < 2; ++b) { L.o_ext[b] = o; o += up256(L.slots * 16); }
   L.o_paths = o; o += up256(path_rows * (int64_t)stride * 4);
   L.total = o;
   return L;
@@ -68,7 +67,7 @@ struct srw_mig {
   unsigned long long *d_scratch = nullptr;     // cursor, done, out_cnt[kMigMaxDest], stats[8]
   int32_t *d_lens = nullptr;
   unsigned grid = 0;
-  bool stats = false;
+  bool stats = false, attr_set = false;
   MigArgs base;                                // everything that does not change between super-steps
 };
 
@@ -126,6 +125,7 @@ extern "C" srw_status srw_mig_create(const srw_graph *g, const srw_params *p, in
   m->g = g; m->prm = *p; m->world = g->shard_world; m->rank = g->shard_rank; m->n_rounds = n_rounds;
   m->grid = mig_grid();
   m->seg_cap = ((seg_cap > 0 ? seg_cap : default_seg_cap(g, n_rounds, m->grid)) + 31) & ~(int64_t)31;
+  if (m->seg_cap < kMigChunk) m->seg_cap = kMigChunk;      // a region must hold at least one chunk, or nothing is ever delivered
   m->spill_cap = (g->nv * n_rounds + (int64_t)m->grid * 8 * kMigChunk + 1024 + 31) & ~(int64_t)31;
   m->stride = p->walk_length + 2;
   m->home_rows = (g->nv - m->rank + m->world - 1) / m->world;
@@ -215,7 +215,6 @@ extern "C" srw_status srw_mig_superstep(srw_mig *m, int64_t s, unsigned long lon
   const int cur = (int)(s & 1), nxt = cur ^ 1;
   a.walker_base = (uint64_t)m->round_first * (uint64_t)m->g->nv;
   a.in_base = (const int4 *)(m->block + m->L.o_base[cur]);
-  a.in_ext = (const int4 *)(m->block + m->L.o_ext[cur]);
   a.in_cnt = (const unsigned long long *)(m->block + m->L.o_cnt) + cur * kMigMaxDest;
   a.n_rounds = m->n_active;
   {
@@ -228,11 +227,16 @@ extern "C" srw_status srw_mig_superstep(srw_mig *m, int64_t s, unsigned long lon
     char *blk = d == m->world ? m->block : m->peers[d];
     const int64_t first = d == m->world ? (int64_t)m->world * m->seg_cap : (int64_t)m->rank * m->seg_cap;
     a.out_base[d] = (int4 *)(blk + m->L.o_base[nxt]) + 3 * first;
-    a.out_ext[d] = (int4 *)(blk + m->L.o_ext[nxt]) + first;
     a.out_cnt_pub[d] = (unsigned long long *)(blk + m->L.o_cnt) + nxt * kMigMaxDest + (d == m->world ? m->world : m->rank);
   }
-  if (m->stats) mig_step_kernel<true><<<m->grid, 256, 0, stream>>>(a);
-  else mig_step_kernel<false><<<m->grid, 256, 0, stream>>>(a);
+  const size_t dyn = (size_t)8 * m->world * 3 * kMigStage * sizeof(int4);      // the warps' stages (migrate.cuh)
+  if (!m->attr_set) {
+    SRW_CUDA(cudaFuncSetAttribute(mig_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    SRW_CUDA(cudaFuncSetAttribute(mig_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    m->attr_set = true;
+  }
+  if (m->stats) mig_step_kernel<true><<<m->grid, 256, dyn, stream>>>(a);
+  else mig_step_kernel<false><<<m->grid, 256, dyn, stream>>>(a);
   SRW_CUDA(cudaGetLastError());
   if (d_sent) SRW_CUDA(cudaMemcpyAsync(d_sent, a.stats, 8, cudaMemcpyDeviceToDevice, stream));
   return SRW_OK;

@@ -22,6 +22,11 @@
 // => ~(1 - 1/world) hops per step instead of ~2.8 with the test at owner(prev) (round 1), identical decisions: every draw
 // is the pure function Philox(seed; walker, step, trial) of the single-GPU kernel (walk_fold_conv_kernel) and of the CPU twin.
 //
+// NVLink moves ~1e10 store REQUESTS per second and GPU whatever their size (measured: 2, 4 and 8 GPUs all levelled at ~230 GB/s
+// of 16-byte peer stores per GPU while the same kernel ran twice as fast with every shard on one device), so a departing walker
+// is first collected in SHARED MEMORY -- kMigStage tuples per warp and destination -- and a full stage leaves as one coalesced
+// copy: three runs of 256 contiguous bytes.
+//
 // Path entries go to the walker's HOME GPU (home(v) = v mod world, as shard.cu) as peer stores into its path matrix -- but not
 // one by one: a 4-byte store into a matrix far larger than L2 costs a DRAM read-modify-write on the home GPU, about as much as
 // one of the step's own gathers (measured: the first version ran at 8.5e9 steps/s per GPU against 13.3e9 with local paths).
@@ -46,8 +51,9 @@ enum : uint32_t { MIG_SETTLED = 0, MIG_PENDING = 1, MIG_NOP = 2, MIG_KIND_MASK =
                   MIG_POWN_SHIFT = 4 /* bits 4-7: owner(prev) */, MIG_M_SHIFT = 8 /* bits 8-31: parallel edges curr-prev */ };
 enum : int { MS_EMPTY = 0, MS_LOAD, MS_EXTENT, MS_TRIAL, MS_EXACT };
 
-constexpr int kMigChunk = 32;        // inbox slots a warp claims at a time per destination
-constexpr int kMigClaim = 64;        // inbox items a warp claims at a time
+constexpr int kMigChunk = 64;        // inbox slots a warp claims at a time per destination (a multiple of the 32-slot block of mig_word)
+constexpr int kMigStage = 16;        // tuples a warp collects in shared memory per destination before ONE coalesced flush over NVLink
+constexpr int kMigClaim = 128;       // inbox items a warp claims at a time
 constexpr int kMigMaxDest = SRW_MAX_SHARDS + 1;   // peers + the local spill region
 constexpr uint32_t kMigRowMask = 0x0FFFFFFFu;     // MigTuple::home_row: [31:28] home shard, [27:0] path row on it
 
@@ -70,7 +76,6 @@ struct MigArgs {
   int64_t n_rounds;
   // inbox of THIS super-step: regions 0..world-1 (filled by the peers), region `world` (local spill), then n_seed virtual seeds
   const int4 *__restrict__ in_base;       // 3 x int4 per slot (MigTuple)
-  const int4 *__restrict__ in_ext;        // 1 x int4 per slot
   const unsigned long long *__restrict__ in_cnt;   // [world + 1] slots used per region (published by the senders)
   int64_t seg_cap, spill_cap;             // slots per peer region / in the spill region (world * seg_cap + spill_cap < 2^32)
   int64_t n_seed;                         // virtual seeds of THIS super-step: seed j is walker number seed_first + j * seed_step of the
@@ -79,7 +84,6 @@ struct MigArgs {
                                           // slosh back and forth for the whole walk; staggering the seeds damps that mode at once)
   // destinations: region `rank` of every peer's NEXT inbox (index world = own spill region)
   int4 *out_base[kMigMaxDest];
-  int4 *out_ext[kMigMaxDest];
   unsigned long long *out_cnt_pub[kMigMaxDest];   // where the slot count of that region is published (peer memory)
   int32_t *home_paths[SRW_MAX_SHARDS];    // path matrix of every home GPU: [n_rounds * home_rows[h]][stride]
   int64_t home_rows[SRW_MAX_SHARDS];      // vertices v with v mod world == h
@@ -101,11 +105,9 @@ struct MigTuple {            // 48 bytes: three 16-byte words
   int32_t carry[3];          // decided path entries not yet stored: positions len - n .. len - 1, n = mig_carried(phase, len)
   uint32_t home_row;         // [31:28] home shard of the walker, [27:0] its path row there (no division on the hot path)
 };
-struct MigExt {              // 16 bytes, only for MIG_PENDING: the proposal under test
-  int32_t x;
-  uint32_t xoff, xdeg;
-  uint32_t xm_own;           // [31:8] parallel edges curr-x, [7:4] owner(curr), [3:0] owner(x)
-};
+// A MIG_PENDING tuple (a proposal x whose adjacency to prev is verified at owner(x)) reuses two words: `off` holds x and `deg`
+// holds [31:8] parallel edges curr-x, [7:4] owner(curr), [3:0] owner(x).  Row extents are not carried: owner(x) reads x's from its
+// own row table before the test, and a rejected walker goes back to owner(curr) with MIG_NEEDEXT.
 
 // number of path entries a walker with `len` ids holds back (positions >= 1 only: position 0 is written by the home GPU);
 // phase = (row * stride) & 3: chunk boundaries are the multiples of 4 of the GLOBAL int index row * stride + pos
@@ -141,19 +143,80 @@ __device__ __forceinline__ unsigned mig_reduce_or(unsigned v) { return __reduce_
 __device__ __forceinline__ unsigned mig_atomic_add32(unsigned long long *p, unsigned v) { return atomicAdd(reinterpret_cast<unsigned *>(p), v); }
 #endif
 
+// The whole warp copies the n staged tuples of destination d (stage: [3 words][kMigStage], word by word) into the open chunk of d's
+// inbox region: per word ONE run of n contiguous 16-byte stores (mig_word keeps a stage inside one 32-slot block).  A new chunk is
+// claimed from the region's counter when the open one is used up; a region that is full diverts the stage to the local spill region
+// with MIG_FWD set (routed again in the next super-step).
+template <class Args>
+__device__ __forceinline__ void mig_flush(const Args &a, int d, int n, int4 *stage, unsigned int *chunk, unsigned int *fill, int lane,
+                                           unsigned int &n_spill, unsigned int &n_err) {
+  const int W = a.world;
+  int dest = d;
+  uint32_t fwd_flag = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    unsigned f = fill[dest];
+    unsigned cb = chunk[dest];
+    __syncwarp();
+    bool ok = true;
+    if (f + (unsigned)kMigStage > (unsigned)kMigChunk) {              // no room in the open chunk: claim the next one
+      // (the tail of the old chunk, if any, is padded at the end of the kernel only when it is the last one: a chunk is used in
+      // whole stages of kMigStage slots, and kMigChunk is a multiple of kMigStage, so a used-up chunk has no tail)
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(a.out_cnt + dest, (unsigned long long)kMigChunk);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      const unsigned long long cap = dest == W ? (unsigned long long)a.spill_cap : (unsigned long long)a.seg_cap;
+      if (base + kMigChunk > cap) {
+        if (lane == 0) atomicAdd(a.out_cnt + dest, (unsigned long long)(0ull - (unsigned long long)kMigChunk));
+        ok = false;
+      } else {
+        cb = (unsigned int)base; f = 0;
+        if (lane == 0) chunk[dest] = cb;
+      }
+    }
+    if (ok) {
+      int4 *out = a.out_base[dest];
+      const int4 *sp = stage + d * (3 * kMigStage);
+      for (int e = lane; e < 3 * kMigStage; e += 32) {
+        const int k = e / kMigStage, j = e % kMigStage;
+        if (j < n) {
+          int4 v = sp[e];
+          if (k == 1) v.y |= (int)fwd_flag;
+          out[mig_word(cb + f + (unsigned)j, (uint32_t)k)] = v;
+        } else if (k == 1) {
+          out[mig_word(cb + f + (unsigned)j, 1)] = make_int4(0, (int)MIG_NOP, 0, 0);     // a partial stage (end of the kernel): the rest of its slots
+        }
+      }
+      if (lane == 0) fill[dest] = f + (unsigned)kMigStage;
+      __syncwarp();
+      return;
+    }
+    if (dest == W) { if (lane == 0) n_err |= 2; return; }       // the spill region is sized for every walker of the batch: cannot happen
+    if (lane == 0) n_spill += (unsigned)n;
+    dest = W; fwd_flag = MIG_FWD;                                  // region full: park the stage locally
+  }
+}
+
 template <bool STATS, int MINB = 4>
 __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
   // per-warp send state: open chunk (first slot, slots used) per destination region; prefix of the inbox regions (+ seeds)
-  __shared__ unsigned int s_chunk[8][kMigMaxDest];
-  __shared__ unsigned int s_used[8][kMigMaxDest];
+  __shared__ unsigned int s_chunk[8][kMigMaxDest];     // open chunk of the destination region: first slot ...
+  __shared__ unsigned int s_fill[8][kMigMaxDest];      // ... and slots of it already written (kMigChunk = none open)
+  __shared__ unsigned int s_used[8][kMigMaxDest];      // tuples in the stage
+#ifdef SRW_EMU
+  static int4 mig_dyn[8 * kMigMaxDest * kMigStage * 3];
+#else
+  extern __shared__ int4 mig_dyn[];                    // [8 warps][world][3 words][kMigStage] staged tuples
+#endif
   __shared__ unsigned int s_pre[8][kMigMaxDest + 2];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
   const int W = a.world, me = a.rank;
   unsigned int *chunk = s_chunk[wib];
   unsigned int *used = s_used[wib];
+  unsigned int *fill = s_fill[wib];
   unsigned int *pre = s_pre[wib];
-  if (lane <= W) { chunk[lane] = 0; used[lane] = kMigChunk; }
+  int4 *stage = mig_dyn + (size_t)wib * W * (3 * kMigStage);
+  if (lane <= W) { chunk[lane] = 0; fill[lane] = kMigChunk; used[lane] = 0; }
   if (lane == 0) {
     unsigned int acc = 0;
     for (int r = 0; r <= W; ++r) { pre[r] = acc; acc += a.in_cnt ? (unsigned int)a.in_cnt[r] : 0u; }
@@ -253,12 +316,13 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
       }
       if (__any_sync(0xffffffffu, pend)) {
         if (pend) {                                                        // a proposal under test arrives: t in N(x)? in x's own row
-          const int4 q0 = gather16<0>(a.in_ext + item);
-          x = q0.x; xoff = (uint32_t)q0.y; xdeg = (uint32_t)q0.z; xm = (uint32_t)q0.w >> 8; xown = (uint32_t)q0.w & 15u;
-          cown = ((uint32_t)q0.w >> 4) & 15u;                              // owner(curr): where a rejected walker goes back to
+          x = (int32_t)off; xm = deg >> 8; cown = (deg >> 4) & 15u; xown = deg & 15u;       // (see MIG_PENDING: `off` / `deg` carry x and its tags)
           if (fwd && (int)xown != me) { send = (int)xown; send_kind = MIG_PENDING; }        // spilled: forward
           else {
             if (STATS) n_exact++;
+            const int64_t *o = a.off + ((int64_t)x - a.row_first);         // x's row extent from this shard's own row table
+            const int64_t e0 = __ldg(o), e1 = __ldg(o + 1);
+            xoff = (uint32_t)e0; xdeg = (uint32_t)(e1 - e0);
             pnb = srw_hash_buckets((int64_t)xoff, xdeg);
             if (pnb) bkt = __umulhi(srw_hash32((uint32_t)prev), pnb); else { lo = 0; hi = xdeg; }
             st = MS_EXACT;
@@ -365,7 +429,7 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
     } else if (verdict == 2) {
       trial++;
       if ((int)cown == me) st = MS_TRIAL;
-      else { send = (int)cown; send_kind = MIG_SETTLED; }  // the test ran at owner(x): back to the row of curr
+      else { send = (int)cown; send_kind = MIG_SETTLED | MIG_NEEDEXT; }  // the test ran at owner(x): back to the row of curr, whose extent is re-read there
     }
     if (moved) {                                           // RW:114: the step is decided -> the walker's home path row, four entries at a time
       const uint32_t phase = ((hrow & kMigRowMask) * stride) & 3u;
@@ -389,55 +453,47 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
       else if ((int)cown == me) st = needext ? MS_EXTENT : MS_TRIAL;
       else { send = (int)cown; send_kind = MIG_SETTLED | (needext ? MIG_NEEDEXT : 0u); }
     }
-    // ---- D: sends (tuples to the next inbox of their destination) ----
-    // A slot is claimed with ONE shared-memory atomic per sending lane on the warp's open chunk of that destination; only when a
-    // chunk fills up (once per 32 tuples and destination) does the warp claim the next one from the region's counter.  A chunk is
-    // full to the last slot before the next one is opened, so NOP padding exists only at the end of the kernel.
+    // ---- D: sends ----
+    // A departing walker is written into the warp's shared-memory stage of its destination (one shared-memory atomic per lane);
+    // a stage that fills up (kMigStage tuples) is flushed by the whole warp into the destination's inbox region.
     if (__any_sync(0xffffffffu, send >= 0)) {
-      unsigned pos = 0, cb = 0;
-      if (send >= 0) { pos = atomicAdd(&used[send], 1u); cb = chunk[send]; }      // the chunk this position belongs to (while pos < 32)
+      const uint32_t w_off = (send_kind & MIG_KIND_MASK) == MIG_PENDING ? (uint32_t)x : off;
+      const uint32_t w_deg = (send_kind & MIG_KIND_MASK) == MIG_PENDING ? ((xm << 8) | ((cown & 15u) << 4) | (xown & 15u)) : deg;
+      const int4 t0 = make_int4((int)walker, prev, curr, (int)w_off);
+      const int4 t1 = make_int4((int)w_deg, (int)((m << MIG_M_SHIFT) | ((pown & 15u) << MIG_POWN_SHIFT) | send_kind), (int)trial, (int)len);
+      const int4 t2 = make_int4(c0, c1, c2, (int)hrow);
+      unsigned pos = (unsigned)kMigStage;
+      if (send >= 0) {
+        pos = atomicAdd(&used[send], 1u);
+        if (pos < (unsigned)kMigStage) { int4 *sp = stage + send * (3 * kMigStage) + pos; sp[0] = t0; sp[kMigStage] = t1; sp[2 * kMigStage] = t2; }
+      }
       __syncwarp();
-      unsigned ovf = __ballot_sync(0xffffffffu, send >= 0 && pos >= (unsigned)kMigChunk);
-      while (ovf) {
+      unsigned ovf = __ballot_sync(0xffffffffu, send >= 0 && pos >= (unsigned)kMigStage);
+      while (ovf) {                                              // the stage of destination d is full: flush it, then retry
         const int d = __shfl_sync(0xffffffffu, send, __ffs(ovf) - 1);
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(a.out_cnt + d, (unsigned long long)kMigChunk);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        const unsigned long long cap = d == W ? (unsigned long long)a.spill_cap : (unsigned long long)a.seg_cap;
-        const bool mine = send == d && pos >= (unsigned)kMigChunk;
-        if (base + kMigChunk > cap) {                                  // region full
-          if (lane == 0) atomicAdd(a.out_cnt + d, (unsigned long long)(0ull - (unsigned long long)kMigChunk));
-          if (mine) {
-            if (d == W) { n_err |= 2; send = -1; st = MS_EMPTY; }     // the spill region is sized for every walker of the batch: cannot happen
-            else { send = W; n_spill++; }                            // park locally: routed again next super-step
-          }
-          __syncwarp();
-          if (send == W && mine) { pos = atomicAdd(&used[W], 1u); cb = chunk[W]; }
-        } else {
-          if (lane == 0) { chunk[d] = (unsigned int)base; used[d] = 0; }
-          __syncwarp();
-          if (mine) { pos = atomicAdd(&used[d], 1u); cb = (unsigned int)base; }
+        mig_flush(a, d, kMigStage, stage, chunk, fill, lane, n_spill, n_err);
+        if (lane == 0) used[d] = 0;
+        __syncwarp();
+        if (send == d && pos >= (unsigned)kMigStage) {
+          pos = atomicAdd(&used[d], 1u);
+          if (pos < (unsigned)kMigStage) { int4 *sp = stage + d * (3 * kMigStage) + pos; sp[0] = t0; sp[kMigStage] = t1; sp[2 * kMigStage] = t2; }
         }
         __syncwarp();
-        ovf = __ballot_sync(0xffffffffu, send >= 0 && pos >= (unsigned)kMigChunk);
+        ovf = __ballot_sync(0xffffffffu, send >= 0 && pos >= (unsigned)kMigStage);
       }
-      if (send >= 0) {
-        const unsigned int slot = cb + pos;
-        int4 *p = a.out_base[send];
-        const uint32_t flags = send_kind | (send == W ? (uint32_t)MIG_FWD : 0u);     // parked in the spill region: routed again next super-step
-        p[mig_word(slot, 0)] = make_int4((int)walker, prev, curr, (int)off);
-        p[mig_word(slot, 1)] = make_int4((int)deg, (int)((m << MIG_M_SHIFT) | ((pown & 15u) << MIG_POWN_SHIFT) | flags), (int)trial, (int)len);
-        p[mig_word(slot, 2)] = make_int4(c0, c1, c2, (int)hrow);
-        if ((send_kind & MIG_KIND_MASK) == MIG_PENDING) a.out_ext[send][slot] = make_int4(x, (int)xoff, (int)xdeg, (int)((xm << 8) | ((cown & 15u) << 4) | (xown & 15u)));
-        st = MS_EMPTY;
-      }
-      __syncwarp();
+      if (send >= 0) st = MS_EMPTY;
     }
   }
-  // pad the open chunks, then hand the counts over
+  // flush what is staged, pad the open chunks with NOPs, then hand the counts over
+  for (int d = 0; d < W; ++d) {
+    const unsigned n = used[d];
+    __syncwarp();
+    if (n) mig_flush(a, d, (int)n, stage, chunk, fill, lane, n_spill, n_err);
+  }
+  __syncwarp();
   for (int d = 0; d <= W; ++d) {
-    const unsigned u = used[d];          // <= kMigChunk here: an overflowing claim is resolved in the iteration it happens
-    if (u + (unsigned)lane < (unsigned)kMigChunk) a.out_base[d][mig_word(chunk[d] + u + (unsigned)lane, 1)] = make_int4(0, (int)MIG_NOP, 0, 0);
+    const unsigned f = fill[d];          // slots of the open chunk in use (kMigChunk: no open chunk)
+    for (unsigned j = f + (unsigned)lane; j < (unsigned)kMigChunk; j += 32) a.out_base[d][mig_word(chunk[d] + j, 1)] = make_int4(0, (int)MIG_NOP, 0, 0);
   }
   if (STATS) {
     for (int o = 16; o > 0; o >>= 1) {

@@ -17,7 +17,7 @@ struct Shard {
   std::vector<int64_t> off;
   std::vector<NbrEntry> ent;
   std::vector<int32_t> hash;
-  std::vector<int4> base[2], ext[2];
+  std::vector<int4> base[2];
   unsigned long long cnt[2][kMigMaxDest];
   std::vector<int32_t> paths;
   unsigned long long scratch[2 + kMigMaxDest + 9];
@@ -75,7 +75,7 @@ extern "C" int emu_migrate_walk(int64_t nv, const int64_t *off, const int32_t *c
     const int64_t n = off[r1] - off[r0];
     R.ent.resize((size_t)n);
     R.hash.assign((size_t)(((n >> 2) + 1) * 8), -1);
-    for (int b = 0; b < 2; ++b) { R.base[b].assign((size_t)slots * 3, make_int4(-1, -1, -1, -1)); R.ext[b].assign((size_t)slots, make_int4(-1, -1, -1, -1)); }
+    for (int b = 0; b < 2; ++b) { R.base[b].assign((size_t)slots * 3, make_int4(-1, -1, -1, -1)); }
     memset(R.cnt, 0, sizeof(R.cnt));
     memset(R.scratch, 0, sizeof(R.scratch));
     const int64_t hrows = (nv - s + W - 1) / W;
@@ -114,7 +114,7 @@ extern "C" int emu_migrate_walk(int64_t nv, const int64_t *off, const int32_t *c
       a.a = f.a; a.mp = f.mp; a.t_ret = f.t_ret; a.t_common = f.t_common; a.t_far = f.t_far;
       a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32); a.stride = stride;
       a.walker_base = (uint64_t)round_first * (uint64_t)nv; a.n_rounds = n_rounds;
-      a.in_base = R.base[cur].data(); a.in_ext = R.ext[cur].data(); a.in_cnt = R.cnt[cur];
+      a.in_base = R.base[cur].data(); a.in_cnt = R.cnt[cur];
       a.seg_cap = seg_cap; a.spill_cap = spill_cap;
       {
         const int64_t seeds = (bounds[r + 1] - bounds[r]) * n_rounds;
@@ -125,7 +125,6 @@ extern "C" int emu_migrate_walk(int64_t nv, const int64_t *off, const int32_t *c
         Shard &D = d == W ? R : sh[(size_t)d];
         const int64_t first = d == W ? (int64_t)W * seg_cap : (int64_t)r * seg_cap;
         a.out_base[d] = D.base[nxt].data() + 3 * first;
-        a.out_ext[d] = D.ext[nxt].data() + first;
         a.out_cnt_pub[d] = &D.cnt[nxt][d == W ? W : r];
       }
       for (int h = 0; h < W; ++h) { a.home_paths[h] = sh[(size_t)h].paths.data(); a.home_rows[h] = (nv - h + W - 1) / W; }

@@ -52,7 +52,7 @@ def test_migrate_equals_twin(oracle, world, sampler, p, q):
     mw.free()
 
 
-@pytest.mark.parametrize("world,seg_cap,bloom_bits", [(4, 128, 16), (8, 64, 16), (4, 0, 1), (8, 64, 2)])
+@pytest.mark.parametrize("world,seg_cap,bloom_bits", [(4, 256, 16), (8, 128, 16), (4, 0, 1), (8, 128, 2)])
 def test_migrate_spill_and_weak_filter(oracle, monkeypatch, world, seg_cap, bloom_bits):
     """Regions of a few chunks (tuples spill locally and are forwarded a super-step later) and a 1-2 bit/edge filter (most
     tests go to the exact check at owner(x): PENDING tuples, bounces).  Same paths."""

@@ -70,7 +70,7 @@ def test_migrate_equals_twin_karate(emu, oracle, shards, p, q):
     assert st["steps"] == sum(len(x) - 1 for x in want)
 
 
-@pytest.mark.parametrize("shards,bloom_bits,seg_cap", [(2, 16, 0), (4, 16, 0), (8, 16, 0), (4, 1, 0), (3, 16, 96), (8, 2, 32)])
+@pytest.mark.parametrize("shards,bloom_bits,seg_cap", [(2, 16, 0), (4, 16, 0), (8, 16, 0), (4, 1, 0), (3, 16, 64), (8, 2, 64)])
 def test_migrate_equals_twin_rmat(emu, oracle, shards, bloom_bits, seg_cap):
     """RMAT-8 (multi-edges, self-loops, hubs).  bloom_bits = 1 or 2: a filter that says "maybe" most of the time, so the
     exact test at owner(x), its PENDING tuples and the bounce back run all the time.  seg_cap 64 / 96: regions of two or three
