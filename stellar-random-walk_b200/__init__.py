@@ -271,6 +271,18 @@ class Graph:
         return cls(h)
 
     @classmethod
+    def from_edges_multi(cls, src, dst, num_gpus, directed=False):
+        """One vertex-range shard per GPU of this process inside one handle (srw_graph_from_edges_multi): walk it with
+        Params(gpus=num_gpus)."""
+        src = np.ascontiguousarray(src, dtype=np.int32)
+        dst = np.ascontiguousarray(dst, dtype=np.int32)
+        h = C.c_void_p()
+        L = lib()
+        L.srw_graph_from_edges_multi.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        check(L.srw_graph_from_edges_multi(len(src), _ptr(src), _ptr(dst), int(directed), num_gpus, C.byref(h)))
+        return cls(h)
+
+    @classmethod
     def from_device_edges(cls, n, d_src, d_dst, d_w=None, directed=False, flags=BUILD_ALIAS):
         h = C.c_void_p()
         check(lib().srw_graph_from_device_edges(n, d_src, d_dst, d_w, None, int(directed), flags, C.byref(h)))

@@ -113,6 +113,7 @@ srw_status multi_barrier(MultiWalk *w) {
 }  // namespace
 
 void srw_multi_free(MultiWalk *w) { multi_release(w); }
+bool g_srw_log_supersteps = false;
 
 // Rounds [round_first, round_first + n_rounds) of the walk over a multi-GPU container graph, delivered on device 0 in walker
 // order: d_paths0 [n_rounds * nv][walk_length + 2] vertex ids, d_lens0 [n_rounds * nv].  Blocking.
@@ -138,6 +139,7 @@ srw_status srw_multi_walk_rounds(const srw_graph *g, const srw_params *p, int64_
     if (s >= 1 && ((s & 3) == 3 || W == 1)) {
       int64_t sent = 0, c8[8];
       for (int d = 0; d < W; ++d) { SRW_TRY(srw_mig_counters(w->ctx[(size_t)d], c8, w->streams[(size_t)d])); sent += c8[0]; }
+      if (g_srw_log_supersteps) printf("Unfinished Walkers: %lld\n", (long long)sent);      // RW:154 (inbox slots in flight, read back every 4th super-step)
       if (sent == 0) break;
     }
     if (s > (int64_t)1 << 20) { srw_set_error("multi-GPU walk did not terminate"); return SRW_ERR_CUDA; }

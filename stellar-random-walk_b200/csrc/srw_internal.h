@@ -84,6 +84,8 @@ struct srw_graph {
   struct MultiWalk *multi = nullptr;
 };
 void srw_multi_free(struct MultiWalk *w);
+extern bool g_srw_log_supersteps;     // srw_main: print the reference's per-super-step `Unfinished Walkers: N` line (RW:154)
+int64_t srw_last_short_paths();        // paths of this thread's last srw_walk_save that ended at a dead end (RW:115-119 `Zero Neighbors`)
 srw_status srw_build_graph_device_multi(int64_t n, const int32_t *d_src, const int32_t *d_dst, const float *d_w, int directed,
                                         int num_gpus, srw_graph **out);
 // rounds [round_first, round_first + n_rounds) over a container graph, delivered on device 0 in walker order

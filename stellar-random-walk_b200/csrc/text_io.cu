@@ -206,6 +206,17 @@ extern "C" srw_status srw_paths_format_device(const int32_t *d_paths, const int3
   return SRW_OK;
 }
 
+namespace {
+__global__ void k_count_short(int64_t n, int32_t stride, const int32_t *__restrict__ lens, unsigned long long *out) {
+  unsigned long long c = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) c += lens[i] < stride ? 1u : 0u;
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+thread_local int64_t t_short_paths = 0;
+}  // namespace
+int64_t srw_last_short_paths() { return t_short_paths; }
+
 // RW:75-176 + RW:234-241 streamed: numWalks rounds in walker order, formatted on the device, written as
 // `parts` contiguous blocks of lines (Spark's repartition spreads lines arbitrarily, RW:240).
 extern "C" srw_status srw_walk_save(const srw_graph *g, const srw_params *params) {
@@ -238,7 +249,9 @@ extern "C" srw_status srw_walk_save(const srw_graph *g, const srw_params *params
   const int64_t chunk_bytes = getenv("SRW_SAVE_CHUNK_BYTES") ? atoll(getenv("SRW_SAVE_CHUNK_BYTES")) : ((int64_t)256 << 20);
   int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(batch, chunk_bytes / ((int64_t)stride * 12)));
   const int64_t text_cap = chunk * stride * 12;
-  DBuf d_paths, d_lens, d_text[2];
+  DBuf d_paths, d_lens, d_text[2], d_short;
+  t_short_paths = 0;
+  SRW_CUDA(d_short.alloc(8));
   PinBuf h_text[2], h_off[2];
   SRW_CUDA(d_paths.alloc((size_t)batch * stride * 4));
   SRW_CUDA(d_lens.alloc((size_t)batch * 4));
@@ -292,6 +305,15 @@ extern "C" srw_status srw_walk_save(const srw_graph *g, const srw_params *params
     rc = srw_walk_device(g, params, (uint64_t)first, nb, d_paths.as<int32_t>(), d_lens.as<int32_t>(), st);
     if (rc != SRW_OK) break;
     if (multi) SRW_CUDA(cudaSetDevice(g->device));
+    {
+      // walkers that stopped at a vertex without out-neighbours (RW:115-119; the reference's `Zero Neighbors` accumulator)
+      SRW_CUDA(cudaMemsetAsync(d_short.p, 0, 8, st));
+      k_count_short<<<148 * 4, 256, 0, st>>>(nb, stride, d_lens.as<int32_t>(), (unsigned long long *)d_short.p);
+      unsigned long long h = 0;
+      SRW_CUDA(cudaMemcpyAsync(&h, d_short.p, 8, cudaMemcpyDeviceToHost, st));
+      SRW_CUDA(cudaStreamSynchronize(st));
+      t_short_paths += (int64_t)h;
+    }
     srw_walk_info wi;
     srw_last_walk_info(&wi);
     kernel_ms += wi.kernel_ms; launches += wi.kernel_launches; steps += wi.steps;

@@ -118,3 +118,35 @@ def test_two_ranks_nccl():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29571", os.path.join(ROOT, "tests", "dist_sharded_check.py")], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "SHARDED_DIST_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
+
+
+def test_one_process_two_gpus_through_the_abi(oracle, tmp_path):
+    """`--gpus 2` behind the ordinary entry points (csrc/multi.cu): srw_graph_from_edges_multi / srw_graph_load build one shard
+    per device in ONE handle, srw_walk and srw_walk_save (the CLI) walk it with the migrating-walker kernel over peer memory, CUDA
+    events as the barrier.  Same paths and the same output files as one GPU.  Needs two GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (the driver's multi-GPU tier runs it)")
+    s, d = synth.rmat_edges(12, 8, seed=42)
+    twin = oracle.AliasGraph(oracle.Graph().load_edges(s, d, None))
+    ids, offs, st = twin.walk(walk_length=30, num_walks=3, p=0.5, q=2.0, seed=9, fold=1)
+    g = srw.Graph.from_edges_multi(s, d, 2)
+    assert g.stats() == (twin.nv, int(twin.view()["offsets"][-1]))
+    v0 = int(twin.view()["vids"][0])
+    assert len(g.neighbors(v0)) == int(np.diff(twin.view()["offsets"])[0])
+    got_ids, got_offs = g.walk(srw.Params(walkLength=30, numWalks=3, p=0.5, q=2.0, seed=9, sampler="fold", gpus=2)).arrays()
+    assert (got_offs == offs).all() and (got_ids == ids).all()
+    with pytest.raises(srw.SrwError):          # weighted / directed graphs are refused, not walked wrongly
+        srw.Graph.from_edges_multi(s, d, 2, directed=True)
+    g.free()
+    # the CLI: same files with --gpus 2 as with one GPU
+    inp = tmp_path / "edges.txt"
+    inp.write_text(synth.edges_to_text(s[:20000], d[:20000]))
+    outs = []
+    for gpus in (1, 2):
+        out = tmp_path / ("out%d" % gpus)
+        rc = srw.Main.main(["--cmd", "randomwalk", "--input", str(inp), "--output", str(out), "--walkLength", "20", "--numWalks", "2",
+                            "--p", "0.5", "--q", "2.0", "--weighted", "false", "--seed", "4", "--gpus", str(gpus)])
+        assert rc == 0
+        outs.append((out / "path" / "part-00000").read_bytes())
+    assert outs[0] == outs[1] and len(outs[0]) > 0
