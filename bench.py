@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--no-host-abi", action="store_true")
     ap.add_argument("--sampler", default="fold", choices=["fold", "alias"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--build", choices=["lean", "full"], default="lean",
+                    help="lean: SRW_BUILD_LEAN (only the arrays the alias/fold sampler reads stay in HBM); full: every array of SRW_BUILD_ALIAS")
     ap.add_argument("--e2e-reps", type=int, default=2)
     ap.add_argument("--async-rounds", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -79,6 +81,11 @@ def log(msg):
     if os.environ.get("RANK", "0") == "0":
         sys.stderr.write("[bench %7.1fs] %s\n" % (time.time() - _T0, msg))
         sys.stderr.flush()
+
+
+def build_flags(a, srw):
+    """SRW_BUILD_ALIAS, plus SRW_BUILD_LEAN unless --build full (the library ignores LEAN where it does not apply: weighted graphs)."""
+    return srw.BUILD_ALIAS | (srw.BUILD_LEAN if a.build == "lean" else 0)
 
 
 def workload_name(a):
@@ -327,7 +334,7 @@ def run_b200(a):
     def build(s, d, w):
         torch.cuda.synchronize()
         t = time.time()
-        g = srw.Graph.from_device_edges(n_edges, s.data_ptr(), d.data_ptr(), None if w is None else w.data_ptr(), False, srw.BUILD_ALIAS)
+        g = srw.Graph.from_device_edges(n_edges, s.data_ptr(), d.data_ptr(), None if w is None else w.data_ptr(), False, build_flags(a, srw))
         torch.cuda.synchronize()
         return g, time.time() - t
 
@@ -349,6 +356,7 @@ def run_b200(a):
     torch.cuda.empty_cache()
     nv, nnz = g.stats()
     graph_bytes = int(lib.srw_graph_device_bytes(g.h))
+    build_prof = json.loads(lib.srw_graph_build_profile(g.h).decode() or "{}")
 
     # walkers of one round are split across ranks (replicated graph) -- the sharded mode lives in shard.cu
     lo, hi = nv * rank // world, nv * (rank + 1) // world
@@ -513,7 +521,7 @@ def run_b200(a):
             barrier()
             t0 = time.time()
             dd = [t.to(dev, non_blocking=True) for t in h_edges]
-            g2 = srw.Graph.from_device_edges(n_edges, dd[0].data_ptr(), dd[1].data_ptr(), dd[2].data_ptr() if len(dd) > 2 else None, False, srw.BUILD_ALIAS)
+            g2 = srw.Graph.from_device_edges(n_edges, dd[0].data_ptr(), dd[1].data_ptr(), dd[2].data_ptr() if len(dd) > 2 else None, False, build_flags(a, srw))
             del dd
             torch.cuda.synchronize()
             t_built = time.time() - t0
@@ -649,7 +657,7 @@ def run_b200(a):
                 torch.cuda.empty_cache()
                 hs, hd = h_edges[0].numpy(), h_edges[1].numpy()
                 t0 = time.time()
-                gh = srw.Graph.from_edges(hs, hd, None, flags=srw.BUILD_ALIAS)
+                gh = srw.Graph.from_edges(hs, hd, None, flags=build_flags(a, srw))
                 t_b = time.time() - t0
                 prm_h = srw.Params(walkLength=a.walk_length, numWalks=k_rounds, p=a.p, q=a.q, seed=a.seed, sampler=a.sampler)
                 res_h = gh.walk(prm_h)
@@ -712,7 +720,8 @@ def run_b200(a):
                 "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "u32 (integer thresholds; f64 only in the Vose build)",
                 "data": "synthetic",
                 "config": {"workload": workload_name(a), "vertices_present": nv, "adjacency_entries": nnz, "walkers_per_step": nv,
-                           "graph_bytes_hbm": graph_bytes, "build_s": round(build_s, 3),
+                           "graph_bytes_hbm": graph_bytes, "build_s": round(build_s, 3), "build": a.build,
+                           "build_ms_per_phase": build_prof,
                            "l2": "inputs larger than L2 (CSR %.1f GB >> 126 MB), no flush needed" % (nnz * 4 / 1e9),
                            "parallelism": "1 GPU" if world == 1 else
                            "walkers (the independent units) split %d ways, no data-path collective; every rank holds the whole CSR "
@@ -895,7 +904,7 @@ def run_b200_multi(a):
     if not a.no_parity:
         try:
             d_src, d_dst = gen_edges()
-            g = srw.Graph.from_device_edges(n_edges, d_src.data_ptr(), d_dst.data_ptr(), None, False, srw.BUILD_ALIAS)
+            g = srw.Graph.from_device_edges(n_edges, d_src.data_ptr(), d_dst.data_ptr(), None, False, build_flags(a, srw))
             del d_src, d_dst
             torch.cuda.empty_cache()
             lo, hi = nv * rank // world, nv * (rank + 1) // world

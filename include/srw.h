@@ -112,6 +112,10 @@ srw_status srw_edges_parse_buffer_device(const char *buf, size_t len, int weight
 #define SRW_BUILD_ALIAS 2u   /* build neighbour-sorted rows + Vose slots (needed by SRW_SAMPLER_ALIAS) */
 #define SRW_BUILD_ALL 3u
 #define SRW_BUILD_MIGRATE 4u /* sharded builds: also the replicated edge filter the migrating-walker exchange needs (srw_mig_*) */
+#define SRW_BUILD_LEAN 8u    /* with SRW_BUILD_ALIAS on an unweighted, undirected, unsharded graph with non-negative ids: keep ONLY
+                              * what --sampler alias|fold reads (16-byte neighbour entries + id-labelled hash sets: 24 bytes per
+                              * adjacency entry instead of 36); the sorted column array, the rank-labelled hash sets and the row
+                              * descriptors are dropped.  Ignored (full build) where the conditions do not hold.  Same paths. */
 srw_status srw_graph_from_edges(int64_t n, const int32_t *h_src, const int32_t *h_dst, const float *h_w /*NULL=1.0f*/,
                                 const int32_t *h_pid /*NULL*/, int directed, unsigned flags, srw_graph **out);
 srw_status srw_graph_from_device_edges(int64_t n, const int32_t *d_src, const int32_t *d_dst, const float *d_w,
@@ -121,6 +125,9 @@ srw_status srw_graph_from_device_edges(int64_t n, const int32_t *d_src, const in
  * below) over peer memory; srw_graph_stats / _neighbors / _vertex_ids answer for the whole graph.  Undirected, unweighted.
  * srw_graph_load builds the same when params->num_gpus > 1. */
 srw_status srw_graph_from_edges_multi(int64_t n, const int32_t *h_src, const int32_t *h_dst, int directed, int num_gpus, srw_graph **out);
+/* Where the build of this handle spent its time: a JSON object {"phase": milliseconds, ...} (host clock around
+ * device-synchronised phases of K1-K3); valid until the handle is freed. */
+const char *srw_graph_build_profile(const srw_graph *g);
 /* loadGraph(): URW:17-88 / VRW:13-98 chosen by params->partitioned (Main:54-57) */
 srw_status srw_graph_load(const srw_params *params, unsigned flags, srw_graph **out);
 /* RW:23-24 nVertices / nEdges (= adjacency entries) */

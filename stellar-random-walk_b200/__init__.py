@@ -26,13 +26,14 @@ TASK_NODE2VEC, TASK_RANDOMWALK, TASK_EMBEDDING = 0, 1, 2
 SAMPLER_ALIAS, SAMPLER_EXACT, SAMPLER_ALIAS_FOLD = 0, 1, 2
 U_PHILOX, U_CONST = 0, 1
 BUILD_EXACT, BUILD_ALIAS, BUILD_ALL = 1, 2, 3
+BUILD_MIGRATE, BUILD_LEAN = 4, 8      # srw.h
 
 # every symbol include/srw.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "srw_last_error", "srw_version", "srw_device_count", "srw_params_default", "srw_params_parse_argv", "srw_usage",
     "srw_edges_parse_file", "srw_edges_parse_buffer", "srw_edges_view", "srw_edges_free",
     "srw_graph_from_edges", "srw_graph_from_device_edges", "srw_graph_load", "srw_graph_stats", "srw_graph_neighbors",
-    "srw_graph_partition", "srw_graph_vertex_ids", "srw_graph_layout", "srw_graph_device_bytes", "srw_graph_free",
+    "srw_graph_partition", "srw_graph_vertex_ids", "srw_graph_layout", "srw_graph_device_bytes", "srw_graph_build_profile", "srw_graph_free",
     "srw_graphmap_new", "srw_graphmap_add_vertex", "srw_graphmap_reset", "srw_graphmap_counts", "srw_graphmap_finalize",
     "srw_graphmap_free", "srw_sample", "srw_second_order_weights", "srw_second_order_sample", "srw_philox4x32_10",
     "srw_walk", "srw_walk_device", "srw_last_walk_info", "srw_walk_collect_stats", "srw_paths_view", "srw_paths_counts",
@@ -104,6 +105,9 @@ def lib():
     L.srw_graph_layout.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_int)]
     L.srw_graph_device_bytes.restype = C.c_int64
     L.srw_graph_device_bytes.argtypes = [vp]
+    L.srw_graph_build_profile.restype = C.c_char_p
+    L.srw_last_walk_kernel.restype = C.c_char_p
+    L.srw_graph_build_profile.argtypes = [vp]
     L.srw_graph_free.argtypes = [vp]
     L.srw_graphmap_new.argtypes = [C.POINTER(vp)]
     L.srw_graphmap_add_vertex.argtypes = [vp, C.c_int32, C.c_int64, vp, vp, vp]

@@ -16,6 +16,8 @@
 // build runs once per graph and is timed separately from the walk.
 #include <cub/cub.cuh>
 
+#include <chrono>
+
 #include "philox.cuh"
 #include "srw_internal.h"
 
@@ -397,6 +399,19 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
   g->directed = directed != 0;
   g->flags = flags;
   SRW_CUDA(cudaGetDevice(&g->device));
+  // build-time breakdown (srw_graph_build_profile): host clock around device-synchronised phases
+  auto t_last = std::chrono::steady_clock::now();
+  g->build_profile = "{";
+  auto phase = [&](const char *name) {
+    cudaDeviceSynchronize();
+    const auto now = std::chrono::steady_clock::now();
+    char buf[96];
+    snprintf(buf, sizeof buf, "%s\"%s\": %.3f", g->build_profile.size() > 1 ? ", " : "", name,
+             std::chrono::duration<double, std::milli>(now - t_last).count());
+    g->build_profile += buf;
+    t_last = now;
+  };
+  struct CloseProfile { std::string &s; ~CloseProfile() { s += "}"; } } close_profile{g->build_profile};
   if (n + n_extra <= 0) {  // empty graph
     SRW_CUDA(cudaMalloc(&g->d_off, sizeof(int64_t)));
     SRW_CUDA(cudaMemset(g->d_off, 0, sizeof(int64_t)));
@@ -443,6 +458,7 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
   g->nnz = nnz;
   SRW_CUDA(cudaMalloc(&g->d_vids, (size_t)nv * 4));
   k_vids<<<grid((int64_t)words), kThreads>>>(words, g->d_bitmap, g->d_wordrank, mn, g->d_vids);
+  phase("id_bitmap_rank");
 
   // ---- adjacency entries + degrees -> row offsets ----
   const bool sharded = shard_world > 1;
@@ -523,6 +539,7 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
   }
   const uint32_t *gidx = sharded ? ent_gidx.as<uint32_t>() : nullptr;
   deg.alloc(0);
+  phase(sharded ? "k_entries_range_sort" : "k_entries_scan");
   if ((flags & SRW_BUILD_MIGRATE) && !directed && n > 0) {
     // replicated on every shard: 16 bits per input edge by default (1 byte per adjacency entry; false positives ~0.4 %)
     const char *eb = getenv("SRW_BLOOM_BITS");
@@ -534,6 +551,7 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
     SRW_CUDA(cudaMemset(g->d_bloom, 0, g->bloom_words * 8));
     k_bloom_insert<<<grid(n), kThreads>>>(n, d_src, d_dst, g->d_bitmap, g->d_wordrank, mn, g->d_bloom, (uint32_t)g->bloom_words);
     SRW_CUDA(cudaDeviceSynchronize());
+    phase("k_bloom_insert");
   }
 
   if (d_pid) {  // GM:21,31
@@ -565,6 +583,7 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
     k_gather_u32<<<grid(nnz), kThreads>>>(nnz, v_in, ent_col.as<uint32_t>(), (uint32_t *)g->d_col_app);
     k_gather_w<<<grid(nnz), kThreads>>>(nnz, v_in, gidx, d_w, wshift, g->d_w_app);
     SRW_CUDA(cudaDeviceSynchronize());
+    phase("appearance_rows_sort");
   }
 
   // ---- K2: neighbour-sorted rows = stable sort by column, then stable sort by row ----
@@ -578,6 +597,7 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
   SRW_CUDA(cudaDeviceSynchronize());
   ent_row.alloc(0); ent_col.alloc(0);
   (void)ent_gidx;
+  phase("sorted_rows_2_sorts");
 
   bool weighted_graph = false;     // any weight != 1.0f (RS semantics are weight-relative; 1.0f rows need no table)
   if (d_w) {
@@ -591,14 +611,21 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
   }
 
   // ---- packed row descriptors + neighbour hash sets (membership test of the alias sampler) ----
+  // SRW_BUILD_LEAN: only what the id-space alias-fold kernel reads survives the build (d_off, d_vids, d_ent, d_hash_id)
+  const bool ids_ok = !sharded && !(flags & SRW_BUILD_MIGRATE) /* the migrating walk routes by rank */ && g->id_min >= 0 /* -1 marks an empty hash slot */ &&
+                      !(getenv("SRW_FOLD_IDS") && atoi(getenv("SRW_FOLD_IDS")) == 0);
+  const bool lean = (flags & SRW_BUILD_LEAN) && (flags & SRW_BUILD_ALIAS) && !(flags & SRW_BUILD_EXACT) && !weighted_graph && !directed && ids_ok;
   if (flags & SRW_BUILD_ALIAS) {
     g->hash_buckets = (nnz >> 2) + 1;
     SRW_CUDA(cudaMalloc(&g->d_meta, (size_t)(nrows ? nrows : 1) * sizeof(RowMeta)));
     k_row_meta<<<grid(nrows), kThreads>>>(nrows, g->d_off, g->d_meta);
-    SRW_CUDA(cudaMalloc(&g->d_hash, (size_t)g->hash_buckets * 32));
-    SRW_CUDA(cudaMemset(g->d_hash, 0xFF, (size_t)g->hash_buckets * 32));
-    k_hash_insert<<<grid(nnz), kThreads>>>(nnz, k_in, g->d_col, g->d_meta, g->d_hash);   // k_in = row keys in d_col order
-    SRW_CUDA(cudaDeviceSynchronize());
+    if (!lean) {
+      SRW_CUDA(cudaMalloc(&g->d_hash, (size_t)g->hash_buckets * 32));
+      SRW_CUDA(cudaMemset(g->d_hash, 0xFF, (size_t)g->hash_buckets * 32));
+      k_hash_insert<<<grid(nnz), kThreads>>>(nnz, k_in, g->d_col, g->d_meta, g->d_hash);   // k_in = row keys in d_col order
+      SRW_CUDA(cudaDeviceSynchronize());
+      phase("k_hash_insert");
+    }
     if (!weighted_graph) {
       DevBuf ovf;
       SRW_CUDA(ovf.alloc(4));
@@ -609,21 +636,30 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
       int h = 0;
       SRW_CUDA(cudaMemcpy(&h, ovf.p, 4, cudaMemcpyDeviceToHost));
       if (h) { cudaFree(g->d_ent); g->d_ent = nullptr; }    // absurd multiplicities: fold sampler unavailable
+      phase("k_nbr_entries");
+      if (lean && !g->d_ent) { srw_set_error("SRW_BUILD_LEAN: an edge multiplicity or a row offset does not fit the neighbour entry; build without the flag"); return SRW_ERR_UNSUPPORTED; }
       // ID SPACE (default; SRW_FOLD_IDS=0 at build time keeps the entries in rank space for A/B runs): the fold kernel treats a neighbour as an opaque label -- it compares it with prev,
       // hashes it and appends it to the path -- so the entries can carry ORIGINAL VERTEX IDS and the walk emits ids directly:
       // the rank -> id pass over the path matrix disappears (measured at RMAT-26, profiles/r1_fold_ids_ab.jsonl: 186.8 -> 174.2 ms per round).  Costs a second, id-labelled copy
       // of the hash sets (the rank-labelled one serves the other kernels).  Ranks ascend with ids, so rows stay sorted.
-      if (g->d_ent && !sharded && !(flags & SRW_BUILD_MIGRATE) /* the migrating walk routes by rank */ && g->id_min >= 0 /* -1 marks an empty hash slot */ && !(getenv("SRW_FOLD_IDS") && atoi(getenv("SRW_FOLD_IDS")) == 0)) {
+      if (g->d_ent && ids_ok) {
         if (cudaMalloc(&g->d_hash_id, (size_t)g->hash_buckets * 32) == cudaSuccess) {
           SRW_CUDA(cudaMemset(g->d_hash_id, 0xFF, (size_t)g->hash_buckets * 32));
           k_hash_insert_ids<<<grid(nnz), kThreads>>>(nnz, k_in, g->d_col, g->d_meta, g->d_vids, g->d_hash_id);
           k_ent_relabel<<<grid(nnz), kThreads>>>(nnz, g->d_vids, g->d_ent);
           SRW_CUDA(cudaDeviceSynchronize());
           g->ent_ids = true;
+          phase("k_hash_insert_ids");
         } else {
           cudaGetLastError();
           g->d_hash_id = nullptr;
+          if (lean) { srw_set_error("SRW_BUILD_LEAN: not enough device memory for the hash sets"); return SRW_ERR_CUDA; }
         }
+      }
+      if (lean) {                       // the fold kernel reads d_off, d_vids, d_ent and d_hash_id: nothing else is kept
+        cudaFree(g->d_col); g->d_col = nullptr;
+        cudaFree(g->d_meta); g->d_meta = nullptr;
+        g->lean = true;
       }
     }
   }
@@ -638,6 +674,7 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
       k_alias_rows<<<grid_for(nrows, 64), 64>>>(nrows, g->d_off, g->d_col, ws.as<float>(), g->d_slot, g->d_meta);
       SRW_CUDA(cudaDeviceSynchronize());
       g->has_alias = true;
+      phase("k_alias_rows");
       // weighted alias-fold (undirected, unsharded): 32-byte slots with the bundle weights.  48 bytes per entry in all:
       // HBM capacity is spent to keep a proposal at ONE memory request.
       if (!directed && !sharded && g->d_meta && !getenv("SRW_NO_WFOLD")) {
@@ -647,6 +684,7 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
         if (cudaMalloc(&g->d_slotw, (size_t)nnz * sizeof(AliasSlotW)) == cudaSuccess) {
           k_slots_w<<<grid(nnz), kThreads>>>(nnz, k_in, g->d_off, g->d_slot, wb.as<double>(), g->d_slotw);
           SRW_CUDA(cudaDeviceSynchronize());
+          phase("bundle_weights_wide_slots");
         } else {
           cudaGetLastError();            // not enough HBM for the wide slots: the classic alias sampler still runs
           g->d_slotw = nullptr;
@@ -655,8 +693,28 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
     }
   }
   SRW_CUDA(cudaGetLastError());
-  g->device_bytes = (int64_t)(words * 8 + (size_t)nv * 12 + (size_t)nnz * 4) + (g->d_col_app ? nnz * 8 : 0) +
+  g->device_bytes = (int64_t)(words * 8 + (size_t)nv * 12 + (g->d_col ? (size_t)nnz * 4 : 0)) + (g->d_col_app ? nnz * 8 : 0) +
                     (g->d_slot ? nnz * 16 : 0) + (g->d_slotw ? nnz * 32 : 0) + (g->d_vpid ? nv * 4 : 0) + (g->d_meta ? nrows * 32 : 0) + (g->d_hash ? g->hash_buckets * 32 : 0) + (g->d_hash_id ? g->hash_buckets * 32 : 0) + (g->d_ent ? nnz * 16 : 0) + (int64_t)g->bloom_words * 8;
+  return SRW_OK;
+}
+
+namespace {
+__global__ void k_ent_ranks(int64_t n, const NbrEntry *__restrict__ ent, const uint32_t *__restrict__ bitmap,
+                            const uint32_t *__restrict__ wordrank, int32_t id_min, int32_t *out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = rank_of(bitmap, wordrank, id_min, ent[i].x);
+}
+}  // namespace
+srw_status srw_ent_ranks_to_host(const srw_graph *g, int32_t *h_col) {
+  SRW_CUDA(cudaSetDevice(g->device));
+  const int64_t chunk = (int64_t)1 << 26;
+  DevBuf tmp;
+  SRW_CUDA(tmp.alloc((size_t)std::min<int64_t>(chunk, g->nnz) * 4));
+  for (int64_t at = 0; at < g->nnz; at += chunk) {
+    const int64_t m = std::min<int64_t>(chunk, g->nnz - at);
+    k_ent_ranks<<<grid_for(m) > 148 * 16 ? 148 * 16 : grid_for(m), kThreads>>>(m, g->d_ent + at, g->d_bitmap, g->d_wordrank, g->id_min, tmp.as<int32_t>());
+    SRW_CUDA(cudaMemcpy(h_col + at, tmp.p, (size_t)m * 4, cudaMemcpyDeviceToHost));
+  }
   return SRW_OK;
 }
 

@@ -129,6 +129,7 @@ extern "C" srw_status srw_graph_neighbors(const srw_graph *g, int32_t vid, int32
   const int64_t m = std::min(deg, cap);
   if (m <= 0) return SRW_OK;
   const int32_t *col = g->d_col_app ? g->d_col_app : g->d_col;  // appearance order when it was kept
+  if (!col) { srw_set_error("srw_graph_neighbors: this handle was built with SRW_BUILD_LEAN (no column array)"); return SRW_ERR_UNSUPPORTED; }
   if (h_dst) {
     std::vector<int32_t> ranks((size_t)m);
     SRW_CUDA(cudaMemcpy(ranks.data(), col + ext[0], (size_t)m * 4, cudaMemcpyDeviceToHost));
@@ -169,12 +170,22 @@ extern "C" srw_status srw_graph_layout(const srw_graph *g, int64_t *h_off, int32
   // on a vertex-range shard the arrays are shard-local: row_last - row_first + 1 offsets (relative to the shard's first entry)
   const int64_t n_rows = g->shard_world > 1 ? g->row_last - g->row_first : g->nv;
   if (h_off) SRW_CUDA(cudaMemcpy(h_off, g->d_off, (size_t)(n_rows + 1) * 8, cudaMemcpyDeviceToHost));
-  if (h_col && g->nnz) SRW_CUDA(cudaMemcpy(h_col, g->d_col, (size_t)g->nnz * 4, cudaMemcpyDeviceToHost));
+  if (h_col && g->nnz && g->d_col) SRW_CUDA(cudaMemcpy(h_col, g->d_col, (size_t)g->nnz * 4, cudaMemcpyDeviceToHost));
+  else if (h_col && g->nnz) {
+    // SRW_BUILD_LEAN: the sorted column array was dropped; the neighbour entries carry the same ids in the same order
+    if (!g->d_ent || !g->ent_ids) { srw_set_error("srw_graph_layout: this handle holds no column array"); return SRW_ERR_UNSUPPORTED; }
+    SRW_TRY(srw_ent_ranks_to_host(g, h_col));
+  }
   if (h_slots4 && g->has_alias) SRW_CUDA(cudaMemcpy(h_slots4, g->d_slot, (size_t)g->nnz * 16, cudaMemcpyDeviceToHost));
   return SRW_OK;
 }
 
 extern "C" int64_t srw_graph_device_bytes(const srw_graph *g) { return g ? g->device_bytes : 0; }
+extern "C" const char *srw_graph_build_profile(const srw_graph *g) {
+  if (!g) return "{}";
+  if (!g->shards.empty()) return g->shards[0] ? g->shards[0]->build_profile.c_str() : "{}";
+  return g->build_profile.empty() ? "{}" : g->build_profile.c_str();
+}
 
 extern "C" void srw_graph_free(srw_graph *g) {
   if (!g) return;
@@ -298,7 +309,8 @@ extern "C" int srw_main(int argc, const char *const *argv) {
     return 1;
   }
   // alias and fold share a layout; the exact sampler also uses the neighbour hash sets of the alias layout
-  const unsigned flags = prm.sampler == SRW_SAMPLER_EXACT ? SRW_BUILD_ALL : SRW_BUILD_ALIAS;
+  // (alias | fold: lean -- only the arrays the walk kernel reads stay in HBM; ignored where it does not apply)
+  const unsigned flags = prm.sampler == SRW_SAMPLER_EXACT ? SRW_BUILD_ALL : (SRW_BUILD_ALIAS | SRW_BUILD_LEAN);
   srw_graph *g = nullptr;
   auto t0 = std::chrono::steady_clock::now();
   if (srw_graph_load(&prm, flags, &g) != SRW_OK) { fprintf(stderr, "Exception: %s\n", srw_last_error()); return 2; }

@@ -58,6 +58,8 @@ struct srw_graph {
   NbrEntry *d_ent = nullptr;         // [nnz] unweighted, unsharded graphs (fold sampler)
   int32_t *d_hash_id = nullptr;      // id-space fold (SRW_FOLD_IDS): hash sets of original ids; d_ent[].x then holds ids too
   bool ent_ids = false;
+  bool lean = false;                 // SRW_BUILD_LEAN took effect: d_col, d_hash and d_meta were dropped
+  std::string build_profile;         // srw_graph_build_profile
   unsigned long long *d_bloom = nullptr;   // SRW_BUILD_MIGRATE: replicated edge filter of the migrating sharded walk (migrate.cuh), 64-bit words
   uint64_t bloom_words = 0;
   int64_t device_bytes = 0;
@@ -130,6 +132,8 @@ srw_status srw_build_graph_device(int64_t n, const int32_t *d_src, const int32_t
 srw_status srw_build_graph_rows(int64_t n_rows, const int32_t *h_vids, const int64_t *h_row_off, const int64_t *h_row_len,
                                 const int32_t *h_dst, const int32_t *h_pid, const float *h_w, unsigned flags,
                                 srw_graph **out);
+// lean handles: neighbour ranks of every entry (d_ent[].x holds ids) copied to the host in chunks
+srw_status srw_ent_ranks_to_host(const srw_graph *g, int32_t *h_col);
 void srw_alias_thresholds(double p, double q, uint64_t *t_ret, uint64_t *t_common, uint64_t *t_far);
 
 // text_io.cu

@@ -197,12 +197,15 @@ static srw_status walk_enqueue(const srw_graph *g, const srw_params *p, const Wa
     // oracle_alias_walk); unweighted graphs fold over multiplicities (walk_fold_conv_kernel), weighted ones over bundle weights
     FoldArgs f{};
     bool fold = false;
-    if ((peer || p->sampler == SRW_SAMPLER_ALIAS_FOLD) && (peer || (g->d_ent && g->d_hash)) && !g->directed && !g->has_alias) {
+    // a SRW_BUILD_LEAN handle holds only d_ent + d_hash_id: every alias-class walk on it runs through the id-space fold kernel
+    const bool lean = g->lean && g->d_ent && g->d_hash_id && g->ent_ids;
+    if ((peer || lean || p->sampler == SRW_SAMPLER_ALIAS_FOLD) && (peer || lean || (g->d_ent && g->d_hash)) && !g->directed && !g->has_alias) {
       fold = srw_fold_args(p->p, p->q, p->sampler == SRW_SAMPLER_ALIAS_FOLD, &f);
       f.ent = g->d_ent; f.hash = g->d_hash;
-      if (peer && !fold) {
+      if ((peer || lean) && !fold) {
         // classic rejection under M = max(1/p, 1, 1/q) through the same kernel: no return component
         f.a = 0.0; f.mp = 1.0; f.t_ret = a.t_ret; f.t_common = a.t_common; f.t_far = a.t_far;
+        if (lean) fold = true;
       }
     }
     FoldArgs wf{};

@@ -391,6 +391,47 @@ def test_fold_sampler_bit_equal(oracle, scale, ef, p, q, seed):
     assert (got_offs == offs).all() and (got_ids == ids).all()
 
 
+# ---- SRW_BUILD_LEAN: only d_ent + d_hash_id stay in HBM; every alias-class walk gives the full build's (= the twin's) paths ----
+@pytest.mark.parametrize("p,q,sampler,fold", [(0.5, 2.0, "fold", 1), (0.25, 4.0, "fold", 1), (2.0, 0.5, "fold", 0), (1.0, 1.0, "fold", 0), (0.5, 2.0, "alias", 0)])
+def test_lean_build_same_paths(oracle, p, q, sampler, fold):
+    s, d = synth.rmat_edges(10, 16, seed=42)
+    og = oracle.Graph().load_edges(s, d)
+    twin = oracle.AliasGraph(og)
+    full = srw.Graph.from_edges(s, d, None, flags=srw.BUILD_ALIAS)
+    lean = srw.Graph.from_edges(s, d, None, flags=srw.BUILD_ALIAS | srw.BUILD_LEAN)
+    assert srw.lib().srw_graph_device_bytes(lean.h) < 0.75 * srw.lib().srw_graph_device_bytes(full.h)
+    prm = srw.Params(walkLength=40, numWalks=2, p=p, q=q, seed=9, sampler=sampler)
+    ids, offs, _ = twin.walk(walk_length=40, num_walks=2, p=p, q=q, seed=9, fold=fold)
+    a = full.walk(prm).arrays()
+    b = lean.walk(prm).arrays()
+    assert srw.lib().srw_last_walk_kernel().decode().endswith(",1>")          # the id-space fold kernel
+    assert (a[1] == offs).all() and (a[0] == ids).all()
+    assert (b[1] == offs).all() and (b[0] == ids).all()
+    # the layout query rebuilds the sorted column array from the neighbour entries
+    nv, nnz = lean.stats()
+    o1, c1 = np.zeros(nv + 1, np.int64), np.zeros(nnz, np.int32)
+    o2, c2 = np.zeros(nv + 1, np.int64), np.zeros(nnz, np.int32)
+    srw.check(srw.lib().srw_graph_layout(full.h, o1.ctypes.data, c1.ctypes.data, None, None))
+    srw.check(srw.lib().srw_graph_layout(lean.h, o2.ctypes.data, c2.ctypes.data, None, None))
+    assert (o1 == o2).all() and (c1 == c2).all()
+    prof = __import__("json").loads(srw.lib().srw_graph_build_profile(lean.h).decode())
+    assert "k_hash_insert_ids" in prof and "k_hash_insert" not in prof
+    # what a lean handle cannot do fails loudly
+    with pytest.raises(srw.SrwError):
+        lean.walk(srw.Params(walkLength=5, numWalks=1, sampler="exact"))
+
+
+def test_lean_flag_is_ignored_where_it_does_not_apply(oracle):
+    s, d = synth.rmat_edges(8, 8, seed=42)
+    w = synth.edge_weights(len(s), seed=43)
+    for kw in (dict(w=w, directed=False), dict(w=None, directed=True)):
+        g0 = srw.Graph.from_edges(s, d, kw["w"], directed=kw["directed"], flags=srw.BUILD_ALIAS)
+        g1 = srw.Graph.from_edges(s, d, kw["w"], directed=kw["directed"], flags=srw.BUILD_ALIAS | srw.BUILD_LEAN)
+        prm = srw.Params(walkLength=20, numWalks=2, p=0.5, q=2.0, seed=3, sampler="fold")
+        a, b = g0.walk(prm).arrays(), g1.walk(prm).arrays()
+        assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+
+
 def test_fold_sampler_fallbacks(oracle):
     s, d = synth.rmat_edges(9, 8, seed=42)
     w = synth.edge_weights(len(s), seed=43)
