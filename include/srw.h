@@ -125,6 +125,10 @@ srw_status srw_graph_from_device_edges(int64_t n, const int32_t *d_src, const in
  * below) over peer memory; srw_graph_stats / _neighbors / _vertex_ids answer for the whole graph.  Undirected, unweighted.
  * srw_graph_load builds the same when params->num_gpus > 1. */
 srw_status srw_graph_from_edges_multi(int64_t n, const int32_t *h_src, const int32_t *h_dst, int directed, int num_gpus, srw_graph **out);
+/* The same with the partition-id column as the shard map (VCutRandomWalk: `--partitioned true --gpus N`; see
+ * srw_graph_from_device_edges_vcut).  srw_graph_load does this when params->partitioned && params->num_gpus > 1. */
+srw_status srw_graph_from_edges_multi_vcut(int64_t n, const int32_t *h_src, const int32_t *h_dst, const int32_t *h_pid, int directed,
+                                           int num_gpus, srw_graph **out);
 /* Where the build of this handle spent its time: a JSON object {"phase": milliseconds, ...} (host clock around
  * device-synchronised phases of K1-K3); valid until the handle is freed. */
 const char *srw_graph_build_profile(const srw_graph *g);
@@ -234,6 +238,15 @@ int srw_main(int argc, const char *const *argv);
  * stellar-random-walk_b200/sharded.py for the loop (RW:91-162).  Alias sampler only. ---- */
 srw_status srw_graph_from_device_edges_sharded(int64_t n, const int32_t *d_src, const int32_t *d_dst, const float *d_w,
                                                int directed, unsigned flags, int rank, int world, srw_graph **out);
+/* SURVEY 8(f)3 -- the VCut shard map (VRW:23-26 partition-id column, VRW:43-54 one GraphMap per partition, VRW:121-134 routing by
+ * GraphMap.getPartition(steps.last), GM:31,66-68): owner(v) = getPartition(v) mod world, where getPartition(v) is the partition id
+ * of the last input line in which v is a neighbour (srw_graph_partition).  Rank `rank` holds the complete rows of the vertices it
+ * owns -- not a contiguous rank range; an 8-byte-per-vertex extent table and a 1-byte-per-vertex owner table are replicated on
+ * every shard.  Walked by the migrating walk (srw_mig_*) only; same paths as any other sharding.  For such a shard
+ * srw_graph_shard_info reports row_first = 0, row_last = its row count, bounds = group sizes as a prefix sum.
+ * Undirected, unweighted; flags as srw_graph_from_device_edges_sharded. */
+srw_status srw_graph_from_device_edges_vcut(int64_t n, const int32_t *d_src, const int32_t *d_dst, const int32_t *d_pid,
+                                            int directed, unsigned flags, int rank, int world, srw_graph **out);
 /* bounds: world+1 first-ranks of the shards (identical on every rank) */
 srw_status srw_graph_shard_info(const srw_graph *g, int *rank, int *world, int64_t *row_first, int64_t *row_last,
                                 int64_t *bounds, int64_t *nnz_local);

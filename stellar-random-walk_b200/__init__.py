@@ -45,6 +45,7 @@ ABI_SYMBOLS = [
     "srw_shard_rows_info", "srw_shard_rows_relocate", "srw_shard_attach_block",
     "srw_mig_block_bytes", "srw_mig_create", "srw_mig_collect_stats", "srw_mig_begin", "srw_mig_superstep", "srw_mig_counters",
     "srw_mig_finish", "srw_mig_info", "srw_mig_free", "srw_graph_from_edges_multi",
+    "srw_graph_from_device_edges_vcut", "srw_graph_from_edges_multi_vcut",
 ]
 
 
@@ -284,6 +285,19 @@ class Graph:
         L = lib()
         L.srw_graph_from_edges_multi.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         check(L.srw_graph_from_edges_multi(len(src), _ptr(src), _ptr(dst), int(directed), num_gpus, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_edges_multi_vcut(cls, src, dst, pid, num_gpus, directed=False):
+        """The same with the partition-id column as the shard map (VCutRandomWalk on N GPUs: owner(v) = getPartition(v) mod N,
+        srw_graph_from_edges_multi_vcut)."""
+        src = np.ascontiguousarray(src, dtype=np.int32)
+        dst = np.ascontiguousarray(dst, dtype=np.int32)
+        pid = np.ascontiguousarray(pid, dtype=np.int32)
+        h = C.c_void_p()
+        L = lib()
+        L.srw_graph_from_edges_multi_vcut.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        check(L.srw_graph_from_edges_multi_vcut(len(src), _ptr(src), _ptr(dst), _ptr(pid), int(directed), num_gpus, C.byref(h)))
         return cls(h)
 
     @classmethod

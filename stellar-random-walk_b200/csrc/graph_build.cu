@@ -125,6 +125,46 @@ __global__ void k_entries_range(int64_t n, const int32_t *__restrict__ src, cons
     if (k1) { ent_row[p1] = rd - row_first; ent_col[p1] = rs; ent_gidx[p1] = (uint32_t)(2 * e + 1); }
   }
 }
+// ---- VCut shard map (VRW:23-26,121-134; GM:31,66-68): owner(v) = getPartition(v) mod world ----
+__global__ void k_vcut_owner(int64_t nv, const int32_t *__restrict__ vpid, int world, uint8_t *owner, uint32_t *key) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nv; v += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t p = vpid[v];                      // (-1: a vertex no edge leads to -- cannot happen on an undirected graph)
+    const int o = ((int)(p % world) + world) % world;     // Spark HashPartitioner: nonNegativeMod(pid.hashCode, numPartitions)
+    owner[v] = (uint8_t)o; key[v] = (uint32_t)o;
+  }
+}
+// first position of every owner's group in the sorted key array (groups that exist)
+__global__ void k_vcut_group_first(int64_t nv, const uint32_t *__restrict__ key, long long *first) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x)
+    if (i == 0 || key[i] != key[i - 1]) first[key[i]] = i;
+}
+struct VcutGroups { int64_t first[SRW_MAX_SHARDS + 1]; int64_t base[SRW_MAX_SHARDS + 1]; };
+// position i of the (owner, vertex)-sorted order holds vertex perm[i]: its row starts at poff[i] - base[owner] inside the owner's arrays
+__global__ void k_vcut_ext(int64_t nv, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ key, const int64_t *__restrict__ poff,
+                           VcutGroups gr, MigExt *ext, uint32_t *lrow) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t v = perm[i], o = key[i];
+    MigExt e; e.off = (uint32_t)(poff[i] - gr.base[o]); e.deg = (uint32_t)(poff[i + 1] - poff[i]);
+    ext[v] = e; lrow[v] = (uint32_t)(i - gr.first[o]);
+  }
+}
+__global__ void k_entries_owner(int64_t n, const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int directed,
+                                const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ wordrank, int32_t id_min,
+                                const uint8_t *__restrict__ owner, const uint32_t *__restrict__ lrow, int rank, uint32_t *ent_row,
+                                uint32_t *ent_col, uint32_t *ent_gidx, unsigned long long *cursor) {
+  const int64_t n_pad = (n + 31) & ~(int64_t)31;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_pad; e += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t rs = 0, rd = 0;
+    const bool live = e < n;
+    if (live) { rs = rank_of(bitmap, wordrank, id_min, src[e]); rd = rank_of(bitmap, wordrank, id_min, dst[e]); }
+    const bool k0 = live && owner[rs] == rank;
+    const bool k1 = live && !directed && owner[rd] == rank;
+    const uint32_t p0 = warp_reserve(k0, cursor);
+    if (k0) { ent_row[p0] = lrow[rs]; ent_col[p0] = rd; ent_gidx[p0] = (uint32_t)(directed ? e : 2 * e); }
+    const uint32_t p1 = warp_reserve(k1, cursor);
+    if (k1) { ent_row[p1] = lrow[rd]; ent_col[p1] = rs; ent_gidx[p1] = (uint32_t)(2 * e + 1); }
+  }
+}
 // SRW_BUILD_MIGRATE: every undirected input edge {rank(src), rank(dst)} sets kMigBloomK bits of one 64-bit word
 __global__ void k_bloom_insert(int64_t n, const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
                                const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ wordrank, int32_t id_min,
@@ -272,8 +312,8 @@ struct ShardBounds {
   int64_t base[SRW_MAX_SHARDS];        // global offset of the shard's first entry
 };
 __global__ void k_nbr_entries(int64_t nnz, const uint32_t *__restrict__ row_of, const int32_t *__restrict__ col,
-                              const int64_t *__restrict__ off, const int64_t *__restrict__ goff, ShardBounds sb, NbrEntry *ent,
-                              int *overflow) {
+                              const int64_t *__restrict__ off, const int64_t *__restrict__ goff, ShardBounds sb,
+                              const MigExt *__restrict__ ext, const uint8_t *__restrict__ own, NbrEntry *ent, int *overflow) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t lo = off[row_of[i]], hi = off[row_of[i] + 1];
     const int32_t x = col[i];
@@ -283,7 +323,9 @@ __global__ void k_nbr_entries(int64_t nnz, const uint32_t *__restrict__ row_of, 
     const int64_t mult = b - a + 1;
     int64_t xo, xd;
     uint32_t owner = 0;
-    if (goff) {
+    if (ext) {                       // VCut shard map
+      owner = own[x]; xo = ext[x].off; xd = ext[x].deg;
+    } else if (goff) {
       while ((int)owner + 1 < sb.world && (int64_t)x >= sb.first[owner + 1]) owner++;
       xo = goff[x] - sb.base[owner];
       xd = goff[x + 1] - goff[x];
@@ -395,7 +437,7 @@ void srw_alias_thresholds(double p, double q, uint64_t *t_ret, uint64_t *t_commo
 
 static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_dst, const float *d_w, const int32_t *d_pid,
                              int directed, unsigned flags, int64_t n_extra, const int32_t *d_extra, srw_graph *g, int shard_rank = 0,
-                             int shard_world = 1) {
+                             int shard_world = 1, bool vcut = false) {
   g->directed = directed != 0;
   g->flags = flags;
   SRW_CUDA(cudaGetDevice(&g->device));
@@ -475,6 +517,18 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
     SRW_CUDA(cudaDeviceSynchronize());
     return SRW_OK;
   };
+  auto build_vpid = [&]() -> srw_status {   // GM:21,31
+    if (!d_pid || g->d_vpid) return SRW_OK;
+    DevBuf last;
+    SRW_CUDA(last.alloc((size_t)nv * 8));
+    SRW_CUDA(cudaMemset(last.p, 0, (size_t)nv * 8));
+    k_vpid_last<<<grid(n), kThreads>>>(n, d_src, d_dst, directed, g->d_bitmap, g->d_wordrank, mn, last.as<unsigned long long>());
+    SRW_CUDA(cudaMalloc(&g->d_vpid, (size_t)nv * 4));
+    k_vpid_fill<<<grid(nv), kThreads>>>(nv, last.as<unsigned long long>(), d_pid, g->d_vpid);
+    SRW_CUDA(cudaDeviceSynchronize());
+    g->has_pid = true;
+    return SRW_OK;
+  };
   g->shard_rank = shard_rank; g->shard_world = shard_world;
   g->row_first = 0; g->row_last = nv; g->nnz_global = nnz;
   g->bounds.assign((size_t)shard_world + 1, 0);
@@ -491,6 +545,78 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
                                        ent_col.as<uint32_t>(), deg.as<uint32_t>());
     SRW_CUDA(cudaMalloc(&g->d_off, (size_t)(nv + 1) * 8));
     SRW_TRY(scan_degrees(g->d_off));
+  } else if (vcut) {
+    // VCut shard map: owner(v) = getPartition(v) mod world (GM:66-68 via VRW:126) -- every rank derives the same map from the
+    // partition-id column.  Rows of a shard = the vertices it owns in ascending rank order, back to back.
+    if (!d_pid) { srw_set_error("the VCut shard map needs the partition-id column"); return SRW_ERR_ARG; }
+    if (n > 0) k_degrees<<<grid(n), kThreads>>>(n, d_src, d_dst, directed, g->d_bitmap, g->d_wordrank, mn, deg.as<uint32_t>());
+    SRW_TRY(build_vpid());
+    DevBuf key0, key1, val0, val1, pdeg, poff, lrow;
+    SRW_CUDA(key0.alloc((size_t)nv * 4)); SRW_CUDA(key1.alloc((size_t)nv * 4)); SRW_CUDA(val0.alloc((size_t)nv * 4)); SRW_CUDA(val1.alloc((size_t)nv * 4));
+    SRW_CUDA(cudaMalloc(&g->d_owner, (size_t)nv));
+    k_vcut_owner<<<grid(nv), kThreads>>>(nv, g->d_vpid, shard_world, g->d_owner, key0.as<uint32_t>());
+    k_iota<<<grid(nv), kThreads>>>(nv, val0.as<uint32_t>());
+    uint32_t *ok_in = key0.as<uint32_t>(), *ok_out = key1.as<uint32_t>(), *ov_in = val0.as<uint32_t>(), *ov_out = val1.as<uint32_t>();
+    SRW_TRY(sort_pairs(ok_in, ok_out, ov_in, ov_out, nv, bits_for(shard_world) + 1));      // stable: ascending vertex inside a group
+    SRW_CUDA(pdeg.alloc((size_t)(nv + 1) * 4));
+    SRW_CUDA(cudaMemset(pdeg.p, 0, (size_t)(nv + 1) * 4));
+    k_gather_u32<<<grid(nv), kThreads>>>(nv, ov_in, deg.as<uint32_t>(), pdeg.as<uint32_t>());
+    SRW_CUDA(poff.alloc((size_t)(nv + 1) * 8));
+    {
+      cub::TransformInputIterator<int64_t, CastU32ToI64, uint32_t *> it(pdeg.as<uint32_t>(), CastU32ToI64());
+      size_t tb = 0;
+      DevBuf tmp;
+      SRW_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, it, poff.as<int64_t>(), nv + 1));
+      SRW_CUDA(tmp.alloc(tb));
+      SRW_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, it, poff.as<int64_t>(), nv + 1));
+      SRW_CUDA(cudaDeviceSynchronize());
+    }
+    VcutGroups gr{};
+    {
+      DevBuf first;
+      SRW_CUDA(first.alloc((SRW_MAX_SHARDS + 1) * 8));
+      SRW_CUDA(cudaMemset(first.p, 0xFF, (SRW_MAX_SHARDS + 1) * 8));
+      k_vcut_group_first<<<grid(nv), kThreads>>>(nv, ok_in, first.as<long long>());
+      long long h_first[SRW_MAX_SHARDS + 1];
+      SRW_CUDA(cudaMemcpy(h_first, first.p, sizeof h_first, cudaMemcpyDeviceToHost));
+      gr.first[shard_world] = nv;
+      for (int o = shard_world - 1; o >= 0; --o) gr.first[o] = h_first[o] >= 0 ? h_first[o] : gr.first[o + 1];    // empty group
+      for (int o = 0; o <= shard_world; ++o) SRW_CUDA(cudaMemcpy(&gr.base[o], poff.as<int64_t>() + gr.first[o], 8, cudaMemcpyDeviceToHost));
+    }
+    SRW_CUDA(cudaMalloc(&g->d_ext, (size_t)nv * sizeof(MigExt)));
+    SRW_CUDA(lrow.alloc((size_t)nv * 4));
+    k_vcut_ext<<<grid(nv), kThreads>>>(nv, ov_in, ok_in, poff.as<int64_t>(), gr, g->d_ext, lrow.as<uint32_t>());
+    nrows = gr.first[shard_rank + 1] - gr.first[shard_rank];
+    nnz = gr.base[shard_rank + 1] - gr.base[shard_rank];
+    g->nnz = nnz; g->vcut = true;
+    g->row_first = 0; g->row_last = nrows;            // LOCAL row count: the rows are not a rank range (owner / ext / lverts say which)
+    for (int r = 0; r <= shard_world; ++r) g->bounds[(size_t)r] = gr.first[r];          // group starts in (owner, vertex) order: sizes only
+    if (nnz >= ((int64_t)1 << 32)) { srw_set_error("shard %d would hold %lld adjacency entries (limit 2^32 - 1 per shard)", shard_rank, (long long)nnz); return SRW_ERR_UNSUPPORTED; }
+    SRW_CUDA(cudaMalloc(&g->d_lverts, (size_t)(nrows ? nrows : 1) * 4));
+    if (nrows) SRW_CUDA(cudaMemcpy(g->d_lverts, ov_in + gr.first[shard_rank], (size_t)nrows * 4, cudaMemcpyDeviceToDevice));
+    SRW_CUDA(cudaMalloc(&g->d_off, (size_t)(nrows + 1) * 8));
+    k_rebase_off<<<grid(nrows + 1), kThreads>>>(nrows, poff.as<int64_t>(), gr.first[shard_rank], g->d_off);
+    DevBuf raw_row, raw_col, raw_gidx, cursor, ka, va;
+    SRW_CUDA(raw_row.alloc((size_t)nnz * 4)); SRW_CUDA(raw_col.alloc((size_t)nnz * 4)); SRW_CUDA(raw_gidx.alloc((size_t)nnz * 4));
+    SRW_CUDA(cursor.alloc(8));
+    SRW_CUDA(cudaMemset(cursor.p, 0, 8));
+    if (n > 0)
+      k_entries_owner<<<grid(n), kThreads>>>(n, d_src, d_dst, directed, g->d_bitmap, g->d_wordrank, mn, g->d_owner, lrow.as<uint32_t>(), shard_rank,
+                                             raw_row.as<uint32_t>(), raw_col.as<uint32_t>(), raw_gidx.as<uint32_t>(), cursor.as<unsigned long long>());
+    SRW_CUDA(cudaDeviceSynchronize());
+    if (nnz > 0) {
+      SRW_CUDA(ka.alloc((size_t)nnz * 4)); SRW_CUDA(va.alloc((size_t)nnz * 4));
+      DevBuf vb;
+      SRW_CUDA(vb.alloc((size_t)nnz * 4));
+      uint32_t *k_in = raw_gidx.as<uint32_t>(), *k_out = ka.as<uint32_t>(), *v_in = va.as<uint32_t>(), *v_out = vb.as<uint32_t>();
+      k_iota<<<grid(nnz), kThreads>>>(nnz, v_in);
+      SRW_TRY(sort_pairs(k_in, k_out, v_in, v_out, nnz, 32));
+      SRW_CUDA(ent_row.alloc((size_t)nnz * 4)); SRW_CUDA(ent_col.alloc((size_t)nnz * 4)); SRW_CUDA(ent_gidx.alloc((size_t)nnz * 4));
+      k_gather_u32<<<grid(nnz), kThreads>>>(nnz, v_in, raw_row.as<uint32_t>(), ent_row.as<uint32_t>());
+      k_gather_u32<<<grid(nnz), kThreads>>>(nnz, v_in, raw_col.as<uint32_t>(), ent_col.as<uint32_t>());
+      SRW_CUDA(cudaMemcpy(ent_gidx.p, k_in, (size_t)nnz * 4, cudaMemcpyDeviceToDevice));
+      SRW_CUDA(cudaDeviceSynchronize());
+    }
   } else {
     // global degrees -> global offsets -> edge-balanced contiguous vertex ranges (same on every rank)
     if (n > 0) k_degrees<<<grid(n), kThreads>>>(n, d_src, d_dst, directed, g->d_bitmap, g->d_wordrank, mn, deg.as<uint32_t>());
@@ -554,16 +680,7 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
     phase("k_bloom_insert");
   }
 
-  if (d_pid) {  // GM:21,31
-    DevBuf last;
-    SRW_CUDA(last.alloc((size_t)nv * 8));
-    SRW_CUDA(cudaMemset(last.p, 0, (size_t)nv * 8));
-    k_vpid_last<<<grid(n), kThreads>>>(n, d_src, d_dst, directed, g->d_bitmap, g->d_wordrank, mn, last.as<unsigned long long>());
-    SRW_CUDA(cudaMalloc(&g->d_vpid, (size_t)nv * 4));
-    k_vpid_fill<<<grid(nv), kThreads>>>(nv, last.as<unsigned long long>(), d_pid, g->d_vpid);
-    SRW_CUDA(cudaDeviceSynchronize());
-    g->has_pid = true;
-  }
+  SRW_TRY(build_vpid());
   if (nnz == 0) return SRW_OK;
 
   const int rbits = bits_for(nrows), cbits = bits_for(nv);
@@ -631,8 +748,8 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
       SRW_CUDA(ovf.alloc(4));
       SRW_CUDA(cudaMemset(ovf.p, 0, 4));
       SRW_CUDA(cudaMalloc(&g->d_ent, (size_t)nnz * sizeof(NbrEntry)));
-      k_nbr_entries<<<grid(nnz), kThreads>>>(nnz, k_in, g->d_col, g->d_off, sharded ? goff.as<int64_t>() : nullptr, sb, g->d_ent,
-                                             ovf.as<int>());
+      k_nbr_entries<<<grid(nnz), kThreads>>>(nnz, k_in, g->d_col, g->d_off, sharded && !vcut ? goff.as<int64_t>() : nullptr, sb,
+                                             vcut ? g->d_ext : nullptr, vcut ? g->d_owner : nullptr, g->d_ent, ovf.as<int>());
       int h = 0;
       SRW_CUDA(cudaMemcpy(&h, ovf.p, 4, cudaMemcpyDeviceToHost));
       if (h) { cudaFree(g->d_ent); g->d_ent = nullptr; }    // absurd multiplicities: fold sampler unavailable
@@ -693,7 +810,8 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
     }
   }
   SRW_CUDA(cudaGetLastError());
-  g->device_bytes = (int64_t)(words * 8 + (size_t)nv * 12 + (g->d_col ? (size_t)nnz * 4 : 0)) + (g->d_col_app ? nnz * 8 : 0) +
+  if (vcut) g->device_bytes += nv * 9 + nrows * 4;
+  g->device_bytes += (int64_t)(words * 8 + (size_t)nv * 12 + (g->d_col ? (size_t)nnz * 4 : 0)) + (g->d_col_app ? nnz * 8 : 0) +
                     (g->d_slot ? nnz * 16 : 0) + (g->d_slotw ? nnz * 32 : 0) + (g->d_vpid ? nv * 4 : 0) + (g->d_meta ? nrows * 32 : 0) + (g->d_hash ? g->hash_buckets * 32 : 0) + (g->d_hash_id ? g->hash_buckets * 32 : 0) + (g->d_ent ? nnz * 16 : 0) + (int64_t)g->bloom_words * 8;
   return SRW_OK;
 }
@@ -760,14 +878,15 @@ srw_status srw_build_graph_rows(int64_t n_rows, const int32_t *h_vids, const int
 }
 
 srw_status srw_build_graph_device_sharded(int64_t n, const int32_t *d_src, const int32_t *d_dst, const float *d_w, int directed,
-                                          unsigned flags, int rank, int world, srw_graph **out) {
+                                          unsigned flags, int rank, int world, srw_graph **out, const int32_t *d_pid) {
   SRW_TRY(srw_require_device());
   if (n < 0 || !out || (n > 0 && (!d_src || !d_dst)) || world < 1 || world > SRW_MAX_SHARDS || rank < 0 || rank >= world) {
     srw_set_error("srw_graph_from_device_edges_sharded: bad argument");
     return SRW_ERR_ARG;
   }
   srw_graph *g = new srw_graph();
-  srw_status s = build_impl(n, d_src, d_dst, d_w, nullptr, directed, flags ? flags : SRW_BUILD_ALIAS, 0, nullptr, g, rank, world);
+  // d_pid != NULL: the VCut shard map -- owner(v) = getPartition(v) mod world instead of edge-balanced vertex ranges
+  srw_status s = build_impl(n, d_src, d_dst, d_w, d_pid, directed, flags ? flags : SRW_BUILD_ALIAS, 0, nullptr, g, rank, world, d_pid != nullptr && world > 1);
   if (s != SRW_OK) { srw_graph_free(g); return s; }
   g->peer_off[rank] = g->d_off; g->peer_ent[rank] = g->d_ent; g->peer_hash[rank] = g->d_hash;
   g->peer_attached[rank] = true;

@@ -64,6 +64,11 @@ SRW_LAYOUT_HD uint32_t srw_hash32(uint32_t x) {
 
 #define SRW_MAX_SHARDS 16
 
+// VCut shard map (VRW:23-26,121-134, GM:31,66-68): owner(v) = getPartition(v) mod world comes from the partition-id
+// column of the edge file, so a shard's rows are not a contiguous rank range; this table -- replicated on every shard, 8 bytes
+// per vertex -- says where the row of ANY vertex lives inside its owner's arrays.
+struct SRW_ALIGN(8) MigExt { uint32_t off, deg; };
+
 // The replicated edge filter of the migrating sharded walk (migrate.cuh): one 64-bit Bloom word per probe, kMigBloomK bits
 // per undirected edge {a, b} of vertex ranks -- two in each 32-bit half of the word, all from 32-bit arithmetic (the probe sits
 // on the walk kernel's instruction-bound path).  The word index and the bit positions come from two INDEPENDENT 32-bit hashes

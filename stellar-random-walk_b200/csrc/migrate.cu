@@ -152,6 +152,7 @@ extern "C" srw_status srw_mig_create(const srw_graph *g, const srw_params *p, in
   memset(&a, 0, sizeof(a));
   a.off = g->d_off; a.ent = g->d_ent; a.hash = g->d_hash; a.bloom = (const unsigned long long *)g->d_bloom; a.bloom_words = (uint32_t)g->bloom_words;
   a.nv = g->nv; a.row_first = g->row_first; a.row_last = g->row_last; a.world = m->world; a.rank = m->rank;
+  if (g->vcut) { a.ext = g->d_ext; a.owner = g->d_owner; a.lverts = g->d_lverts; a.rows_local = g->row_last - g->row_first; }
   for (int r = 0; r <= m->world; ++r) a.bounds[r] = g->bounds[(size_t)r];
   FoldArgs f;
   const bool folded = srw_fold_args(p->p, p->q, p->sampler == SRW_SAMPLER_ALIAS_FOLD, &f);
@@ -233,9 +234,14 @@ extern "C" srw_status srw_mig_superstep(srw_mig *m, int64_t s, unsigned long lon
   if (!m->attr_set) {
     SRW_CUDA(cudaFuncSetAttribute(mig_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     SRW_CUDA(cudaFuncSetAttribute(mig_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    SRW_CUDA(cudaFuncSetAttribute(mig_step_kernel<true, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    SRW_CUDA(cudaFuncSetAttribute(mig_step_kernel<false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     m->attr_set = true;
   }
-  if (m->stats) mig_step_kernel<true><<<m->grid, 256, dyn, stream>>>(a);
+  if (m->g->vcut) {          // VCut shard map: extents / owners / seeds through the replicated tables
+    if (m->stats) mig_step_kernel<true, 4, true><<<m->grid, 256, dyn, stream>>>(a);
+    else mig_step_kernel<false, 4, true><<<m->grid, 256, dyn, stream>>>(a);
+  } else if (m->stats) mig_step_kernel<true><<<m->grid, 256, dyn, stream>>>(a);
   else mig_step_kernel<false><<<m->grid, 256, dyn, stream>>>(a);
   SRW_CUDA(cudaGetLastError());
   if (d_sent) SRW_CUDA(cudaMemcpyAsync(d_sent, a.stats, 8, cudaMemcpyDeviceToDevice, stream));

@@ -58,6 +58,12 @@ constexpr int kMigMaxDest = SRW_MAX_SHARDS + 1;   // peers + the local spill reg
 constexpr uint32_t kMigRowMask = 0x0FFFFFFFu;     // MigTuple::home_row: [31:28] home shard, [27:0] path row on it
 
 struct MigArgs {
+  // VCut shard map (template flag VCUT; all NULL for vertex ranges): owner(v) = getPartition(v) mod world comes from the
+  // partition-id column of the edge file instead of `bounds`, so a shard's rows are not a contiguous range of ranks
+  const MigExt *__restrict__ ext;         // [nv] row extent of every vertex inside its owner's arrays
+  const uint8_t *__restrict__ owner;      // [nv] owner(v)
+  const int32_t *__restrict__ lverts;     // [rows_local] the vertices this shard owns, ascending (seed order)
+  int64_t rows_local;
   // this shard's rows
   const int64_t *__restrict__ off;        // [rows + 1] shard-local offsets
   const NbrEntry *__restrict__ ent;       // [nnz_local]
@@ -196,7 +202,7 @@ __device__ __forceinline__ void mig_flush(const Args &a, int d, int n, int4 *sta
   }
 }
 
-template <bool STATS, int MINB = 4>
+template <bool STATS, int MINB = 4, bool VCUT = false>
 __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
   // per-warp send state: open chunk (first slot, slots used) per destination region; prefix of the inbox regions (+ seeds)
   __shared__ unsigned int s_chunk[8][kMigMaxDest];     // open chunk of the destination region: first slot ...
@@ -263,9 +269,9 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
       if (st == MS_EMPTY && mine < w_end) {
         if (mine >= seed0) {                             // a virtual seed: walker (round, row) of this shard, path = [v]
           const unsigned long long j = (unsigned long long)a.seed_first + (unsigned long long)(mine - seed0) * (unsigned long long)a.seed_step;
-          const int64_t rows = a.row_last - a.row_first;
+          const int64_t rows = VCUT ? a.rows_local : a.row_last - a.row_first;
           const int64_t round = (int64_t)(j / (unsigned long long)rows), row = (int64_t)(j % (unsigned long long)rows);
-          curr = (int32_t)(a.row_first + row); prev = -1;
+          curr = VCUT ? __ldg(a.lverts + row) : (int32_t)(a.row_first + row); prev = -1;
           walker = (uint32_t)((unsigned long long)round * (unsigned long long)a.nv + (unsigned long long)curr);
           m = 1; trial = 0; len = 1; cown = (uint32_t)me; pown = 0;
           const uint32_t h = (uint32_t)curr % (uint32_t)W;
@@ -310,7 +316,7 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
         cown = (uint32_t)me;
         if (kind == MIG_NOP) st = MS_EMPTY;
         else if (kind == MIG_PENDING) pend = true;
-        else if (fwd && (cown = (uint32_t)mig_owner(a, curr)) != (uint32_t)me) {           // spilled last super-step: forward as it is
+        else if (fwd && (cown = VCUT ? (uint32_t)__ldg(a.owner + curr) : (uint32_t)mig_owner(a, curr)) != (uint32_t)me) {           // spilled last super-step: forward as it is
           send = (int)cown; send_kind = (uint32_t)q1.y & (MIG_KIND_MASK | MIG_NEEDEXT);
         } else st = ((uint32_t)q1.y & MIG_NEEDEXT) ? MS_EXTENT : MS_TRIAL;
       }
@@ -320,9 +326,12 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
           if (fwd && (int)xown != me) { send = (int)xown; send_kind = MIG_PENDING; }        // spilled: forward
           else {
             if (STATS) n_exact++;
-            const int64_t *o = a.off + ((int64_t)x - a.row_first);         // x's row extent from this shard's own row table
-            const int64_t e0 = __ldg(o), e1 = __ldg(o + 1);
-            xoff = (uint32_t)e0; xdeg = (uint32_t)(e1 - e0);
+            if (VCUT) { const MigExt e = a.ext[x]; xoff = e.off; xdeg = e.deg; }
+            else {
+              const int64_t *o = a.off + ((int64_t)x - a.row_first);       // x's row extent from this shard's own row table
+              const int64_t e0 = __ldg(o), e1 = __ldg(o + 1);
+              xoff = (uint32_t)e0; xdeg = (uint32_t)(e1 - e0);
+            }
             pnb = srw_hash_buckets((int64_t)xoff, xdeg);
             if (pnb) bkt = __umulhi(srw_hash32((uint32_t)prev), pnb); else { lo = 0; hi = xdeg; }
             st = MS_EXACT;
@@ -332,9 +341,12 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
     }
     if (__any_sync(0xffffffffu, st == MS_EXTENT)) {
       if (st == MS_EXTENT) {
-        const int64_t *o = a.off + ((int64_t)curr - a.row_first);
-        const int64_t e0 = __ldg(o), e1 = __ldg(o + 1);
-        off = (uint32_t)e0; deg = (uint32_t)(e1 - e0);
+        if (VCUT) { const MigExt e = a.ext[curr]; off = e.off; deg = e.deg; }
+        else {
+          const int64_t *o = a.off + ((int64_t)curr - a.row_first);
+          const int64_t e0 = __ldg(o), e1 = __ldg(o + 1);
+          off = (uint32_t)e0; deg = (uint32_t)(e1 - e0);
+        }
         if (deg == 0) { n_err |= 1; st = MS_EMPTY; }      // cannot happen on an undirected graph (every vertex has an entry)
         else st = MS_TRIAL;
       }

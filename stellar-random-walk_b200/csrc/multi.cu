@@ -174,8 +174,9 @@ srw_status srw_multi_walk_rounds(const srw_graph *g, const srw_params *p, int64_
 }
 
 // Builds one vertex-range shard per device from an edge list resident on the CURRENT device.
+// d_pid != NULL (`--partitioned true`): the partition-id column is the shard map (VCut: owner(v) = getPartition(v) mod num_gpus).
 srw_status srw_build_graph_device_multi(int64_t n, const int32_t *d_src, const int32_t *d_dst, const float *d_w, int directed,
-                                        int num_gpus, srw_graph **out) {
+                                        int num_gpus, srw_graph **out, const int32_t *d_pid) {
   SRW_TRY(srw_require_device());
   int have = 0;
   cudaGetDeviceCount(&have);
@@ -200,20 +201,21 @@ srw_status srw_build_graph_device_multi(int64_t n, const int32_t *d_src, const i
   srw_status rc = SRW_OK;
   for (int d = 0; d < num_gpus && rc == SRW_OK; ++d) {
     cudaSetDevice(d);
-    int32_t *s = nullptr, *t = nullptr;
+    int32_t *s = nullptr, *t = nullptr, *pv = nullptr;
     float *wv = nullptr;
-    if (d == 0) { s = const_cast<int32_t *>(d_src); t = const_cast<int32_t *>(d_dst); wv = const_cast<float *>(d_w); }
+    if (d == 0) { s = const_cast<int32_t *>(d_src); t = const_cast<int32_t *>(d_dst); wv = const_cast<float *>(d_w); pv = const_cast<int32_t *>(d_pid); }
     else if (n > 0) {
       if (cudaMalloc(&s, (size_t)n * 4) != cudaSuccess || cudaMalloc(&t, (size_t)n * 4) != cudaSuccess || (d_w && cudaMalloc(&wv, (size_t)n * 4) != cudaSuccess) ||
+          (d_pid && cudaMalloc(&pv, (size_t)n * 4) != cudaSuccess) ||
           cudaMemcpyPeer(s, d, d_src, 0, (size_t)n * 4) != cudaSuccess || cudaMemcpyPeer(t, d, d_dst, 0, (size_t)n * 4) != cudaSuccess ||
-          (d_w && cudaMemcpyPeer(wv, d, d_w, 0, (size_t)n * 4) != cudaSuccess)) {
+          (d_w && cudaMemcpyPeer(wv, d, d_w, 0, (size_t)n * 4) != cudaSuccess) || (d_pid && cudaMemcpyPeer(pv, d, d_pid, 0, (size_t)n * 4) != cudaSuccess)) {
         srw_set_error("multi-GPU build: copying the edge list to device %d failed: %s", d, cudaGetErrorString(cudaGetLastError()));
         rc = SRW_ERR_CUDA;
       }
     }
     srw_graph *sh = nullptr;
-    if (rc == SRW_OK) rc = srw_build_graph_device_sharded(n, s, t, wv, 0, SRW_BUILD_ALIAS | SRW_BUILD_MIGRATE, d, num_gpus, &sh);
-    if (d != 0) { cudaFree(s); cudaFree(t); cudaFree(wv); }
+    if (rc == SRW_OK) rc = srw_build_graph_device_sharded(n, s, t, wv, 0, SRW_BUILD_ALIAS | SRW_BUILD_MIGRATE, d, num_gpus, &sh, n > 0 ? pv : nullptr);
+    if (d != 0) { cudaFree(s); cudaFree(t); cudaFree(wv); cudaFree(pv); }
     if (rc == SRW_OK) {
       c->shards.push_back(sh);
       if (sh->nnz > 0 && !sh->d_ent) { srw_set_error("--gpus > 1 walks unweighted graphs (weighted rows carry Vose slots, which the sharded walk does not read yet)"); rc = SRW_ERR_UNSUPPORTED; }
@@ -223,26 +225,38 @@ srw_status srw_build_graph_device_multi(int64_t n, const int32_t *d_src, const i
   if (rc != SRW_OK) { srw_graph_free(c); return rc; }
   c->nv = c->shards[0]->nv; c->nnz = c->shards[0]->nnz_global; c->nnz_global = c->nnz;
   c->bounds = c->shards[0]->bounds; c->row_first = 0; c->row_last = c->nv;
-  c->id_min = c->shards[0]->id_min;
+  c->id_min = c->shards[0]->id_min; c->vcut = c->shards[0]->vcut; c->has_pid = c->shards[0]->has_pid;
   for (auto *sh : c->shards) c->device_bytes += sh->device_bytes;
   *out = c;
   return SRW_OK;
 }
 
-extern "C" srw_status srw_graph_from_edges_multi(int64_t n, const int32_t *h_src, const int32_t *h_dst, int directed, int num_gpus,
-                                                 srw_graph **out) {
+static srw_status from_edges_multi(int64_t n, const int32_t *h_src, const int32_t *h_dst, const int32_t *h_pid, int directed, int num_gpus,
+                                   srw_graph **out) {
   SRW_TRY(srw_require_device());
   if (n < 0 || !out || (n > 0 && (!h_src || !h_dst))) { srw_set_error("srw_graph_from_edges_multi: bad argument"); return SRW_ERR_ARG; }
   SRW_CUDA(cudaSetDevice(0));
-  int32_t *s = nullptr, *d = nullptr;
+  int32_t *s = nullptr, *d = nullptr, *pp = nullptr;
   SRW_CUDA(cudaMalloc(&s, (size_t)(n ? n : 1) * 4));
-  if (cudaMalloc(&d, (size_t)(n ? n : 1) * 4) != cudaSuccess) { cudaFree(s); srw_set_error("out of device memory"); return SRW_ERR_CUDA; }
+  if (cudaMalloc(&d, (size_t)(n ? n : 1) * 4) != cudaSuccess || (h_pid && cudaMalloc(&pp, (size_t)(n ? n : 1) * 4) != cudaSuccess)) {
+    cudaFree(s); cudaFree(d); srw_set_error("out of device memory"); return SRW_ERR_CUDA;
+  }
   srw_status rc = SRW_OK;
-  if (cudaMemcpy(s, h_src, (size_t)n * 4, cudaMemcpyHostToDevice) != cudaSuccess || cudaMemcpy(d, h_dst, (size_t)n * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+  if (cudaMemcpy(s, h_src, (size_t)n * 4, cudaMemcpyHostToDevice) != cudaSuccess || cudaMemcpy(d, h_dst, (size_t)n * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+      (h_pid && cudaMemcpy(pp, h_pid, (size_t)n * 4, cudaMemcpyHostToDevice) != cudaSuccess)) {
     srw_set_error("srw_graph_from_edges_multi: H2D copy failed");
     rc = SRW_ERR_CUDA;
   }
-  if (rc == SRW_OK) rc = srw_build_graph_device_multi(n, s, d, nullptr, directed, num_gpus, out);
-  cudaFree(s); cudaFree(d);
+  if (rc == SRW_OK) rc = srw_build_graph_device_multi(n, s, d, nullptr, directed, num_gpus, out, pp);
+  cudaFree(s); cudaFree(d); cudaFree(pp);
   return rc;
+}
+extern "C" srw_status srw_graph_from_edges_multi(int64_t n, const int32_t *h_src, const int32_t *h_dst, int directed, int num_gpus,
+                                                 srw_graph **out) {
+  return from_edges_multi(n, h_src, h_dst, nullptr, directed, num_gpus, out);
+}
+extern "C" srw_status srw_graph_from_edges_multi_vcut(int64_t n, const int32_t *h_src, const int32_t *h_dst, const int32_t *h_pid, int directed,
+                                                      int num_gpus, srw_graph **out) {
+  if (!h_pid && n > 0) { srw_set_error("srw_graph_from_edges_multi_vcut: the partition-id column is the shard map"); return SRW_ERR_ARG; }
+  return from_edges_multi(n, h_src, h_dst, h_pid, directed, num_gpus, out);
 }

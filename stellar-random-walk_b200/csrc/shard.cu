@@ -318,6 +318,7 @@ constexpr int kCounters = 2 + 4 * SRW_MAX_SHARDS;
 
 srw_status fill_args(const srw_graph *g, const srw_params *p, int64_t round_first, int64_t n_rounds, ShardArgs *a) {
   if (!g || !p) { srw_set_error("shard call: null graph or params"); return SRW_ERR_ARG; }
+  if (g->vcut) { srw_set_error("a shard built from the partition-id column (VCut shard map) is walked by the migrating walk (srw_mig_*) only"); return SRW_ERR_UNSUPPORTED; }
   // SRW_SAMPLER_ALIAS_FOLD (the default of srw_params_default) runs as the classic alias sampler here, as it does wherever
   // folding does not apply: the same distribution, the classic thresholds (the migrating walk, migrate.cu, implements the fold)
   if (p->sampler == SRW_SAMPLER_EXACT) { srw_set_error("the sharded walk implements --sampler alias (fold runs as alias), not exact"); return SRW_ERR_UNSUPPORTED; }
@@ -368,6 +369,11 @@ inline unsigned blocks_for(int64_t n) {
 extern "C" srw_status srw_graph_from_device_edges_sharded(int64_t n, const int32_t *d_src, const int32_t *d_dst, const float *d_w,
                                                           int directed, unsigned flags, int rank, int world, srw_graph **out) {
   return srw_build_graph_device_sharded(n, d_src, d_dst, d_w, directed, flags, rank, world, out);
+}
+extern "C" srw_status srw_graph_from_device_edges_vcut(int64_t n, const int32_t *d_src, const int32_t *d_dst, const int32_t *d_pid,
+                                                       int directed, unsigned flags, int rank, int world, srw_graph **out) {
+  if (n > 0 && !d_pid) { srw_set_error("srw_graph_from_device_edges_vcut: the partition-id column is the shard map"); return SRW_ERR_ARG; }
+  return srw_build_graph_device_sharded(n, d_src, d_dst, nullptr, directed, flags, rank, world, out, d_pid);
 }
 
 extern "C" srw_status srw_graph_shard_info(const srw_graph *g, int *rank, int *world, int64_t *row_first, int64_t *row_last,
@@ -561,6 +567,7 @@ extern "C" srw_status srw_shard_attach_local(srw_graph *g, const srw_graph *peer
     srw_set_error("srw_shard_attach_local: not two shards of the same graph");
     return SRW_ERR_ARG;
   }
+  if (g->vcut) { srw_set_error("peer-gather needs vertex-range shards (this one follows the partition-id column)"); return SRW_ERR_UNSUPPORTED; }
   const int r = peer->shard_rank;
   if (r == g->shard_rank) return SRW_OK;
   if (peer->nnz > 0 && !peer->d_ent) { srw_set_error("shard %d has no neighbour entries (weighted graph?): the peer-gather walk needs an unweighted SRW_BUILD_ALIAS build", r); return SRW_ERR_UNSUPPORTED; }

@@ -116,14 +116,24 @@ extern "C" srw_status srw_graph_neighbors(const srw_graph *g, int32_t vid, int32
   SRW_TRY(host_vids(g));
   int64_t r = host_rank(g, vid);
   if (r < 0) { *n = -1; return SRW_OK; }                       // GM:118 case None => null
-  if (g->shard_world > 1) {
-    // a vertex-range shard holds rows [row_first, row_last) only and indexes them locally: a vertex owned by another
-    // shard is "not on this shard" -- the reference's null (GM:118, the RW:121-129 case)
-    if (r < g->row_first || r >= g->row_last) { *n = -1; return SRW_OK; }
-    r -= g->row_first;
-  }
   int64_t ext[2];
-  SRW_CUDA(cudaMemcpy(ext, g->d_off + r, 16, cudaMemcpyDeviceToHost));
+  if (g->vcut) {
+    // VCut shard map: owner(v) = getPartition(v) mod world; the replicated tables say whether the row is here, and where
+    uint8_t o = 0;
+    MigExt e;
+    SRW_CUDA(cudaMemcpy(&o, g->d_owner + r, 1, cudaMemcpyDeviceToHost));
+    if ((int)o != g->shard_rank) { *n = -1; return SRW_OK; }
+    SRW_CUDA(cudaMemcpy(&e, g->d_ext + r, sizeof e, cudaMemcpyDeviceToHost));
+    ext[0] = e.off; ext[1] = (int64_t)e.off + e.deg;
+  } else {
+    if (g->shard_world > 1) {
+      // a vertex-range shard holds rows [row_first, row_last) only and indexes them locally: a vertex owned by another
+      // shard is "not on this shard" -- the reference's null (GM:118, the RW:121-129 case)
+      if (r < g->row_first || r >= g->row_last) { *n = -1; return SRW_OK; }
+      r -= g->row_first;
+    }
+    SRW_CUDA(cudaMemcpy(ext, g->d_off + r, 16, cudaMemcpyDeviceToHost));
+  }
   const int64_t deg = ext[1] - ext[0];
   *n = deg;
   const int64_t m = std::min(deg, cap);
@@ -145,6 +155,10 @@ extern "C" srw_status srw_graph_neighbors(const srw_graph *g, int32_t vid, int32
 extern "C" srw_status srw_graph_partition(const srw_graph *g, int32_t vid, int32_t *pid, int *found) {
   if (!g || !found) return SRW_ERR_ARG;
   *found = 0;
+  if (!g->shards.empty()) {                       // container: the map is replicated on every shard
+    SRW_CUDA(cudaSetDevice(g->shards[0]->device));
+    return srw_graph_partition(g->shards[0], vid, pid, found);
+  }
   if (!g->d_vpid) return SRW_OK;
   SRW_TRY(host_vids(g));
   const int64_t r = host_rank(g, vid);
@@ -198,7 +212,7 @@ extern "C" void srw_graph_free(srw_graph *g) {
   }
   cudaFree(g->d_bitmap); cudaFree(g->d_wordrank); cudaFree(g->d_vids);
   cudaFree(g->d_col_app); cudaFree(g->d_w_app); cudaFree(g->d_col); cudaFree(g->d_slot); cudaFree(g->d_slotw); cudaFree(g->d_vpid);
-  cudaFree(g->d_meta); cudaFree(g->d_hash_id); cudaFree(g->d_bloom);
+  cudaFree(g->d_meta); cudaFree(g->d_hash_id); cudaFree(g->d_bloom); cudaFree(g->d_ext); cudaFree(g->d_owner); cudaFree(g->d_lverts);
   if (!g->rows_external) { cudaFree(g->d_off); cudaFree(g->d_hash); cudaFree(g->d_ent); }
   for (int r = 0; r < SRW_MAX_SHARDS; ++r)
     if (g->peer_ipc[r]) {

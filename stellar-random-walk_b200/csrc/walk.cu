@@ -159,6 +159,7 @@ static srw_status walk_enqueue(const srw_graph *g, const srw_params *p, const Wa
   if (!(p->p > 0.0) || !(p->q > 0.0)) { srw_set_error("p and q must be > 0"); return SRW_ERR_ARG; }
   ev.pending = false;
   const bool peer = g->shard_world > 1;
+  if (peer && g->vcut) { srw_set_error("a shard built from the partition-id column (VCut shard map) is walked by the migrating walk (srw_mig_*, --gpus N) only"); return SRW_ERR_UNSUPPORTED; }
   if (peer) {
     // one shard of several: only the peer-gather walk runs through this entry point (the tuple-exchange
     // walk is driven per super-step through srw_shard_step)

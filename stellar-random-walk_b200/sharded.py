@@ -29,6 +29,7 @@ def _bind():
         return L
     vp, i64p = C.c_void_p, C.POINTER(C.c_int64)
     L.srw_graph_from_device_edges_sharded.argtypes = [C.c_int64, vp, vp, vp, C.c_int, C.c_uint, C.c_int, C.c_int, C.POINTER(vp)]
+    L.srw_graph_from_device_edges_vcut.argtypes = [C.c_int64, vp, vp, vp, C.c_int, C.c_uint, C.c_int, C.c_int, C.POINTER(vp)]
     L.srw_graph_shard_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), i64p, i64p, i64p, i64p]
     L.srw_shard_seed.argtypes = [vp, vp, C.c_int64, C.c_int64, vp, C.c_int64, i64p, vp, vp, vp]
     L.srw_shard_step.argtypes = [vp, vp, C.c_int64, C.c_int64, vp, C.c_int64, vp, vp, C.c_int64, vp, vp, i64p, i64p, i64p, vp]
@@ -79,11 +80,16 @@ def owner_of(bounds, v):
 class Shard:
     """One rank's rows of the graph plus its walker pools (device buffers owned here)."""
 
-    def __init__(self, n_edges, d_src, d_dst, d_w, rank, world, directed=False, device=None, migrate=False):
+    def __init__(self, n_edges, d_src, d_dst, d_w, rank, world, directed=False, device=None, migrate=False, d_pid=None):
+        """d_pid (device pointer to the partition id of every input edge): the VCut shard map -- owner(v) = getPartition(v) mod
+        world (VRW:121-134, GM:66-68) instead of an edge-balanced vertex range; such shards are walked by MigrateWalker only."""
         L = _bind()
         self.h = C.c_void_p()
         flags = BUILD_ALIAS | (BUILD_MIGRATE if migrate else 0)
-        check(L.srw_graph_from_device_edges_sharded(n_edges, d_src, d_dst, d_w, int(directed), flags, rank, world, C.byref(self.h)))
+        if d_pid is not None:
+            check(L.srw_graph_from_device_edges_vcut(n_edges, d_src, d_dst, d_pid, int(directed), flags, rank, world, C.byref(self.h)))
+        else:
+            check(L.srw_graph_from_device_edges_sharded(n_edges, d_src, d_dst, d_w, int(directed), flags, rank, world, C.byref(self.h)))
         r, w = C.c_int(), C.c_int()
         rf, rl, nl = C.c_int64(), C.c_int64(), C.c_int64()
         b = (C.c_int64 * (world + 1))()

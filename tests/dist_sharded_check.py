@@ -139,6 +139,26 @@ def full():
                 mw.free()
                 dist.barrier()
             mshard.free()
+            # the same walk over the VCut shard map (owner(v) = getPartition(v) mod world from a partition-id column)
+            pid = np.random.default_rng(17).integers(0, 9, len(s)).astype(np.int32)
+            dp = torch.from_numpy(pid).cuda()
+            vshard = sh.Shard(len(s), ds.data_ptr(), dd.data_ptr(), None, rank, world, migrate=True, d_pid=dp.data_ptr())
+            ids, offs, st = twin.walk(walk_length=30, num_walks=2, p=p, q=q, seed=23, fold=1)
+            want = oracle_lib.paths_as_lists(ids, offs)
+            mw = sh.MigrateWalker([vshard], srw.Params(walkLength=30, numWalks=2, p=p, q=q, seed=23, sampler="fold"), 2)
+            mout, mstats = mw.run(0)
+            P, Ln = mout[0][0].cpu().numpy(), mout[0][1].cpu().numpy()
+            for rnd in range(2):
+                for k, v in enumerate(vshard.home_vertices()):
+                    row = rnd * vshard.home_rows + k
+                    if P[row, :Ln[row]].tolist() != want[rnd * twin.nv + v]:
+                        ok = False
+            t = torch.tensor([mstats["steps"]], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t)
+            ok = ok and int(t[0].item()) == st.steps
+            mw.free()
+            dist.barrier()
+            vshard.free()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -43,12 +43,27 @@ void hash_insert(std::vector<int32_t> &hash, int64_t off, uint32_t deg, int32_t 
 extern "C" int emu_migrate_walk(int64_t nv, const int64_t *off, const int32_t *col, const uint32_t *mult, int shards, const int64_t *bounds,
                                 double p, double q, int fold, uint64_t t_ret, uint64_t t_common, uint64_t t_far, uint64_t seed,
                                 int32_t walk_length, int64_t round_first, int64_t n_rounds, int64_t seg_cap, int bloom_bits, int grid_blocks,
-                                int32_t *out_paths, unsigned long long *stats_out) {
+                                int32_t *out_paths, unsigned long long *stats_out, const uint8_t *owner_map /* NULL = vertex ranges; else the VCut shard map */) {
   if (shards < 1 || shards > SRW_MAX_SHARDS) return -1;
   const int W = shards;
   const int32_t stride = walk_length + 2;
   const int64_t nnz = off[nv];
-  auto owner_of = [&](int64_t v) { int o = 0; while (o + 1 < W && v >= bounds[o + 1]) o++; return o; };
+  auto owner_of = [&](int64_t v) { if (owner_map) return (int)owner_map[v]; int o = 0; while (o + 1 < W && v >= bounds[o + 1]) o++; return o; };
+  // rows of a shard = the vertices it owns in ascending order (a contiguous range without a shard map), laid out back to back
+  std::vector<std::vector<int32_t>> lverts((size_t)W);
+  std::vector<MigExt> ext((size_t)nv);
+  std::vector<uint8_t> own((size_t)nv);
+  {
+    std::vector<int64_t> fill((size_t)W, 0);
+    for (int64_t v = 0; v < nv; ++v) {
+      const int o = owner_of(v);
+      if (o < 0 || o >= W) return -2;
+      own[(size_t)v] = (uint8_t)o;
+      lverts[(size_t)o].push_back((int32_t)v);
+      ext[(size_t)v].off = (uint32_t)fill[(size_t)o]; ext[(size_t)v].deg = (uint32_t)(off[v + 1] - off[v]);
+      fill[(size_t)o] += off[v + 1] - off[v];
+    }
+  }
   // the replicated filter
   uint32_t bloom_words = (uint32_t)((nnz / 2 * bloom_bits + 63) / 64);
   if (bloom_words < 4) bloom_words = 4;
@@ -65,14 +80,13 @@ extern "C" int emu_migrate_walk(int64_t nv, const int64_t *off, const int32_t *c
   seg_cap = (seg_cap + 31) & ~(int64_t)31;       // whole 32-slot blocks (mig_word)
   const int64_t slots = (int64_t)W * seg_cap + spill_cap;
   std::vector<Shard> sh((size_t)W);
-  std::vector<int64_t> base((size_t)W);
   for (int s = 0; s < W; ++s) {
     Shard &R = sh[(size_t)s];
-    const int64_t r0 = bounds[s], r1 = bounds[s + 1];
-    base[(size_t)s] = off[r0];
-    R.off.resize((size_t)(r1 - r0 + 1));
-    for (int64_t r = r0; r <= r1; ++r) R.off[(size_t)(r - r0)] = off[r] - off[r0];
-    const int64_t n = off[r1] - off[r0];
+    const std::vector<int32_t> &lv = lverts[(size_t)s];
+    R.off.resize(lv.size() + 1);
+    int64_t n = 0;
+    for (size_t i = 0; i < lv.size(); ++i) { R.off[i] = n; n += off[lv[i] + 1] - off[lv[i]]; }
+    R.off[lv.size()] = n;
     R.ent.resize((size_t)n);
     R.hash.assign((size_t)(((n >> 2) + 1) * 8), -1);
     for (int b = 0; b < 2; ++b) { R.base[b].assign((size_t)slots * 3, make_int4(-1, -1, -1, -1)); }
@@ -81,19 +95,15 @@ extern "C" int emu_migrate_walk(int64_t nv, const int64_t *off, const int32_t *c
     const int64_t hrows = (nv - s + W - 1) / W;
     R.paths.assign((size_t)(hrows * n_rounds * stride + 1), -7);
     for (int64_t i = 0; i < hrows * n_rounds; ++i) R.paths[(size_t)(i * stride)] = (int32_t)(s + (i % hrows) * W);
-  }
-  for (int s = 0; s < W; ++s) {
-    Shard &R = sh[(size_t)s];
-    for (int64_t r = bounds[s]; r < bounds[s + 1]; ++r) {
-      const int64_t lo = off[r] - base[(size_t)s];
+    for (size_t i = 0; i < lv.size(); ++i) {
+      const int64_t r = lv[i], lo = R.off[i];
       const uint32_t deg = (uint32_t)(off[r + 1] - off[r]);
       for (int64_t e = off[r]; e < off[r + 1]; ++e) {
         const int32_t x = col[e];
-        const int ox = owner_of(x);
         NbrEntry ne;
-        ne.x = x; ne.deg = (uint32_t)(off[x + 1] - off[x]); ne.off_lo = (uint32_t)(off[x] - base[(size_t)ox]);
-        ne.off_hi_mult = (uint32_t)ox | (mult[e] << 8);
-        R.ent[(size_t)(e - base[(size_t)s])] = ne;
+        ne.x = x; ne.deg = ext[(size_t)x].deg; ne.off_lo = ext[(size_t)x].off;
+        ne.off_hi_mult = (uint32_t)own[(size_t)x] | (mult[e] << 8);
+        R.ent[(size_t)(lo + (e - off[r]))] = ne;
         hash_insert(R.hash, lo, deg, x);
       }
     }
@@ -109,15 +119,19 @@ extern "C" int emu_migrate_walk(int64_t nv, const int64_t *off, const int32_t *c
       Shard &R = sh[(size_t)r];
       MigArgs a{};
       a.off = R.off.data(); a.ent = R.ent.data(); a.hash = R.hash.data(); a.bloom = bloom.data(); a.bloom_words = bloom_words;
-      a.nv = nv; a.row_first = bounds[r]; a.row_last = bounds[r + 1]; a.world = W; a.rank = r;
-      for (int k = 0; k <= W; ++k) a.bounds[k] = bounds[k];
+      a.nv = nv; a.world = W; a.rank = r;
+      if (owner_map) { a.ext = ext.data(); a.owner = own.data(); a.lverts = lverts[(size_t)r].data(); a.rows_local = (int64_t)lverts[(size_t)r].size(); }
+      else {
+        a.row_first = bounds[r]; a.row_last = bounds[r + 1];
+        for (int k = 0; k <= W; ++k) a.bounds[k] = bounds[k];
+      }
       a.a = f.a; a.mp = f.mp; a.t_ret = f.t_ret; a.t_common = f.t_common; a.t_far = f.t_far;
       a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32); a.stride = stride;
       a.walker_base = (uint64_t)round_first * (uint64_t)nv; a.n_rounds = n_rounds;
       a.in_base = R.base[cur].data(); a.in_cnt = R.cnt[cur];
       a.seg_cap = seg_cap; a.spill_cap = spill_cap;
       {
-        const int64_t seeds = (bounds[r + 1] - bounds[r]) * n_rounds;
+        const int64_t seeds = (int64_t)lverts[(size_t)r].size() * n_rounds;
         a.seed_step = 2; a.seed_first = s;
         a.n_seed = s == 0 ? (seeds + 1) / 2 : s == 1 ? seeds / 2 : 0;
       }
@@ -130,7 +144,8 @@ extern "C" int emu_migrate_walk(int64_t nv, const int64_t *off, const int32_t *c
       for (int h = 0; h < W; ++h) { a.home_paths[h] = sh[(size_t)h].paths.data(); a.home_rows[h] = (nv - h + W - 1) / W; }
       a.cursor = R.scratch; a.done_warps = R.scratch + 1; a.out_cnt = R.scratch + 2; a.stats = R.scratch + 2 + kMigMaxDest;
       gridDim.x = (unsigned)grid_blocks;
-      emu_launch_warps((int64_t)grid_blocks * 8, [&] { mig_step_kernel<true>(a); });
+      if (owner_map) emu_launch_warps((int64_t)grid_blocks * 8, [&] { mig_step_kernel<true, 4, true>(a); });
+      else emu_launch_warps((int64_t)grid_blocks * 8, [&] { mig_step_kernel<true>(a); });
     }
     unsigned long long sent = 0;
     for (int r = 0; r < W; ++r) sent += sh[(size_t)r].scratch[2 + kMigMaxDest];

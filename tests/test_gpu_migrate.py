@@ -109,6 +109,55 @@ def test_migrate_refuses_what_it_cannot_do():
         sh.MigrateWalker(directed, srw.Params(walkLength=10, numWalks=1), 1)
 
 
+# ---- the VCut shard map -- owner(v) = getPartition(v) mod world from the partition-id column (VRW:23-26,121-134) ----
+def _vcut_shards(s, d, pid, world):
+    import torch
+    sh = importlib.import_module("stellar-random-walk_b200.sharded")
+    ds, dd, dp = torch.from_numpy(s).cuda(), torch.from_numpy(d).cuda(), torch.from_numpy(pid).cuda()
+    return sh, [sh.Shard(len(s), ds.data_ptr(), dd.data_ptr(), None, r, world, migrate=True, d_pid=dp.data_ptr()) for r in range(world)]
+
+
+@pytest.mark.parametrize("world,pid_kind", [(2, "random"), (4, "random"), (4, "skewed"), (3, "wide"), (8, "random")])
+def test_vcut_shard_map_equals_twin(oracle, world, pid_kind):
+    """Shards follow the partition-id column: every vertex lives on getPartition(v) mod world (the pid of the LAST input line in
+    which it is a neighbour, GM:31), rows are not rank ranges, walkers are routed by that map -- and the paths are the twin's."""
+    s, d = synth.rmat_edges(11, 8, seed=42)
+    rng = np.random.default_rng(world)
+    if pid_kind == "random":
+        pid = rng.integers(0, world, len(s)).astype(np.int32)
+    elif pid_kind == "skewed":                       # one partition gets most edges, one none
+        pid = np.where(rng.random(len(s)) < 0.7, 0, rng.integers(2, world, len(s))).astype(np.int32)
+    else:                                            # partition ids beyond the GPU count: HashPartitioner's pid mod numPartitions
+        pid = rng.integers(0, 40, len(s)).astype(np.int32)
+    og = oracle.Graph().load_edges(s, d, None, pid=pid)
+    twin = oracle.AliasGraph(og)
+    ids, offs, st = twin.walk(walk_length=30, num_walks=3, p=0.5, q=2.0, seed=9, fold=1)
+    sh, shards = _vcut_shards(s, d, pid, world)
+    # the shard map is getPartition: every vertex's row is on exactly that shard, complete
+    vids = twin.view()["vids"]
+    off = twin.view()["offsets"]
+    probe = rng.choice(len(vids), 64, replace=False)
+    L = srw.lib()
+    for r in probe:
+        v = int(vids[r])
+        want_owner = og.partition(v) % world
+        for x in shards:
+            n = srw.C.c_int64()
+            srw.check(L.srw_graph_neighbors(x.h, v, None, None, 0, srw.C.byref(n)))
+            assert n.value == (int(off[r + 1] - off[r]) if x.rank == want_owner else -1), (v, x.rank, want_owner)
+    assert sum(x.row_last - x.row_first for x in shards) == twin.nv
+    assert sum(x.nnz_local for x in shards) == int(off[-1])
+    mw = sh.MigrateWalker(shards, srw.Params(walkLength=30, numWalks=3, p=0.5, q=2.0, seed=9, sampler="fold"), 3, stats=True)
+    out, stats = mw.run(0)
+    rows = _assemble(shards, out, twin.nv, 3, 32)
+    assert (rows.reshape(-1) == ids).all()
+    assert stats["steps"] == st.steps
+    mw.free()
+    # the other sharded modes refuse such shards instead of walking them with range arithmetic
+    with pytest.raises(srw.SrwError):
+        shards[0].attach_local(shards)
+
+
 def test_two_ranks_nccl():
     """tests/dist_sharded_check.py under torchrun with one rank per GPU: the NCCL tuple exchange, peer-gather over symmetric
     memory and the migrating walk over real peer memory, each against the CPU twin.  Needs two GPUs."""
@@ -150,3 +199,17 @@ def test_one_process_two_gpus_through_the_abi(oracle, tmp_path):
         assert rc == 0
         outs.append((out / "path" / "part-00000").read_bytes())
     assert outs[0] == outs[1] and len(outs[0]) > 0
+    # VCutRandomWalk on two GPUs: `--partitioned true --gpus 2` shards by the partition-id column (owner(v) = getPartition(v) mod 2)
+    pid = np.random.default_rng(3).integers(0, 7, 20000).astype(np.int32)
+    inp2 = tmp_path / "edges_pid.txt"
+    inp2.write_text("".join("%d %d %d\n" % (a, b, c) for a, b, c in zip(s[:20000], d[:20000], pid)))
+    out = tmp_path / "out_vcut"
+    rc = srw.Main.main(["--cmd", "randomwalk", "--input", str(inp2), "--output", str(out), "--walkLength", "20", "--numWalks", "2",
+                        "--p", "0.5", "--q", "2.0", "--weighted", "false", "--seed", "4", "--gpus", "2", "--partitioned", "true"])
+    assert rc == 0
+    assert (out / "path" / "part-00000").read_bytes() == outs[0]
+    gv = srw.Graph.from_edges_multi_vcut(s, d, np.random.default_rng(4).integers(0, 5, len(s)).astype(np.int32), 2)
+    got_ids, got_offs = gv.walk(srw.Params(walkLength=30, numWalks=3, p=0.5, q=2.0, seed=9, sampler="fold", gpus=2)).arrays()
+    assert (got_offs == offs).all() and (got_ids == ids).all()
+    assert gv.partition(v0) is not None
+    gv.free()

@@ -33,11 +33,12 @@ def emu():
     lib.emu_migrate_walk.restype = C.c_int
     lib.emu_migrate_walk.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_int,
                                      C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int,
-                                     C.c_void_p, C.c_void_p]
+                                     C.c_void_p, C.c_void_p, C.c_void_p]
     return lib
 
 
-def _emu_migrate(emu, oracle, tw, *, walk_length, p, q, seed, fold=True, shards=2, rounds=1, round_first=0, seg_cap=0, bloom_bits=16, blocks=2):
+def _emu_migrate(emu, oracle, tw, *, walk_length, p, q, seed, fold=True, shards=2, rounds=1, round_first=0, seg_cap=0, bloom_bits=16, blocks=2,
+                 owner=None):
     v = tw.view()
     off = np.ascontiguousarray(v["offsets"], np.int64)
     col = np.ascontiguousarray(v["col"], np.int32)
@@ -50,7 +51,7 @@ def _emu_migrate(emu, oracle, tw, *, walk_length, p, q, seed, fold=True, shards=
     st = np.zeros(8, np.uint64)
     rc = emu.emu_migrate_walk(nv, off.ctypes.data, col.ctypes.data, mult.ctypes.data, shards, bounds.ctypes.data, p, q, int(fold),
                               t_ret, t_common, t_far, seed, walk_length, round_first, rounds, seg_cap, bloom_bits, blocks,
-                              paths.ctypes.data, st.ctypes.data)
+                              paths.ctypes.data, st.ctypes.data, None if owner is None else np.ascontiguousarray(owner, np.uint8).ctypes.data)
     assert rc >= 0, rc
     assert int(st[6]) == 0, "device error flags %d" % int(st[6])
     assert (paths >= 0).all(), "a path slot was never written"
@@ -103,3 +104,31 @@ def test_migrate_short_walks(emu, oracle, walk_length):
     want, _ = _twin_paths(oracle, tw, walk_length=walk_length, num_walks=1, p=0.5, q=2.0, seed=3, fold=1)
     got, _, _ = _emu_migrate(emu, oracle, tw, walk_length=walk_length, p=0.5, q=2.0, seed=3, shards=3)
     assert got == want
+
+
+# ---- VCut shard map: owner(v) = getPartition(v) mod world from a partition-id column instead of vertex ranges ----
+@pytest.mark.parametrize("shards,bloom_bits,seg_cap", [(2, 16, 0), (4, 16, 0), (8, 2, 0), (3, 16, 64), (4, 1, 0)])
+def test_migrate_vcut_owner_map_equals_twin(emu, oracle, shards, bloom_bits, seg_cap):
+    """An arbitrary vertex -> shard map (interleaved, unbalanced, one shard possibly empty): the rows of a shard are no longer
+    a contiguous rank range, extents come from the replicated table, seeds from the shard's vertex list.  Same paths."""
+    tw = _rmat_twin(oracle, 8, 8)
+    nv = len(tw.view()["offsets"]) - 1
+    rng = np.random.default_rng(shards * 7 + bloom_bits)
+    owner = rng.integers(0, shards, nv).astype(np.uint8)
+    if shards == 4:
+        owner[owner == 2] = 0                                     # an empty shard, an overloaded one
+    want, _ = _twin_paths(oracle, tw, walk_length=24, num_walks=2, p=0.5, q=2.0, seed=5, fold=1)
+    got, _, st = _emu_migrate(emu, oracle, tw, walk_length=24, p=0.5, q=2.0, seed=5, shards=shards, rounds=2, bloom_bits=bloom_bits,
+                              seg_cap=seg_cap, blocks=1, owner=owner)
+    assert got == want
+    assert st["steps"] == sum(len(x) - 1 for x in want)
+
+
+def test_migrate_vcut_classic_thresholds_karate(emu, oracle):
+    tw = oracle.AliasGraph(oracle.Graph().load_file(KARATE))
+    nv = len(tw.view()["offsets"]) - 1
+    owner = (np.arange(nv) * 5 % 3).astype(np.uint8)
+    for p, q in ((2.0, 0.5), (1.0, 1.0), (0.25, 4.0)):
+        want, _ = _twin_paths(oracle, tw, walk_length=20, num_walks=2, p=p, q=q, seed=11, fold=1)
+        got, _, _ = _emu_migrate(emu, oracle, tw, walk_length=20, p=p, q=q, seed=11, shards=3, rounds=2, owner=owner)
+        assert got == want
