@@ -339,23 +339,33 @@ __global__ void k_nbr_entries(int64_t nnz, const uint32_t *__restrict__ row_of, 
     ent[i] = e;
   }
 }
+// Insert x into the hash set of a row (buckets [hoff, hoff + nb), 8 slots each, filled from slot 0).  The bucket is READ first
+// (one 32-byte L2 load) and the compare-and-swap goes straight to its first free slot: ~1 load + ~1 atomic per entry instead of a
+// chain of ~4 dependent atomics through the occupied slots (the build's top kernel at RMAT-26: 0.40 s).
+__device__ __forceinline__ void hash_set_insert(int32_t *hash, int64_t hoff, uint32_t nb, int32_t x) {
+  uint32_t b = __umulhi(srw_hash32((uint32_t)x), nb);
+  for (;;) {
+    int32_t *bucket = hash + (hoff + b) * 8;
+    const int4 q0 = __ldcg(reinterpret_cast<const int4 *>(bucket)), q1 = __ldcg(reinterpret_cast<const int4 *>(bucket) + 1);
+    const int32_t v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    int s = 8;
+#pragma unroll
+    for (int k = 7; k >= 0; --k) if (v[k] == -1 || v[k] == x) s = k;        // first slot that is free or already holds x
+    if (s < 8 && v[s] == x) return;                    // a parallel edge already did
+    for (; s < 8; ++s) {                               // (slots are never emptied: a bucket that looked full is full)
+      const int32_t old = atomicCAS(bucket + s, -1, x);
+      if (old == -1 || old == x) return;               // inserted, or a parallel edge did meanwhile
+    }
+    b = b + 1 == nb ? 0 : b + 1;
+  }
+}
 // one thread per adjacency entry (row keys come from the sort that produced d_col)
 __global__ void k_hash_insert(int64_t nnz, const uint32_t *__restrict__ row_of, const int32_t *__restrict__ col,
                               const RowMeta *__restrict__ meta, int32_t *hash) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
     const RowMeta m = meta[row_of[i]];
     if (m.nb == 0) continue;
-    const int32_t x = col[i];
-    uint32_t b = __umulhi(srw_hash32((uint32_t)x), m.nb);
-    bool done = false;
-    while (!done) {
-      int32_t *bucket = hash + (m.hoff + b) * 8;
-      for (int s = 0; s < 8 && !done; ++s) {
-        const int32_t old = atomicCAS(bucket + s, -1, x);
-        if (old == -1 || old == x) done = true;       // inserted, or a parallel edge already did
-      }
-      b = b + 1 == m.nb ? 0 : b + 1;
-    }
+    hash_set_insert(hash, m.hoff, m.nb, col[i]);
   }
 }
 
@@ -365,17 +375,7 @@ __global__ void k_hash_insert_ids(int64_t nnz, const uint32_t *__restrict__ row_
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
     const RowMeta m = meta[row_of[i]];
     if (m.nb == 0) continue;
-    const int32_t x = vids[col[i]];
-    uint32_t b = __umulhi(srw_hash32((uint32_t)x), m.nb);
-    bool done = false;
-    while (!done) {
-      int32_t *bucket = hash + (m.hoff + b) * 8;
-      for (int s = 0; s < 8 && !done; ++s) {
-        const int32_t old = atomicCAS(bucket + s, -1, x);
-        if (old == -1 || old == x) done = true;
-      }
-      b = b + 1 == m.nb ? 0 : b + 1;
-    }
+    hash_set_insert(hash, m.hoff, m.nb, vids[col[i]]);
   }
 }
 __global__ void k_ent_relabel(int64_t nnz, const int32_t *__restrict__ vids, NbrEntry *ent) {

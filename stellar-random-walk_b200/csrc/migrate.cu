@@ -77,7 +77,8 @@ constexpr int kScratchWords = 2 + kMigMaxDest + 8 + 1;   // cursor, done, out_cn
 srw_status mig_check(const srw_graph *g, const srw_params *p) {
   if (!g || !p) { srw_set_error("srw_mig: null graph or params"); return SRW_ERR_ARG; }
   if (g->directed) { srw_set_error("the migrating sharded walk needs an undirected graph (the membership test runs at owner(x): t in N(x))"); return SRW_ERR_UNSUPPORTED; }
-  if (!g->d_ent || !g->d_hash || !g->d_bloom) { srw_set_error("the migrating sharded walk needs an unweighted shard built with SRW_BUILD_ALIAS | SRW_BUILD_MIGRATE"); return SRW_ERR_UNSUPPORTED; }
+  // (a shard without rows -- a partition id no edge carries -- holds no row arrays)
+  if ((g->nnz > 0 && (!g->d_ent || !g->d_hash)) || !g->d_bloom) { srw_set_error("the migrating sharded walk needs an unweighted shard built with SRW_BUILD_ALIAS | SRW_BUILD_MIGRATE"); return SRW_ERR_UNSUPPORTED; }
   if (p->sampler == SRW_SAMPLER_EXACT) { srw_set_error("the sharded walk implements --sampler alias | fold"); return SRW_ERR_UNSUPPORTED; }
   if (p->walk_length < 0 || p->walk_length > 65000) { srw_set_error("sharded walk: walkLength must be in [0, 65000]"); return SRW_ERR_ARG; }
   if (!(p->p > 0.0) || !(p->q > 0.0)) { srw_set_error("p and q must be > 0"); return SRW_ERR_ARG; }
