@@ -349,9 +349,10 @@ __device__ __forceinline__ void hash_set_insert(int32_t *hash, int64_t hoff, uin
     const int4 q0 = __ldcg(reinterpret_cast<const int4 *>(bucket)), q1 = __ldcg(reinterpret_cast<const int4 *>(bucket) + 1);
     const int32_t v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
     int s = 8;
+    bool dup = false;
 #pragma unroll
-    for (int k = 7; k >= 0; --k) if (v[k] == -1 || v[k] == x) s = k;        // first slot that is free or already holds x
-    if (s < 8 && v[s] == x) return;                    // a parallel edge already did
+    for (int k = 7; k >= 0; --k) { dup |= v[k] == x; if (v[k] == -1) s = k; }      // s = first free slot
+    if (dup) return;                                   // a parallel edge already did
     for (; s < 8; ++s) {                               // (slots are never emptied: a bucket that looked full is full)
       const int32_t old = atomicCAS(bucket + s, -1, x);
       if (old == -1 || old == x) return;               // inserted, or a parallel edge did meanwhile
