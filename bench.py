@@ -53,6 +53,9 @@ def parse_args():
     ap.add_argument("--no-host-abi", action="store_true")
     ap.add_argument("--sampler", default="fold", choices=["fold", "alias"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--hub-fraction", type=float, default=0.5,
+                    help="N > 1: the highest-degree rows holding up to this share of the adjacency entries are replicated on every shard "
+                         "(a step onto a hub does not migrate); 0 = pure vertex-range shards")
     ap.add_argument("--build", choices=["lean", "full"], default="lean",
                     help="lean: SRW_BUILD_LEAN (only the arrays the alias/fold sampler reads stay in HBM); full: every array of SRW_BUILD_ALIAS")
     ap.add_argument("--e2e-reps", type=int, default=2)
@@ -790,12 +793,16 @@ def run_b200_multi(a):
     h_slice = [t[e_lo:e_hi].cpu().pin_memory() for t in (d_src, d_dst)] if want_e2e else None
     torch.cuda.synchronize()
     t0 = time.time()
-    shard = sh.Shard(n_edges, d_src.data_ptr(), d_dst.data_ptr(), None, rank, world, False, dev, migrate=True)
+    shard = sh.Shard(n_edges, d_src.data_ptr(), d_dst.data_ptr(), None, rank, world, False, dev, migrate=True, hub_fraction=a.hub_fraction)
     torch.cuda.synchronize()
     build_s = time.time() - t0
+    hub = {"fraction_requested": a.hub_fraction, "rows": shard.hub_rows, "entries": shard.hub_entries, "min_degree": shard.hub_min_degree,
+           "bytes_per_rank": shard.hub_entries * 24}
     del d_src, d_dst
     torch.cuda.empty_cache()
     nv = shard.nv
+    _, nnz_g = C.c_int64(), C.c_int64()
+    nnz_global = 2 * n_edges
     shard_bytes = int(lib.srw_graph_device_bytes(shard.h))
     batch = max(1, min(a.batch_rounds, max(a.steps, 1), ((1 << 32) - 1) // max(1, nv)))
     prm = srw.Params(walkLength=a.walk_length, numWalks=1, p=a.p, q=a.q, seed=a.seed, sampler=a.sampler)
@@ -856,7 +863,7 @@ def run_b200_multi(a):
         full = [torch.empty(n_edges, dtype=torch.int32, device=dev) for _ in range(2)]
         for f_, p_ in zip(full, parts):
             dist.all_gather_into_tensor(f_, p_)
-        sh2 = sh.Shard(n_edges, full[0].data_ptr(), full[1].data_ptr(), None, rank, world, False, dev, migrate=True)
+        sh2 = sh.Shard(n_edges, full[0].data_ptr(), full[1].data_ptr(), None, rank, world, False, dev, migrate=True, hub_fraction=a.hub_fraction)
         torch.cuda.synchronize()
         t_built = time.time() - t0
         del full, parts
@@ -949,6 +956,9 @@ def run_b200_multi(a):
                 "ms_per_step": elapsed_ms / max(1, a.steps), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "u32 (integer thresholds; f64 only in the return-component test)", "data": "synthetic",
                 "config": {"workload": workload_name(a), "vertices_present": nv, "walkers_per_step": nv,
+                           "hub_replication": dict(hub, entries_share=hub["entries"] / max(1, nnz_global),
+                                                   note="vertex-cut: the rows of the highest-degree vertices are kept by every shard, a step onto one does not migrate "
+                                                        "(VRW:43-54 replicates a vertex's adjacency into every partition it has an edge in); --hub-fraction 0 = pure ranges"),
                            "parallelism": "graph sharded into %d edge-balanced vertex ranges (one per GPU); walkers migrate to owner(curr): the step kernel "
                                           "stores 32-byte walker tuples straight into the destination GPU's inbox over NVLink (peer memory) and path entries into "
                                           "the home GPU's path rows; NCCL all-reduce of the tuple count = barrier + termination test between super-steps; "

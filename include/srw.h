@@ -238,15 +238,22 @@ int srw_main(int argc, const char *const *argv);
  * stellar-random-walk_b200/sharded.py for the loop (RW:91-162).  Alias sampler only. ---- */
 srw_status srw_graph_from_device_edges_sharded(int64_t n, const int32_t *d_src, const int32_t *d_dst, const float *d_w,
                                                int directed, unsigned flags, int rank, int world, srw_graph **out);
-/* SURVEY 8(f)3 -- the VCut shard map (VRW:23-26 partition-id column, VRW:43-54 one GraphMap per partition, VRW:121-134 routing by
- * GraphMap.getPartition(steps.last), GM:31,66-68): owner(v) = getPartition(v) mod world, where getPartition(v) is the partition id
- * of the last input line in which v is a neighbour (srw_graph_partition).  Rank `rank` holds the complete rows of the vertices it
- * owns -- not a contiguous rank range; an 8-byte-per-vertex extent table and a 1-byte-per-vertex owner table are replicated on
- * every shard.  Walked by the migrating walk (srw_mig_*) only; same paths as any other sharding.  For such a shard
- * srw_graph_shard_info reports row_first = 0, row_last = its row count, bounds = group sizes as a prefix sum.
+/* SURVEY 8(f)3 -- VERTEX-CUT shards (VCutRandomWalk): table-mapped instead of plain vertex ranges.
+ *   d_pid != NULL: the VCut shard map (VRW:23-26 partition-id column, VRW:121-134 routing by GraphMap.getPartition(steps.last),
+ *     GM:31,66-68): owner(v) = getPartition(v) mod world, where getPartition(v) is the partition id of the last input line in
+ *     which v is a neighbour (srw_graph_partition).  d_pid == NULL: edge-balanced vertex ranges.
+ *   hub_fraction in [0, 0.95]: the rows of the highest-degree vertices -- as many as hold up to that share of all adjacency entries
+ *     -- are REPLICATED on every shard (VRW:43-54 replicates a vertex's adjacency into every partition it has an edge in): a walker
+ *     that steps onto a hub does not migrate.  Costs hub_fraction x 24 bytes per adjacency entry of HBM on every shard.
+ * An 8-byte-per-vertex extent table and a 1-byte-per-vertex owner table are replicated on every shard.  Walked by the migrating
+ * walk (srw_mig_*) only; same paths as any other sharding.  For such a shard srw_graph_shard_info reports row_first = 0,
+ * row_last = its local row count (hub rows + own rows), bounds = own-row group sizes as a prefix sum.
  * Undirected, unweighted; flags as srw_graph_from_device_edges_sharded. */
-srw_status srw_graph_from_device_edges_vcut(int64_t n, const int32_t *d_src, const int32_t *d_dst, const int32_t *d_pid,
-                                            int directed, unsigned flags, int rank, int world, srw_graph **out);
+srw_status srw_graph_from_device_edges_vcut(int64_t n, const int32_t *d_src, const int32_t *d_dst, const int32_t *d_pid /*NULL*/,
+                                            int directed, unsigned flags, int rank, int world, double hub_fraction, srw_graph **out);
+/* What hub_fraction selected on this shard (identical on every shard; 0 / 0 / 0xFFFFFFFF when nothing is replicated): replicated
+ * rows, the adjacency entries they hold, the smallest replicated degree; *seed_rows = the vertices this shard starts walkers for. */
+srw_status srw_graph_hub_info(const srw_graph *g, int64_t *hub_rows, int64_t *hub_entries, uint32_t *hub_min_degree, int64_t *seed_rows);
 /* bounds: world+1 first-ranks of the shards (identical on every rank) */
 srw_status srw_graph_shard_info(const srw_graph *g, int *rank, int *world, int64_t *row_first, int64_t *row_last,
                                 int64_t *bounds, int64_t *nnz_local);

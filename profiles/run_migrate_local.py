@@ -40,8 +40,9 @@ g.free()
 del paths, lens
 torch.cuda.empty_cache()
 only = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-for world in ((only,) if only else (1, 2, 4, 8)):
-    shards = [sh.Shard(n, s.data_ptr(), d.data_ptr(), None, r, world, migrate=True) for r in range(world)]
+hub_fracs = [float(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else [0.0]
+for world, hub in [(w, h) for w in ((only,) if only else (1, 2, 4, 8)) for h in hub_fracs]:
+    shards = [sh.Shard(n, s.data_ptr(), d.data_ptr(), None, r, world, migrate=True, hub_fraction=hub if world > 1 else 0.0) for r in range(world)]
     for stats in (True, False):
         mw = sh.MigrateWalker(shards, prm, rounds, stats=stats, check_every=8)
         mw.run(0)
@@ -57,7 +58,9 @@ for world in ((only,) if only else (1, 2, 4, 8)):
         if not stats:
             # round 1 is the first round of this batch: rows [0, home_rows) of every shard
             chk = sum(int((p[:x.home_rows].long() * torch.arange(1, 83, device="cuda")).sum()) for x, (p, _) in zip(shards, out))
-        print(json.dumps({"config": "rmat-%d migrate, %d shards on one GPU" % (scale, world), "instrumented": stats, "rounds": rounds,
+        print(json.dumps({"config": "rmat-%d migrate, %d shards on one GPU" % (scale, world), "hub_fraction": hub, "hub_rows": shards[0].hub_rows,
+                          "hub_entries_share": shards[0].hub_entries / max(1, nnz), "shard_bytes": [int(lib.srw_graph_device_bytes(x.h)) for x in shards],
+                          "instrumented": stats, "rounds": rounds,
                           "steps": st["steps"], "ms": ms, "steps_per_s": st["steps"] / (ms * 1e-3), "super_steps": st["super_steps"],
                           "launched": st["super_steps_launched"], "tuples_per_step": st["tuples_sent_all_ranks"] / max(1, st["steps"]),
                           "proposals_per_step": st["proposals"] / max(1, st["steps"]), "filter_probes_per_step": st["filter_probes"] / max(1, st["steps"]),

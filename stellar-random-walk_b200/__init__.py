@@ -45,7 +45,7 @@ ABI_SYMBOLS = [
     "srw_shard_rows_info", "srw_shard_rows_relocate", "srw_shard_attach_block",
     "srw_mig_block_bytes", "srw_mig_create", "srw_mig_collect_stats", "srw_mig_begin", "srw_mig_superstep", "srw_mig_counters",
     "srw_mig_finish", "srw_mig_info", "srw_mig_free", "srw_graph_from_edges_multi",
-    "srw_graph_from_device_edges_vcut", "srw_graph_from_edges_multi_vcut",
+    "srw_graph_from_device_edges_vcut", "srw_graph_from_edges_multi_vcut", "srw_graph_hub_info",
 ]
 
 

@@ -97,6 +97,7 @@ __global__ void k_degrees(int64_t n, const int32_t *__restrict__ src, const int3
     if (!directed) atomicAdd(&deg[rank_of(bitmap, wordrank, id_min, dst[e])], 1u);
   }
 }
+struct ShardBoundsLite { int world; int64_t first[SRW_MAX_SHARDS + 1]; };
 __device__ __forceinline__ uint32_t warp_reserve(bool want, unsigned long long *cursor) {
   const unsigned m = __ballot_sync(0xffffffffu, want);
   if (!m) return 0;
@@ -125,28 +126,63 @@ __global__ void k_entries_range(int64_t n, const int32_t *__restrict__ src, cons
     if (k1) { ent_row[p1] = rd - row_first; ent_col[p1] = rs; ent_gidx[p1] = (uint32_t)(2 * e + 1); }
   }
 }
-// ---- VCut shard map (VRW:23-26,121-134; GM:31,66-68): owner(v) = getPartition(v) mod world ----
-__global__ void k_vcut_owner(int64_t nv, const int32_t *__restrict__ vpid, int world, uint8_t *owner, uint32_t *key) {
+// ---- table-mapped shards: the VCut shard map (VRW:23-26,121-134; GM:31,66-68: owner(v) = getPartition(v) mod world) and/or
+// REPLICATED HUB ROWS (VRW:43-54 replicates a vertex's adjacency into every partition it has an edge in; here the rows of the
+// highest-degree vertices are kept by EVERY shard, so a walker that steps onto a hub does not migrate) ----
+constexpr uint32_t kHubOwner = 0xFFu;        // d_owner[v] / NbrEntry owner byte: "this row is on every shard"
+__global__ void k_map_owner_pid(int64_t nv, const int32_t *__restrict__ vpid, int world, uint8_t *owner_true) {
   for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nv; v += (int64_t)gridDim.x * blockDim.x) {
     const int32_t p = vpid[v];                      // (-1: a vertex no edge leads to -- cannot happen on an undirected graph)
-    const int o = ((int)(p % world) + world) % world;     // Spark HashPartitioner: nonNegativeMod(pid.hashCode, numPartitions)
-    owner[v] = (uint8_t)o; key[v] = (uint32_t)o;
+    owner_true[v] = (uint8_t)(((int)(p % world) + world) % world);     // Spark HashPartitioner: nonNegativeMod(pid.hashCode, numPartitions)
   }
 }
-// first position of every owner's group in the sorted key array (groups that exist)
-__global__ void k_vcut_group_first(int64_t nv, const uint32_t *__restrict__ key, long long *first) {
+__global__ void k_map_owner_ranges(int64_t nv, ShardBoundsLite sb, uint8_t *owner_true) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nv; v += (int64_t)gridDim.x * blockDim.x) {
+    int o = 0;
+    while (o + 1 < sb.world && v >= sb.first[o + 1]) o++;
+    owner_true[v] = (uint8_t)o;
+  }
+}
+// degree with the hub rows masked out (ranges are balanced on the entries that are NOT replicated)
+__global__ void k_map_masked_deg(int64_t nv, const uint32_t *__restrict__ deg, uint32_t hub_deg, uint32_t *out) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v <= nv; v += (int64_t)gridDim.x * blockDim.x)
+    out[v] = v < nv && deg[v] < hub_deg ? deg[v] : 0u;
+}
+// routing owner (kHubOwner for replicated rows) and the sort key that groups the rows: 0 = hubs, o + 1 = shard o
+__global__ void k_map_keys(int64_t nv, const uint32_t *__restrict__ deg, uint32_t hub_deg, const uint8_t *__restrict__ owner_true,
+                           uint8_t *owner, uint32_t *key) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nv; v += (int64_t)gridDim.x * blockDim.x) {
+    const bool hub = deg[v] >= hub_deg;
+    owner[v] = hub ? (uint8_t)kHubOwner : owner_true[v];
+    key[v] = hub ? 0u : (uint32_t)owner_true[v] + 1u;
+  }
+}
+// first position of every group in the sorted key array (groups that exist)
+__global__ void k_map_group_first(int64_t nv, const uint32_t *__restrict__ key, long long *first) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x)
     if (i == 0 || key[i] != key[i - 1]) first[key[i]] = i;
 }
-struct VcutGroups { int64_t first[SRW_MAX_SHARDS + 1]; int64_t base[SRW_MAX_SHARDS + 1]; };
-// position i of the (owner, vertex)-sorted order holds vertex perm[i]: its row starts at poff[i] - base[owner] inside the owner's arrays
-__global__ void k_vcut_ext(int64_t nv, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ key, const int64_t *__restrict__ poff,
-                           VcutGroups gr, MigExt *ext, uint32_t *lrow) {
+struct MapGroups { int64_t first[SRW_MAX_SHARDS + 2]; int64_t base[SRW_MAX_SHARDS + 2]; };
+// position i of the (group, vertex)-sorted order holds vertex perm[i].  Every shard lays its arrays out as [hub rows | own rows]:
+// a hub row starts at poff[i] (the same on every shard), an own row at hub_entries + poff[i] - base[group] inside its owner's arrays
+__global__ void k_map_ext(int64_t nv, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ key, const int64_t *__restrict__ poff,
+                          MapGroups gr, MigExt *ext, uint32_t *lrow) {
+  const int64_t hub_rows = gr.first[1], hub_entries = gr.base[1];
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
-    const uint32_t v = perm[i], o = key[i];
-    MigExt e; e.off = (uint32_t)(poff[i] - gr.base[o]); e.deg = (uint32_t)(poff[i + 1] - poff[i]);
-    ext[v] = e; lrow[v] = (uint32_t)(i - gr.first[o]);
+    const uint32_t v = perm[i], k = key[i];
+    MigExt e;
+    e.deg = (uint32_t)(poff[i + 1] - poff[i]);
+    if (k == 0) { e.off = (uint32_t)poff[i]; lrow[v] = (uint32_t)i; }
+    else { e.off = (uint32_t)(hub_entries + poff[i] - gr.base[k]); lrow[v] = (uint32_t)(hub_rows + i - gr.first[k]); }
+    ext[v] = e;
   }
+}
+// local row offsets of shard `rank`: the hub rows, then its own rows
+__global__ void k_map_local_off(int64_t hub_rows, int64_t own_rows, int64_t own_first, int64_t own_base, int64_t hub_entries,
+                                const int64_t *__restrict__ poff, int64_t *off) {
+  const int64_t rows = hub_rows + own_rows;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r <= rows; r += (int64_t)gridDim.x * blockDim.x)
+    off[r] = r < hub_rows ? poff[r] : hub_entries + poff[own_first + (r - hub_rows)] - own_base;
 }
 __global__ void k_entries_owner(int64_t n, const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int directed,
                                 const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ wordrank, int32_t id_min,
@@ -157,14 +193,18 @@ __global__ void k_entries_owner(int64_t n, const int32_t *__restrict__ src, cons
     uint32_t rs = 0, rd = 0;
     const bool live = e < n;
     if (live) { rs = rank_of(bitmap, wordrank, id_min, src[e]); rd = rank_of(bitmap, wordrank, id_min, dst[e]); }
-    const bool k0 = live && owner[rs] == rank;
-    const bool k1 = live && !directed && owner[rd] == rank;
+    const bool k0 = live && (owner[rs] == rank || owner[rs] == kHubOwner);
+    const bool k1 = live && !directed && (owner[rd] == rank || owner[rd] == kHubOwner);
     const uint32_t p0 = warp_reserve(k0, cursor);
     if (k0) { ent_row[p0] = lrow[rs]; ent_col[p0] = rd; ent_gidx[p0] = (uint32_t)(directed ? e : 2 * e); }
     const uint32_t p1 = warp_reserve(k1, cursor);
     if (k1) { ent_row[p1] = lrow[rd]; ent_col[p1] = rs; ent_gidx[p1] = (uint32_t)(2 * e + 1); }
   }
 }
+struct IsOwner {
+  const uint8_t *owner_true; int rank;
+  __host__ __device__ bool operator()(uint32_t v) const { return owner_true[v] == rank; }
+};
 // SRW_BUILD_MIGRATE: every undirected input edge {rank(src), rank(dst)} sets kMigBloomK bits of one 64-bit word
 __global__ void k_bloom_insert(int64_t n, const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
                                const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ wordrank, int32_t id_min,
@@ -438,7 +478,7 @@ void srw_alias_thresholds(double p, double q, uint64_t *t_ret, uint64_t *t_commo
 
 static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_dst, const float *d_w, const int32_t *d_pid,
                              int directed, unsigned flags, int64_t n_extra, const int32_t *d_extra, srw_graph *g, int shard_rank = 0,
-                             int shard_world = 1, bool vcut = false) {
+                             int shard_world = 1, bool vcut = false, double hub_fraction = 0.0) {
   g->directed = directed != 0;
   g->flags = flags;
   SRW_CUDA(cudaGetDevice(&g->device));
@@ -547,18 +587,69 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
     SRW_CUDA(cudaMalloc(&g->d_off, (size_t)(nv + 1) * 8));
     SRW_TRY(scan_degrees(g->d_off));
   } else if (vcut) {
-    // VCut shard map: owner(v) = getPartition(v) mod world (GM:66-68 via VRW:126) -- every rank derives the same map from the
-    // partition-id column.  Rows of a shard = the vertices it owns in ascending rank order, back to back.
-    if (!d_pid) { srw_set_error("the VCut shard map needs the partition-id column"); return SRW_ERR_ARG; }
+    // Table-mapped shards.  owner_true(v): the VCut shard map -- getPartition(v) mod world (GM:66-68 via VRW:126), every rank derives
+    // the same map from the partition-id column -- or, without the column, edge-balanced vertex ranges.  Rows whose degree reaches
+    // hub_deg are REPLICATED: every shard keeps them in front of its own rows, and their routing owner is kHubOwner ("wherever
+    // the walker is"); ranges are balanced on the entries that are not replicated.
     if (n > 0) k_degrees<<<grid(n), kThreads>>>(n, d_src, d_dst, directed, g->d_bitmap, g->d_wordrank, mn, deg.as<uint32_t>());
     SRW_TRY(build_vpid());
-    DevBuf key0, key1, val0, val1, pdeg, poff, lrow;
+    uint32_t hub_deg = 0xFFFFFFFFu;                 // no row reaches it: nothing replicated
+    if (hub_fraction > 0.0 && nnz > 0) {
+      // the smallest degree threshold whose rows hold at most hub_fraction of the entries: degrees sorted, prefix-summed from the top
+      DevBuf dk0, dk1, dv0, dv1;
+      SRW_CUDA(dk0.alloc((size_t)nv * 4)); SRW_CUDA(dk1.alloc((size_t)nv * 4)); SRW_CUDA(dv0.alloc((size_t)nv * 4)); SRW_CUDA(dv1.alloc((size_t)nv * 4));
+      SRW_CUDA(cudaMemcpy(dk0.p, deg.p, (size_t)nv * 4, cudaMemcpyDeviceToDevice));
+      uint32_t *a_in = dk0.as<uint32_t>(), *a_out = dk1.as<uint32_t>(), *b_in = dv0.as<uint32_t>(), *b_out = dv1.as<uint32_t>();
+      SRW_TRY(sort_pairs(a_in, a_out, b_in, b_out, nv, 32));        // ascending (values unused)
+      std::vector<uint32_t> h_deg((size_t)nv);
+      SRW_CUDA(cudaMemcpy(h_deg.data(), a_in, (size_t)nv * 4, cudaMemcpyDeviceToHost));
+      const double budget = hub_fraction * (double)nnz;
+      double acc = 0.0;
+      int64_t i = nv;
+      while (i > 0 && acc + (double)h_deg[(size_t)i - 1] <= budget) { acc += (double)h_deg[(size_t)i - 1]; i--; }
+      // rows i .. nv-1 fit; a degree value must be wholly in or wholly out: drop the partial run of equal degrees at the cut
+      if (i < nv) {
+        uint32_t T = h_deg[(size_t)i];
+        if (i > 0 && h_deg[(size_t)i - 1] == T) T++;
+        hub_deg = T < 2 ? 2 : T;
+      }
+    }
+    DevBuf otrue, key0, key1, val0, val1, pdeg, poff, lrow;
+    SRW_CUDA(otrue.alloc((size_t)nv));
+    if (d_pid) k_map_owner_pid<<<grid(nv), kThreads>>>(nv, g->d_vpid, shard_world, otrue.as<uint8_t>());
+    else {
+      // edge-balanced contiguous vertex ranges over the entries that are not replicated (same on every rank)
+      DevBuf mdeg, moff;
+      SRW_CUDA(mdeg.alloc((size_t)(nv + 1) * 4)); SRW_CUDA(moff.alloc((size_t)(nv + 1) * 8));
+      k_map_masked_deg<<<grid(nv + 1), kThreads>>>(nv, deg.as<uint32_t>(), hub_deg, mdeg.as<uint32_t>());
+      {
+        cub::TransformInputIterator<int64_t, CastU32ToI64, uint32_t *> it(mdeg.as<uint32_t>(), CastU32ToI64());
+        size_t tb = 0;
+        DevBuf tmp;
+        SRW_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, it, moff.as<int64_t>(), nv + 1));
+        SRW_CUDA(tmp.alloc(tb));
+        SRW_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, it, moff.as<int64_t>(), nv + 1));
+      }
+      std::vector<int64_t> h_moff((size_t)nv + 1);
+      SRW_CUDA(cudaMemcpy(h_moff.data(), moff.p, (size_t)(nv + 1) * 8, cudaMemcpyDeviceToHost));
+      ShardBoundsLite bl{};
+      bl.world = shard_world;
+      bl.first[0] = 0; bl.first[shard_world] = nv;
+      for (int r = 1; r < shard_world; ++r) {
+        const int64_t target = (int64_t)((__int128)h_moff[(size_t)nv] * r / shard_world);
+        int64_t bnd = (int64_t)(std::lower_bound(h_moff.begin(), h_moff.end(), target) - h_moff.begin());
+        if (bnd > nv) bnd = nv;
+        if (bnd < bl.first[r - 1]) bnd = bl.first[r - 1];
+        bl.first[r] = bnd;
+      }
+      k_map_owner_ranges<<<grid(nv), kThreads>>>(nv, bl, otrue.as<uint8_t>());
+    }
     SRW_CUDA(key0.alloc((size_t)nv * 4)); SRW_CUDA(key1.alloc((size_t)nv * 4)); SRW_CUDA(val0.alloc((size_t)nv * 4)); SRW_CUDA(val1.alloc((size_t)nv * 4));
     SRW_CUDA(cudaMalloc(&g->d_owner, (size_t)nv));
-    k_vcut_owner<<<grid(nv), kThreads>>>(nv, g->d_vpid, shard_world, g->d_owner, key0.as<uint32_t>());
+    k_map_keys<<<grid(nv), kThreads>>>(nv, deg.as<uint32_t>(), hub_deg, otrue.as<uint8_t>(), g->d_owner, key0.as<uint32_t>());
     k_iota<<<grid(nv), kThreads>>>(nv, val0.as<uint32_t>());
     uint32_t *ok_in = key0.as<uint32_t>(), *ok_out = key1.as<uint32_t>(), *ov_in = val0.as<uint32_t>(), *ov_out = val1.as<uint32_t>();
-    SRW_TRY(sort_pairs(ok_in, ok_out, ov_in, ov_out, nv, bits_for(shard_world) + 1));      // stable: ascending vertex inside a group
+    SRW_TRY(sort_pairs(ok_in, ok_out, ov_in, ov_out, nv, bits_for(shard_world + 1) + 1));      // stable: ascending vertex inside a group
     SRW_CUDA(pdeg.alloc((size_t)(nv + 1) * 4));
     SRW_CUDA(cudaMemset(pdeg.p, 0, (size_t)(nv + 1) * 4));
     k_gather_u32<<<grid(nv), kThreads>>>(nv, ov_in, deg.as<uint32_t>(), pdeg.as<uint32_t>());
@@ -572,31 +663,47 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
       SRW_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, it, poff.as<int64_t>(), nv + 1));
       SRW_CUDA(cudaDeviceSynchronize());
     }
-    VcutGroups gr{};
+    MapGroups gr{};
+    const int n_groups = shard_world + 1;            // group 0 = hubs, group o + 1 = shard o
     {
       DevBuf first;
-      SRW_CUDA(first.alloc((SRW_MAX_SHARDS + 1) * 8));
-      SRW_CUDA(cudaMemset(first.p, 0xFF, (SRW_MAX_SHARDS + 1) * 8));
-      k_vcut_group_first<<<grid(nv), kThreads>>>(nv, ok_in, first.as<long long>());
-      long long h_first[SRW_MAX_SHARDS + 1];
+      SRW_CUDA(first.alloc((SRW_MAX_SHARDS + 2) * 8));
+      SRW_CUDA(cudaMemset(first.p, 0xFF, (SRW_MAX_SHARDS + 2) * 8));
+      k_map_group_first<<<grid(nv), kThreads>>>(nv, ok_in, first.as<long long>());
+      long long h_first[SRW_MAX_SHARDS + 2];
       SRW_CUDA(cudaMemcpy(h_first, first.p, sizeof h_first, cudaMemcpyDeviceToHost));
-      gr.first[shard_world] = nv;
-      for (int o = shard_world - 1; o >= 0; --o) gr.first[o] = h_first[o] >= 0 ? h_first[o] : gr.first[o + 1];    // empty group
-      for (int o = 0; o <= shard_world; ++o) SRW_CUDA(cudaMemcpy(&gr.base[o], poff.as<int64_t>() + gr.first[o], 8, cudaMemcpyDeviceToHost));
+      gr.first[n_groups] = nv;
+      for (int o = n_groups - 1; o >= 0; --o) gr.first[o] = h_first[o] >= 0 ? h_first[o] : gr.first[o + 1];    // empty group
+      for (int o = 0; o <= n_groups; ++o) SRW_CUDA(cudaMemcpy(&gr.base[o], poff.as<int64_t>() + gr.first[o], 8, cudaMemcpyDeviceToHost));
     }
     SRW_CUDA(cudaMalloc(&g->d_ext, (size_t)nv * sizeof(MigExt)));
     SRW_CUDA(lrow.alloc((size_t)nv * 4));
-    k_vcut_ext<<<grid(nv), kThreads>>>(nv, ov_in, ok_in, poff.as<int64_t>(), gr, g->d_ext, lrow.as<uint32_t>());
-    nrows = gr.first[shard_rank + 1] - gr.first[shard_rank];
-    nnz = gr.base[shard_rank + 1] - gr.base[shard_rank];
-    g->nnz = nnz; g->vcut = true;
-    g->row_first = 0; g->row_last = nrows;            // LOCAL row count: the rows are not a rank range (owner / ext / lverts say which)
-    for (int r = 0; r <= shard_world; ++r) g->bounds[(size_t)r] = gr.first[r];          // group starts in (owner, vertex) order: sizes only
+    k_map_ext<<<grid(nv), kThreads>>>(nv, ov_in, ok_in, poff.as<int64_t>(), gr, g->d_ext, lrow.as<uint32_t>());
+    const int64_t hub_rows = gr.first[1], hub_entries = gr.base[1];
+    const int64_t own_rows = gr.first[shard_rank + 2] - gr.first[shard_rank + 1], own_entries = gr.base[shard_rank + 2] - gr.base[shard_rank + 1];
+    nrows = hub_rows + own_rows;
+    nnz = hub_entries + own_entries;
+    g->nnz = nnz; g->vcut = true; g->hub_rows = hub_rows; g->hub_entries = hub_entries; g->hub_deg = hub_deg;
+    g->row_first = 0; g->row_last = nrows;            // LOCAL row count: the rows are not a rank range (d_owner / d_ext say which)
+    for (int r = 0; r <= shard_world; ++r) g->bounds[(size_t)r] = gr.first[r + 1] - gr.first[1];          // own-row group sizes as a prefix sum
     if (nnz >= ((int64_t)1 << 32)) { srw_set_error("shard %d would hold %lld adjacency entries (limit 2^32 - 1 per shard)", shard_rank, (long long)nnz); return SRW_ERR_UNSUPPORTED; }
-    SRW_CUDA(cudaMalloc(&g->d_lverts, (size_t)(nrows ? nrows : 1) * 4));
-    if (nrows) SRW_CUDA(cudaMemcpy(g->d_lverts, ov_in + gr.first[shard_rank], (size_t)nrows * 4, cudaMemcpyDeviceToDevice));
+    {
+      // seeds: the vertices this shard starts walkers for = owner_true(v) == rank (replicated or not), ascending
+      DevBuf iota, cnt, tmp;
+      SRW_CUDA(iota.alloc((size_t)nv * 4)); SRW_CUDA(cnt.alloc(8));
+      k_iota<<<grid(nv), kThreads>>>(nv, iota.as<uint32_t>());
+      SRW_CUDA(cudaMalloc(&g->d_lverts, (size_t)nv * 4));
+      size_t tb = 0;
+      IsOwner pred{otrue.as<uint8_t>(), shard_rank};
+      SRW_CUDA(cub::DeviceSelect::If(nullptr, tb, iota.as<uint32_t>(), (uint32_t *)g->d_lverts, cnt.as<long long>(), nv, pred));
+      SRW_CUDA(tmp.alloc(tb));
+      SRW_CUDA(cub::DeviceSelect::If(tmp.p, tb, iota.as<uint32_t>(), (uint32_t *)g->d_lverts, cnt.as<long long>(), nv, pred));
+      long long h_cnt = 0;
+      SRW_CUDA(cudaMemcpy(&h_cnt, cnt.p, 8, cudaMemcpyDeviceToHost));
+      g->seed_rows = h_cnt;
+    }
     SRW_CUDA(cudaMalloc(&g->d_off, (size_t)(nrows + 1) * 8));
-    k_rebase_off<<<grid(nrows + 1), kThreads>>>(nrows, poff.as<int64_t>(), gr.first[shard_rank], g->d_off);
+    k_map_local_off<<<grid(nrows + 1), kThreads>>>(hub_rows, own_rows, gr.first[shard_rank + 1], gr.base[shard_rank + 1], hub_entries, poff.as<int64_t>(), g->d_off);
     DevBuf raw_row, raw_col, raw_gidx, cursor, ka, va;
     SRW_CUDA(raw_row.alloc((size_t)nnz * 4)); SRW_CUDA(raw_col.alloc((size_t)nnz * 4)); SRW_CUDA(raw_gidx.alloc((size_t)nnz * 4));
     SRW_CUDA(cursor.alloc(8));
@@ -811,7 +918,7 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
     }
   }
   SRW_CUDA(cudaGetLastError());
-  if (vcut) g->device_bytes += nv * 9 + nrows * 4;
+  if (vcut) g->device_bytes += nv * 13;
   g->device_bytes += (int64_t)(words * 8 + (size_t)nv * 12 + (g->d_col ? (size_t)nnz * 4 : 0)) + (g->d_col_app ? nnz * 8 : 0) +
                     (g->d_slot ? nnz * 16 : 0) + (g->d_slotw ? nnz * 32 : 0) + (g->d_vpid ? nv * 4 : 0) + (g->d_meta ? nrows * 32 : 0) + (g->d_hash ? g->hash_buckets * 32 : 0) + (g->d_hash_id ? g->hash_buckets * 32 : 0) + (g->d_ent ? nnz * 16 : 0) + (int64_t)g->bloom_words * 8;
   return SRW_OK;
@@ -879,15 +986,18 @@ srw_status srw_build_graph_rows(int64_t n_rows, const int32_t *h_vids, const int
 }
 
 srw_status srw_build_graph_device_sharded(int64_t n, const int32_t *d_src, const int32_t *d_dst, const float *d_w, int directed,
-                                          unsigned flags, int rank, int world, srw_graph **out, const int32_t *d_pid) {
+                                          unsigned flags, int rank, int world, srw_graph **out, const int32_t *d_pid, double hub_fraction) {
   SRW_TRY(srw_require_device());
   if (n < 0 || !out || (n > 0 && (!d_src || !d_dst)) || world < 1 || world > SRW_MAX_SHARDS || rank < 0 || rank >= world) {
     srw_set_error("srw_graph_from_device_edges_sharded: bad argument");
     return SRW_ERR_ARG;
   }
   srw_graph *g = new srw_graph();
-  // d_pid != NULL: the VCut shard map -- owner(v) = getPartition(v) mod world instead of edge-balanced vertex ranges
-  srw_status s = build_impl(n, d_src, d_dst, d_w, d_pid, directed, flags ? flags : SRW_BUILD_ALIAS, 0, nullptr, g, rank, world, d_pid != nullptr && world > 1);
+  // d_pid != NULL: the VCut shard map -- owner(v) = getPartition(v) mod world instead of edge-balanced vertex ranges;
+  // hub_fraction > 0: the highest-degree rows holding up to that share of the entries are replicated on every shard
+  if (!(hub_fraction >= 0.0) || hub_fraction > 0.95) { srw_set_error("hub_fraction must be in [0, 0.95]"); delete g; return SRW_ERR_ARG; }
+  const bool mapped = world > 1 && (d_pid != nullptr || hub_fraction > 0.0);
+  srw_status s = build_impl(n, d_src, d_dst, d_w, d_pid, directed, flags ? flags : SRW_BUILD_ALIAS, 0, nullptr, g, rank, world, mapped, hub_fraction);
   if (s != SRW_OK) { srw_graph_free(g); return s; }
   g->peer_off[rank] = g->d_off; g->peer_ent[rank] = g->d_ent; g->peer_hash[rank] = g->d_hash;
   g->peer_attached[rank] = true;

@@ -153,7 +153,7 @@ extern "C" srw_status srw_mig_create(const srw_graph *g, const srw_params *p, in
   memset(&a, 0, sizeof(a));
   a.off = g->d_off; a.ent = g->d_ent; a.hash = g->d_hash; a.bloom = (const unsigned long long *)g->d_bloom; a.bloom_words = (uint32_t)g->bloom_words;
   a.nv = g->nv; a.row_first = g->row_first; a.row_last = g->row_last; a.world = m->world; a.rank = m->rank;
-  if (g->vcut) { a.ext = g->d_ext; a.owner = g->d_owner; a.lverts = g->d_lverts; a.rows_local = g->row_last - g->row_first; }
+  if (g->vcut) { a.ext = g->d_ext; a.owner = g->d_owner; a.lverts = g->d_lverts; a.rows_local = g->seed_rows; }
   for (int r = 0; r <= m->world; ++r) a.bounds[r] = g->bounds[(size_t)r];
   FoldArgs f;
   const bool folded = srw_fold_args(p->p, p->q, p->sampler == SRW_SAMPLER_ALIAS_FOLD, &f);
@@ -221,7 +221,7 @@ extern "C" srw_status srw_mig_superstep(srw_mig *m, int64_t s, unsigned long lon
   a.n_rounds = m->n_active;
   {
     // seeds: every other walker of this shard in super-step 0, the rest in super-step 1 (see MigArgs::seed_step)
-    const int64_t seeds = (m->g->row_last - m->g->row_first) * m->n_active;
+    const int64_t seeds = (m->g->vcut ? m->g->seed_rows : m->g->row_last - m->g->row_first) * m->n_active;
     a.seed_step = 2; a.seed_first = s;
     a.n_seed = s == 0 ? (seeds + 1) / 2 : s == 1 ? seeds / 2 : 0;
   }

@@ -56,13 +56,17 @@ constexpr int kMigStage = 16;        // tuples a warp collects in shared memory 
 constexpr int kMigClaim = 128;       // inbox items a warp claims at a time
 constexpr int kMigMaxDest = SRW_MAX_SHARDS + 1;   // peers + the local spill region
 constexpr uint32_t kMigRowMask = 0x0FFFFFFFu;     // MigTuple::home_row: [31:28] home shard, [27:0] path row on it
+constexpr uint32_t kMigHub = 0xFFu;               // owner byte of a REPLICATED row (table-mapped shards): the row is wherever the walker is
 
 struct MigArgs {
-  // VCut shard map (template flag VCUT; all NULL for vertex ranges): owner(v) = getPartition(v) mod world comes from the
-  // partition-id column of the edge file instead of `bounds`, so a shard's rows are not a contiguous range of ranks
-  const MigExt *__restrict__ ext;         // [nv] row extent of every vertex inside its owner's arrays
-  const uint8_t *__restrict__ owner;      // [nv] owner(v)
-  const int32_t *__restrict__ lverts;     // [rows_local] the vertices this shard owns, ascending (seed order)
+  // Table-mapped shards (template flag VCUT; all NULL for plain vertex ranges).  (1) The VCut shard map: owner(v) =
+  // getPartition(v) mod world comes from the partition-id column of the edge file instead of `bounds`, so a shard's rows are not
+  // a contiguous range of ranks.  (2) Replicated hub rows: the rows of the highest-degree vertices are on EVERY shard (owner
+  // kMigHub), so a step onto a hub does not migrate -- under the degree-biased walk a row is visited in proportion to its length,
+  // so replicating the rows that hold a fraction f of the entries keeps a fraction f of the steps local on top of the 1 / world.
+  const MigExt *__restrict__ ext;         // [nv] row extent of every vertex inside its owner's arrays (hub rows: the same on every shard)
+  const uint8_t *__restrict__ owner;      // [nv] owner(v), kMigHub for a replicated row
+  const int32_t *__restrict__ lverts;     // [rows_local] the vertices this shard starts walkers for, ascending (seed order)
   int64_t rows_local;
   // this shard's rows
   const int64_t *__restrict__ off;        // [rows + 1] shard-local offsets
@@ -130,6 +134,7 @@ __device__ __forceinline__ uint32_t mig_carried(uint32_t phase, uint32_t len) {
 // a few large write packets instead of a 16-byte packet per lane and word -- and lanes that refill together read the same way.
 __device__ __forceinline__ uint64_t mig_word(uint32_t slot, uint32_t k) { return (uint64_t)(slot >> 5) * 96u + k * 32u + (slot & 31u); }
 
+__device__ __forceinline__ uint32_t mig_here(uint32_t owner, uint32_t me) { return owner == kMigHub ? me : owner; }
 __device__ __forceinline__ int mig_owner(const MigArgs &a, int32_t v) {
   int o = 0;
   while (o + 1 < a.world && (int64_t)v >= a.bounds[o + 1]) o++;
@@ -316,7 +321,7 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
         cown = (uint32_t)me;
         if (kind == MIG_NOP) st = MS_EMPTY;
         else if (kind == MIG_PENDING) pend = true;
-        else if (fwd && (cown = VCUT ? (uint32_t)__ldg(a.owner + curr) : (uint32_t)mig_owner(a, curr)) != (uint32_t)me) {           // spilled last super-step: forward as it is
+        else if (fwd && (cown = VCUT ? mig_here((uint32_t)__ldg(a.owner + curr), (uint32_t)me) : (uint32_t)mig_owner(a, curr)) != (uint32_t)me) {           // spilled last super-step: forward as it is
           send = (int)cown; send_kind = (uint32_t)q1.y & (MIG_KIND_MASK | MIG_NEEDEXT);
         } else st = ((uint32_t)q1.y & MIG_NEEDEXT) ? MS_EXTENT : MS_TRIAL;
       }
@@ -384,6 +389,7 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
       const int4 q0 = gather16<1>(reinterpret_cast<const int4 *>(a.ent + ((uint64_t)off + k)));
       x = q0.x; xdeg = (uint32_t)q0.y; xoff = (uint32_t)q0.z;
       xown = (uint32_t)q0.w & 0xFFu; xm = (uint32_t)q0.w >> 8;
+      if (VCUT) xown = mig_here(xown, (uint32_t)me);                     // a replicated hub row: the walker stays where it is
       if (STATS && len > 1) n_prop++;
       if (len == 1 || deg == 1) verdict = 1;                             // first-order step (RW:57) / single choice
       else if (x == prev) verdict = ((uint64_t)y < a.t_ret) ? 1 : 2;     // RS:36

@@ -176,8 +176,16 @@ srw_status srw_multi_walk_rounds(const srw_graph *g, const srw_params *p, int64_
 // Builds one vertex-range shard per device from an edge list resident on the CURRENT device.
 // d_pid != NULL (`--partitioned true`): the partition-id column is the shard map (VCut: owner(v) = getPartition(v) mod num_gpus).
 srw_status srw_build_graph_device_multi(int64_t n, const int32_t *d_src, const int32_t *d_dst, const float *d_w, int directed,
-                                        int num_gpus, srw_graph **out, const int32_t *d_pid) {
+                                        int num_gpus, srw_graph **out, const int32_t *d_pid, double hub_fraction) {
   SRW_TRY(srw_require_device());
+  // replicated hub rows (srw.h, srw_graph_from_device_edges_vcut): the rows holding up to this share of the adjacency entries are
+  // kept by every shard.  Default 0.5 (12 extra bytes per adjacency entry of the whole graph on every GPU); SRW_HUB_FRACTION overrides.
+  if (hub_fraction < 0.0) {
+    const char *e = getenv("SRW_HUB_FRACTION");
+    hub_fraction = e ? atof(e) : 0.5;
+    if (!(hub_fraction >= 0.0)) hub_fraction = 0.0;
+    if (hub_fraction > 0.95) hub_fraction = 0.95;
+  }
   int have = 0;
   cudaGetDeviceCount(&have);
   if (num_gpus < 2 || num_gpus > SRW_MAX_SHARDS || num_gpus > have) { srw_set_error("--gpus %d: this process sees %d CUDA device(s) (at most %d shards)", num_gpus, have, SRW_MAX_SHARDS); return SRW_ERR_ARG; }
@@ -214,7 +222,7 @@ srw_status srw_build_graph_device_multi(int64_t n, const int32_t *d_src, const i
       }
     }
     srw_graph *sh = nullptr;
-    if (rc == SRW_OK) rc = srw_build_graph_device_sharded(n, s, t, wv, 0, SRW_BUILD_ALIAS | SRW_BUILD_MIGRATE, d, num_gpus, &sh, n > 0 ? pv : nullptr);
+    if (rc == SRW_OK) rc = srw_build_graph_device_sharded(n, s, t, wv, 0, SRW_BUILD_ALIAS | SRW_BUILD_MIGRATE, d, num_gpus, &sh, n > 0 ? pv : nullptr, hub_fraction);
     if (d != 0) { cudaFree(s); cudaFree(t); cudaFree(wv); cudaFree(pv); }
     if (rc == SRW_OK) {
       c->shards.push_back(sh);
@@ -247,7 +255,7 @@ static srw_status from_edges_multi(int64_t n, const int32_t *h_src, const int32_
     srw_set_error("srw_graph_from_edges_multi: H2D copy failed");
     rc = SRW_ERR_CUDA;
   }
-  if (rc == SRW_OK) rc = srw_build_graph_device_multi(n, s, d, nullptr, directed, num_gpus, out, pp);
+  if (rc == SRW_OK) rc = srw_build_graph_device_multi(n, s, d, nullptr, directed, num_gpus, out, pp, -1.0);
   cudaFree(s); cudaFree(d); cudaFree(pp);
   return rc;
 }

@@ -371,9 +371,8 @@ extern "C" srw_status srw_graph_from_device_edges_sharded(int64_t n, const int32
   return srw_build_graph_device_sharded(n, d_src, d_dst, d_w, directed, flags, rank, world, out);
 }
 extern "C" srw_status srw_graph_from_device_edges_vcut(int64_t n, const int32_t *d_src, const int32_t *d_dst, const int32_t *d_pid,
-                                                       int directed, unsigned flags, int rank, int world, srw_graph **out) {
-  if (n > 0 && !d_pid) { srw_set_error("srw_graph_from_device_edges_vcut: the partition-id column is the shard map"); return SRW_ERR_ARG; }
-  return srw_build_graph_device_sharded(n, d_src, d_dst, nullptr, directed, flags, rank, world, out, d_pid);
+                                                       int directed, unsigned flags, int rank, int world, double hub_fraction, srw_graph **out) {
+  return srw_build_graph_device_sharded(n, d_src, d_dst, nullptr, directed, flags, rank, world, out, d_pid, hub_fraction);
 }
 
 extern "C" srw_status srw_graph_shard_info(const srw_graph *g, int *rank, int *world, int64_t *row_first, int64_t *row_last,
@@ -385,6 +384,17 @@ extern "C" srw_status srw_graph_shard_info(const srw_graph *g, int *rank, int *w
   if (row_last) *row_last = g->row_last;
   if (nnz_local) *nnz_local = g->nnz;
   if (bounds) for (int r = 0; r <= g->shard_world; ++r) bounds[r] = r < (int)g->bounds.size() ? g->bounds[(size_t)r] : g->nv;
+  return SRW_OK;
+}
+
+// replicated hub rows of a table-mapped shard (0 / 0 / 0xFFFFFFFF on any other handle); seed_rows = vertices this shard starts walkers for
+extern "C" srw_status srw_graph_hub_info(const srw_graph *g, int64_t *hub_rows, int64_t *hub_entries, uint32_t *hub_min_degree, int64_t *seed_rows) {
+  if (!g) return SRW_ERR_ARG;
+  const srw_graph *s = g->shards.empty() ? g : g->shards[0];
+  if (hub_rows) *hub_rows = s->hub_rows;
+  if (hub_entries) *hub_entries = s->hub_entries;
+  if (hub_min_degree) *hub_min_degree = s->hub_deg;
+  if (seed_rows) *seed_rows = s->vcut ? s->seed_rows : s->row_last - s->row_first;
   return SRW_OK;
 }
 

@@ -122,7 +122,7 @@ extern "C" srw_status srw_graph_neighbors(const srw_graph *g, int32_t vid, int32
     uint8_t o = 0;
     MigExt e;
     SRW_CUDA(cudaMemcpy(&o, g->d_owner + r, 1, cudaMemcpyDeviceToHost));
-    if ((int)o != g->shard_rank) { *n = -1; return SRW_OK; }
+    if ((int)o != g->shard_rank && o != 0xFF /* a replicated hub row: on every shard */) { *n = -1; return SRW_OK; }
     SRW_CUDA(cudaMemcpy(&e, g->d_ext + r, sizeof e, cudaMemcpyDeviceToHost));
     ext[0] = e.off; ext[1] = (int64_t)e.off + e.deg;
   } else {

@@ -72,10 +72,12 @@ struct srw_graph {
   std::vector<int64_t> bounds;          // [world+1] first rank of every shard
   // VCut shard map: owner(v) = getPartition(v) mod world; this shard's rows are the vertices d_lverts[0 .. row_last)
   // (row_first = 0, row_last = the LOCAL row count); d_ext / d_owner are replicated on every shard
-  bool vcut = false;
+  bool vcut = false;                    // table-mapped shard: VCut shard map and/or replicated hub rows
   MigExt *d_ext = nullptr;              // [nv] (offset inside owner(v)'s arrays, degree)
-  uint8_t *d_owner = nullptr;           // [nv]
-  int32_t *d_lverts = nullptr;          // [row_last] vertices owned by this shard, ascending
+  uint8_t *d_owner = nullptr;           // [nv] routing owner; 0xFF = hub row, replicated on every shard
+  int32_t *d_lverts = nullptr;          // [seed_rows] vertices this shard starts walkers for, ascending
+  int64_t seed_rows = 0, hub_rows = 0, hub_entries = 0;   // local arrays = [hub rows | own rows]
+  uint32_t hub_deg = 0xFFFFFFFFu;       // rows of at least this degree are replicated
   struct ShardScratch *scratch = nullptr;
   // peer-gather mode (SURVEY 8(e) "NVLink peer loads"): the row arrays of every shard, addressable from
   // this device -- own pointers for shard_rank, cudaIpcOpenMemHandle mappings (or same-process pointers)
@@ -95,13 +97,14 @@ void srw_multi_free(struct MultiWalk *w);
 extern bool g_srw_log_supersteps;     // srw_main: print the reference's per-super-step `Unfinished Walkers: N` line (RW:154)
 int64_t srw_last_short_paths();        // paths of this thread's last srw_walk_save that ended at a dead end (RW:115-119 `Zero Neighbors`)
 srw_status srw_build_graph_device_multi(int64_t n, const int32_t *d_src, const int32_t *d_dst, const float *d_w, int directed,
-                                        int num_gpus, srw_graph **out, const int32_t *d_pid = nullptr);
+                                        int num_gpus, srw_graph **out, const int32_t *d_pid = nullptr, double hub_fraction = -1.0);
 // rounds [round_first, round_first + n_rounds) over a container graph, delivered on device 0 in walker order
 srw_status srw_multi_walk_rounds(const srw_graph *g, const srw_params *p, int64_t round_first, int64_t n_rounds, int32_t *d_paths0,
                                  int32_t *d_lens0, srw_walk_info *info);
 
 srw_status srw_build_graph_device_sharded(int64_t n, const int32_t *d_src, const int32_t *d_dst, const float *d_w, int directed,
-                                          unsigned flags, int rank, int world, srw_graph **out, const int32_t *d_pid = nullptr);
+                                          unsigned flags, int rank, int world, srw_graph **out, const int32_t *d_pid = nullptr,
+                                          double hub_fraction = 0.0);
 void srw_shard_scratch_free(struct ShardScratch *s);
 
 struct srw_paths {

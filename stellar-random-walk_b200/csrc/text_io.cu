@@ -628,7 +628,7 @@ extern "C" srw_status srw_edges_parse_buffer_device(const char *buf, size_t len,
 static srw_status build_for(const srw_params *params, int64_t n, const int32_t *s, const int32_t *d, const float *w, const int32_t *p,
                             unsigned flags, srw_graph **out) {
   // (--partitioned true: VRW -- the partition-id column is the shard map, owner(v) = getPartition(v) mod num_gpus)
-  if (params->num_gpus > 1) return srw_build_graph_device_multi(n, s, d, w, params->directed, params->num_gpus, out, params->partitioned ? p : nullptr);
+  if (params->num_gpus > 1) return srw_build_graph_device_multi(n, s, d, w, params->directed, params->num_gpus, out, params->partitioned ? p : nullptr, -1.0);
   return srw_build_graph_device(n, s, d, w, p, params->directed, flags, out);
 }
 

@@ -29,7 +29,7 @@ def _bind():
         return L
     vp, i64p = C.c_void_p, C.POINTER(C.c_int64)
     L.srw_graph_from_device_edges_sharded.argtypes = [C.c_int64, vp, vp, vp, C.c_int, C.c_uint, C.c_int, C.c_int, C.POINTER(vp)]
-    L.srw_graph_from_device_edges_vcut.argtypes = [C.c_int64, vp, vp, vp, C.c_int, C.c_uint, C.c_int, C.c_int, C.POINTER(vp)]
+    L.srw_graph_from_device_edges_vcut.argtypes = [C.c_int64, vp, vp, vp, C.c_int, C.c_uint, C.c_int, C.c_int, C.c_double, C.POINTER(vp)]
     L.srw_graph_shard_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), i64p, i64p, i64p, i64p]
     L.srw_shard_seed.argtypes = [vp, vp, C.c_int64, C.c_int64, vp, C.c_int64, i64p, vp, vp, vp]
     L.srw_shard_step.argtypes = [vp, vp, C.c_int64, C.c_int64, vp, C.c_int64, vp, vp, C.c_int64, vp, vp, i64p, i64p, i64p, vp]
@@ -77,17 +77,22 @@ def owner_of(bounds, v):
     return o
 
 
+vp_t = C.c_void_p
+
+
 class Shard:
     """One rank's rows of the graph plus its walker pools (device buffers owned here)."""
 
-    def __init__(self, n_edges, d_src, d_dst, d_w, rank, world, directed=False, device=None, migrate=False, d_pid=None):
+    def __init__(self, n_edges, d_src, d_dst, d_w, rank, world, directed=False, device=None, migrate=False, d_pid=None, hub_fraction=0.0):
         """d_pid (device pointer to the partition id of every input edge): the VCut shard map -- owner(v) = getPartition(v) mod
-        world (VRW:121-134, GM:66-68) instead of an edge-balanced vertex range; such shards are walked by MigrateWalker only."""
+        world (VRW:121-134, GM:66-68) instead of an edge-balanced vertex range.  hub_fraction > 0: the highest-degree rows holding
+        up to that share of the adjacency entries are replicated on every shard (a step onto a hub does not migrate).  Either one
+        makes a table-mapped shard, which MigrateWalker walks (the other sharded modes refuse it)."""
         L = _bind()
         self.h = C.c_void_p()
         flags = BUILD_ALIAS | (BUILD_MIGRATE if migrate else 0)
-        if d_pid is not None:
-            check(L.srw_graph_from_device_edges_vcut(n_edges, d_src, d_dst, d_pid, int(directed), flags, rank, world, C.byref(self.h)))
+        if d_pid is not None or hub_fraction > 0.0:
+            check(L.srw_graph_from_device_edges_vcut(n_edges, d_src, d_dst, d_pid, int(directed), flags, rank, world, float(hub_fraction), C.byref(self.h)))
         else:
             check(L.srw_graph_from_device_edges_sharded(n_edges, d_src, d_dst, d_w, int(directed), flags, rank, world, C.byref(self.h)))
         r, w = C.c_int(), C.c_int()
@@ -101,6 +106,10 @@ class Shard:
         self.nv = nv.value
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self._block = self._symm = None
+        hr, he, hd, sr = C.c_int64(), C.c_int64(), C.c_uint32(), C.c_int64()
+        L.srw_graph_hub_info.argtypes = [vp_t, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_uint32), C.POINTER(C.c_int64)]
+        check(L.srw_graph_hub_info(self.h, C.byref(hr), C.byref(he), C.byref(hd), C.byref(sr)))
+        self.hub_rows, self.hub_entries, self.hub_min_degree, self.seed_rows = hr.value, he.value, hd.value, sr.value
 
     def free(self):
         if self.h:

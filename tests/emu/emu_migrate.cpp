@@ -43,23 +43,36 @@ void hash_insert(std::vector<int32_t> &hash, int64_t off, uint32_t deg, int32_t 
 extern "C" int emu_migrate_walk(int64_t nv, const int64_t *off, const int32_t *col, const uint32_t *mult, int shards, const int64_t *bounds,
                                 double p, double q, int fold, uint64_t t_ret, uint64_t t_common, uint64_t t_far, uint64_t seed,
                                 int32_t walk_length, int64_t round_first, int64_t n_rounds, int64_t seg_cap, int bloom_bits, int grid_blocks,
-                                int32_t *out_paths, unsigned long long *stats_out, const uint8_t *owner_map /* NULL = vertex ranges; else the VCut shard map */) {
+                                int32_t *out_paths, unsigned long long *stats_out, const uint8_t *owner_map /* NULL = vertex ranges; else the VCut shard map */,
+                                uint32_t hub_deg /* 0 = none; else rows of at least this degree are replicated on every shard */) {
   if (shards < 1 || shards > SRW_MAX_SHARDS) return -1;
   const int W = shards;
   const int32_t stride = walk_length + 2;
   const int64_t nnz = off[nv];
   auto owner_of = [&](int64_t v) { if (owner_map) return (int)owner_map[v]; int o = 0; while (o + 1 < W && v >= bounds[o + 1]) o++; return o; };
-  // rows of a shard = the vertices it owns in ascending order (a contiguous range without a shard map), laid out back to back
-  std::vector<std::vector<int32_t>> lverts((size_t)W);
+  // table-mapped shards (graph_build.cu): every shard lays its arrays out as [hub rows | own rows]; a hub row (routing owner
+  // kMigHub) sits at the same offset on every shard.  Seeds belong to the TRUE owner of a vertex, hub or not.
+  const bool mapped = owner_map != nullptr || hub_deg > 0;
+  std::vector<std::vector<int32_t>> rows((size_t)W), seeds((size_t)W);
+  std::vector<int32_t> hubs;
   std::vector<MigExt> ext((size_t)nv);
   std::vector<uint8_t> own((size_t)nv);
+  int64_t hub_entries = 0;
+  for (int64_t v = 0; v < nv; ++v) {
+    const int o = owner_of(v);
+    if (o < 0 || o >= W) return -2;
+    seeds[(size_t)o].push_back((int32_t)v);
+    const uint32_t deg = (uint32_t)(off[v + 1] - off[v]);
+    if (hub_deg > 0 && deg >= hub_deg) { own[(size_t)v] = (uint8_t)kMigHub; hubs.push_back((int32_t)v); ext[(size_t)v].off = (uint32_t)hub_entries; ext[(size_t)v].deg = deg; hub_entries += deg; }
+    else own[(size_t)v] = (uint8_t)o;
+  }
   {
-    std::vector<int64_t> fill((size_t)W, 0);
+    std::vector<int64_t> fill((size_t)W, hub_entries);
+    for (int s = 0; s < W; ++s) rows[(size_t)s] = hubs;
     for (int64_t v = 0; v < nv; ++v) {
-      const int o = owner_of(v);
-      if (o < 0 || o >= W) return -2;
-      own[(size_t)v] = (uint8_t)o;
-      lverts[(size_t)o].push_back((int32_t)v);
+      if (own[(size_t)v] == (uint8_t)kMigHub) continue;
+      const int o = own[(size_t)v];
+      rows[(size_t)o].push_back((int32_t)v);
       ext[(size_t)v].off = (uint32_t)fill[(size_t)o]; ext[(size_t)v].deg = (uint32_t)(off[v + 1] - off[v]);
       fill[(size_t)o] += off[v + 1] - off[v];
     }
@@ -82,7 +95,7 @@ extern "C" int emu_migrate_walk(int64_t nv, const int64_t *off, const int32_t *c
   std::vector<Shard> sh((size_t)W);
   for (int s = 0; s < W; ++s) {
     Shard &R = sh[(size_t)s];
-    const std::vector<int32_t> &lv = lverts[(size_t)s];
+    const std::vector<int32_t> &lv = rows[(size_t)s];
     R.off.resize(lv.size() + 1);
     int64_t n = 0;
     for (size_t i = 0; i < lv.size(); ++i) { R.off[i] = n; n += off[lv[i] + 1] - off[lv[i]]; }
@@ -97,6 +110,7 @@ extern "C" int emu_migrate_walk(int64_t nv, const int64_t *off, const int32_t *c
     for (int64_t i = 0; i < hrows * n_rounds; ++i) R.paths[(size_t)(i * stride)] = (int32_t)(s + (i % hrows) * W);
     for (size_t i = 0; i < lv.size(); ++i) {
       const int64_t r = lv[i], lo = R.off[i];
+      if ((uint32_t)lo != ext[(size_t)r].off) return -4;
       const uint32_t deg = (uint32_t)(off[r + 1] - off[r]);
       for (int64_t e = off[r]; e < off[r + 1]; ++e) {
         const int32_t x = col[e];
@@ -120,7 +134,7 @@ extern "C" int emu_migrate_walk(int64_t nv, const int64_t *off, const int32_t *c
       MigArgs a{};
       a.off = R.off.data(); a.ent = R.ent.data(); a.hash = R.hash.data(); a.bloom = bloom.data(); a.bloom_words = bloom_words;
       a.nv = nv; a.world = W; a.rank = r;
-      if (owner_map) { a.ext = ext.data(); a.owner = own.data(); a.lverts = lverts[(size_t)r].data(); a.rows_local = (int64_t)lverts[(size_t)r].size(); }
+      if (mapped) { a.ext = ext.data(); a.owner = own.data(); a.lverts = seeds[(size_t)r].data(); a.rows_local = (int64_t)seeds[(size_t)r].size(); }
       else {
         a.row_first = bounds[r]; a.row_last = bounds[r + 1];
         for (int k = 0; k <= W; ++k) a.bounds[k] = bounds[k];
@@ -131,9 +145,9 @@ extern "C" int emu_migrate_walk(int64_t nv, const int64_t *off, const int32_t *c
       a.in_base = R.base[cur].data(); a.in_cnt = R.cnt[cur];
       a.seg_cap = seg_cap; a.spill_cap = spill_cap;
       {
-        const int64_t seeds = (int64_t)lverts[(size_t)r].size() * n_rounds;
+        const int64_t n_seeds = (int64_t)seeds[(size_t)r].size() * n_rounds;
         a.seed_step = 2; a.seed_first = s;
-        a.n_seed = s == 0 ? (seeds + 1) / 2 : s == 1 ? seeds / 2 : 0;
+        a.n_seed = s == 0 ? (n_seeds + 1) / 2 : s == 1 ? n_seeds / 2 : 0;
       }
       for (int d = 0; d <= W; ++d) {
         Shard &D = d == W ? R : sh[(size_t)d];
@@ -144,7 +158,7 @@ extern "C" int emu_migrate_walk(int64_t nv, const int64_t *off, const int32_t *c
       for (int h = 0; h < W; ++h) { a.home_paths[h] = sh[(size_t)h].paths.data(); a.home_rows[h] = (nv - h + W - 1) / W; }
       a.cursor = R.scratch; a.done_warps = R.scratch + 1; a.out_cnt = R.scratch + 2; a.stats = R.scratch + 2 + kMigMaxDest;
       gridDim.x = (unsigned)grid_blocks;
-      if (owner_map) emu_launch_warps((int64_t)grid_blocks * 8, [&] { mig_step_kernel<true, 4, true>(a); });
+      if (mapped) emu_launch_warps((int64_t)grid_blocks * 8, [&] { mig_step_kernel<true, 4, true>(a); });
       else emu_launch_warps((int64_t)grid_blocks * 8, [&] { mig_step_kernel<true>(a); });
     }
     unsigned long long sent = 0;

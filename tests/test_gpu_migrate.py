@@ -158,6 +158,49 @@ def test_vcut_shard_map_equals_twin(oracle, world, pid_kind):
         shards[0].attach_local(shards)
 
 
+# ---- replicated hub rows (vertex-cut): the highest-degree rows are kept by every shard, a step onto a hub does not migrate ----
+@pytest.mark.parametrize("world,hub_fraction,with_pid", [(2, 0.5, False), (4, 0.5, False), (8, 0.75, False), (4, 0.25, True), (3, 0.95, False)])
+def test_replicated_hub_rows_equal_twin(oracle, monkeypatch, world, hub_fraction, with_pid):
+    import torch
+    monkeypatch.setenv("SRW_MIG_BLOCKS", "8")            # few warps: the slot counts below are tuples, not the NOP padding of open chunks
+    sh = importlib.import_module("stellar-random-walk_b200.sharded")
+    s, d = synth.rmat_edges(12, 8, seed=42)
+    twin = oracle.AliasGraph(oracle.Graph().load_edges(s, d, None))
+    ids, offs, st = twin.walk(walk_length=30, num_walks=3, p=0.5, q=2.0, seed=9, fold=1)
+    ds, dd = torch.from_numpy(s).cuda(), torch.from_numpy(d).cuda()
+    dp = torch.from_numpy(np.random.default_rng(1).integers(0, world, len(s)).astype(np.int32)).cuda() if with_pid else None
+    prm = srw.Params(walkLength=30, numWalks=3, p=0.5, q=2.0, seed=9, sampler="fold")
+    tuples = {}
+    for hf in (0.0, hub_fraction):
+        shards = [sh.Shard(len(s), ds.data_ptr(), dd.data_ptr(), None, r, world, migrate=True, hub_fraction=hf,
+                           d_pid=None if dp is None else dp.data_ptr()) for r in range(world)]
+        if hf > 0:
+            nnz = int(twin.view()["offsets"][-1])
+            deg = np.diff(twin.view()["offsets"])
+            x = shards[0]
+            assert 0 < x.hub_entries <= hf * nnz
+            assert x.hub_entries == int(deg[deg >= x.hub_min_degree].sum()) and x.hub_rows == int((deg >= x.hub_min_degree).sum())
+            assert all((y.hub_rows, y.hub_entries, y.hub_min_degree) == (x.hub_rows, x.hub_entries, x.hub_min_degree) for y in shards)
+            assert sum(y.nnz_local for y in shards) == nnz + (world - 1) * x.hub_entries      # every shard holds the hub rows
+            assert sum(y.seed_rows for y in shards) == twin.nv
+            # a hub's row answers on every shard (GM:109-120 through the replicated tables)
+            hub_v = int(twin.view()["vids"][int(np.argmax(deg))])
+            for y in shards:
+                n = srw.C.c_int64()
+                srw.check(srw.lib().srw_graph_neighbors(y.h, hub_v, None, None, 0, srw.C.byref(n)))
+                assert n.value == int(deg.max())
+        mw = sh.MigrateWalker(shards, prm, 3, stats=True)
+        out, stats = mw.run(0)
+        rows = _assemble(shards, out, twin.nv, 3, 32)
+        assert (rows.reshape(-1) == ids).all()
+        assert stats["steps"] == st.steps
+        tuples[hf] = stats["tuples_sent_all_ranks"]
+        mw.free()
+        for y in shards:
+            y.free()
+    assert tuples[hub_fraction] < tuples[0.0]            # roughly (1 - f) of the migrations remain (plus chunk padding)
+
+
 def test_two_ranks_nccl():
     """tests/dist_sharded_check.py under torchrun with one rank per GPU: the NCCL tuple exchange, peer-gather over symmetric
     memory and the migrating walk over real peer memory, each against the CPU twin.  Needs two GPUs."""

@@ -33,12 +33,12 @@ def emu():
     lib.emu_migrate_walk.restype = C.c_int
     lib.emu_migrate_walk.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_int,
                                      C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int,
-                                     C.c_void_p, C.c_void_p, C.c_void_p]
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
     return lib
 
 
 def _emu_migrate(emu, oracle, tw, *, walk_length, p, q, seed, fold=True, shards=2, rounds=1, round_first=0, seg_cap=0, bloom_bits=16, blocks=2,
-                 owner=None):
+                 owner=None, hub_deg=0):
     v = tw.view()
     off = np.ascontiguousarray(v["offsets"], np.int64)
     col = np.ascontiguousarray(v["col"], np.int32)
@@ -51,7 +51,7 @@ def _emu_migrate(emu, oracle, tw, *, walk_length, p, q, seed, fold=True, shards=
     st = np.zeros(8, np.uint64)
     rc = emu.emu_migrate_walk(nv, off.ctypes.data, col.ctypes.data, mult.ctypes.data, shards, bounds.ctypes.data, p, q, int(fold),
                               t_ret, t_common, t_far, seed, walk_length, round_first, rounds, seg_cap, bloom_bits, blocks,
-                              paths.ctypes.data, st.ctypes.data, None if owner is None else np.ascontiguousarray(owner, np.uint8).ctypes.data)
+                              paths.ctypes.data, st.ctypes.data, None if owner is None else np.ascontiguousarray(owner, np.uint8).ctypes.data, hub_deg)
     assert rc >= 0, rc
     assert int(st[6]) == 0, "device error flags %d" % int(st[6])
     assert (paths >= 0).all(), "a path slot was never written"
@@ -132,3 +132,21 @@ def test_migrate_vcut_classic_thresholds_karate(emu, oracle):
         want, _ = _twin_paths(oracle, tw, walk_length=20, num_walks=2, p=p, q=q, seed=11, fold=1)
         got, _, _ = _emu_migrate(emu, oracle, tw, walk_length=20, p=p, q=q, seed=11, shards=3, rounds=2, owner=owner)
         assert got == want
+
+
+# ---- replicated hub rows: the highest-degree rows are on every shard, a step onto a hub does not migrate ----
+@pytest.mark.parametrize("shards,hub_deg,with_map,bloom_bits", [(2, 40, False, 16), (4, 20, False, 16), (8, 12, False, 2), (3, 30, True, 16), (4, 1, False, 16)])
+def test_migrate_replicated_hub_rows_equal_twin(emu, oracle, shards, hub_deg, with_map, bloom_bits):
+    """Same paths, fewer tuples.  hub_deg = 1: EVERY row is replicated (nothing migrates after the seeds)."""
+    tw = _rmat_twin(oracle, 8, 8)
+    nv = len(tw.view()["offsets"]) - 1
+    owner = np.random.default_rng(shards).integers(0, shards, nv).astype(np.uint8) if with_map else None
+    want, _ = _twin_paths(oracle, tw, walk_length=24, num_walks=2, p=0.5, q=2.0, seed=5, fold=1)
+    base, _, st0 = _emu_migrate(emu, oracle, tw, walk_length=24, p=0.5, q=2.0, seed=5, shards=shards, rounds=2, bloom_bits=bloom_bits, blocks=1, owner=owner)
+    got, _, st = _emu_migrate(emu, oracle, tw, walk_length=24, p=0.5, q=2.0, seed=5, shards=shards, rounds=2, bloom_bits=bloom_bits, blocks=1, owner=owner,
+                              hub_deg=hub_deg)
+    assert base == want and got == want
+    assert st["steps"] == st0["steps"]
+    assert st["tuples"] < st0["tuples"]
+    if hub_deg == 1:
+        assert st["tuples"] == 0
