@@ -628,35 +628,50 @@ static int64_t rank_of(const int32_t *vids, int64_t nv, int32_t v) {
   return lo;
 }
 
-/* Vose alias table by the in-order "sweep" (two cursors, no work lists):
- *   scaled(k) = (double)w[k] * (double)n / W,  W = sequential double sum of the row.
- *   i walks the light items (scaled < 1) upward, j the heavy ones; r is heavy j's residual. */
+/* Vose alias table by the in-order "sweep" (two cursors, no work lists), in EXACT INTEGER arithmetic so that the result does not
+ * depend on the order of evaluation and the device can build it in parallel (graph_build.cu K3):
+ *   W      = the row's weight sum: 32 strided partial sums (partial l adds w[l], w[l+32], ... in order, in double) combined by a
+ *            butterfly (distance 16, 8, 4, 2, 1) -- the one floating-point reduction, in a fixed shape;
+ *   t[k]   = floor((((double)w[k] * (double)n) / W) * 2^32) as a 64-bit integer: the scaled weight in units of 2^-32;
+ *            k is light iff t[k] < 2^32;
+ *   sweep  : i walks the light items upward, j the heavy ones; r is heavy j's residual (an integer). */
+static double alias_row_wsum(int64_t n, const float *w) {
+  double part[32], nx[32];
+  for (int l = 0; l < 32; ++l) part[l] = 0.0;
+  for (int64_t k = 0; k < n; ++k) part[k & 31] = part[k & 31] + (double)w[k];
+  for (int o = 16; o > 0; o >>= 1) {
+    for (int l = 0; l < 32; ++l) nx[l] = part[l] + part[l ^ o];
+    for (int l = 0; l < 32; ++l) part[l] = nx[l];
+  }
+  return part[0];
+}
 static double alias_row(int64_t n, const float *w, uint32_t *thr, uint32_t *alias) {
-  double W = 0.0;
-  for (int64_t k = 0; k < n; ++k) { W = W + (double)w[k]; thr[k] = 0xFFFFFFFFu; alias[k] = (uint32_t)k; }
+  const double W = alias_row_wsum(n, w);
+  for (int64_t k = 0; k < n; ++k) { thr[k] = 0xFFFFFFFFu; alias[k] = (uint32_t)k; }
   const double dn = (double)n;
-#define SCALED(k) (((double)w[(k)] * dn) / W)
+  const uint64_t ONE = 4294967296ULL;
+#define SCALED(k) ((uint64_t)((((double)w[(k)] * dn) / W) * 4294967296.0))
   int64_t i = 0, j = 0;
-  while (i < n && !(SCALED(i) < 1.0)) i++;
-  while (j < n && (SCALED(j) < 1.0)) j++;
+  while (i < n && !(SCALED(i) < ONE)) i++;
+  while (j < n && (SCALED(j) < ONE)) j++;
   if (j >= n) return W;
-  double r = SCALED(j);
+  uint64_t r = SCALED(j);
   while (j < n) {
-    if (!(r < 1.0)) {
+    if (!(r < ONE)) {
       if (i >= n) break;
-      double si = SCALED(i);
-      thr[i] = (uint32_t)(si * 4294967296.0);
+      const uint64_t ti = SCALED(i);
+      thr[i] = (uint32_t)ti;
       alias[i] = (uint32_t)j;
-      r = (r + si) - 1.0;
+      r = (r + ti) - ONE;
       i++;
-      while (i < n && !(SCALED(i) < 1.0)) i++;
+      while (i < n && !(SCALED(i) < ONE)) i++;
     } else {
       int64_t j2 = j + 1;
-      while (j2 < n && (SCALED(j2) < 1.0)) j2++;
+      while (j2 < n && (SCALED(j2) < ONE)) j2++;
       if (j2 >= n) break;
-      thr[j] = (uint32_t)(r * 4294967296.0);
+      thr[j] = (uint32_t)r;
       alias[j] = (uint32_t)j2;
-      r = (r + SCALED(j2)) - 1.0;
+      r = (r + SCALED(j2)) - ONE;
       j = j2;
     }
   }

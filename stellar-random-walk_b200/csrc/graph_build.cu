@@ -256,54 +256,87 @@ __global__ void k_vpid_fill(int64_t nv, const unsigned long long *__restrict__ l
     vpid[v] = last_line[v] ? pid[last_line[v] - 1] : -1;
 }
 
-// K3: Vose alias table by the in-order sweep (two cursors, no work lists), one row per thread.
-// Arithmetic is IEEE double with explicit rounding intrinsics so that oracle/srw_oracle.c
-// (alias_row) reproduces every bit.
-__device__ __forceinline__ double scaled_w(const float *__restrict__ w, int64_t k, double dn, double W) {
-  return __ddiv_rn(__dmul_rn((double)w[k], dn), W);
+// K3: Vose alias tables by the in-order sweep (two cursors, no work lists) -- built IN PARALLEL over all adjacency entries.
+// The sweep is defined in exact integer arithmetic (oracle/srw_oracle.c alias_row is the sequential statement):
+//   W    = the row's weight sum, 32 strided partial sums combined by a butterfly (k_row_wsum: one warp per row);
+//   t[k] = floor((w[k] * n / W) * 2^32): the scaled weight in units of 2^-32; light iff t < 2^32, else heavy with excess t - 2^32.
+// With E_k = the summed excess of the row's first k heavy items and D_m = the summed deficit (2^32 - t) of its first m light items,
+// the sweep's state (heavy k active, m light items filled) has residual 2^32 + E_k - D_m, so
+//   * light item m + 1 is filled by the FIRST heavy k with E_k >= D_m           (threshold t, alias = that heavy item);
+//   * heavy item k retires at the FIRST m with D_m > E_k, if a next heavy exists (threshold 2^32 + E_k - D_m, alias = the next heavy);
+//   * everything the sweep never reaches keeps threshold 2^32 - 1 and itself as alias.
+// Integer sums do not depend on the order of evaluation: E and D are segmented prefix sums (cub::DeviceScan::InclusiveSumByKey), the
+// two "first" searches are binary searches over the row's compacted heavy / light lists -- one thread per entry, no O(max degree)
+// chain on a single lane (round 1's builder walked a million-entry hub row with one thread).
+__device__ __forceinline__ uint64_t alias_scaled(float w, double dn, double W) {
+  return __double2ull_rz(__dmul_rn(__ddiv_rn(__dmul_rn((double)w, dn), W), 4294967296.0));
 }
-__global__ void k_alias_rows(int64_t nv, const int64_t *__restrict__ off, const int32_t *__restrict__ col,
-                             const float *__restrict__ w_all, AliasSlot *slot_all, RowMeta *meta) {
-  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nv; v += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t o = off[v], n = off[v + 1] - o;
-    if (n <= 0) continue;
-    const float *w = w_all + o;
-    const int32_t *c = col + o;
-    AliasSlot *slot = slot_all + o;
-    double W = 0.0;
-    for (int64_t k = 0; k < n; ++k) {
-      W = __dadd_rn(W, (double)w[k]);
-      AliasSlot s; s.thr = 0xFFFFFFFFu; s.own = c[k]; s.alias_vertex = c[k]; s.alias_index = (uint32_t)k;
-      slot[k] = s;
-    }
-    if (meta) meta[v].w_sum = W;
-    const double dn = (double)n;
-    int64_t i = 0, j = 0;
-    while (i < n && !(scaled_w(w, i, dn, W) < 1.0)) i++;
-    while (j < n && (scaled_w(w, j, dn, W) < 1.0)) j++;
-    if (j >= n) continue;
-    double r = scaled_w(w, j, dn, W);
-    while (j < n) {
-      if (!(r < 1.0)) {
-        if (i >= n) break;
-        const double si = scaled_w(w, i, dn, W);
-        slot[i].thr = (uint32_t)__dmul_rn(si, 4294967296.0);
-        slot[i].alias_vertex = c[j];
-        slot[i].alias_index = (uint32_t)j;
-        r = __dadd_rn(__dadd_rn(r, si), -1.0);
-        i++;
-        while (i < n && !(scaled_w(w, i, dn, W) < 1.0)) i++;
-      } else {
-        int64_t j2 = j + 1;
-        while (j2 < n && (scaled_w(w, j2, dn, W) < 1.0)) j2++;
-        if (j2 >= n) break;
-        slot[j].thr = (uint32_t)__dmul_rn(r, 4294967296.0);
-        slot[j].alias_vertex = c[j2];
-        slot[j].alias_index = (uint32_t)j2;
-        r = __dadd_rn(__dadd_rn(r, scaled_w(w, j2, dn, W)), -1.0);
-        j = j2;
+__global__ void k_row_wsum(int64_t rows, const int64_t *__restrict__ off, const float *__restrict__ w, double *wsum, RowMeta *meta) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += n_warps) {
+    const int64_t o = off[r], n = off[r + 1] - o;
+    double s = 0.0;
+    for (int64_t k = lane; k < n; k += 32) s = __dadd_rn(s, (double)w[o + k]);
+    for (int d = 16; d > 0; d >>= 1) s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, d));
+    if (lane == 0) { wsum[r] = s; if (meta && n > 0) meta[r].w_sum = s; }
+  }
+}
+__global__ void k_alias_classify(int64_t nnz, const uint32_t *__restrict__ row_of, const int64_t *__restrict__ off, const float *__restrict__ w,
+                                 const double *__restrict__ wsum, unsigned long long *exc, unsigned long long *def, uint8_t *heavy) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t r = row_of[i];
+    const uint64_t t = alias_scaled(w[i], (double)(off[r + 1] - off[r]), wsum[r]);
+    const bool h = t >= 4294967296ULL;
+    heavy[i] = h ? 1 : 0;
+    exc[i] = h ? t - 4294967296ULL : 0ULL;
+    def[i] = h ? 0ULL : 4294967296ULL - t;
+  }
+}
+__global__ void k_alias_totals(int64_t nnz, const uint8_t *__restrict__ heavy, uint32_t *pos_h, uint32_t *pos_l) {
+  pos_h[nnz] = pos_h[nnz - 1] + (heavy[nnz - 1] ? 1u : 0u);
+  pos_l[nnz] = pos_l[nnz - 1] + (heavy[nnz - 1] ? 0u : 1u);
+}
+struct IsHeavy { __host__ __device__ uint32_t operator()(uint8_t h) const { return h ? 1u : 0u; } };
+struct IsLight { __host__ __device__ uint32_t operator()(uint8_t h) const { return h ? 0u : 1u; } };
+// pos_h / pos_l: exclusive counts of heavy / light entries before entry i (over the whole array, [nnz + 1])
+__global__ void k_alias_lists(int64_t nnz, const uint8_t *__restrict__ heavy, const uint32_t *__restrict__ pos_h, const uint32_t *__restrict__ pos_l,
+                              uint32_t *list_h, uint32_t *list_l) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+    if (heavy[i]) list_h[pos_h[i]] = (uint32_t)i; else list_l[pos_l[i]] = (uint32_t)i;
+  }
+}
+__global__ void k_alias_assign(int64_t nnz, const uint32_t *__restrict__ row_of, const int64_t *__restrict__ off, const int32_t *__restrict__ col,
+                               const float *__restrict__ w, const double *__restrict__ wsum, const uint8_t *__restrict__ heavy,
+                               const unsigned long long *__restrict__ E, const unsigned long long *__restrict__ D,
+                               const uint32_t *__restrict__ pos_h, const uint32_t *__restrict__ pos_l, const uint32_t *__restrict__ list_h,
+                               const uint32_t *__restrict__ list_l, AliasSlot *slot) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t r = row_of[i];
+    const int64_t o = off[r], n = off[r + 1] - o;
+    AliasSlot s;
+    s.thr = 0xFFFFFFFFu; s.own = col[i]; s.alias_vertex = col[i]; s.alias_index = (uint32_t)(i - o);
+    const uint32_t hb = pos_h[o], he = pos_h[o + n], lb = pos_l[o], le = pos_l[o + n];     // the row's heavy / light items in the lists
+    if (!heavy[i]) {
+      const uint64_t t = alias_scaled(w[i], (double)n, wsum[r]);
+      const unsigned long long d_before = D[i] - (4294967296ULL - t);      // D_m: the deficit of the light items before this one
+      uint32_t lo = hb, hi = he;                                            // first heavy k with E_k >= D_m
+      while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (E[list_h[mid]] >= d_before) hi = mid; else lo = mid + 1; }
+      if (lo < he) { const uint32_t j = list_h[lo]; s.thr = (uint32_t)t; s.alias_vertex = col[j]; s.alias_index = (uint32_t)(j - o); }
+    } else {
+      const uint32_t x = pos_h[i];
+      if (x + 1 < he) {                                                     // a next heavy item exists
+        const unsigned long long e_k = E[i];
+        uint32_t lo = lb, hi = le;                                          // first m with D_m > E_k
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (D[list_l[mid]] > e_k) hi = mid; else lo = mid + 1; }
+        if (lo < le) {
+          const uint32_t j2 = list_h[x + 1];
+          s.thr = (uint32_t)(4294967296ULL + e_k - D[list_l[lo]]);
+          s.alias_vertex = col[j2]; s.alias_index = (uint32_t)(j2 - o);
+        }
       }
     }
+    slot[i] = s;
   }
 }
 
@@ -896,10 +929,39 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
       SRW_CUDA(ws.alloc((size_t)nnz * 4));
       k_gather_w<<<grid(nnz), kThreads>>>(nnz, v_in, gidx, d_w, wshift, ws.as<float>());
       SRW_CUDA(cudaMalloc(&g->d_slot, (size_t)nnz * sizeof(AliasSlot)));
-      k_alias_rows<<<grid_for(nrows, 64), 64>>>(nrows, g->d_off, g->d_col, ws.as<float>(), g->d_slot, g->d_meta);
-      SRW_CUDA(cudaDeviceSynchronize());
+      {
+        DevBuf wsum, exc, def, hv, E, D, pos_h, pos_l, list, tmp;
+        SRW_CUDA(wsum.alloc((size_t)(nrows ? nrows : 1) * 8));
+        k_row_wsum<<<grid(nrows * 32), kThreads>>>(nrows, g->d_off, ws.as<float>(), wsum.as<double>(), g->d_meta);
+        SRW_CUDA(exc.alloc((size_t)nnz * 8)); SRW_CUDA(def.alloc((size_t)nnz * 8)); SRW_CUDA(hv.alloc((size_t)nnz));
+        k_alias_classify<<<grid(nnz), kThreads>>>(nnz, k_in, g->d_off, ws.as<float>(), wsum.as<double>(), exc.as<unsigned long long>(),
+                                                  def.as<unsigned long long>(), hv.as<uint8_t>());
+        SRW_CUDA(E.alloc((size_t)nnz * 8)); SRW_CUDA(D.alloc((size_t)nnz * 8));
+        SRW_CUDA(pos_h.alloc((size_t)(nnz + 1) * 4)); SRW_CUDA(pos_l.alloc((size_t)(nnz + 1) * 4));
+        size_t tb = 0, tb2 = 0;
+        SRW_CUDA(cub::DeviceScan::InclusiveSumByKey(nullptr, tb, k_in, exc.as<unsigned long long>(), E.as<unsigned long long>(), nnz));
+        cub::TransformInputIterator<uint32_t, IsHeavy, uint8_t *> it_h(hv.as<uint8_t>(), IsHeavy());
+        cub::TransformInputIterator<uint32_t, IsLight, uint8_t *> it_l(hv.as<uint8_t>(), IsLight());
+        SRW_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb2, it_h, pos_h.as<uint32_t>(), nnz));
+        SRW_CUDA(tmp.alloc(tb > tb2 ? tb : tb2));
+        SRW_CUDA(cub::DeviceScan::InclusiveSumByKey(tmp.p, tb, k_in, exc.as<unsigned long long>(), E.as<unsigned long long>(), nnz));
+        SRW_CUDA(cub::DeviceScan::InclusiveSumByKey(tmp.p, tb, k_in, def.as<unsigned long long>(), D.as<unsigned long long>(), nnz));
+        SRW_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb2, it_h, pos_h.as<uint32_t>(), nnz));
+        SRW_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb2, it_l, pos_l.as<uint32_t>(), nnz));
+        k_alias_totals<<<1, 1>>>(nnz, hv.as<uint8_t>(), pos_h.as<uint32_t>(), pos_l.as<uint32_t>());
+        exc.alloc(0); def.alloc(0);
+        SRW_CUDA(list.alloc((size_t)nnz * 4 + 8));         // heavy list from the front, light list behind it
+        uint32_t n_heavy = 0;
+        SRW_CUDA(cudaMemcpy(&n_heavy, pos_h.as<uint32_t>() + nnz, 4, cudaMemcpyDeviceToHost));
+        uint32_t *list_h = list.as<uint32_t>(), *list_l = list.as<uint32_t>() + n_heavy;
+        k_alias_lists<<<grid(nnz), kThreads>>>(nnz, hv.as<uint8_t>(), pos_h.as<uint32_t>(), pos_l.as<uint32_t>(), list_h, list_l);
+        k_alias_assign<<<grid(nnz), kThreads>>>(nnz, k_in, g->d_off, g->d_col, ws.as<float>(), wsum.as<double>(), hv.as<uint8_t>(),
+                                                E.as<unsigned long long>(), D.as<unsigned long long>(), pos_h.as<uint32_t>(), pos_l.as<uint32_t>(),
+                                                list_h, list_l, g->d_slot);
+        SRW_CUDA(cudaDeviceSynchronize());
+      }
       g->has_alias = true;
-      phase("k_alias_rows");
+      phase("k_alias_parallel_vose");
       // weighted alias-fold (undirected, unsharded): 32-byte slots with the bundle weights.  48 bytes per entry in all:
       // HBM capacity is spent to keep a proposal at ONE memory request.
       if (!directed && !sharded && g->d_meta && !getenv("SRW_NO_WFOLD")) {

@@ -210,3 +210,62 @@ def test_fold_walk_over_dense_csr_is_the_twin(oracle):
         steps = fn(a.nv, off.ctypes.data, col.ctypes.data, C.addressof(cfg), 1, 0, 1e9, C.byref(el), C.byref(done), C.byref(chk), out.ctypes.data)
         assert done.value == a.nv and steps == st.steps
         assert (v["vids"][out] == want).all()
+
+
+# ---- K3 in parallel: the formulation graph_build.cu evaluates with one thread per entry == the sequential integer sweep ----
+def _parallel_vose_rows(off, w, col):
+    """numpy restatement of graph_build.cu's parallel formulation"""
+    nnz = len(w)
+    thr = np.full(nnz, 0xFFFFFFFF, np.uint64); alias = np.zeros(nnz, np.int64)
+    ONE = 1 << 32
+    for r in range(len(off) - 1):
+        o, n = int(off[r]), int(off[r + 1] - off[r])
+        if n == 0: continue
+        ww = w[o:o + n].astype(np.float64)
+        part = np.zeros(32)
+        for k in range(n): part[k & 31] = part[k & 31] + ww[k]
+        for d in (16, 8, 4, 2, 1):
+            part = np.array([part[l] + part[l ^ d] for l in range(32)])
+        W = part[0]
+        t = [int(np.floor(((x * float(n)) / W) * 4294967296.0)) for x in ww]
+        heavy = [x >= ONE for x in t]
+        E, D = [], []
+        e = dd = 0
+        Ecum = [0] * n; Dcum = [0] * n
+        lh, ll = [], []
+        for k in range(n):
+            if heavy[k]: e += t[k] - ONE; lh.append(k)
+            else: dd += ONE - t[k]; ll.append(k)
+            Ecum[k] = e; Dcum[k] = dd
+        for k in range(n):
+            alias[o + k] = k
+            if not heavy[k]:
+                d_before = Dcum[k] - (ONE - t[k])
+                x = next((q for q in range(len(lh)) if Ecum[lh[q]] >= d_before), None)
+                if x is not None: thr[o + k] = t[k]; alias[o + k] = lh[x]
+            else:
+                x = lh.index(k)
+                if x + 1 < len(lh):
+                    m = next((q for q in range(len(ll)) if Dcum[ll[q]] > Ecum[k]), None)
+                    if m is not None: thr[o + k] = ONE + Ecum[k] - Dcum[ll[m]]; alias[o + k] = lh[x + 1]
+    return thr, alias
+
+
+def test_parallel_vose_formulation_equals_the_sequential_sweep(oracle):
+    """graph_build.cu builds the Vose tables with segmented prefix sums (E = heavy excess, D = light deficit) and two binary searches
+    per entry instead of the two-cursor sweep.  This numpy restatement of THAT formulation must give the twin's (oracle alias_row)
+    thresholds and aliases on every row: RMAT rows with smooth / five-valued / nearly-uniform weights, a Pareto hub row, a 5-entry row."""
+    rng = np.random.default_rng(0)
+    cases = []
+    s, d = synth.rmat_edges(8, 8, seed=42)
+    cases.append((s, d, synth.edge_weights(len(s), seed=43)))
+    cases.append((s, d, rng.choice([0.25, 1.0, 4.0, 1e-3, 1e3], len(s)).astype(np.float32)))
+    cases.append((s, d, (np.full(len(s), 3.0) + (np.arange(len(s)) % 7 == 0) * 0.5).astype(np.float32)))
+    hub, leaves = np.zeros(300, np.int32), np.arange(1, 301, dtype=np.int32)
+    cases.append((hub, leaves, (rng.pareto(1.2, 300) + 0.01).astype(np.float32)))
+    cases.append((hub[:5], leaves[:5], np.array([1, 2, 3, 4, 5], np.float32)))
+    for s, d, w in cases:
+        v = oracle.AliasGraph(oracle.Graph().load_edges(s, d, w)).view()
+        thr, alias = _parallel_vose_rows(v["offsets"], v["w"], v["col"])
+        assert (thr == v["thr"].astype(np.uint64)).all() and (alias == v["alias"].astype(np.int64)).all()
+        assert int((v["thr"] != 0xFFFFFFFF).sum()) > 0
