@@ -77,6 +77,14 @@ def full():
     synth = importlib.import_module("stellar-random-walk_b200.synth")
     rank, world = dist.get_rank(), dist.get_world_size()
     ok = True
+    seen = {"ok": True}
+
+    def leg(name):
+        """prints which leg turned the verdict (every rank, its own view)"""
+        if seen["ok"] and not ok:
+            print("LEG_FAIL rank %d: %s" % (rank, name), flush=True)
+            seen["ok"] = False
+
     for weighted, p, q in ((False, 0.5, 2.0), (True, 0.25, 4.0)):
         s, d = synth.rmat_edges(11, 8, seed=42)
         w = synth.edge_weights(len(s), seed=43) if weighted else None
@@ -97,6 +105,7 @@ def full():
         t = torch.tensor([stats["steps"]], dtype=torch.int64, device="cuda")
         dist.all_reduce(t)
         ok = ok and int(t.item()) == st.steps
+        leg("tuple exchange, weighted=%s" % weighted)
         if not weighted:
             # peer-gather mode over CUDA IPC: this rank walks its slice of the walkers against the whole graph
             shard.attach_dist()
@@ -116,6 +125,7 @@ def full():
                 t = torch.tensor([wi.steps], dtype=torch.int64, device="cuda")
                 dist.all_reduce(t)
                 ok = ok and int(t.item()) == st.steps
+                leg("peer-gather %s" % sampler)
             dist.barrier()
             # migrating walkers (csrc/migrate.cuh): the step kernel stores the tuples into the peer's inbox, NCCL all-reduce as barrier
             mshard = sh.Shard(len(s), ds.data_ptr(), dd.data_ptr(), None, rank, world, migrate=True)
@@ -136,6 +146,7 @@ def full():
                     ok = ok and int(t[0].item()) == st.steps
                     if seg_cap:
                         ok = ok and int(t[1].item()) > 0
+                    leg("migrating walk %s seg_cap=%d rep=%d" % (sampler, seg_cap, rep))
                 mw.free()
                 dist.barrier()
             mshard.free()
@@ -156,6 +167,7 @@ def full():
             t = torch.tensor([mstats["steps"]], dtype=torch.int64, device="cuda")
             dist.all_reduce(t)
             ok = ok and int(t[0].item()) == st.steps
+            leg("VCut shard map")
             mw.free()
             dist.barrier()
             vshard.free()
