@@ -945,6 +945,10 @@ def run_b200_multi(a):
         except Exception as ex:   # noqa: BLE001
             replicas = {"value": None, "error": str(ex)}
         log("replicas: %s; parity: %s" % (None if not replicas else replicas.get("value"), parity))
+    # the sharded walk's own full-round checksum, whether or not a replicated graph could be built beside it (a graph beyond 2^32 - 1
+    # adjacency entries exists only sharded: its checksum is compared across DIFFERENT shardings, profiles/README.md)
+    ck = torch.tensor([chk["sharded"]], dtype=torch.int64, device=dev)
+    dist.all_reduce(ck)
     if rank == 0:
         peak, peak_src = peaks()
         # algorithmic bytes per step: the single-GPU figure + what the exchange adds per step
@@ -979,7 +983,7 @@ def run_b200_multi(a):
                                                     "note": "one extra untimed round with CUDA events around every kernel and every all-reduce; barrier = "
                                                             "all-reduce latency + waiting for the slowest rank of the super-step"}},
                 "cpu_baseline": None, "e2e": e2e, "gpu_launches": super_steps, "clocks": clk,
-                "replicas": replicas, "parity_at_scale": parity}
+                "replicas": replicas, "parity_at_scale": parity, "checksum_sharded_last_round": int(ck[0])}
         emit(line)
         if parity is not None and not parity["equal"]:
             dist.destroy_process_group()
