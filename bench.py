@@ -869,6 +869,8 @@ def run_b200_multi(a):
         del full, parts
         mw = sh.MigrateWalker([sh2], prm, batch, check_every=8)
         snap = torch.empty((sh2.home_rows * batch, stride), dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        t_ctx = time.time() - t0 - t_built          # exchange blocks: symmetric-memory allocation + rendezvous of the inboxes / path rows
         state = {"ev": None, "d2h": 0, "steps": 0}
 
         def read_back(first, count, paths):
@@ -892,12 +894,13 @@ def run_b200_multi(a):
         copy_stream.synchronize()
         torch.cuda.synchronize()
         dt = time.time() - t0
-        tt = torch.tensor([dt, t_built], dtype=torch.float64, device=dev)
+        tt = torch.tensor([dt, t_built, t_ctx], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         cc = torch.tensor([steps_e, sum(x.numel() * 4 for x in h_slice), state["d2h"]], dtype=torch.int64, device=dev)
         dist.all_reduce(cc)
         e2e = {"value": int(cc[0]) / float(tt[0]), "unit": UNIT, "h2d_bytes_per_step": int(cc[1]) // max(1, a.steps), "d2h_bytes_per_step": int(cc[2]) // max(1, a.steps),
-               "seconds": float(tt[0]), "h2d_allgather_build_s": float(tt[1]),
+               "seconds": float(tt[0]), "h2d_allgather_build_s": float(tt[1]), "exchange_block_setup_s": float(tt[2]),
+               "walk_and_d2h_s": float(tt[0]) - float(tt[1]) - float(tt[2]),
                "includes": "every rank copies 1/%d of the edge list from pinned host memory (H2D), NCCL all-gather of the edge list, shard build "
                            "(rows + hash sets + replicated edge filter), %d rounds of the sharded walk in batches of %d, D2H of every batch's home path "
                            "rows through a pinned ring (the copy of batch b overlaps the walk of batch b+1); wall clock, max over ranks" % (world, a.steps, batch)}
