@@ -67,7 +67,9 @@ struct srw_mig {
   unsigned long long *d_scratch = nullptr;     // cursor, done, out_cnt[kMigMaxDest], stats[8]
   int32_t *d_lens = nullptr;
   unsigned grid = 0;
-  bool stats = false, attr_set = false;
+  bool stats = false;
+  int minb = 4, stage = kMigStage;
+  void *attr_kern = nullptr;
   MigArgs base;                                // everything that does not change between super-steps
 };
 
@@ -96,10 +98,17 @@ int64_t default_seg_cap(const srw_graph *g, int64_t n_rounds, unsigned grid) {
   if (cap > n) cap = n;
   return (cap + (int64_t)grid * 8 * kMigChunk + 1024 + 31) & ~(int64_t)31;      // whole 32-slot blocks (mig_word)
 }
+void mig_variant(int *minb, int *stage) {
+  *minb = 4; *stage = kMigStage;
+  const char *e = getenv("SRW_MIG_VARIANT");
+  if (e) { int a = 0, b = 0; if (sscanf(e, "%d,%d", &a, &b) == 2 && a > 0 && b > 0) { *minb = a; *stage = b; } }
+}
 unsigned mig_grid() {
   const char *e = getenv("SRW_MIG_BLOCKS");
   if (e && atoi(e) > 0) return (unsigned)atoi(e);
-  return 148 * 4;     // persistent: one wave at the 4 blocks per SM the kernel is compiled for
+  int minb, stage;
+  mig_variant(&minb, &stage);
+  return 148u * (unsigned)minb;     // persistent: one wave at the blocks per SM the kernel is compiled for
 }
 }  // namespace
 
@@ -125,6 +134,7 @@ extern "C" srw_status srw_mig_create(const srw_graph *g, const srw_params *p, in
   srw_mig *m = new srw_mig();
   m->g = g; m->prm = *p; m->world = g->shard_world; m->rank = g->shard_rank; m->n_rounds = n_rounds;
   m->grid = mig_grid();
+  mig_variant(&m->minb, &m->stage);
   m->seg_cap = ((seg_cap > 0 ? seg_cap : default_seg_cap(g, n_rounds, m->grid)) + 31) & ~(int64_t)31;
   if (m->seg_cap < kMigChunk) m->seg_cap = kMigChunk;      // a region must hold at least one chunk, or nothing is ever delivered
   m->spill_cap = (g->nv * n_rounds + (int64_t)m->grid * 8 * kMigChunk + 1024 + 31) & ~(int64_t)31;
@@ -231,19 +241,22 @@ extern "C" srw_status srw_mig_superstep(srw_mig *m, int64_t s, unsigned long lon
     a.out_base[d] = (int4 *)(blk + m->L.o_base[nxt]) + 3 * first;
     a.out_cnt_pub[d] = (unsigned long long *)(blk + m->L.o_cnt) + nxt * kMigMaxDest + (d == m->world ? m->world : m->rank);
   }
-  const size_t dyn = (size_t)8 * m->world * 3 * kMigStage * sizeof(int4);      // the warps' stages (migrate.cuh)
-  if (!m->attr_set) {
-    SRW_CUDA(cudaFuncSetAttribute(mig_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    SRW_CUDA(cudaFuncSetAttribute(mig_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    SRW_CUDA(cudaFuncSetAttribute(mig_step_kernel<true, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    SRW_CUDA(cudaFuncSetAttribute(mig_step_kernel<false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    m->attr_set = true;
+  // kernel variant = (resident blocks per SM the kernel is compiled for, tuples staged per warp and destination): (4, 16) by default;
+  // SRW_MIG_VARIANT=minb,stage selects another one (measurement knob: the kernel is latency-bound, profiles/README.md)
+  const size_t dyn = (size_t)8 * m->world * 3 * m->stage * sizeof(int4);      // the warps' stages (migrate.cuh)
+  void (*kern)(const MigArgs) = nullptr;
+#define MIG_PICK(MB, ST)                                                                                                              \
+  if (m->minb == MB && m->stage == ST)                                                                                                \
+    kern = m->g->vcut ? (m->stats ? mig_step_kernel<true, MB, true, ST> : mig_step_kernel<false, MB, true, ST>)                       \
+                      : (m->stats ? mig_step_kernel<true, MB, false, ST> : mig_step_kernel<false, MB, false, ST>);
+  MIG_PICK(4, 16) MIG_PICK(4, 8) MIG_PICK(5, 8) MIG_PICK(6, 8) MIG_PICK(5, 16)
+#undef MIG_PICK
+  if (!kern) { srw_set_error("SRW_MIG_VARIANT: no kernel variant (%d blocks per SM, %d staged tuples)", m->minb, m->stage); return SRW_ERR_ARG; }
+  if (m->attr_kern != (void *)kern) {
+    SRW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    m->attr_kern = (void *)kern;
   }
-  if (m->g->vcut) {          // VCut shard map: extents / owners / seeds through the replicated tables
-    if (m->stats) mig_step_kernel<true, 4, true><<<m->grid, 256, dyn, stream>>>(a);
-    else mig_step_kernel<false, 4, true><<<m->grid, 256, dyn, stream>>>(a);
-  } else if (m->stats) mig_step_kernel<true><<<m->grid, 256, dyn, stream>>>(a);
-  else mig_step_kernel<false><<<m->grid, 256, dyn, stream>>>(a);
+  kern<<<m->grid, 256, dyn, stream>>>(a);
   SRW_CUDA(cudaGetLastError());
   if (d_sent) SRW_CUDA(cudaMemcpyAsync(d_sent, a.stats, 8, cudaMemcpyDeviceToDevice, stream));
   return SRW_OK;

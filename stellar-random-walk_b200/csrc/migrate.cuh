@@ -158,7 +158,7 @@ __device__ __forceinline__ unsigned mig_atomic_add32(unsigned long long *p, unsi
 // inbox region: per word ONE run of n contiguous 16-byte stores (mig_word keeps a stage inside one 32-slot block).  A new chunk is
 // claimed from the region's counter when the open one is used up; a region that is full diverts the stage to the local spill region
 // with MIG_FWD set (routed again in the next super-step).
-template <class Args>
+template <int STAGE, class Args>
 __device__ __forceinline__ void mig_flush(const Args &a, int d, int n, int4 *stage, unsigned int *chunk, unsigned int *fill, int lane,
                                            unsigned int &n_spill, unsigned int &n_err) {
   const int W = a.world;
@@ -169,9 +169,9 @@ __device__ __forceinline__ void mig_flush(const Args &a, int d, int n, int4 *sta
     unsigned cb = chunk[dest];
     __syncwarp();
     bool ok = true;
-    if (f + (unsigned)kMigStage > (unsigned)kMigChunk) {              // no room in the open chunk: claim the next one
+    if (f + (unsigned)STAGE > (unsigned)kMigChunk) {              // no room in the open chunk: claim the next one
       // (the tail of the old chunk, if any, is padded at the end of the kernel only when it is the last one: a chunk is used in
-      // whole stages of kMigStage slots, and kMigChunk is a multiple of kMigStage, so a used-up chunk has no tail)
+      // whole stages of STAGE slots, and kMigChunk is a multiple of STAGE, so a used-up chunk has no tail)
       unsigned long long base = 0;
       if (lane == 0) base = atomicAdd(a.out_cnt + dest, (unsigned long long)kMigChunk);
       base = __shfl_sync(0xffffffffu, base, 0);
@@ -186,9 +186,9 @@ __device__ __forceinline__ void mig_flush(const Args &a, int d, int n, int4 *sta
     }
     if (ok) {
       int4 *out = a.out_base[dest];
-      const int4 *sp = stage + d * (3 * kMigStage);
-      for (int e = lane; e < 3 * kMigStage; e += 32) {
-        const int k = e / kMigStage, j = e % kMigStage;
+      const int4 *sp = stage + d * (3 * STAGE);
+      for (int e = lane; e < 3 * STAGE; e += 32) {
+        const int k = e / STAGE, j = e % STAGE;
         if (j < n) {
           int4 v = sp[e];
           if (k == 1) v.y |= (int)fwd_flag;
@@ -197,7 +197,7 @@ __device__ __forceinline__ void mig_flush(const Args &a, int d, int n, int4 *sta
           out[mig_word(cb + f + (unsigned)j, 1)] = make_int4(0, (int)MIG_NOP, 0, 0);     // a partial stage (end of the kernel): the rest of its slots
         }
       }
-      if (lane == 0) fill[dest] = f + (unsigned)kMigStage;
+      if (lane == 0) fill[dest] = f + (unsigned)STAGE;
       __syncwarp();
       return;
     }
@@ -207,16 +207,17 @@ __device__ __forceinline__ void mig_flush(const Args &a, int d, int n, int4 *sta
   }
 }
 
-template <bool STATS, int MINB = 4, bool VCUT = false>
+template <bool STATS, int MINB = 4, bool VCUT = false, int STAGE = kMigStage>
 __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
+  static_assert(kMigChunk % STAGE == 0 && STAGE <= 32, "a chunk is used in whole stages");
   // per-warp send state: open chunk (first slot, slots used) per destination region; prefix of the inbox regions (+ seeds)
   __shared__ unsigned int s_chunk[8][kMigMaxDest];     // open chunk of the destination region: first slot ...
   __shared__ unsigned int s_fill[8][kMigMaxDest];      // ... and slots of it already written (kMigChunk = none open)
   __shared__ unsigned int s_used[8][kMigMaxDest];      // tuples in the stage
 #ifdef SRW_EMU
-  static int4 mig_dyn[8 * kMigMaxDest * kMigStage * 3];
+  static int4 mig_dyn[8 * kMigMaxDest * STAGE * 3];
 #else
-  extern __shared__ int4 mig_dyn[];                    // [8 warps][world][3 words][kMigStage] staged tuples
+  extern __shared__ int4 mig_dyn[];                    // [8 warps][world][3 words][STAGE] staged tuples
 #endif
   __shared__ unsigned int s_pre[8][kMigMaxDest + 2];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
   unsigned int *used = s_used[wib];
   unsigned int *fill = s_fill[wib];
   unsigned int *pre = s_pre[wib];
-  int4 *stage = mig_dyn + (size_t)wib * W * (3 * kMigStage);
+  int4 *stage = mig_dyn + (size_t)wib * W * (3 * STAGE);
   if (lane <= W) { chunk[lane] = 0; fill[lane] = kMigChunk; used[lane] = 0; }
   if (lane == 0) {
     unsigned int acc = 0;
@@ -473,31 +474,31 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
     }
     // ---- D: sends ----
     // A departing walker is written into the warp's shared-memory stage of its destination (one shared-memory atomic per lane);
-    // a stage that fills up (kMigStage tuples) is flushed by the whole warp into the destination's inbox region.
+    // a stage that fills up (STAGE tuples) is flushed by the whole warp into the destination's inbox region.
     if (__any_sync(0xffffffffu, send >= 0)) {
       const uint32_t w_off = (send_kind & MIG_KIND_MASK) == MIG_PENDING ? (uint32_t)x : off;
       const uint32_t w_deg = (send_kind & MIG_KIND_MASK) == MIG_PENDING ? ((xm << 8) | ((cown & 15u) << 4) | (xown & 15u)) : deg;
       const int4 t0 = make_int4((int)walker, prev, curr, (int)w_off);
       const int4 t1 = make_int4((int)w_deg, (int)((m << MIG_M_SHIFT) | ((pown & 15u) << MIG_POWN_SHIFT) | send_kind), (int)trial, (int)len);
       const int4 t2 = make_int4(c0, c1, c2, (int)hrow);
-      unsigned pos = (unsigned)kMigStage;
+      unsigned pos = (unsigned)STAGE;
       if (send >= 0) {
         pos = atomicAdd(&used[send], 1u);
-        if (pos < (unsigned)kMigStage) { int4 *sp = stage + send * (3 * kMigStage) + pos; sp[0] = t0; sp[kMigStage] = t1; sp[2 * kMigStage] = t2; }
+        if (pos < (unsigned)STAGE) { int4 *sp = stage + send * (3 * STAGE) + pos; sp[0] = t0; sp[STAGE] = t1; sp[2 * STAGE] = t2; }
       }
       __syncwarp();
-      unsigned ovf = __ballot_sync(0xffffffffu, send >= 0 && pos >= (unsigned)kMigStage);
+      unsigned ovf = __ballot_sync(0xffffffffu, send >= 0 && pos >= (unsigned)STAGE);
       while (ovf) {                                              // the stage of destination d is full: flush it, then retry
         const int d = __shfl_sync(0xffffffffu, send, __ffs(ovf) - 1);
-        mig_flush(a, d, kMigStage, stage, chunk, fill, lane, n_spill, n_err);
+        mig_flush<STAGE>(a, d, STAGE, stage, chunk, fill, lane, n_spill, n_err);
         if (lane == 0) used[d] = 0;
         __syncwarp();
-        if (send == d && pos >= (unsigned)kMigStage) {
+        if (send == d && pos >= (unsigned)STAGE) {
           pos = atomicAdd(&used[d], 1u);
-          if (pos < (unsigned)kMigStage) { int4 *sp = stage + d * (3 * kMigStage) + pos; sp[0] = t0; sp[kMigStage] = t1; sp[2 * kMigStage] = t2; }
+          if (pos < (unsigned)STAGE) { int4 *sp = stage + d * (3 * STAGE) + pos; sp[0] = t0; sp[STAGE] = t1; sp[2 * STAGE] = t2; }
         }
         __syncwarp();
-        ovf = __ballot_sync(0xffffffffu, send >= 0 && pos >= (unsigned)kMigStage);
+        ovf = __ballot_sync(0xffffffffu, send >= 0 && pos >= (unsigned)STAGE);
       }
       if (send >= 0) st = MS_EMPTY;
     }
@@ -506,7 +507,7 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
   for (int d = 0; d < W; ++d) {
     const unsigned n = used[d];
     __syncwarp();
-    if (n) mig_flush(a, d, (int)n, stage, chunk, fill, lane, n_spill, n_err);
+    if (n) mig_flush<STAGE>(a, d, (int)n, stage, chunk, fill, lane, n_spill, n_err);
   }
   __syncwarp();
   for (int d = 0; d <= W; ++d) {
