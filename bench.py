@@ -796,6 +796,7 @@ def run_b200_multi(a):
     shard = sh.Shard(n_edges, d_src.data_ptr(), d_dst.data_ptr(), None, rank, world, False, dev, migrate=True, hub_fraction=a.hub_fraction)
     torch.cuda.synchronize()
     build_s = time.time() - t0
+    shard_build_prof = json.loads(lib.srw_graph_build_profile(shard.h).decode() or "{}")
     hub = {"fraction_requested": a.hub_fraction, "rows": shard.hub_rows, "entries": shard.hub_entries, "min_degree": shard.hub_min_degree,
            "bytes_per_rank": shard.hub_entries * 24}
     del d_src, d_dst
@@ -970,7 +971,7 @@ def run_b200_multi(a):
                                           "stores 32-byte walker tuples straight into the destination GPU's inbox over NVLink (peer memory) and path entries into "
                                           "the home GPU's path rows; NCCL all-reduce of the tuple count = barrier + termination test between super-steps; "
                                           "membership test = replicated edge filter (1 byte per adjacency entry) + exact symmetric test at owner(x)" % world,
-                           "shard_bytes_hbm_rank0": shard_bytes, "build_s": round(build_s, 3), "batch_rounds": batch, "super_steps": super_steps,
+                           "shard_bytes_hbm_rank0": shard_bytes, "build_s": round(build_s, 3), "build_ms_per_phase_rank0": shard_build_prof, "batch_rounds": batch, "super_steps": super_steps,
                            "tuples_per_step": tuples_per_step, "spills": int(tot[1]),
                            "l2": "inputs larger than L2 (shard rows + 2 GB filter >> 126 MB), no flush needed", "sampler": "alias-fold" if a.sampler == "fold" else "alias"},
                 "roofline": {"bound": "hbm", "achieved": per_gpu_steps * (B + B_mem + B_x) / 1e9, "peak": peak, "unit": "GB/s",

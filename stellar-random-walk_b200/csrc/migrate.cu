@@ -98,8 +98,11 @@ int64_t default_seg_cap(const srw_graph *g, int64_t n_rounds, unsigned grid) {
   if (cap > n) cap = n;
   return (cap + (int64_t)grid * 8 * kMigChunk + 1024 + 31) & ~(int64_t)31;      // whole 32-slot blocks (mig_word)
 }
-void mig_variant(int *minb, int *stage) {
-  *minb = 4; *stage = kMigStage;
+// Default: 4 blocks per SM; 16 staged tuples per warp and destination up to 4 shards, 8 beyond -- the stages of 8 destinations x 16
+// tuples take 49 KB of shared memory per block and leave the four resident blocks ~50 KB of L1; with 8 tuples (128-byte runs over
+// NVLink instead of 256-byte ones) the same kernel ran 21 % faster (profiles/README.md, r2_mig_variants.txt).
+void mig_variant(int world, int *minb, int *stage) {
+  *minb = 4; *stage = world > 4 ? 8 : kMigStage;
   const char *e = getenv("SRW_MIG_VARIANT");
   if (e) { int a = 0, b = 0; if (sscanf(e, "%d,%d", &a, &b) == 2 && a > 0 && b > 0) { *minb = a; *stage = b; } }
 }
@@ -107,7 +110,7 @@ unsigned mig_grid() {
   const char *e = getenv("SRW_MIG_BLOCKS");
   if (e && atoi(e) > 0) return (unsigned)atoi(e);
   int minb, stage;
-  mig_variant(&minb, &stage);
+  mig_variant(1, &minb, &stage);
   return 148u * (unsigned)minb;     // persistent: one wave at the blocks per SM the kernel is compiled for
 }
 }  // namespace
@@ -134,7 +137,7 @@ extern "C" srw_status srw_mig_create(const srw_graph *g, const srw_params *p, in
   srw_mig *m = new srw_mig();
   m->g = g; m->prm = *p; m->world = g->shard_world; m->rank = g->shard_rank; m->n_rounds = n_rounds;
   m->grid = mig_grid();
-  mig_variant(&m->minb, &m->stage);
+  mig_variant(m->world, &m->minb, &m->stage);
   m->seg_cap = ((seg_cap > 0 ? seg_cap : default_seg_cap(g, n_rounds, m->grid)) + 31) & ~(int64_t)31;
   if (m->seg_cap < kMigChunk) m->seg_cap = kMigChunk;      // a region must hold at least one chunk, or nothing is ever delivered
   m->spill_cap = (g->nv * n_rounds + (int64_t)m->grid * 8 * kMigChunk + 1024 + 31) & ~(int64_t)31;
@@ -249,7 +252,7 @@ extern "C" srw_status srw_mig_superstep(srw_mig *m, int64_t s, unsigned long lon
   if (m->minb == MB && m->stage == ST)                                                                                                \
     kern = m->g->vcut ? (m->stats ? mig_step_kernel<true, MB, true, ST> : mig_step_kernel<false, MB, true, ST>)                       \
                       : (m->stats ? mig_step_kernel<true, MB, false, ST> : mig_step_kernel<false, MB, false, ST>);
-  MIG_PICK(4, 16) MIG_PICK(4, 8) MIG_PICK(5, 8) MIG_PICK(6, 8) MIG_PICK(5, 16)
+  MIG_PICK(4, 16) MIG_PICK(4, 8) MIG_PICK(5, 8) MIG_PICK(6, 8) MIG_PICK(4, 4) MIG_PICK(3, 8) MIG_PICK(4, 32)
 #undef MIG_PICK
   if (!kern) { srw_set_error("SRW_MIG_VARIANT: no kernel variant (%d blocks per SM, %d staged tuples)", m->minb, m->stage); return SRW_ERR_ARG; }
   if (m->attr_kern != (void *)kern) {
