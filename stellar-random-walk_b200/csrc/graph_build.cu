@@ -755,6 +755,7 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
     }
     SRW_CUDA(cudaMalloc(&g->d_off, (size_t)(nrows + 1) * 8));
     k_map_local_off<<<grid(nrows + 1), kThreads>>>(hub_rows, own_rows, gr.first[shard_rank + 1], gr.base[shard_rank + 1], hub_entries, poff.as<int64_t>(), g->d_off);
+    phase("shard_map_tables");
     DevBuf raw_row, raw_col, raw_gidx, cursor, ka, va;
     SRW_CUDA(raw_row.alloc((size_t)nnz * 4)); SRW_CUDA(raw_col.alloc((size_t)nnz * 4)); SRW_CUDA(raw_gidx.alloc((size_t)nnz * 4));
     SRW_CUDA(cursor.alloc(8));
