@@ -958,7 +958,7 @@ def run_b200_multi(a):
         # algorithmic bytes per step: the single-GPU figure + what the exchange adds per step
         B = 8 + T_bar * 4 + 4                                # row extent + neighbour ids + path write, as the N = 1 line
         B_mem = probes_ps * 8                                # one 8-byte filter word per test (the binary-search charge of the N=1 line does not apply)
-        B_x = tuples_per_step * 64                           # tuple written to the peer inbox + read back from the own inbox, 32 bytes each
+        B_x = tuples_per_step * 96                           # tuple written to the peer inbox + read back from the own inbox, 48 bytes each
         per_gpu_steps = steps_all / world / (elapsed_ms * 1e-3)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": elapsed_ms / max(1, a.steps), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -968,7 +968,7 @@ def run_b200_multi(a):
                                                    note="vertex-cut: the rows of the highest-degree vertices are kept by every shard, a step onto one does not migrate "
                                                         "(VRW:43-54 replicates a vertex's adjacency into every partition it has an edge in); --hub-fraction 0 = pure ranges"),
                            "parallelism": "graph sharded into %d edge-balanced vertex ranges (one per GPU); walkers migrate to owner(curr): the step kernel "
-                                          "stores 32-byte walker tuples straight into the destination GPU's inbox over NVLink (peer memory) and path entries into "
+                                          "stores 48-byte walker tuples straight into the destination GPU's inbox over NVLink (peer memory) and path entries into "
                                           "the home GPU's path rows; NCCL all-reduce of the tuple count = barrier + termination test between super-steps; "
                                           "membership test = replicated edge filter (1 byte per adjacency entry) + exact symmetric test at owner(x)" % world,
                            "shard_bytes_hbm_rank0": shard_bytes, "build_s": round(build_s, 3), "build_ms_per_phase_rank0": shard_build_prof, "batch_rounds": batch, "super_steps": super_steps,
@@ -978,7 +978,7 @@ def run_b200_multi(a):
                              "frac": per_gpu_steps * (B + B_mem + B_x) / 1e9 / peak, "traffic": None, "kernel": "mig_step_kernel<0>", "peak_source": peak_src,
                              "per": "GPU (steps/s/GPU x algorithmic bytes per step)", "bytes_per_step": B + B_mem + B_x,
                              "proposals_per_step": T_bar, "filter_probes_per_step": probes_ps, "exact_tests_per_step": exact_ps,
-                             "nvlink_GBps_per_gpu_out": per_gpu_steps * (tuples_per_step * 32 + 4 * (1 - 1.0 / world)) / 1e9,
+                             "nvlink_GBps_per_gpu_out": per_gpu_steps * (tuples_per_step * 48 + 4 * (1 - 1.0 / world)) / 1e9,
                              "nvlink_peak_GBps": 770.0,
                              "super_step_profile": {"round": last_first, "super_steps": prof["super_steps"], "kernel_ms_mean_rank": float(pk[0]) / world,
                                                     "kernel_ms_max_rank": float(pmax[0]), "barrier_ms_mean_rank": float(pk[1]) / world,
