@@ -7,7 +7,7 @@ S=gpurun_out/r2r_summary.txt
 : > $S
 for v in ${VARIANTS:-4,16 4,8 5,8 6,8}; do
   echo "== variant $v" >> $S
-  SRW_MIG_VARIANT=$v timeout 300 python profiles/run_migrate_local.py 24 3 8 0.5 2> gpurun_out/r2r_err_$v.txt | python -c "
+  SRW_MIG_VARIANT=$v timeout 300 python profiles/run_migrate_local.py 24 3 ${WORLD:-8} 0.5 2> gpurun_out/r2r_err_$v.txt | python -c "
 import sys, json
 for l in sys.stdin:
     d = json.loads(l)
