@@ -69,6 +69,7 @@ struct srw_mig {
   unsigned grid = 0;
   bool stats = false;
   int minb = 4, stage = kMigStage;
+  bool prefetch = false;
   void *attr_kern = nullptr;
   MigArgs base;                                // everything that does not change between super-steps
 };
@@ -138,6 +139,7 @@ extern "C" srw_status srw_mig_create(const srw_graph *g, const srw_params *p, in
   m->g = g; m->prm = *p; m->world = g->shard_world; m->rank = g->shard_rank; m->n_rounds = n_rounds;
   m->grid = mig_grid();
   mig_variant(m->world, &m->minb, &m->stage);
+  m->prefetch = getenv("SRW_MIG_PREFETCH") && atoi(getenv("SRW_MIG_PREFETCH")) != 0;
   m->seg_cap = ((seg_cap > 0 ? seg_cap : default_seg_cap(g, n_rounds, m->grid)) + 31) & ~(int64_t)31;
   if (m->seg_cap < kMigChunk) m->seg_cap = kMigChunk;      // a region must hold at least one chunk, or nothing is ever delivered
   m->spill_cap = (g->nv * n_rounds + (int64_t)m->grid * 8 * kMigChunk + 1024 + 31) & ~(int64_t)31;
@@ -254,6 +256,12 @@ extern "C" srw_status srw_mig_superstep(srw_mig *m, int64_t s, unsigned long lon
                       : (m->stats ? mig_step_kernel<true, MB, false, ST> : mig_step_kernel<false, MB, false, ST>);
   MIG_PICK(4, 16) MIG_PICK(4, 8) MIG_PICK(5, 8) MIG_PICK(6, 8) MIG_PICK(4, 4) MIG_PICK(3, 8) MIG_PICK(4, 32)
 #undef MIG_PICK
+  if (m->prefetch && m->minb == 4 && (m->stage == 8 || m->stage == 16)) {      // SRW_MIG_PREFETCH=1: inbox lines of a claim pulled into L2 ahead of their use
+    if (m->stage == 8) kern = m->g->vcut ? (m->stats ? mig_step_kernel<true, 4, true, 8, true> : mig_step_kernel<false, 4, true, 8, true>)
+                                         : (m->stats ? mig_step_kernel<true, 4, false, 8, true> : mig_step_kernel<false, 4, false, 8, true>);
+    else kern = m->g->vcut ? (m->stats ? mig_step_kernel<true, 4, true, 16, true> : mig_step_kernel<false, 4, true, 16, true>)
+                           : (m->stats ? mig_step_kernel<true, 4, false, 16, true> : mig_step_kernel<false, 4, false, 16, true>);
+  }
   if (!kern) { srw_set_error("SRW_MIG_VARIANT: no kernel variant (%d blocks per SM, %d staged tuples)", m->minb, m->stage); return SRW_ERR_ARG; }
   if (m->attr_kern != (void *)kern) {
     SRW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));

@@ -207,7 +207,7 @@ __device__ __forceinline__ void mig_flush(const Args &a, int d, int n, int4 *sta
   }
 }
 
-template <bool STATS, int MINB = 4, bool VCUT = false, int STAGE = kMigStage>
+template <bool STATS, int MINB = 4, bool VCUT = false, int STAGE = kMigStage, bool PREFETCH = false>
 __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
   static_assert(kMigChunk % STAGE == 0 && STAGE <= 32, "a chunk is used in whole stages");
   // per-warp send state: open chunk (first slot, slots used) per destination region; prefix of the inbox regions (+ seeds)
@@ -269,6 +269,20 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
           w_next = base; w_end = total - base > (unsigned)kMigClaim ? base + kMigClaim : total;
           w_seg = 0;
           while ((int)w_seg <= W && base >= pre[w_seg + 1]) w_seg++;       // region of the first claimed item (W + 1 = seeds)
+#ifndef SRW_EMU
+          if (PREFETCH) {
+            // The lanes consume these items over the next passes, one dependent 48-byte load each (6-9 % of the kernel's stall samples
+            // sat on its first use): pull the claim's inbox lines into L2 now -- every lane asks for the three words of four items.
+            for (unsigned int it = base + (unsigned)lane; it < w_end && it < seed0; it += 32) {
+              uint32_t r = w_seg;
+              while ((int)r < W && it >= pre[r + 1]) r++;
+              const uint32_t slot = r * (uint32_t)a.seg_cap + (it - pre[r]);
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(a.in_base + mig_word(slot, 0)));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(a.in_base + mig_word(slot, 1)));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(a.in_base + mig_word(slot, 2)));
+            }
+          }
+#endif
         }
       }
       const unsigned int mine = w_next + (unsigned)__popc(em & lt);
