@@ -69,7 +69,7 @@ struct srw_mig {
   unsigned grid = 0;
   bool stats = false;
   int minb = 4, stage = kMigStage;
-  bool prefetch = false;
+  int flags = 0;
   void *attr_kern = nullptr;
   MigArgs base;                                // everything that does not change between super-steps
 };
@@ -139,7 +139,7 @@ extern "C" srw_status srw_mig_create(const srw_graph *g, const srw_params *p, in
   m->g = g; m->prm = *p; m->world = g->shard_world; m->rank = g->shard_rank; m->n_rounds = n_rounds;
   m->grid = mig_grid();
   mig_variant(m->world, &m->minb, &m->stage);
-  m->prefetch = getenv("SRW_MIG_PREFETCH") && atoi(getenv("SRW_MIG_PREFETCH")) != 0;
+  m->flags = getenv("SRW_MIG_FLAGS") ? atoi(getenv("SRW_MIG_FLAGS")) : 0;
   m->seg_cap = ((seg_cap > 0 ? seg_cap : default_seg_cap(g, n_rounds, m->grid)) + 31) & ~(int64_t)31;
   if (m->seg_cap < kMigChunk) m->seg_cap = kMigChunk;      // a region must hold at least one chunk, or nothing is ever delivered
   m->spill_cap = (g->nv * n_rounds + (int64_t)m->grid * 8 * kMigChunk + 1024 + 31) & ~(int64_t)31;
@@ -256,12 +256,13 @@ extern "C" srw_status srw_mig_superstep(srw_mig *m, int64_t s, unsigned long lon
                       : (m->stats ? mig_step_kernel<true, MB, false, ST> : mig_step_kernel<false, MB, false, ST>);
   MIG_PICK(4, 16) MIG_PICK(4, 8) MIG_PICK(5, 8) MIG_PICK(6, 8) MIG_PICK(4, 4) MIG_PICK(3, 8) MIG_PICK(4, 32)
 #undef MIG_PICK
-  if (m->prefetch && m->minb == 4 && (m->stage == 8 || m->stage == 16)) {      // SRW_MIG_PREFETCH=1: inbox lines of a claim pulled into L2 ahead of their use
-    if (m->stage == 8) kern = m->g->vcut ? (m->stats ? mig_step_kernel<true, 4, true, 8, true> : mig_step_kernel<false, 4, true, 8, true>)
-                                         : (m->stats ? mig_step_kernel<true, 4, false, 8, true> : mig_step_kernel<false, 4, false, 8, true>);
-    else kern = m->g->vcut ? (m->stats ? mig_step_kernel<true, 4, true, 16, true> : mig_step_kernel<false, 4, true, 16, true>)
-                           : (m->stats ? mig_step_kernel<true, 4, false, 16, true> : mig_step_kernel<false, 4, false, 16, true>);
-  }
+#define MIG_PICK_F(ST, FL)                                                                                                            \
+  if (m->minb == 4 && m->stage == ST && m->flags == FL)                                                                               \
+    kern = m->g->vcut ? (m->stats ? mig_step_kernel<true, 4, true, ST, FL> : mig_step_kernel<false, 4, true, ST, FL>)                 \
+                      : (m->stats ? mig_step_kernel<true, 4, false, ST, FL> : mig_step_kernel<false, 4, false, ST, FL>);
+  // SRW_MIG_FLAGS (measurement knobs): 1 = the inbox lines of a claim are prefetched into L2, 2 = random gathers do not allocate in L1
+  MIG_PICK_F(8, 1) MIG_PICK_F(16, 1) MIG_PICK_F(8, 2) MIG_PICK_F(16, 2)
+#undef MIG_PICK_F
   if (!kern) { srw_set_error("SRW_MIG_VARIANT: no kernel variant (%d blocks per SM, %d staged tuples)", m->minb, m->stage); return SRW_ERR_ARG; }
   if (m->attr_kern != (void *)kern) {
     SRW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));

@@ -207,9 +207,10 @@ __device__ __forceinline__ void mig_flush(const Args &a, int d, int n, int4 *sta
   }
 }
 
-template <bool STATS, int MINB = 4, bool VCUT = false, int STAGE = kMigStage, bool PREFETCH = false>
+template <bool STATS, int MINB = 4, bool VCUT = false, int STAGE = kMigStage, int FLAGS = 0>
 __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
   static_assert(kMigChunk % STAGE == 0 && STAGE <= 32, "a chunk is used in whole stages");
+  constexpr int GV = (FLAGS & 2) ? 3 : 1;       // random gathers: L2::64B; FLAGS bit 1: and no L1 allocation (measurement knob)
   // per-warp send state: open chunk (first slot, slots used) per destination region; prefix of the inbox regions (+ seeds)
   __shared__ unsigned int s_chunk[8][kMigMaxDest];     // open chunk of the destination region: first slot ...
   __shared__ unsigned int s_fill[8][kMigMaxDest];      // ... and slots of it already written (kMigChunk = none open)
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
           w_seg = 0;
           while ((int)w_seg <= W && base >= pre[w_seg + 1]) w_seg++;       // region of the first claimed item (W + 1 = seeds)
 #ifndef SRW_EMU
-          if (PREFETCH) {
+          if (FLAGS & 1) {
             // The lanes consume these items over the next passes, one dependent 48-byte load each (6-9 % of the kernel's stall samples
             // sat on its first use): pull the claim's inbox lines into L2 now -- every lane asks for the three words of four items.
             for (unsigned int it = base + (unsigned)lane; it < w_end && it < seed0; it += 32) {
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
     uint32_t bword = 0;
     uint64_t bmask = 0;
     if (prop) {
-      const int4 q0 = gather16<1>(reinterpret_cast<const int4 *>(a.ent + ((uint64_t)off + k)));
+      const int4 q0 = gather16<GV>(reinterpret_cast<const int4 *>(a.ent + ((uint64_t)off + k)));
       x = q0.x; xdeg = (uint32_t)q0.y; xoff = (uint32_t)q0.z;
       xown = (uint32_t)q0.w & 0xFFu; xm = (uint32_t)q0.w >> 8;
       if (VCUT) xown = mig_here(xown, (uint32_t)me);                     // a replicated hub row: the walker stays where it is
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
     } else if (st == MS_EXACT && send < 0) {
       if (pnb) {
         int4 q0, q1;
-        gather32<1>(reinterpret_cast<const int4 *>(a.hash + ((uint64_t)(xoff >> 2) + bkt) * 8), q0, q1);
+        gather32<GV>(reinterpret_cast<const int4 *>(a.hash + ((uint64_t)(xoff >> 2) + bkt) * 8), q0, q1);
         const int32_t t = prev;
         const bool found = q0.x == t || q0.y == t || q0.z == t || q0.w == t || q1.x == t || q1.y == t || q1.z == t || q1.w == t;
         if (found) member = 1;
@@ -426,7 +427,7 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
         else bkt = bkt + 1 == pnb ? 0 : bkt + 1;
       } else {
         const uint32_t mid = (lo + hi) >> 1;
-        const int4 q0 = gather16<1>(reinterpret_cast<const int4 *>(a.ent + ((uint64_t)xoff + mid)));
+        const int4 q0 = gather16<GV>(reinterpret_cast<const int4 *>(a.ent + ((uint64_t)xoff + mid)));
         if (q0.x == prev) member = 1;
         else {
           if (q0.x < prev) lo = mid + 1; else hi = mid;
@@ -441,7 +442,8 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
 #ifdef SRW_EMU
         bw = a.bloom[bword];
 #else
-        asm("ld.global.nc.L2::64B.u64 %0, [%1];" : "=l"(bw) : "l"(a.bloom + bword));     // a missing probe fills 64 bytes, not a 128-byte line
+        if (FLAGS & 2) asm("ld.global.nc.L1::no_allocate.L2::64B.u64 %0, [%1];" : "=l"(bw) : "l"(a.bloom + bword));
+        else asm("ld.global.nc.L2::64B.u64 %0, [%1];" : "=l"(bw) : "l"(a.bloom + bword));     // a missing probe fills 64 bytes, not a 128-byte line
 #endif
         if ((bw & bmask) != bmask) member = 0;                             // definitely not adjacent
         else if ((int)xown != me) { send = (int)xown; send_kind = MIG_PENDING; }   // verify where the walker would go anyway

@@ -79,7 +79,7 @@ constexpr int kStage = 16;
 //                one 32-byte bucket as a single 256-bit load -- the address is selected, the load is shared;
 //   C  consume   accept / reject / next probe; the single push site and the single flush site follow.
 // Row offsets are kept as u32 (the ABI caps nnz below 2^32).  VAR bit 0: loads carry L2::64B (the L2 fills
-// 64 instead of 128 bytes per missing gather, profiles/README.md "gather_probe").
+// 64 instead of 128 bytes per missing gather, profiles/README.md "gather_probe"); bit 1 (with bit 0): the gather does not allocate in L1.
 // ------------------------------------------------------------------------------------------
 
 template <int VAR>
@@ -88,7 +88,8 @@ __device__ __forceinline__ int4 gather16(const int4 *p) {
   return *p;
 #else
   int4 v;
-  if (VAR & 1) asm("ld.global.nc.L2::64B.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  if ((VAR & 3) == 3) asm("ld.global.nc.L1::no_allocate.L2::64B.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  else if (VAR & 1) asm("ld.global.nc.L2::64B.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   else v = __ldg(p);
   return v;
 #endif
@@ -98,7 +99,10 @@ __device__ __forceinline__ void gather32(const int4 *p, int4 &lo, int4 &hi) {   
 #ifdef SRW_EMU
   lo = p[0]; hi = p[1];
 #else
-  if (VAR & 1)
+  if ((VAR & 3) == 3)
+    asm("ld.global.nc.L1::no_allocate.L2::64B.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(p));
+  else if (VAR & 1)
     asm("ld.global.nc.L2::64B.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(p));
   else
