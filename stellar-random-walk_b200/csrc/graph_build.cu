@@ -143,6 +143,30 @@ __global__ void k_map_owner_ranges(int64_t nv, ShardBoundsLite sb, uint8_t *owne
     owner_true[v] = (uint8_t)o;
   }
 }
+// sorted[] ascending degrees, pre[] their inclusive prefix sums: rows i .. nv-1 hold pre[nv-1] - pre[i-1] entries.  The cut is the
+// smallest i whose tail fits the budget; a degree value is wholly in or wholly out (a partial run of equal degrees at the cut is dropped).
+__global__ void k_hub_threshold(int64_t nv, const uint32_t *__restrict__ sorted, const int64_t *__restrict__ pre, int64_t budget, uint32_t *hub_deg) {
+  const int64_t total = pre[nv - 1], need = total - budget;      // tail(i) <= budget  <=>  pre[i-1] >= need
+  int64_t lo = 0, hi = nv;                                       // first index j with pre[j] >= need; the cut is i = j + 1 (i = 0 if need <= 0)
+  while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (pre[mid] >= need) hi = mid; else lo = mid + 1; }
+  const int64_t i = need <= 0 ? 0 : lo + 1;
+  uint32_t T = 0xFFFFFFFFu;
+  if (i < nv) {
+    T = sorted[i];
+    if (i > 0 && sorted[i - 1] == T) T++;
+    if (T < 2) T = 2;
+  }
+  *hub_deg = T;
+}
+// first rank of shard r = lower bound of r * total / world in the exclusive prefix sums moff[0 .. nv] (one thread per boundary)
+__global__ void k_range_bounds(int64_t nv, const int64_t *__restrict__ moff, int world, int64_t *bounds) {
+  const int r = threadIdx.x;
+  if (r < 1 || r >= world) return;
+  const int64_t target = (int64_t)((__int128)moff[nv] * r / world);
+  int64_t lo = 0, hi = nv + 1;
+  while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (moff[mid] >= target) hi = mid; else lo = mid + 1; }
+  bounds[r] = lo;
+}
 // degree with the hub rows masked out (ranges are balanced on the entries that are NOT replicated)
 __global__ void k_map_masked_deg(int64_t nv, const uint32_t *__restrict__ deg, uint32_t hub_deg, uint32_t *out) {
   for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v <= nv; v += (int64_t)gridDim.x * blockDim.x)
@@ -646,24 +670,24 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
     SRW_TRY(build_vpid());
     uint32_t hub_deg = 0xFFFFFFFFu;                 // no row reaches it: nothing replicated
     if (hub_fraction > 0.0 && nnz > 0) {
-      // the smallest degree threshold whose rows hold at most hub_fraction of the entries: degrees sorted, prefix-summed from the top
-      DevBuf dk0, dk1, dv0, dv1;
+      // the smallest degree threshold whose rows hold at most hub_fraction of the entries: degrees sorted ascending, prefix-summed; one
+      // device thread finds the cut (nothing but the 4-byte answer leaves the device)
+      DevBuf dk0, dk1, dv0, dv1, pre, ans, tmp;
       SRW_CUDA(dk0.alloc((size_t)nv * 4)); SRW_CUDA(dk1.alloc((size_t)nv * 4)); SRW_CUDA(dv0.alloc((size_t)nv * 4)); SRW_CUDA(dv1.alloc((size_t)nv * 4));
       SRW_CUDA(cudaMemcpy(dk0.p, deg.p, (size_t)nv * 4, cudaMemcpyDeviceToDevice));
       uint32_t *a_in = dk0.as<uint32_t>(), *a_out = dk1.as<uint32_t>(), *b_in = dv0.as<uint32_t>(), *b_out = dv1.as<uint32_t>();
       SRW_TRY(sort_pairs(a_in, a_out, b_in, b_out, nv, 32));        // ascending (values unused)
-      std::vector<uint32_t> h_deg((size_t)nv);
-      SRW_CUDA(cudaMemcpy(h_deg.data(), a_in, (size_t)nv * 4, cudaMemcpyDeviceToHost));
-      const double budget = hub_fraction * (double)nnz;
-      double acc = 0.0;
-      int64_t i = nv;
-      while (i > 0 && acc + (double)h_deg[(size_t)i - 1] <= budget) { acc += (double)h_deg[(size_t)i - 1]; i--; }
-      // rows i .. nv-1 fit; a degree value must be wholly in or wholly out: drop the partial run of equal degrees at the cut
-      if (i < nv) {
-        uint32_t T = h_deg[(size_t)i];
-        if (i > 0 && h_deg[(size_t)i - 1] == T) T++;
-        hub_deg = T < 2 ? 2 : T;
+      SRW_CUDA(pre.alloc((size_t)nv * 8)); SRW_CUDA(ans.alloc(4));
+      {
+        cub::TransformInputIterator<int64_t, CastU32ToI64, uint32_t *> it(a_in, CastU32ToI64());
+        size_t tb = 0;
+        SRW_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, it, pre.as<int64_t>(), nv));
+        SRW_CUDA(tmp.alloc(tb));
+        SRW_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tb, it, pre.as<int64_t>(), nv));
       }
+      const int64_t budget = (int64_t)(hub_fraction * (double)nnz);
+      k_hub_threshold<<<1, 1>>>(nv, a_in, pre.as<int64_t>(), budget, ans.as<uint32_t>());
+      SRW_CUDA(cudaMemcpy(&hub_deg, ans.p, 4, cudaMemcpyDeviceToHost));
     }
     DevBuf otrue, key0, key1, val0, val1, pdeg, poff, lrow;
     SRW_CUDA(otrue.alloc((size_t)nv));
@@ -681,17 +705,21 @@ static srw_status build_impl(int64_t n, const int32_t *d_src, const int32_t *d_d
         SRW_CUDA(tmp.alloc(tb));
         SRW_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, it, moff.as<int64_t>(), nv + 1));
       }
-      std::vector<int64_t> h_moff((size_t)nv + 1);
-      SRW_CUDA(cudaMemcpy(h_moff.data(), moff.p, (size_t)(nv + 1) * 8, cudaMemcpyDeviceToHost));
       ShardBoundsLite bl{};
       bl.world = shard_world;
-      bl.first[0] = 0; bl.first[shard_world] = nv;
-      for (int r = 1; r < shard_world; ++r) {
-        const int64_t target = (int64_t)((__int128)h_moff[(size_t)nv] * r / shard_world);
-        int64_t bnd = (int64_t)(std::lower_bound(h_moff.begin(), h_moff.end(), target) - h_moff.begin());
-        if (bnd > nv) bnd = nv;
-        if (bnd < bl.first[r - 1]) bnd = bl.first[r - 1];
-        bl.first[r] = bnd;
+      {
+        DevBuf db;
+        SRW_CUDA(db.alloc((SRW_MAX_SHARDS + 1) * 8));
+        k_range_bounds<<<1, 32>>>(nv, moff.as<int64_t>(), shard_world, db.as<int64_t>());
+        int64_t h_b[SRW_MAX_SHARDS + 1];
+        SRW_CUDA(cudaMemcpy(h_b, db.p, sizeof h_b, cudaMemcpyDeviceToHost));
+        bl.first[0] = 0; bl.first[shard_world] = nv;
+        for (int r = 1; r < shard_world; ++r) {
+          int64_t bnd = h_b[r];
+          if (bnd > nv) bnd = nv;
+          if (bnd < bl.first[r - 1]) bnd = bl.first[r - 1];
+          bl.first[r] = bnd;
+        }
       }
       k_map_owner_ranges<<<grid(nv), kThreads>>>(nv, bl, otrue.as<uint8_t>());
     }
