@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <memory>
 #include <vector>
 
 #include "philox.cuh"
@@ -256,7 +257,8 @@ extern "C" srw_status srw_walk(const srw_graph *g, const srw_params *params, srw
   SRW_CUDA(cudaSetDevice(g->device));
   const int32_t stride = params->walk_length + 2;
   const int64_t total = (int64_t)params->num_walks * g->nv;
-  srw_paths *P = new srw_paths();
+  std::unique_ptr<srw_paths> owner(new srw_paths());     // released into *out on success only: no error path leaks it
+  srw_paths *P = owner.get();
   P->stride = stride;
   P->offsets.push_back(0);
   size_t free_b = 0, total_b = 0;
@@ -278,7 +280,7 @@ extern "C" srw_status srw_walk(const srw_graph *g, const srw_params *params, srw
   for (int64_t first = 0; first < total; first += batch) {
     const int64_t n = std::min(batch, total - first);
     srw_status s = srw_walk_device(g, params, (uint64_t)first, n, d_paths.p, d_lens.p, nullptr);
-    if (s != SRW_OK) { delete P; return s; }
+    if (s != SRW_OK) return s;
     srw_walk_info wi;
     srw_last_walk_info(&wi);
     kernel_ms += wi.kernel_ms; launches += wi.kernel_launches; steps += wi.steps;
@@ -304,7 +306,7 @@ extern "C" srw_status srw_walk(const srw_graph *g, const srw_params *params, srw
   P->n_steps = steps;
   // expose the totals of the whole call
   srw_set_walk_info(kernel_ms, launches, steps, props, mem, logs);
-  *out = P;
+  *out = owner.release();
   return SRW_OK;
 }
 
