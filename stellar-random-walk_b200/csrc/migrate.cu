@@ -248,7 +248,7 @@ extern "C" srw_status srw_mig_superstep(srw_mig *m, int64_t s, unsigned long lon
   }
   // kernel variant = (resident blocks per SM the kernel is compiled for, tuples staged per warp and destination): (4, 16) by default;
   // SRW_MIG_VARIANT=minb,stage selects another one (measurement knob: the kernel is latency-bound, profiles/README.md)
-  const size_t dyn = (size_t)8 * m->world * 3 * m->stage * sizeof(int4);      // the warps' stages (migrate.cuh)
+  const size_t dyn = (size_t)8 * (m->world > 1 ? m->world - 1 : 1) * 3 * m->stage * sizeof(int4);      // the warps' stages (migrate.cuh): one per OTHER rank
   void (*kern)(const MigArgs) = nullptr;
 #define MIG_PICK(MB, ST)                                                                                                              \
   if (m->minb == MB && m->stage == ST)                                                                                                \

@@ -134,6 +134,10 @@ __device__ __forceinline__ uint32_t mig_carried(uint32_t phase, uint32_t len) {
 // a few large write packets instead of a 16-byte packet per lane and word -- and lanes that refill together read the same way.
 __device__ __forceinline__ uint64_t mig_word(uint32_t slot, uint32_t k) { return (uint64_t)(slot >> 5) * 96u + k * 32u + (slot & 31u); }
 
+// A warp stages tuples for every destination but its own rank: world - 1 stages (at 8 shards the eighth would push four resident
+// blocks from the 100 KB shared-memory configuration into the 132 KB one, i.e. cost 32 KB of L1 -- and L1 capacity is what holds the
+// kernel's outstanding gathers, profiles/README.md)
+__device__ __forceinline__ int mig_sidx(int dest, int me) { return dest - (dest > me ? 1 : 0); }
 __device__ __forceinline__ uint32_t mig_here(uint32_t owner, uint32_t me) { return owner == kMigHub ? me : owner; }
 __device__ __forceinline__ int mig_owner(const MigArgs &a, int32_t v) {
   int o = 0;
@@ -186,7 +190,7 @@ __device__ __forceinline__ void mig_flush(const Args &a, int d, int n, int4 *sta
     }
     if (ok) {
       int4 *out = a.out_base[dest];
-      const int4 *sp = stage + d * (3 * STAGE);
+      const int4 *sp = stage + mig_sidx(d, a.rank) * (3 * STAGE);
       for (int e = lane; e < 3 * STAGE; e += 32) {
         const int k = e / STAGE, j = e % STAGE;
         if (j < n) {
@@ -218,7 +222,7 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
 #ifdef SRW_EMU
   static int4 mig_dyn[8 * kMigMaxDest * STAGE * 3];
 #else
-  extern __shared__ int4 mig_dyn[];                    // [8 warps][world][3 words][STAGE] staged tuples
+  extern __shared__ int4 mig_dyn[];                    // [8 warps][world - 1][3 words][STAGE] staged tuples
 #endif
   __shared__ unsigned int s_pre[8][kMigMaxDest + 2];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -228,7 +232,7 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
   unsigned int *used = s_used[wib];
   unsigned int *fill = s_fill[wib];
   unsigned int *pre = s_pre[wib];
-  int4 *stage = mig_dyn + (size_t)wib * W * (3 * STAGE);
+  int4 *stage = mig_dyn + (size_t)wib * (W - 1) * (3 * STAGE);
   if (lane <= W) { chunk[lane] = 0; fill[lane] = kMigChunk; used[lane] = 0; }
   if (lane == 0) {
     unsigned int acc = 0;
@@ -500,7 +504,7 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
       unsigned pos = (unsigned)STAGE;
       if (send >= 0) {
         pos = atomicAdd(&used[send], 1u);
-        if (pos < (unsigned)STAGE) { int4 *sp = stage + send * (3 * STAGE) + pos; sp[0] = t0; sp[STAGE] = t1; sp[2 * STAGE] = t2; }
+        if (pos < (unsigned)STAGE) { int4 *sp = stage + mig_sidx(send, me) * (3 * STAGE) + pos; sp[0] = t0; sp[STAGE] = t1; sp[2 * STAGE] = t2; }
       }
       __syncwarp();
       unsigned ovf = __ballot_sync(0xffffffffu, send >= 0 && pos >= (unsigned)STAGE);
@@ -511,7 +515,7 @@ __global__ void __launch_bounds__(256, MINB) mig_step_kernel(const MigArgs a) {
         __syncwarp();
         if (send == d && pos >= (unsigned)STAGE) {
           pos = atomicAdd(&used[d], 1u);
-          if (pos < (unsigned)STAGE) { int4 *sp = stage + d * (3 * STAGE) + pos; sp[0] = t0; sp[STAGE] = t1; sp[2 * STAGE] = t2; }
+          if (pos < (unsigned)STAGE) { int4 *sp = stage + mig_sidx(d, me) * (3 * STAGE) + pos; sp[0] = t0; sp[STAGE] = t1; sp[2 * STAGE] = t2; }
         }
         __syncwarp();
         ovf = __ballot_sync(0xffffffffu, send >= 0 && pos >= (unsigned)STAGE);
