@@ -99,9 +99,9 @@ int64_t default_seg_cap(const srw_graph *g, int64_t n_rounds, unsigned grid) {
   if (cap > n) cap = n;
   return (cap + (int64_t)grid * 8 * kMigChunk + 1024 + 31) & ~(int64_t)31;      // whole 32-slot blocks (mig_word)
 }
-// Default: 4 blocks per SM; 16 staged tuples per warp and destination up to 4 shards, 8 beyond -- the stages of 8 destinations x 16
-// tuples take 49 KB of shared memory per block and leave the four resident blocks ~50 KB of L1; with 8 tuples (128-byte runs over
-// NVLink instead of 256-byte ones) the same kernel ran 21 % faster (profiles/README.md, r2_mig_variants.txt).
+// Default: 4 blocks per SM; 16 staged tuples per warp and destination up to 4 shards, 8 beyond.  What matters is the shared-memory
+// CONFIGURATION the four resident blocks force on the SM: 8 destinations x 16 tuples were 49 KB per block = the 228 KB configuration =
+// 28 KB of L1, too little to hold the outstanding gathers of 1024 threads (+27 % at N = 8 with 8-tuple stages, profiles/README.md).
 void mig_variant(int world, int *minb, int *stage) {
   *minb = 4; *stage = world > 4 ? 8 : kMigStage;
   const char *e = getenv("SRW_MIG_VARIANT");
