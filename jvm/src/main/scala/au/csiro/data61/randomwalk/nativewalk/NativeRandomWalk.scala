@@ -13,8 +13,10 @@ import org.apache.spark.rdd.RDD
   */
 object NativeRandomWalk {
 
-  /** The options CommandParser accepted (CommandParser.scala:34-90), as an argv for srw_main. */
-  def toArgv(param: Params): Array[String] = Array(
+  /** The options CommandParser accepted (CommandParser.scala:34-90), as an argv for srw_main.  `gpus` > 1 shards the graph over
+    * the GPUs of the box; with `--partitioned true` (VCutRandomWalk, Main.scala:54-57) the partition-id column of the edge file is
+    * then the shard map: a vertex lives on GraphMap.getPartition(v) mod gpus (VCutRandomWalk.scala:121-134). */
+  def toArgv(param: Params, gpus: Int = 1): Array[String] = Array(
     "--cmd", "randomwalk",
     "--input", param.input,
     "--output", param.output,
@@ -26,11 +28,12 @@ object NativeRandomWalk {
     "--directed", param.directed.toString,
     "--partitioned", param.partitioned.toString,
     "--rddPartitions", param.rddPartitions.toString,
-    "--singleOutput", param.singleOutput.toString)
+    "--singleOutput", param.singleOutput.toString,
+    "--gpus", gpus.toString)
 
-  def run(context: SparkContext, param: Params): RDD[Array[Int]] = {
-    require(SrwNative.deviceCount() > 0, "libsrw needs a CUDA device")
-    SrwNative.runRandomWalk(toArgv(param))
+  def run(context: SparkContext, param: Params, gpus: Int = 1): RDD[Array[Int]] = {
+    require(SrwNative.deviceCount() >= gpus, s"libsrw needs $gpus CUDA device(s)")
+    SrwNative.runRandomWalk(toArgv(param, gpus))
     // what RandomWalk.save wrote (RandomWalk.scala:234-241), back as the RDD the embedding stage expects
     context.textFile(s"${param.output}/${Property.pathSuffix}").map(_.split("\t").map(_.toInt))
   }
