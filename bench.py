@@ -495,7 +495,10 @@ def run_b200(a):
             # (weighted / classic kernels, whose entries do not carry the neighbour's row extent) one row descriptor
             req = T_bar + st.member_tests / max(1, st.steps) + 0.125 + (0.0 if kernel_name == "walk_fold_conv_kernel" else 1.0)
             roofline["gather_ceiling"] = {"table": "8 GiB, 16-byte L2::64B gathers (profiles/probes/gather_sweep.cu, measured in this run)",
-                                          "gathers_per_s": gc, "best": max(gc.values())}
+                                          "gathers_per_s": gc, "best": max(gc.values()),
+                                          "note": "a LOWER bound of the ceiling: these are the probe's long plain points; its short points under ncu reach "
+                                                  "43-45e9 (profiles/r2_gather_sweep_ncu.csv).  frac_of_gather_ceiling above 1 means the walk kernel sustains "
+                                                  "more random accesses per second than the dedicated probe does over an equally long run"}
             roofline["requests_per_step_model"] = req
             roofline["frac_of_gather_ceiling"] = (steps / kernel_s) * req / max(gc.values())
         else:
