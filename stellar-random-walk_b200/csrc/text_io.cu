@@ -262,13 +262,25 @@ extern "C" srw_status srw_walk_save(const srw_graph *g, const srw_params *params
   }
   Formatter fmt;
   SRW_TRY(fmt.init(chunk, stride));
-  cudaStream_t st;
-  SRW_CUDA(cudaStreamCreate(&st));
-  cudaEvent_t ready[2];
-  for (int b = 0; b < 2; ++b) SRW_CUDA(cudaEventCreateWithFlags(&ready[b], cudaEventDisableTiming));
+  // stream, events and the open part file are released on EVERY exit (the SRW_CUDA early returns below included)
+  struct SaveGuard {
+    cudaStream_t st = nullptr;
+    cudaEvent_t ready[2] = {nullptr, nullptr};
+    int fd = -1;
+    ~SaveGuard() {
+      for (int b = 0; b < 2; ++b) if (ready[b]) cudaEventDestroy(ready[b]);
+      if (st) cudaStreamDestroy(st);
+      if (fd >= 0) close(fd);
+    }
+  } guard;
+  SRW_CUDA(cudaStreamCreate(&guard.st));
+  for (int b = 0; b < 2; ++b) SRW_CUDA(cudaEventCreateWithFlags(&guard.ready[b], cudaEventDisableTiming));
+  cudaStream_t st = guard.st;
+  cudaEvent_t *ready = guard.ready;
 
   // output files: part k holds paths [total*k/parts, total*(k+1)/parts)
-  int file_k = -1, fd = -1;
+  int file_k = -1;
+  int &fd = guard.fd;
   bool io_ok = true;
   std::string io_err;
   auto open_part = [&](int k) {
@@ -360,9 +372,7 @@ extern "C" srw_status srw_walk_save(const srw_graph *g, const srw_params *params
     if (file_k < 0) open_part(0);
     while (file_k + 1 < parts && io_ok) open_part(file_k + 1);    // trailing (possibly empty) part files, as Spark writes them
   }
-  if (fd >= 0 && close(fd) != 0) io_ok = false;
-  for (int b = 0; b < 2; ++b) cudaEventDestroy(ready[b]);
-  cudaStreamDestroy(st);
+  if (fd >= 0) { if (close(fd) != 0) io_ok = false; fd = -1; }
   if (rc != SRW_OK) return rc;
   if (!io_ok) { srw_set_error("%s", io_err.empty() ? "I/O error while writing the path files" : io_err.c_str()); return SRW_ERR_IO; }
   FILE *f = fopen((dir + "/_SUCCESS").c_str(), "wb");
