@@ -274,7 +274,17 @@ extern "C" srw_status srw_walk(const srw_graph *g, const srw_params *params, srw
   Dev<int32_t> d_paths, d_lens;
   SRW_CUDA(cudaMalloc(&d_paths.p, (size_t)batch * stride * 4));
   SRW_CUDA(cudaMalloc(&d_lens.p, (size_t)batch * 4));
-  std::vector<int32_t> h_paths((size_t)batch * stride), h_lens((size_t)batch);
+  // The result is ONE flat id array: it is reserved once (no regrowth copies of a 10-GB vector) and every batch is copied from the
+  // device straight into its place in it (no staging vector); ragged paths (dead ends, RW:115-119) are compacted in place.
+  std::vector<int32_t> h_lens((size_t)batch);
+  try {
+    P->ids.reserve((size_t)total * (size_t)stride);
+    P->offsets.reserve((size_t)total + 1);
+  } catch (const std::bad_alloc &) {
+    srw_set_error("srw_walk: %lld paths of up to %d ids do not fit host memory (srw_walk_save streams them to files, srw_walk_device leaves them in HBM)",
+                  (long long)total, (int)stride);
+    return SRW_ERR_ARG;
+  }
   double kernel_ms = 0;
   int64_t launches = 0, steps = 0, props = 0, mem = 0, logs = 0;
   for (int64_t first = 0; first < total; first += batch) {
@@ -285,21 +295,24 @@ extern "C" srw_status srw_walk(const srw_graph *g, const srw_params *params, srw
     srw_last_walk_info(&wi);
     kernel_ms += wi.kernel_ms; launches += wi.kernel_launches; steps += wi.steps;
     props += wi.proposals; mem += wi.member_tests; logs += wi.probes_log2;
-    SRW_CUDA(cudaMemcpy(h_paths.data(), d_paths.p, (size_t)n * stride * 4, cudaMemcpyDeviceToHost));
     SRW_CUDA(cudaMemcpy(h_lens.data(), d_lens.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
-    // full-length paths (every walk on an undirected graph): one bulk append instead of a copy per row
-    bool all_full = true;
+    const size_t base = P->ids.size();
+    P->ids.resize(base + (size_t)n * (size_t)stride);
+    SRW_CUDA(cudaMemcpy(P->ids.data() + base, d_paths.p, (size_t)n * stride * 4, cudaMemcpyDeviceToHost));
+    bool all_full = true;                  // full-length paths: every walk on an undirected graph
     for (int64_t i = 0; i < n && all_full; ++i) all_full = h_lens[i] == stride;
     if (all_full) {
-      const int64_t base = (int64_t)P->ids.size();
-      P->ids.insert(P->ids.end(), h_paths.begin(), h_paths.begin() + n * stride);
-      P->offsets.reserve(P->offsets.size() + (size_t)n);
-      for (int64_t i = 1; i <= n; ++i) P->offsets.push_back(base + i * stride);
+      for (int64_t i = 1; i <= n; ++i) P->offsets.push_back((int64_t)base + i * stride);
     } else {
+      int32_t *ids = P->ids.data();
+      size_t w = base;
       for (int64_t i = 0; i < n; ++i) {
-        P->ids.insert(P->ids.end(), h_paths.begin() + i * stride, h_paths.begin() + i * stride + h_lens[i]);
-        P->offsets.push_back((int64_t)P->ids.size());
+        const size_t len = (size_t)std::max<int32_t>(0, std::min<int32_t>(h_lens[i], stride)), from = base + (size_t)i * (size_t)stride;
+        if (w != from && len) memmove(ids + w, ids + from, len * 4);
+        w += len;
+        P->offsets.push_back((int64_t)w);
       }
+      P->ids.resize(w);
     }
   }
   P->n_paths = total;
