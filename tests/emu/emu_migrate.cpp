@@ -158,7 +158,10 @@ extern "C" int emu_migrate_walk(int64_t nv, const int64_t *off, const int32_t *c
       for (int h = 0; h < W; ++h) { a.home_paths[h] = sh[(size_t)h].paths.data(); a.home_rows[h] = (nv - h + W - 1) / W; }
       a.cursor = R.scratch; a.done_warps = R.scratch + 1; a.out_cnt = R.scratch + 2; a.stats = R.scratch + 2 + kMigMaxDest;
       gridDim.x = (unsigned)grid_blocks;
-      if (mapped) emu_launch_warps((int64_t)grid_blocks * 8, [&] { mig_step_kernel<true, 4, true>(a); });
+      // the product's default variants (migrate.cu mig_variant): 16 staged tuples per warp and destination up to 4 shards, 8 beyond
+      if (mapped && W > 4) emu_launch_warps((int64_t)grid_blocks * 8, [&] { mig_step_kernel<true, 4, true, 8>(a); });
+      else if (mapped) emu_launch_warps((int64_t)grid_blocks * 8, [&] { mig_step_kernel<true, 4, true>(a); });
+      else if (W > 4) emu_launch_warps((int64_t)grid_blocks * 8, [&] { mig_step_kernel<true, 4, false, 8>(a); });
       else emu_launch_warps((int64_t)grid_blocks * 8, [&] { mig_step_kernel<true>(a); });
     }
     unsigned long long sent = 0;
